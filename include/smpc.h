@@ -1,0 +1,210 @@
+/*
+ * smpc.h — C-ABI of libsmpc.so, the B200-native batched social-MPC solver.
+ *
+ * Drop-in boundary for the hot path of PIC4SeR/nav2_social_mpc_controller:
+ *   bool Optimizer::optimize(...)            include/nav2_social_mpc_controller/optimizer.hpp:167-170
+ *   void Optimizer::initialize(params)       include/nav2_social_mpc_controller/optimizer.hpp:152
+ *   struct OptimizerParams                   include/nav2_social_mpc_controller/optimizer.hpp:59-101
+ *   ceres::Solve(options_, &problem, &summary)   src/optimizer.cpp:381
+ *
+ * Everything here is POD: plain pointers, sizes and doubles. No exceptions, no
+ * torch / STL types cross this boundary. All floating point is FP64 except
+ * the costmap (u8) and the obstacle-distance grid (f32 + u32).
+ *
+ * Memory layouts (B = problems, S = optimised steps N_v, NB = parameter blocks,
+ * A = agent columns per step, row-major, last index fastest):
+ *   pose0      [B][3]            x, y, yaw of the first seed pose (yaw already tf2 round-tripped)
+ *   u0         [B][NB][2]        initial (v, w) of block b = seed velocity at TIME INDEX b
+ *   path_xy    [B][2][S+1]       seed positions: row 0 = x, row 1 = y; step index fastest
+ *   goal_yaw   [B]               yaw of the last seed pose (src/optimizer.cpp:298)
+ *   agents     [B][A][6][S+1]    projected people: component c in (x, y, yaw, t, lv, av), step index fastest;
+ *                                t == -1 marks an invalid (padded) agent (src/optimizer.cpp:468-474).
+ *                                The reference shape AgentsTrajectories[step][agent][6]
+ *                                (tools/type_definitions.hpp:6-9) is transposed so the S+1 steps a warp
+ *                                reads are contiguous.
+ *   has_people [B] u8            people.people.size() != 0 (src/optimizer.cpp:263)
+ *   costmaps   [M][size_y][size_x] u8, Nav2 costmap bytes, row = y (src/optimizer.cpp:167-168)
+ *   costmap_origin [M][2]        world origin of each map
+ *   costmap_index  [B] i32       which of the M maps problem b reads (NULL: map b % M)
+ */
+#ifndef SMPC_H_
+#define SMPC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMPC_ABI_VERSION 1
+#define SMPC_MAX_BLOCKS 18 /* control_horizon 18 with parameter_block_length 1: the "36x36 class" */
+
+/* Return codes of every entry point. Per-problem solver outcomes are NOT call
+ * errors: they are reported in smpc_result.termination[] (mirrors
+ * `return false` of Optimizer::optimize, src/optimizer.cpp:384-388). */
+enum smpc_status {
+  SMPC_OK = 0,
+  SMPC_ERR_ARGUMENT = -1,
+  SMPC_ERR_CUDA = -2,
+  SMPC_ERR_UNSUPPORTED = -3,
+  SMPC_ERR_IO = -4,
+  SMPC_ERR_PARAM = -5 /* e.g. invalid linear_solver_type, src/optimizer.cpp:31-45 */
+};
+
+/* ceres::TerminationType as observed through Solver::Summary, plus the reason. */
+enum smpc_termination {
+  SMPC_CONVERGENCE_GRADIENT = 0,  /* gradient_max_norm <= gradient_tolerance */
+  SMPC_CONVERGENCE_PARAMETER = 1, /* step_norm <= param_tol*(x_norm+param_tol) */
+  SMPC_CONVERGENCE_FUNCTION = 2,  /* |cost_change| <= fn_tol*cost */
+  SMPC_CONVERGENCE_RADIUS = 3,    /* trust region radius <= 1e-32 */
+  SMPC_NO_CONVERGENCE = 4,        /* max_num_iterations reached */
+  SMPC_FAILURE_INVALID_STEPS = 5, /* 5 consecutive invalid steps */
+  SMPC_FAILURE_EVALUATION = 6     /* non-finite residual/Jacobian at an accepted point */
+};
+
+/* Mirrors OptimizerParams (optimizer.hpp:59-101) and the defaults declared in
+ * OptimizerParams::get (src/optimizer.cpp:26-84). */
+typedef struct smpc_params {
+  char linear_solver_type[32]; /* validated against the 5-entry map, optimizer.hpp:71-77 */
+  double param_tol;
+  double fn_tol;
+  double gradient_tol;
+  int max_iterations;
+  int debug;
+  int control_horizon;
+  int parameter_block_length;
+  int discretization; /* read from yaml, never used */
+  double distance_w;
+  double socialwork_w;
+  double velocity_w;
+  double angle_w;
+  double agent_angle_w;
+  double proxemics_w;
+  double velocity_feasibility_w;
+  double obstacle_w;
+  double goal_align_w;
+  float current_path_w;
+  float current_cmds_w;
+  float max_time;  /* trajectorizer.max_time */
+  float time_step; /* trajectorizer.time_step (held as float in the reference) */
+  /* trajectorizer.* and top-level plugin parameters (path_trajectorizer.cpp:52-70, social_mpc_controller.cpp:59-65) */
+  int omnidirectional;
+  double traj_desired_linear_vel;
+  double lookahead_dist;
+  double max_angular_vel;
+  double transform_tolerance;
+  char base_frame[64];
+  double desired_linear_vel;
+  double fov_angle;
+  /* Solver-behaviour switches that are not reference yaml (documented in DESIGN.md):
+   * ceres_compat 200 = Ceres 2.0.0 loop (Ubuntu 22.04 / Humble), 220 = Ceres >= 2.1
+   * (parameter / function tolerance only tested after a first successful step). */
+  int ceres_compat;
+} smpc_params;
+
+/* One batch of independent MPC problems, post-projection: exactly the arrays
+ * the Ceres problem of src/optimizer.cpp:241-379 is assembled from. Pointers
+ * are host pointers for smpc_solve_batch and device pointers for
+ * smpc_solve_batch_device. */
+typedef struct smpc_batch {
+  int n_problems; /* B */
+  int n_steps;    /* S = N_v = P_poses - 1, uniform in the batch */
+  int n_agents;   /* A: 3 in the reference (src/optimizer.cpp:468-479); any A >= 0 here */
+  int n_costmaps; /* M */
+  int size_x;
+  int size_y;
+  double resolution;
+  double dt; /* (double)(float)time_step, SURVEY Q15 */
+  const double* pose0;
+  const double* u0;
+  const double* path_xy;
+  const double* goal_yaw;
+  const double* agents;       /* may be NULL when n_agents == 0 */
+  const uint8_t* has_people;  /* may be NULL: no problem has people */
+  const uint8_t* costmaps;
+  const double* costmap_origin;
+  const int32_t* costmap_index; /* may be NULL */
+} smpc_batch;
+
+/* Per-problem outputs. Any pointer may be NULL (that output is skipped).
+ *   u            [B][NB][2]   optimised block values (the Ceres parameter blocks after Solve)
+ *   cmds         [B][S+1][2]  per-step (v, w) after hold-last fill and block expansion, src/optimizer.cpp:390-419
+ *   path         [B][S+1][3]  Euler-rebuilt poses x, y, yaw, pose0 excluded, src/optimizer.cpp:420-446
+ *   cost_initial [B]          Summary::initial_cost
+ *   cost_final   [B]          Summary::final_cost (min over iteration costs)
+ *   iterations   [B]          index of the last recorded TR iteration
+ *   termination  [B]          enum smpc_termination
+ *   usable       [B]          Summary::IsSolutionUsable(); 0 <=> optimize() would return false
+ *   n_evals      [B][2]       {Jacobian evaluations, cost/gradient-only evaluations} spent (roofline numerator)
+ */
+typedef struct smpc_result {
+  double* u;
+  double* cmds;
+  double* path;
+  double* cost_initial;
+  double* cost_final;
+  int32_t* iterations;
+  int32_t* termination;
+  uint8_t* usable;
+  int32_t* n_evals;
+} smpc_result;
+
+/* Normal-equation snapshot of one evaluation (first-slice / test entry):
+ *   cost [B], grad [B][P], hess [B][P*(P+1)/2] (row-major lower triangle), P = 2*NB. */
+typedef struct smpc_eval_out {
+  double* cost;
+  double* grad;
+  double* hess;
+  uint8_t* ok; /* 0 when a residual or Jacobian entry was non-finite */
+} smpc_eval_out;
+
+typedef struct smpc_handle smpc_handle;
+
+/* ---- parameters ------------------------------------------------------- */
+/* Fill with the defaults of OptimizerParams::get (src/optimizer.cpp:26-84). */
+void smpc_params_default(smpc_params* p);
+/* Parse `<plugin_name>:` subtree (e.g. "FollowPath") of a Nav2 params yaml:
+ * trajectorizer.*, optimizer.*, optimizer.weights.* (src/optimizer.cpp:16-85). */
+int smpc_params_from_yaml(const char* yaml_path, const char* plugin_name, smpc_params* p);
+/* Derived sizes of the assembled problem (src/optimizer.cpp:248-249):
+ * ch = min(control_horizon, S), bl = min(block_length, ch), NB = ceil(ch/bl),
+ * n_bounded = ch/bl. Any out pointer may be NULL. */
+int smpc_problem_dims(const smpc_params* p, int n_steps, int* ch, int* bl, int* n_blocks, int* n_bounded);
+
+/* ---- handle ------------------------------------------------------------ */
+/* One handle per caller thread and per GPU; calls on a handle are serialised.
+ * Replaces Optimizer::initialize (src/optimizer.cpp:98-132). */
+int smpc_create(const smpc_params* p, int device, smpc_handle** out);
+void smpc_destroy(smpc_handle* h);
+const char* smpc_last_error(void);
+int smpc_abi_version(void);
+
+/* ---- level-1 solve: replaces ceres::Solve at src/optimizer.cpp:381 ------ */
+/* Host buffers in, host buffers out (H2D, kernels, D2H inside the call). */
+int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out);
+/* Device buffers in/out; asynchronous on `stream` (a cudaStream_t, NULL = default). */
+int smpc_solve_batch_device(smpc_handle* h, const smpc_batch* in, smpc_result* out, void* stream);
+/* Evaluate cost, J^T r and J^T J at given block values x [B][NB][2] (device pointers). */
+int smpc_eval_batch_device(smpc_handle* h, const smpc_batch* in, const double* x, smpc_eval_out* out, void* stream);
+/* Host-buffer convenience wrapper of the above (tests). */
+int smpc_eval_batch(smpc_handle* h, const smpc_batch* in, const double* x, smpc_eval_out* out);
+
+/* Multi-start selection: per robot arg-min of cost_final over `n_starts`
+ * consecutive problems (device pointers). best_index [R] i32 (global problem
+ * index, -1 if no usable start), best_cost [R], best_u [R][NB][2]. */
+int smpc_multistart_argmin_device(smpc_handle* h, int n_robots, int n_starts, int n_blocks, const double* cost_final,
+                                  const uint8_t* usable, const double* u, int32_t* best_index, double* best_cost,
+                                  double* best_u, void* stream);
+
+/* Device-time (ms) of the solve kernel of the last *_device / host solve call,
+ * measured with CUDA events on the launching stream; < 0 if unavailable.
+ * Synchronises the stream. */
+double smpc_last_kernel_ms(smpc_handle* h);
+/* Number of kernels this library launched on the handle since creation. */
+long long smpc_launch_count(smpc_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMPC_H_ */

@@ -1,0 +1,169 @@
+"""ctypes mirror of include/smpc.h (the C-ABI of libsmpc.so).
+
+The structures here are byte-for-byte the PODs declared in include/smpc.h; they are
+also what the CPU oracle (test infrastructure under oracle/) consumes, so parity tests hand the
+same buffers to both. Nothing in this module computes anything.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import numpy as np
+
+SMPC_ABI_VERSION = 1
+SMPC_MAX_BLOCKS = 18
+
+# enum smpc_termination
+CONVERGENCE_GRADIENT = 0
+CONVERGENCE_PARAMETER = 1
+CONVERGENCE_FUNCTION = 2
+CONVERGENCE_RADIUS = 3
+NO_CONVERGENCE = 4
+FAILURE_INVALID_STEPS = 5
+FAILURE_EVALUATION = 6
+TERMINATION_NAMES = {
+    0: "CONVERGENCE(gradient)", 1: "CONVERGENCE(parameter)", 2: "CONVERGENCE(function)",
+    3: "CONVERGENCE(radius)", 4: "NO_CONVERGENCE", 5: "FAILURE(invalid steps)", 6: "FAILURE(evaluation)",
+}
+
+
+class SmpcParams(C.Structure):
+    """struct smpc_params — mirrors OptimizerParams (reference optimizer.hpp:59-101)."""
+    _fields_ = [
+        ("linear_solver_type", C.c_char * 32),
+        ("param_tol", C.c_double),
+        ("fn_tol", C.c_double),
+        ("gradient_tol", C.c_double),
+        ("max_iterations", C.c_int),
+        ("debug", C.c_int),
+        ("control_horizon", C.c_int),
+        ("parameter_block_length", C.c_int),
+        ("discretization", C.c_int),
+        ("distance_w", C.c_double),
+        ("socialwork_w", C.c_double),
+        ("velocity_w", C.c_double),
+        ("angle_w", C.c_double),
+        ("agent_angle_w", C.c_double),
+        ("proxemics_w", C.c_double),
+        ("velocity_feasibility_w", C.c_double),
+        ("obstacle_w", C.c_double),
+        ("goal_align_w", C.c_double),
+        ("current_path_w", C.c_float),
+        ("current_cmds_w", C.c_float),
+        ("max_time", C.c_float),
+        ("time_step", C.c_float),
+        ("omnidirectional", C.c_int),
+        ("traj_desired_linear_vel", C.c_double),
+        ("lookahead_dist", C.c_double),
+        ("max_angular_vel", C.c_double),
+        ("transform_tolerance", C.c_double),
+        ("base_frame", C.c_char * 64),
+        ("desired_linear_vel", C.c_double),
+        ("fov_angle", C.c_double),
+        ("ceres_compat", C.c_int),
+    ]
+
+
+class SmpcBatch(C.Structure):
+    """struct smpc_batch — one batch of post-projection MPC problems."""
+    _fields_ = [
+        ("n_problems", C.c_int),
+        ("n_steps", C.c_int),
+        ("n_agents", C.c_int),
+        ("n_costmaps", C.c_int),
+        ("size_x", C.c_int),
+        ("size_y", C.c_int),
+        ("resolution", C.c_double),
+        ("dt", C.c_double),
+        ("pose0", C.c_void_p),
+        ("u0", C.c_void_p),
+        ("path_xy", C.c_void_p),
+        ("goal_yaw", C.c_void_p),
+        ("agents", C.c_void_p),
+        ("has_people", C.c_void_p),
+        ("costmaps", C.c_void_p),
+        ("costmap_origin", C.c_void_p),
+        ("costmap_index", C.c_void_p),
+    ]
+
+
+class SmpcResult(C.Structure):
+    _fields_ = [
+        ("u", C.c_void_p),
+        ("cmds", C.c_void_p),
+        ("path", C.c_void_p),
+        ("cost_initial", C.c_void_p),
+        ("cost_final", C.c_void_p),
+        ("iterations", C.c_void_p),
+        ("termination", C.c_void_p),
+        ("usable", C.c_void_p),
+        ("n_evals", C.c_void_p),
+    ]
+
+
+class SmpcEvalOut(C.Structure):
+    _fields_ = [
+        ("cost", C.c_void_p),
+        ("grad", C.c_void_p),
+        ("hess", C.c_void_p),
+        ("ok", C.c_void_p),
+    ]
+
+
+def problem_dims(control_horizon: int, block_length: int, n_steps: int):
+    """ch, bl, n_blocks, n_bounded exactly as reference src/optimizer.cpp:248-249,254-261,373."""
+    ch = min(int(control_horizon), int(n_steps))
+    bl = min(int(block_length), ch)
+    nb = (ch + bl - 1) // bl
+    return ch, bl, nb, ch // bl
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    # torch tensor (device or host)
+    return int(a.data_ptr())
+
+
+BATCH_FIELDS = ("pose0", "u0", "path_xy", "goal_yaw", "agents", "has_people", "costmaps",
+                "costmap_origin", "costmap_index")
+BATCH_DTYPES = {"pose0": np.float64, "u0": np.float64, "path_xy": np.float64, "goal_yaw": np.float64,
+                "agents": np.float64, "has_people": np.uint8, "costmaps": np.uint8,
+                "costmap_origin": np.float64, "costmap_index": np.int32}
+
+
+def make_batch_struct(arrays: dict, n_problems: int, n_steps: int, n_agents: int, n_costmaps: int,
+                      size_x: int, size_y: int, resolution: float, dt: float) -> SmpcBatch:
+    """Fill a smpc_batch from numpy arrays or torch tensors (the caller keeps them alive)."""
+    b = SmpcBatch()
+    b.n_problems, b.n_steps, b.n_agents, b.n_costmaps = n_problems, n_steps, n_agents, n_costmaps
+    b.size_x, b.size_y, b.resolution, b.dt = size_x, size_y, float(resolution), float(dt)
+    for f in BATCH_FIELDS:
+        setattr(b, f, _ptr(arrays.get(f)))
+    return b
+
+
+RESULT_FIELDS = ("u", "cmds", "path", "cost_initial", "cost_final", "iterations", "termination", "usable",
+                 "n_evals")
+
+
+def result_shapes(n_problems: int, n_steps: int, n_blocks: int):
+    return {
+        "u": ((n_problems, n_blocks, 2), np.float64),
+        "cmds": ((n_problems, n_steps + 1, 2), np.float64),
+        "path": ((n_problems, n_steps + 1, 3), np.float64),
+        "cost_initial": ((n_problems,), np.float64),
+        "cost_final": ((n_problems,), np.float64),
+        "iterations": ((n_problems,), np.int32),
+        "termination": ((n_problems,), np.int32),
+        "usable": ((n_problems,), np.uint8),
+        "n_evals": ((n_problems, 2), np.int32),
+    }
+
+
+def make_result_struct(arrays: dict) -> SmpcResult:
+    r = SmpcResult()
+    for f in RESULT_FIELDS:
+        setattr(r, f, _ptr(arrays.get(f)))
+    return r
