@@ -1,0 +1,612 @@
+// smpc_host.cu — host side of libsmpc.so: the C-ABI declared in include/smpc.h.
+// Mirrors OptimizerParams::get / Optimizer::initialize / the ceres::Solve call of the reference
+// (src/optimizer.cpp:16-132, :381) for batches of problems. No CPU compute path exists here: every
+// solve / eval entry launches the sm_100a kernels of smpc_kernels.cu or returns an error.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/smpc.h"
+#include "smpc_device.cuh"
+#include "smpc_internal.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(SMPC_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define SMPC_CUDA(call)                                   \
+  do {                                                    \
+    cudaError_t e__ = (call);                             \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+struct DeviceBuffer {
+  void* ptr = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+    const size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&ptr, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+  }
+};
+
+const char* const kSolverTypes[] = {"DENSE_SCHUR", "SPARSE_SCHUR", "DENSE_NORMAL_CHOLESKY", "DENSE_QR",
+                                    "SPARSE_NORMAL_CHOLESKY"};  // reference optimizer.hpp:71-77
+
+bool valid_solver_type(const char* s) {
+  for (const char* t : kSolverTypes)
+    if (std::strcmp(s, t) == 0) return true;
+  return false;
+}
+
+}  // namespace
+
+struct smpc_handle {
+  smpc_params params;
+  int device = 0;
+  int n_sm = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  int* queue = nullptr;
+  long long launches = 0;
+  std::mutex mu;
+  // staging for the host-buffer entry points
+  DeviceBuffer in_buf, out_buf;
+};
+
+namespace {
+
+int derive_dims(const smpc_params* p, int S, int* ch, int* bl, int* nb, int* n_bounded) {
+  if (S < 1) return fail(SMPC_ERR_ARGUMENT, "n_steps must be >= 1 (the reference needs a path of >= 2 poses)");
+  if (p->control_horizon < 1 || p->parameter_block_length < 1)
+    return fail(SMPC_ERR_PARAM, "control_horizon and parameter_block_length must be >= 1");
+  const int c = std::min(p->control_horizon, S);         // src/optimizer.cpp:248
+  const int b = std::min(p->parameter_block_length, c);  // src/optimizer.cpp:249
+  if (ch) *ch = c;
+  if (bl) *bl = b;
+  if (nb) *nb = (c + b - 1) / b;
+  if (n_bounded) *n_bounded = c / b;
+  return SMPC_OK;
+}
+
+int make_dev_params(const smpc_params& p, int S, smpc::DevParams* d) {
+  int rc = derive_dims(&p, S, &d->ch, &d->bl, &d->nb, &d->n_bounded);
+  if (rc != SMPC_OK) return rc;
+  if (d->nb > smpc::max_supported_blocks())
+    return fail(SMPC_ERR_UNSUPPORTED, "more than " + std::to_string(smpc::max_supported_blocks()) +
+                                          " parameter blocks are not built into this libsmpc.so");
+  if (S > 32 * smpc::kMaxChunks) return fail(SMPC_ERR_UNSUPPORTED, "n_steps > 64 is not supported");
+  d->w_distance = p.distance_w;
+  d->w_social = p.socialwork_w;
+  d->w_velocity = p.velocity_w;
+  d->w_angle = p.angle_w;
+  d->w_agent_angle = p.agent_angle_w;
+  d->w_prox = p.proxemics_w;
+  d->w_vf = p.velocity_feasibility_w;
+  d->w_obstacle = p.obstacle_w;
+  d->w_goal = p.goal_align_w;
+  d->param_tol = p.param_tol;
+  d->fn_tol = p.fn_tol;
+  d->gradient_tol = p.gradient_tol;
+  d->max_iterations = p.max_iterations;
+  d->ceres_compat = p.ceres_compat ? p.ceres_compat : 200;
+  return SMPC_OK;
+}
+
+int check_batch(const smpc_batch* in) {
+  if (!in) return fail(SMPC_ERR_ARGUMENT, "batch is NULL");
+  if (in->n_problems < 0) return fail(SMPC_ERR_ARGUMENT, "n_problems < 0");
+  if (in->n_agents < 0) return fail(SMPC_ERR_ARGUMENT, "n_agents < 0");
+  if (in->n_problems == 0) return SMPC_OK;
+  if (!in->pose0 || !in->u0 || !in->path_xy || !in->goal_yaw) return fail(SMPC_ERR_ARGUMENT, "pose0/u0/path_xy/goal_yaw missing");
+  if (!in->costmaps || !in->costmap_origin || in->n_costmaps < 1 || in->size_x < 1 || in->size_y < 1)
+    return fail(SMPC_ERR_ARGUMENT, "costmap missing (the reference always dereferences costmap->getCharMap())");
+  if (!(in->resolution > 0.0)) return fail(SMPC_ERR_ARGUMENT, "costmap resolution must be > 0");
+  if (!(in->dt > 0.0)) return fail(SMPC_ERR_ARGUMENT, "dt must be > 0");
+  return SMPC_OK;
+}
+
+void to_dev_batch(const smpc_batch& in, smpc::DevBatch* d) {
+  d->B = in.n_problems;
+  d->S = in.n_steps;
+  d->A = (in.agents != nullptr) ? in.n_agents : 0;
+  d->M = in.n_costmaps;
+  d->size_x = in.size_x;
+  d->size_y = in.size_y;
+  d->resolution = in.resolution;
+  d->dt = in.dt;
+  d->pose0 = in.pose0;
+  d->u0 = in.u0;
+  d->path_xy = in.path_xy;
+  d->goal_yaw = in.goal_yaw;
+  d->agents = in.agents;
+  d->has_people = in.has_people;
+  d->costmaps = in.costmaps;
+  d->costmap_origin = in.costmap_origin;
+  d->costmap_index = in.costmap_index;
+}
+
+void to_dev_result(const smpc_result& out, smpc::DevResult* d) {
+  d->u = out.u;
+  d->cmds = out.cmds;
+  d->path = out.path;
+  d->cost_initial = out.cost_initial;
+  d->cost_final = out.cost_final;
+  d->iterations = out.iterations;
+  d->termination = out.termination;
+  d->usable = out.usable;
+  d->n_evals = out.n_evals;
+}
+
+size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+struct Carver {  // carve aligned sub-buffers out of one device allocation
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* b) : base(static_cast<char*>(b)) {}
+  void* take(size_t bytes) {
+    void* p = base ? base + off : nullptr;
+    off += align256(bytes);
+    return p;
+  }
+};
+
+// ---- YAML subtree reader (indentation based; enough for Nav2 parameter files) ---------------------------
+std::string trim(const std::string& s) {
+  size_t a = s.find_first_not_of(" \t\r\n");
+  if (a == std::string::npos) return "";
+  size_t b = s.find_last_not_of(" \t\r\n");
+  return s.substr(a, b - a + 1);
+}
+
+std::string strip_comment(const std::string& s) {
+  bool in_s = false, in_d = false;
+  for (size_t i = 0; i < s.size(); ++i) {
+    if (s[i] == '\'' && !in_d) in_s = !in_s;
+    if (s[i] == '"' && !in_s) in_d = !in_d;
+    if (s[i] == '#' && !in_s && !in_d && (i == 0 || s[i - 1] == ' ' || s[i - 1] == '\t')) return s.substr(0, i);
+  }
+  return s;
+}
+
+// Flatten every `key: value` leaf below `<plugin>:` into "a.b.c" -> "value".
+bool read_plugin_subtree(const std::string& path, const std::string& plugin, std::map<std::string, std::string>* kv,
+                         std::string* err) {
+  std::ifstream f(path);
+  if (!f) {
+    *err = "cannot open " + path;
+    return false;
+  }
+  std::string line;
+  bool inside = false;
+  int plugin_indent = -1;
+  std::vector<std::pair<int, std::string>> stack;
+  while (std::getline(f, line)) {
+    const std::string body = strip_comment(line);
+    if (trim(body).empty()) continue;
+    const int indent = static_cast<int>(body.find_first_not_of(' '));
+    const std::string t = trim(body);
+    const size_t colon = t.find(':');
+    if (colon == std::string::npos) continue;
+    const std::string key = trim(t.substr(0, colon));
+    std::string val = trim(t.substr(colon + 1));
+    if (!inside) {
+      if (key == plugin && val.empty()) {
+        inside = true;
+        plugin_indent = indent;
+        stack.clear();
+      }
+      continue;
+    }
+    if (indent <= plugin_indent) break;  // left the subtree
+    while (!stack.empty() && stack.back().first >= indent) stack.pop_back();
+    if (val.empty()) {
+      stack.emplace_back(indent, key);
+      continue;
+    }
+    if (val.size() >= 2 && ((val.front() == '"' && val.back() == '"') || (val.front() == '\'' && val.back() == '\'')))
+      val = val.substr(1, val.size() - 2);
+    std::string full;
+    for (auto& s : stack) full += s.second + ".";
+    (*kv)[full + key] = val;
+  }
+  if (!inside) {
+    *err = "plugin subtree '" + plugin + ":' not found in " + path;
+    return false;
+  }
+  return true;
+}
+
+bool parse_bool(const std::string& v) { return v == "true" || v == "True" || v == "TRUE" || v == "1"; }
+
+}  // namespace
+
+extern "C" {
+
+int smpc_abi_version(void) { return SMPC_ABI_VERSION; }
+
+const char* smpc_last_error(void) { return g_last_error.c_str(); }
+
+void smpc_params_default(smpc_params* p) {
+  if (!p) return;
+  std::memset(p, 0, sizeof(*p));
+  // src/optimizer.cpp:26-84
+  std::snprintf(p->linear_solver_type, sizeof(p->linear_solver_type), "%s", "SPARSE_NORMAL_CHOLESKY");
+  p->param_tol = 1e-15;
+  p->fn_tol = 1e-7;
+  p->gradient_tol = 1e-10;
+  p->max_iterations = 100;
+  p->debug = 0;
+  p->control_horizon = 5;
+  p->parameter_block_length = 5;
+  p->discretization = 0;
+  p->distance_w = 3.0;
+  p->socialwork_w = 1.0;
+  p->velocity_w = 0.5;
+  p->angle_w = 0.0;
+  p->agent_angle_w = 0.5;
+  p->proxemics_w = 90.0;
+  p->velocity_feasibility_w = 0.5;
+  p->obstacle_w = 0.0;
+  p->goal_align_w = 0.0;
+  p->current_path_w = 1.0f;
+  p->current_cmds_w = 1.0f;
+  // src/path_trajectorizer.cpp:52-59
+  p->max_time = 3.0f;
+  p->time_step = 0.05f;
+  p->omnidirectional = 0;
+  p->traj_desired_linear_vel = 0.4;
+  p->lookahead_dist = 0.4;
+  p->max_angular_vel = 1.0;
+  p->transform_tolerance = 0.1;
+  std::snprintf(p->base_frame, sizeof(p->base_frame), "%s", "base_footprint");
+  // src/social_mpc_controller.cpp:59-65
+  p->desired_linear_vel = 0.5;
+  p->fov_angle = M_PI / 4.0;
+  p->ceres_compat = 200;
+}
+
+int smpc_params_from_yaml(const char* yaml_path, const char* plugin_name, smpc_params* p) {
+  if (!yaml_path || !plugin_name || !p) return fail(SMPC_ERR_ARGUMENT, "NULL argument");
+  std::map<std::string, std::string> kv;
+  std::string err;
+  if (!read_plugin_subtree(yaml_path, plugin_name, &kv, &err)) return fail(SMPC_ERR_IO, err);
+  smpc_params_default(p);
+  auto num = [&](const char* key, double* out) {
+    auto it = kv.find(key);
+    if (it != kv.end()) *out = std::strtod(it->second.c_str(), nullptr);
+  };
+  auto inum = [&](const char* key, int* out) {
+    auto it = kv.find(key);
+    if (it != kv.end()) *out = static_cast<int>(std::strtol(it->second.c_str(), nullptr, 10));
+  };
+  auto fnum = [&](const char* key, float* out) {
+    auto it = kv.find(key);
+    if (it != kv.end()) *out = static_cast<float>(std::strtod(it->second.c_str(), nullptr));
+  };
+  if (kv.count("optimizer.linear_solver_type"))
+    std::snprintf(p->linear_solver_type, sizeof(p->linear_solver_type), "%s", kv["optimizer.linear_solver_type"].c_str());
+  if (!valid_solver_type(p->linear_solver_type)) {
+    std::string valid;
+    for (const char* t : kSolverTypes) valid += std::string(valid.empty() ? "" : ", ") + t;
+    // mirrors the std::runtime_error at src/optimizer.cpp:42-44
+    return fail(SMPC_ERR_PARAM, "Invalid parameter: linear_solver_type. Valid values are " + valid);
+  }
+  num("optimizer.param_tol", &p->param_tol);
+  num("optimizer.fn_tol", &p->fn_tol);
+  num("optimizer.gradient_tol", &p->gradient_tol);
+  inum("optimizer.max_iterations", &p->max_iterations);
+  if (kv.count("optimizer.debug_optimizer")) p->debug = parse_bool(kv["optimizer.debug_optimizer"]) ? 1 : 0;
+  inum("optimizer.control_horizon", &p->control_horizon);
+  inum("optimizer.parameter_block_length", &p->parameter_block_length);
+  inum("optimizer.discretization", &p->discretization);
+  fnum("optimizer.current_path_weight", &p->current_path_w);
+  fnum("optimizer.current_cmds_weight", &p->current_cmds_w);
+  num("optimizer.weights.distance_weight", &p->distance_w);
+  num("optimizer.weights.social_weight", &p->socialwork_w);
+  num("optimizer.weights.velocity_weight", &p->velocity_w);
+  num("optimizer.weights.angle_weight", &p->angle_w);
+  num("optimizer.weights.agent_angle_weight", &p->agent_angle_w);
+  num("optimizer.weights.proxemics_weight", &p->proxemics_w);
+  num("optimizer.weights.velocity_feasibility_weight", &p->velocity_feasibility_w);
+  num("optimizer.weights.obstacle_weight", &p->obstacle_w);
+  num("optimizer.weights.goal_align_weight", &p->goal_align_w);
+  fnum("trajectorizer.max_time", &p->max_time);
+  fnum("trajectorizer.time_step", &p->time_step);
+  if (kv.count("trajectorizer.omnidirectional")) p->omnidirectional = parse_bool(kv["trajectorizer.omnidirectional"]) ? 1 : 0;
+  num("trajectorizer.desired_linear_vel", &p->traj_desired_linear_vel);
+  num("trajectorizer.lookahead_dist", &p->lookahead_dist);
+  num("trajectorizer.max_angular_vel", &p->max_angular_vel);
+  num("trajectorizer.transform_tolerance", &p->transform_tolerance);
+  if (kv.count("trajectorizer.base_frame"))
+    std::snprintf(p->base_frame, sizeof(p->base_frame), "%s", kv["trajectorizer.base_frame"].c_str());
+  num("desired_linear_vel", &p->desired_linear_vel);
+  num("fov_angle", &p->fov_angle);
+  return SMPC_OK;
+}
+
+int smpc_problem_dims(const smpc_params* p, int n_steps, int* ch, int* bl, int* n_blocks, int* n_bounded) {
+  if (!p) return fail(SMPC_ERR_ARGUMENT, "params is NULL");
+  return derive_dims(p, n_steps, ch, bl, n_blocks, n_bounded);
+}
+
+int smpc_create(const smpc_params* p, int device, smpc_handle** out) {
+  if (!p || !out) return fail(SMPC_ERR_ARGUMENT, "NULL argument");
+  if (!valid_solver_type(p->linear_solver_type)) return fail(SMPC_ERR_PARAM, "Invalid parameter: linear_solver_type");
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0)
+    return fail(SMPC_ERR_CUDA, std::string("no CUDA device available (libsmpc has no CPU path): ") + cudaGetErrorString(e));
+  if (device < 0 || device >= n_dev) return fail(SMPC_ERR_ARGUMENT, "device index out of range");
+  SMPC_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  SMPC_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(SMPC_ERR_UNSUPPORTED, "libsmpc.so is built for sm_100a (B200); found compute capability " +
+                                          std::to_string(prop.major) + "." + std::to_string(prop.minor));
+  smpc_handle* h = new smpc_handle();
+  h->params = *p;
+  h->device = device;
+  h->n_sm = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
+      cudaMalloc(&h->queue, sizeof(int)) != cudaSuccess) {
+    e = cudaGetLastError();
+    smpc_destroy(h);
+    return cuda_fail(e, "smpc_create resources");
+  }
+  *out = h;
+  return SMPC_OK;
+}
+
+void smpc_destroy(smpc_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  h->in_buf.release();
+  h->out_buf.release();
+  if (h->queue) cudaFree(h->queue);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+static int solve_device_locked(smpc_handle* h, const smpc_batch* in, smpc_result* out, cudaStream_t stream) {
+  int rc = check_batch(in);
+  if (rc != SMPC_OK) return rc;
+  if (!out) return fail(SMPC_ERR_ARGUMENT, "result is NULL");
+  if (in->n_problems == 0) return SMPC_OK;
+  smpc::DevParams prm;
+  rc = make_dev_params(h->params, in->n_steps, &prm);
+  if (rc != SMPC_OK) return rc;
+  smpc::DevBatch bt;
+  to_dev_batch(*in, &bt);
+  smpc::DevResult rs;
+  to_dev_result(*out, &rs);
+  SMPC_CUDA(cudaSetDevice(h->device));
+  SMPC_CUDA(cudaMemsetAsync(h->queue, 0, sizeof(int), stream));
+  SMPC_CUDA(cudaEventRecord(h->ev0, stream));
+  SMPC_CUDA(smpc::launch_solve(prm, bt, rs, h->queue, h->n_sm, stream));
+  SMPC_CUDA(cudaEventRecord(h->ev1, stream));
+  h->timed = true;
+  h->launches += 1;
+  return SMPC_OK;
+}
+
+int smpc_solve_batch_device(smpc_handle* h, const smpc_batch* in, smpc_result* out, void* stream) {
+  if (!h) return fail(SMPC_ERR_ARGUMENT, "handle is NULL");
+  std::lock_guard<std::mutex> lk(h->mu);
+  return solve_device_locked(h, in, out, stream ? static_cast<cudaStream_t>(stream) : h->stream);
+}
+
+int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out) {
+  if (!h) return fail(SMPC_ERR_ARGUMENT, "handle is NULL");
+  std::lock_guard<std::mutex> lk(h->mu);
+  int rc = check_batch(in);
+  if (rc != SMPC_OK) return rc;
+  if (!out) return fail(SMPC_ERR_ARGUMENT, "result is NULL");
+  if (in->n_problems == 0) return SMPC_OK;
+  int nb = 0;
+  rc = derive_dims(&h->params, in->n_steps, nullptr, nullptr, &nb, nullptr);
+  if (rc != SMPC_OK) return rc;
+  SMPC_CUDA(cudaSetDevice(h->device));
+  const size_t B = in->n_problems, S1 = static_cast<size_t>(in->n_steps) + 1, A = in->agents ? in->n_agents : 0;
+  const size_t M = in->n_costmaps, P = 2 * static_cast<size_t>(nb);
+  const size_t map_bytes = M * in->size_x * in->size_y;
+  struct Item { const void* host; size_t bytes; void** dev; };
+  smpc_batch din = *in;
+  std::vector<Item> items = {
+      {in->pose0, B * 3 * 8, (void**)&din.pose0},
+      {in->u0, B * P * 8, (void**)&din.u0},
+      {in->path_xy, B * 2 * S1 * 8, (void**)&din.path_xy},
+      {in->goal_yaw, B * 8, (void**)&din.goal_yaw},
+      {A ? in->agents : nullptr, B * A * 6 * S1 * 8, (void**)&din.agents},
+      {in->has_people, B, (void**)&din.has_people},
+      {in->costmaps, map_bytes, (void**)&din.costmaps},
+      {in->costmap_origin, M * 2 * 8, (void**)&din.costmap_origin},
+      {in->costmap_index, B * 4, (void**)&din.costmap_index},
+  };
+  size_t total = 0;
+  for (auto& it : items) total += it.host ? align256(it.bytes) : 0;
+  SMPC_CUDA(h->in_buf.reserve(total));
+  Carver cin(h->in_buf.ptr);
+  for (auto& it : items) {
+    if (!it.host) {
+      *it.dev = nullptr;
+      continue;
+    }
+    void* d = cin.take(it.bytes);
+    SMPC_CUDA(cudaMemcpyAsync(d, it.host, it.bytes, cudaMemcpyHostToDevice, h->stream));
+    *it.dev = d;
+  }
+  struct OItem { void* host; size_t bytes; void** dev; };
+  smpc_result dout = *out;
+  std::vector<OItem> oitems = {
+      {out->u, B * P * 8, (void**)&dout.u},
+      {out->cmds, B * S1 * 2 * 8, (void**)&dout.cmds},
+      {out->path, B * S1 * 3 * 8, (void**)&dout.path},
+      {out->cost_initial, B * 8, (void**)&dout.cost_initial},
+      {out->cost_final, B * 8, (void**)&dout.cost_final},
+      {out->iterations, B * 4, (void**)&dout.iterations},
+      {out->termination, B * 4, (void**)&dout.termination},
+      {out->usable, B, (void**)&dout.usable},
+      {out->n_evals, B * 2 * 4, (void**)&dout.n_evals},
+  };
+  size_t ototal = 0;
+  for (auto& it : oitems) ototal += it.host ? align256(it.bytes) : 0;
+  SMPC_CUDA(h->out_buf.reserve(ototal));
+  Carver cout_(h->out_buf.ptr);
+  for (auto& it : oitems) *it.dev = it.host ? cout_.take(it.bytes) : nullptr;
+  rc = solve_device_locked(h, &din, &dout, h->stream);
+  if (rc != SMPC_OK) return rc;
+  for (auto& it : oitems)
+    if (it.host) SMPC_CUDA(cudaMemcpyAsync(it.host, *it.dev, it.bytes, cudaMemcpyDeviceToHost, h->stream));
+  SMPC_CUDA(cudaStreamSynchronize(h->stream));
+  return SMPC_OK;
+}
+
+int smpc_eval_batch_device(smpc_handle* h, const smpc_batch* in, const double* x, smpc_eval_out* out, void* stream) {
+  if (!h) return fail(SMPC_ERR_ARGUMENT, "handle is NULL");
+  std::lock_guard<std::mutex> lk(h->mu);
+  int rc = check_batch(in);
+  if (rc != SMPC_OK) return rc;
+  if (!x || !out) return fail(SMPC_ERR_ARGUMENT, "x / out is NULL");
+  if (in->n_problems == 0) return SMPC_OK;
+  smpc::DevParams prm;
+  rc = make_dev_params(h->params, in->n_steps, &prm);
+  if (rc != SMPC_OK) return rc;
+  smpc::DevBatch bt;
+  to_dev_batch(*in, &bt);
+  smpc::DevEvalOut eo{out->cost, out->grad, out->hess, out->ok};
+  SMPC_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+  SMPC_CUDA(smpc::launch_eval(prm, bt, x, eo, h->n_sm, st));
+  h->launches += 1;
+  return SMPC_OK;
+}
+
+int smpc_eval_batch(smpc_handle* h, const smpc_batch* in, const double* x, smpc_eval_out* out) {
+  if (!h) return fail(SMPC_ERR_ARGUMENT, "handle is NULL");
+  int rc = check_batch(in);
+  if (rc != SMPC_OK) return rc;
+  if (!x || !out) return fail(SMPC_ERR_ARGUMENT, "x / out is NULL");
+  if (in->n_problems == 0) return SMPC_OK;
+  int nb = 0;
+  rc = derive_dims(&h->params, in->n_steps, nullptr, nullptr, &nb, nullptr);
+  if (rc != SMPC_OK) return rc;
+  smpc_batch din = *in;
+  smpc_eval_out dout = *out;
+  const double* dx = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    SMPC_CUDA(cudaSetDevice(h->device));
+    const size_t B = in->n_problems, S1 = static_cast<size_t>(in->n_steps) + 1, A = in->agents ? in->n_agents : 0;
+    const size_t M = in->n_costmaps, P = 2 * static_cast<size_t>(nb), NH = P * (P + 1) / 2;
+    struct Item { const void* host; size_t bytes; void** dev; };
+    std::vector<Item> items = {
+        {in->pose0, B * 3 * 8, (void**)&din.pose0},
+        {in->u0, B * P * 8, (void**)&din.u0},
+        {in->path_xy, B * 2 * S1 * 8, (void**)&din.path_xy},
+        {in->goal_yaw, B * 8, (void**)&din.goal_yaw},
+        {A ? in->agents : nullptr, B * A * 6 * S1 * 8, (void**)&din.agents},
+        {in->has_people, B, (void**)&din.has_people},
+        {in->costmaps, M * in->size_x * in->size_y, (void**)&din.costmaps},
+        {in->costmap_origin, M * 2 * 8, (void**)&din.costmap_origin},
+        {in->costmap_index, B * 4, (void**)&din.costmap_index},
+        {x, B * P * 8, (void**)&dx},
+    };
+    size_t total = 0;
+    for (auto& it : items) total += it.host ? align256(it.bytes) : 0;
+    SMPC_CUDA(h->in_buf.reserve(total));
+    Carver cin(h->in_buf.ptr);
+    for (auto& it : items) {
+      if (!it.host) {
+        *it.dev = nullptr;
+        continue;
+      }
+      void* d = cin.take(it.bytes);
+      SMPC_CUDA(cudaMemcpyAsync(d, it.host, it.bytes, cudaMemcpyHostToDevice, h->stream));
+      *it.dev = d;
+    }
+    const size_t ob[4] = {B * 8, B * P * 8, B * NH * 8, B};
+    void* hostp[4] = {out->cost, out->grad, out->hess, out->ok};
+    void** devp[4] = {(void**)&dout.cost, (void**)&dout.grad, (void**)&dout.hess, (void**)&dout.ok};
+    size_t ototal = 0;
+    for (int i = 0; i < 4; ++i) ototal += hostp[i] ? align256(ob[i]) : 0;
+    SMPC_CUDA(h->out_buf.reserve(ototal));
+    Carver co(h->out_buf.ptr);
+    for (int i = 0; i < 4; ++i) *devp[i] = hostp[i] ? co.take(ob[i]) : nullptr;
+  }
+  rc = smpc_eval_batch_device(h, &din, dx, &dout, nullptr);
+  if (rc != SMPC_OK) return rc;
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    const size_t B = in->n_problems, P = 2 * static_cast<size_t>(nb), NH = P * (P + 1) / 2;
+    if (out->cost) SMPC_CUDA(cudaMemcpyAsync(out->cost, dout.cost, B * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (out->grad) SMPC_CUDA(cudaMemcpyAsync(out->grad, dout.grad, B * P * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (out->hess) SMPC_CUDA(cudaMemcpyAsync(out->hess, dout.hess, B * NH * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (out->ok) SMPC_CUDA(cudaMemcpyAsync(out->ok, dout.ok, B, cudaMemcpyDeviceToHost, h->stream));
+    SMPC_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  return SMPC_OK;
+}
+
+int smpc_multistart_argmin_device(smpc_handle* h, int n_robots, int n_starts, int n_blocks, const double* cost_final,
+                                  const uint8_t* usable, const double* u, int32_t* best_index, double* best_cost,
+                                  double* best_u, void* stream) {
+  if (!h) return fail(SMPC_ERR_ARGUMENT, "handle is NULL");
+  if (n_robots < 0 || n_starts < 1 || n_blocks < 1 || !cost_final || !best_index || !best_cost)
+    return fail(SMPC_ERR_ARGUMENT, "bad multistart arguments");
+  if (best_u && !u) return fail(SMPC_ERR_ARGUMENT, "best_u requested without u");
+  if (n_robots == 0) return SMPC_OK;
+  std::lock_guard<std::mutex> lk(h->mu);
+  SMPC_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+  SMPC_CUDA(smpc::launch_argmin(n_robots, n_starts, n_blocks, cost_final, usable, u, best_index, best_cost, best_u, st));
+  h->launches += 1;
+  return SMPC_OK;
+}
+
+double smpc_last_kernel_ms(smpc_handle* h) {
+  if (!h || !h->timed) return -1.0;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.0;
+  float ms = -1.0f;
+  if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.0;
+  return static_cast<double>(ms);
+}
+
+long long smpc_launch_count(smpc_handle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,176 @@
+"""GPU parity tests: the CUDA path (through the C-ABI of libsmpc.so) against the CPU oracle on the same seeded
+inputs. Tolerances are the ones BASELINE.json's north_star states: optimised command sequence within 1e-6
+absolute, final cost within 1e-8 relative, same termination criteria."""
+import numpy as np
+import pytest
+
+from nav2_social_mpc_controller_b200 import scenarios as sc
+
+pytestmark = pytest.mark.gpu
+
+U_ATOL = 1e-6      # north_star: command sequence within 1e-6 absolute
+COST_RTOL = 1e-8   # north_star: final cost within 1e-8 relative
+
+
+@pytest.fixture(scope="module")
+def make_opt():
+    from nav2_social_mpc_controller_b200.optimizer import Optimizer
+    made = []
+
+    def _mk(params):
+        o = Optimizer(0)
+        o.initialize(params)
+        made.append(o)
+        return o
+    yield _mk
+    for o in made:
+        o.close()
+
+
+def _eval_cases():
+    return [
+        ("readme_A3", lambda: sc.single("readme")),
+        ("params_yaml_A3", lambda: sc.single("params_yaml")),
+        ("soc_work_A5", lambda: sc.single("soc_work_obst", n_people=5)),
+        ("soc_work_padded", lambda: sc.single("soc_work_obst", n_people=1)),
+        ("corridor64", lambda: sc.corridor(B=64)),
+        ("crowd64_A20", lambda: sc.crowd(B=64, A=20)),
+        ("crowd32_A3_partial", lambda: sc.crowd(B=32, A=3, n_valid=2, config_id=7)),
+    ]
+
+
+@pytest.mark.parametrize("name,mk", _eval_cases(), ids=[c[0] for c in _eval_cases()])
+def test_eval_matches_oracle(oracle, make_opt, name, mk):
+    """cost, J^T r and J^T J of the analytic CUDA evaluation vs the oracle's jet (autodiff) Jacobian."""
+    from nav2_social_mpc_controller_b200.optimizer import hess_to_dense
+    batch = mk()
+    opt = make_opt(batch.params)
+    rng = np.random.default_rng(11)
+    P = 2 * batch.n_blocks
+    B = batch.n_problems
+    x = batch.arrays["u0"].reshape(B, P) + rng.normal(0, 0.03, (B, P))
+    got = opt.eval_batch(batch, x)
+    H = hess_to_dense(got["hess"], P)
+    for b in range(min(B, 48)):
+        e = oracle.evaluate(batch, b, x[b])
+        assert bool(got["ok"][b]) == e["ok"]
+        if not e["ok"]:
+            continue
+        assert got["cost"][b] == pytest.approx(e["cost"], rel=1e-11)
+        g_ref = e["grad"]
+        H_ref = e["jac"].T @ e["jac"]
+        assert np.abs(got["grad"][b] - g_ref).max() <= 1e-9 * max(1.0, np.abs(g_ref).max())
+        assert np.abs(H[b] - H_ref).max() <= 1e-9 * max(1.0, np.abs(H_ref).max())
+
+
+def _compare_solves(oracle, opt, batch, n_check=None, min_match=0.97):
+    B = batch.n_problems
+    n = B if n_check is None else min(B, n_check)
+    got = opt.solve_batch(batch)
+    sub = batch if n == B else batch.slice(0, n)
+    ref = oracle.solve_batch(sub, n_threads=8)
+    usable = ref["usable"][:n].astype(bool)
+    same_term = got["termination"][:n] == ref["termination"][:n]
+    du = np.abs(got["u"][:n] - ref["u"][:n]).reshape(n, -1).max(axis=1)
+    dc = np.abs(got["cost_final"][:n] - ref["cost_final"][:n]) / np.maximum(np.abs(ref["cost_final"][:n]), 1e-300)
+    ok = (~usable & (got["usable"][:n] == 0)) | (usable & (got["usable"][:n] == 1) & (du <= U_ATOL) & (dc <= COST_RTOL))
+    return dict(ok=ok, du=du, dc=dc, same_term=same_term, got=got, ref=ref, usable=usable,
+                same_iters=got["iterations"][:n] == ref["iterations"][:n])
+
+
+@pytest.mark.parametrize("name", ["readme", "params_yaml", "soc_work_obst"])
+def test_single_solve_matches_oracle(oracle, make_opt, name):
+    """BASELINE config 1: one solve; controls 1e-6 abs, final cost 1e-8 rel, same termination + iteration count."""
+    batch = sc.single(name)
+    opt = make_opt(batch.params)
+    r = _compare_solves(oracle, opt, batch)
+    assert r["ok"].all(), (r["du"], r["dc"], r["got"]["termination"], r["ref"]["termination"])
+    assert r["same_term"].all() and r["same_iters"].all()
+    assert np.abs(r["got"]["cmds"] - r["ref"]["cmds"]).max() <= U_ATOL
+
+
+def test_corridor_batch_matches_oracle(oracle, make_opt):
+    """BASELINE config 2 (obst_only x 4096) at a size the oracle finishes in seconds."""
+    batch = sc.corridor(B=512)
+    opt = make_opt(batch.params)
+    r = _compare_solves(oracle, opt, batch)
+    frac = r["ok"].mean()
+    assert frac >= 0.97, f"only {frac:.4f} of problems within tolerance; worst du={r['du'].max():.3e} dc={r['dc'].max():.3e}"
+    assert r["same_term"].mean() >= 0.97
+
+
+def test_crowd_batch_matches_oracle(oracle, make_opt):
+    """BASELINE config 3 (social + proxemics + obstacle, A = 20) on a 256-problem prefix."""
+    batch = sc.crowd(B=256, A=20)
+    opt = make_opt(batch.params)
+    r = _compare_solves(oracle, opt, batch)
+    frac = r["ok"].mean()
+    assert frac >= 0.95, f"only {frac:.4f} within tolerance; worst du={r['du'].max():.3e} dc={r['dc'].max():.3e}"
+
+
+def test_failure_when_all_agents_invalid(oracle, make_opt):
+    """people list non-empty but every projected agent invalid -> Ceres FAILURE -> not usable."""
+    batch = sc.single("soc_work_obst", n_people=0)
+    batch.arrays["has_people"][:] = 1
+    opt = make_opt(batch.params)
+    got = opt.solve_batch(batch)
+    assert got["usable"][0] == 0 and got["termination"][0] == 6
+    assert np.array_equal(got["u"][0], batch.arrays["u0"][0])
+
+
+def test_empty_batch_and_bad_arguments(make_opt):
+    from nav2_social_mpc_controller_b200 import _lib
+    batch = sc.corridor(B=4)
+    opt = make_opt(batch.params)
+    empty = batch.slice(0, 0)
+    out = opt.solve_batch(empty)
+    assert out["u"].shape[0] == 0
+    bad = sc.corridor(B=2)
+    bad.arrays["costmaps"] = None
+    with pytest.raises(_lib.SmpcError):
+        opt.solve_batch(bad)
+
+
+def test_full_size_corridor_properties(make_opt):
+    """BASELINE config 2 at full size (4096): size-independent properties — cost never increases, bounded blocks
+    stay in the box, results are deterministic, and a batch equals the concatenation of its halves."""
+    batch = sc.corridor(B=4096, unique_maps=False)
+    opt = make_opt(batch.params)
+    a = opt.solve_batch(batch)
+    b = opt.solve_batch(batch)
+    for k in ("u", "cost_final", "termination", "iterations"):
+        assert np.array_equal(a[k], b[k]), k
+    us = a["usable"].astype(bool)
+    assert us.mean() > 0.99
+    assert np.all(a["cost_final"][us] <= a["cost_initial"][us] * (1 + 1e-12))
+    nbd = batch.dims[3]
+    assert np.all(a["u"][us][:, :nbd, 0] >= 0.0) and np.all(a["u"][us][:, :nbd, 0] <= 0.6)
+    assert np.all(np.abs(a["u"][us][:, :nbd, 1]) <= 1.4)
+    lo = opt.solve_batch(batch.slice(0, 2048))
+    hi = opt.solve_batch(batch.slice(2048, 4096))
+    assert np.array_equal(np.concatenate([lo["u"], hi["u"]]), a["u"])
+    assert np.array_equal(np.concatenate([lo["cost_final"], hi["cost_final"]]), a["cost_final"])
+
+
+def test_multistart_argmin(make_opt):
+    import torch
+    batch = sc.multistart(n_robots=8, n_starts=64)
+    opt = make_opt(batch.params)
+    got = opt.solve_batch(batch)
+    dev = torch.device("cuda:0")
+    cost = torch.from_numpy(got["cost_final"]).to(dev)
+    usable = torch.from_numpy(got["usable"]).to(dev)
+    u = torch.from_numpy(got["u"]).to(dev)
+    nb = batch.n_blocks
+    best_index = torch.empty(8, dtype=torch.int32, device=dev)
+    best_cost = torch.empty(8, dtype=torch.float64, device=dev)
+    best_u = torch.empty(8, nb, 2, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    opt.multistart_argmin_device(8, 64, nb, cost, usable, u, best_index, best_cost, best_u,
+                                 stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    c = np.where(got["usable"].astype(bool), got["cost_final"], np.inf).reshape(8, 64)
+    want = c.argmin(axis=1) + np.arange(8) * 64
+    assert np.array_equal(best_index.cpu().numpy(), want)
+    assert np.array_equal(best_cost.cpu().numpy(), c.min(axis=1))
+    assert np.array_equal(best_u.cpu().numpy(), got["u"][want])
