@@ -203,6 +203,9 @@ int smpc_multistart_argmin_device(smpc_handle* h, int n_robots, int n_starts, in
 double smpc_last_kernel_ms(smpc_handle* h);
 /* Number of kernels this library launched on the handle since creation. */
 long long smpc_launch_count(smpc_handle* h);
+/* Measured FP64 FMA throughput of this GPU (TFLOP/s, DFMA-saturating microbenchmark, best of 5): the roofline
+ * denominator of the solve kernel ("of measured"; MEASURED_PEAKS.json carries no FP64 figure). */
+int smpc_measure_fp64_peak(smpc_handle* h, double* tflops);
 
 #ifdef __cplusplus
 }

@@ -609,4 +609,35 @@ double smpc_last_kernel_ms(smpc_handle* h) {
 
 long long smpc_launch_count(smpc_handle* h) { return h ? h->launches : 0; }
 
+int smpc_measure_fp64_peak(smpc_handle* h, double* tflops) {
+  if (!h || !tflops) return fail(SMPC_ERR_ARGUMENT, "NULL argument");
+  std::lock_guard<std::mutex> lk(h->mu);
+  SMPC_CUDA(cudaSetDevice(h->device));
+  double* sink = nullptr;
+  SMPC_CUDA(cudaMalloc(&sink, sizeof(double)));
+  const int iters = 4096;
+  double best = 0.0;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  for (int rep = 0; rep < 6; ++rep) {
+    cudaEventRecord(a, h->stream);
+    cudaError_t e = smpc::launch_dfma_peak(sink, h->n_sm, iters, h->stream);
+    cudaEventRecord(b, h->stream);
+    if (e != cudaSuccess || cudaEventSynchronize(b) != cudaSuccess) {
+      cudaFree(sink);
+      return cuda_fail(e, "dfma peak kernel");
+    }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    const double flops = 2.0 * 8.0 * 16.0 * iters * 256.0 * 8.0 * h->n_sm;
+    if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(sink);
+  *tflops = best;
+  return SMPC_OK;
+}
+
 }  // extern "C"

@@ -248,4 +248,23 @@ cudaError_t launch_argmin(int n_robots, int n_starts, int n_blocks, const double
 
 int max_supported_blocks() { return 6; }
 
+// DFMA-saturating microbenchmark: 8 independent FMA chains per thread (roofline denominator, "of measured").
+__global__ void __launch_bounds__(256) smpc_dfma_peak_kernel(double* sink, int iters, double a, double b) {
+  double r0 = threadIdx.x, r1 = r0 + 1, r2 = r0 + 2, r3 = r0 + 3, r4 = r0 + 4, r5 = r0 + 5, r6 = r0 + 6, r7 = r0 + 7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      r0 = fma(r0, a, b); r1 = fma(r1, a, b); r2 = fma(r2, a, b); r3 = fma(r3, a, b);
+      r4 = fma(r4, a, b); r5 = fma(r5, a, b); r6 = fma(r6, a, b); r7 = fma(r7, a, b);
+    }
+  }
+  const double r = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+  if (r == 123.456) sink[0] = r;  // never true; keeps the chains alive
+}
+
+cudaError_t launch_dfma_peak(double* sink, int n_sm, int iters, cudaStream_t stream) {
+  smpc_dfma_peak_kernel<<<n_sm * 8, 256, 0, stream>>>(sink, iters, 0.999999, 1e-7);
+  return cudaGetLastError();
+}
+
 }  // namespace smpc

@@ -141,6 +141,13 @@ class Optimizer:
         self._need()
         return float(_lib.lib().smpc_last_kernel_ms(self._h))
 
+    def measure_fp64_peak(self) -> float:
+        """TFLOP/s of a DFMA-saturating microbenchmark on this GPU (roofline denominator)."""
+        self._need()
+        v = C.c_double(0.0)
+        _lib.check(_lib.lib().smpc_measure_fp64_peak(self._h, C.byref(v)))
+        return v.value
+
     def launch_count(self) -> int:
         self._need()
         return int(_lib.lib().smpc_launch_count(self._h))
