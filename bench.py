@@ -211,15 +211,16 @@ def main():
     tdt = {np.float64: torch.float64, np.int32: torch.int32, np.uint8: torch.uint8}
     dev_out = {k: torch.zeros(shapes[k][0], dtype=tdt[shapes[k][1]], device=dev) for k in want}
     dstruct = batch.struct(dev_arrays)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)  # non-default stream: the kernel and the events share it
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
     torch.cuda.synchronize()
 
     def step_device():
         opt.solve_batch_device(dstruct, dev_out, stream=stream.cuda_stream)
 
-    for _ in range(args.warmup):
-        step_device()
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step_device()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -228,11 +229,12 @@ def main():
     launches0 = opt.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     torch.cuda.synchronize()
-    for s in range(args.steps):
-        flush.fill_(s & 0xFF)  # L2 flush between timed iterations (outside the event pair)
-        ev[s][0].record(stream)
-        step_device()
-        ev[s][1].record(stream)
+    with torch.cuda.stream(stream):
+        for s in range(args.steps):
+            flush.fill_(s & 0xFF)  # L2 flush between timed iterations (outside the event pair)
+            ev[s][0].record(stream)
+            step_device()
+            ev[s][1].record(stream)
     torch.cuda.synchronize()
     launches = opt.launch_count() - launches0
     step_ms = [a.elapsed_time(b) for a, b in ev]

@@ -206,6 +206,9 @@ long long smpc_launch_count(smpc_handle* h);
 /* Measured FP64 FMA throughput of this GPU (TFLOP/s, DFMA-saturating microbenchmark, best of 5): the roofline
  * denominator of the solve kernel ("of measured"; MEASURED_PEAKS.json carries no FP64 figure). */
 int smpc_measure_fp64_peak(smpc_handle* h, double* tflops);
+/* Diagnostics for unit tests: run the line-search interpolating-polynomial minimiser (Ceres polynomial.cc
+ * restatement) on n host rows of (lo, hi, f0, g0, t1, f1, g1, t2, f2, g2); t2 <= 0 selects the 2-sample case. */
+int smpc_debug_polymin(smpc_handle* h, int n, const double* rows, double* out);
 
 #ifdef __cplusplus
 }

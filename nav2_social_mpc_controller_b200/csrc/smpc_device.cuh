@@ -229,56 +229,92 @@ __device__ __forceinline__ double agent_angle_target(const DevBatch& bt, const P
   if (wb > 0.0) return NAN;
   return pb.yaw0 + (M_PI / 6.0);
 }
-
-template <int NB>
-struct Normal {  // normal equations of one evaluation, warp-uniform after evaluate()
-  static constexpr int P = 2 * NB;
-  static constexpr int NH = P * (P + 1) / 2;
-  double cost;
-  double g[P];
-  double H[NH];  // row-major lower triangle, H[a(a+1)/2 + b], a >= b
-};
-
 #define SMPC_UNROLL _Pragma("unroll")
 
+// Per-warp shared-memory state of one solve. Buffers hold [cost, g[P], H[NH]] (H row-major lower triangle,
+// H[a(a+1)/2 + b], a >= b) of the current iterate and of the trial point; the LM vectors follow.
+template <int NB>
+struct Layout {
+  static constexpr int P = 2 * NB;
+  static constexpr int NH = P * (P + 1) / 2;
+  static constexpr int NE = 1 + P + NH;
+  static constexpr int NG = (NE + 31) / 32;
+  static constexpr int NEP = NG * 32;
+  static constexpr int kBuf0 = 0;
+  static constexpr int kBuf1 = NEP;
+  static constexpr int kX = 2 * NEP;
+  static constexpr int kBest = kX + P;
+  static constexpr int kScale = kBest + P;
+  static constexpr int kDiag = kScale + P;
+  static constexpr int kDelta = kDiag + P;
+  static constexpr int kCand = kDelta + P;
+  static constexpr int kTotal = kCand + P;
+  __host__ __device__ static constexpr int g(int c) { return 1 + c; }
+  __host__ __device__ static constexpr int h(int a, int b) { return 1 + P + a * (a + 1) / 2 + b; }
+};
+
+// Sum 32 per-lane values across the warp so that lane l ends with the total of v[l]:
+// 31 exchanges instead of the 160 of a butterfly all-reduce, and one live register at the end.
+__device__ __forceinline__ double warp_transpose_reduce32(double (&v)[32], int lane) {
+  SMPC_UNROLL for (int r = 0; r < 5; ++r) {
+    const int d = 16 >> r;
+    const bool up = (lane & d) != 0;
+    SMPC_UNROLL for (int k = 0; k < d; ++k) {
+      const double send = up ? v[k] : v[k + d];
+      const double keep = up ? v[k + d] : v[k];
+      v[k] = keep + __shfl_xor_sync(kFullMask, send, d);
+    }
+  }
+  return v[0];
+}
+
+__device__ __forceinline__ double wrap_angle(double a) {
+  // atan2(sin a, cos a) of the reference critics, evaluated as a - 2 pi round(a / 2 pi) (|difference| ~ 1 ulp of pi)
+  return a - (2.0 * M_PI) * rint(a * (0.5 / M_PI));
+}
+
 // ---------------------------------------------------------------------------------------------------
-// Full evaluation at block values x: cost = 1/2 sum r^2, g = J^T r, H = J^T J (all lanes get the result).
-// Residual set and order of reference src/optimizer.cpp:251-371.
+// Full evaluation at block values xs[P] (shared memory): cost = 1/2 sum r^2, g = J^T r, H = J^T J, written to
+// out[NE] (shared memory). Residual set and order of reference src/optimizer.cpp:251-371.
 // ---------------------------------------------------------------------------------------------------
 template <int NB>
-__device__ __noinline__ unsigned evaluate(const DevParams& prm, const DevBatch& bt, const Prob& pb,
-                                          const double (&aa_target)[kMaxChunks], const double (&x)[2 * NB], int lane,
-                                          Normal<NB>& out) {
-  constexpr int P = 2 * NB;
-  constexpr int NH = P * (P + 1) / 2;
+__device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatch& bt, const Prob& pb,
+                                             const double (&aa_target)[kMaxChunks], const double* xs, int lane,
+                                             double* out) {
+  using L = Layout<NB>;
+  constexpr int P = L::P;
   const int S = bt.S, bl = prm.bl, ch = prm.ch;
   const double dt = bt.dt;
   const int stride = S + 1;
+  const double inv_res = 1.0 / bt.resolution;
 
-  double cost = 0.0;
-  double g[P];
-  double H[NH];
-  SMPC_UNROLL for (int c = 0; c < P; ++c) g[c] = 0.0;
-  SMPC_UNROLL for (int e = 0; e < NH; ++e) H[e] = 0.0;
+  double x[P];
+  SMPC_UNROLL for (int c = 0; c < P; ++c) x[c] = xs[c];
+
+  double acc[L::NEP];  // [cost, g, H] partial sums of this lane
+  SMPC_UNROLL for (int e = 0; e < L::NEP; ++e) acc[e] = 0.0;
   unsigned flags = 0;
 
-  // carries of the inclusive scans between 32-step chunks
+  // carries of the inclusive scans between 32-step chunks (dead code when S <= 32)
   double carry_x = pb.x0, carry_y = pb.y0;
   double carry_d[4 * NB];
   SMPC_UNROLL for (int e = 0; e < 4 * NB; ++e) carry_d[e] = 0.0;
 
+#pragma unroll 1
   for (int chunk = 0; chunk * 32 < S; ++chunk) {
     const int j = chunk * 32 + lane;
     const bool act = j < S;
     const int bj = min(j / bl, NB - 1);
     double vj = x[0], wj = x[1];
     double th = pb.yaw0;  // heading before step j
+    double tw_next[NB];   // d Theta_j / d w_b (heading after step j)
     SMPC_UNROLL for (int b = 0; b < NB; ++b) {
       if (b == bj) {
         vj = x[2 * b];
         wj = x[2 * b + 1];
       }
       th += x[2 * b + 1] * (dt * (double)steps_in_block_before<NB>(j, b, bl));
+      tw_next[b] = dt * (double)steps_in_block_before<NB>(j + 1, b, bl);
     }
     double sn, cs;
     sincos(th, &sn, &cs);
@@ -298,20 +334,21 @@ __device__ __noinline__ unsigned evaluate(const DevParams& prm, const DevBatch& 
     SMPC_UNROLL for (int d = 1; d < 32; d <<= 1) {
       const double tx = __shfl_up_sync(kFullMask, sx, d);
       const double ty = __shfl_up_sync(kFullMask, sy, d);
-      if (lane >= d) {
-        sx += tx;
-        sy += ty;
-      }
+      const bool on = lane >= d;
+      sx += on ? tx : 0.0;
+      sy += on ? ty : 0.0;
       SMPC_UNROLL for (int e = 0; e < 4 * NB; ++e) {
         const double t = __shfl_up_sync(kFullMask, sd[e], d);
-        if (lane >= d) sd[e] += t;
+        sd[e] += on ? t : 0.0;
       }
     }
     const double X = carry_x + sx, Y = carry_y + sy;
-    SMPC_UNROLL for (int e = 0; e < 4 * NB; ++e) sd[e] += carry_d[e];
-    carry_x = __shfl_sync(kFullMask, X, 31);
-    carry_y = __shfl_sync(kFullMask, Y, 31);
-    SMPC_UNROLL for (int e = 0; e < 4 * NB; ++e) carry_d[e] = __shfl_sync(kFullMask, sd[e], 31);
+    if (S > 32) {
+      SMPC_UNROLL for (int e = 0; e < 4 * NB; ++e) sd[e] += carry_d[e];
+      carry_x = __shfl_sync(kFullMask, X, 31);
+      carry_y = __shfl_sync(kFullMask, Y, 31);
+      SMPC_UNROLL for (int e = 0; e < 4 * NB; ++e) carry_d[e] = __shfl_sync(kFullMask, sd[e], 31);
+    }
 
     if (act) {
       const double Th = th + wj * dt;  // heading after step j
@@ -321,13 +358,13 @@ __device__ __noinline__ unsigned evaluate(const DevParams& prm, const DevBatch& 
       // per-lane Gauss-Newton block wrt (X, Y, Theta, lv): M = sum c c^T (10 entries), q = sum c r
       double mXX = 0, mXY = 0, mXT = 0, mXL = 0, mYY = 0, mYT = 0, mYL = 0, mTT = 0, mTL = 0, mLL = 0;
       double qX = 0, qY = 0, qT = 0, qL = 0;
+      double cost = 0.0;
 
       if (pb.has_people) {
         // --- AgentAngle (k=0): w * wrap(Theta - target)^2 ------------------------------------------
-        const double tgt = aa_target[chunk];
+        const double tgt = aa_target[chunk & (kMaxChunks - 1)];
         if (tgt == tgt) {
-          const double ad = Th - tgt;
-          const double del = atan2(sin(ad), cos(ad));
+          const double del = wrap_angle(Th - tgt);
           const double r = prm.w_agent_angle * (del * del);
           const double cTh = 2.0 * prm.w_agent_angle * del;
           cost += 0.5 * r * r;
@@ -342,9 +379,10 @@ __device__ __noinline__ unsigned evaluate(const DevParams& prm, const DevBatch& 
         double G4[4] = {0, 0, 0, 0};  // gradient of (wr + wp) wrt (dX, dY, dvx, dvy) of the robot
         double dmin = DBL_MAX, pdx = 0.0, pdy = 0.0;
         const bool do_social = prm.w_social != 0.0;
+#pragma unroll 1
         for (int k = 0; k < bt.A; ++k) {
           const double* a = pb.agents + (size_t)k * 6 * stride + (j + 1);
-          const double ax = a[0], ay = a[stride], at = a[3 * stride];
+          const double ax = __ldg(a), ay = __ldg(a + stride), at = __ldg(a + 3 * stride);
           const bool valid = !(at == -1.0);
           const double ddx = X - ax, ddy = Y - ay;
           if (valid) {
@@ -356,7 +394,7 @@ __device__ __noinline__ unsigned evaluate(const DevParams& prm, const DevBatch& 
             }
           }
           if (do_social) {
-            const double ayaw = a[2 * stride], alv = a[4 * stride];
+            const double ayaw = __ldg(a + 2 * stride), alv = __ldg(a + 4 * stride);
             double sa, ca;
             sincos(ayaw, &sa, &ca);
             const double avx = alv * ca, avy = alv * sa;
@@ -415,8 +453,7 @@ __device__ __noinline__ unsigned evaluate(const DevParams& prm, const DevBatch& 
       }
       // --- GoalAlign (k=4): w * wrap(psi - Theta)^2 -----------------------------------------------------
       {
-        const double ga = pb.goal_yaw - Th;
-        const double turn = atan2(sin(ga), cos(ga));
+        const double turn = wrap_angle(pb.goal_yaw - Th);
         const double r = prm.w_goal * turn * turn;
         const double cTh = -2.0 * prm.w_goal * turn;
         cost += 0.5 * r * r;
@@ -447,11 +484,11 @@ __device__ __noinline__ unsigned evaluate(const DevParams& prm, const DevBatch& 
       // --- Obstacle (k=7): w * bicubic(costmap) 0.25 m ahead ---------------------------------------------
       {
         const double fxw = X + 0.25 * cT, fyw = Y + 0.25 * sT;
-        const double gx = (fxw - pb.org_x) / bt.resolution, gy = (fyw - pb.org_y) / bt.resolution;
+        const double gx = (fxw - pb.org_x) * inv_res, gy = (fyw - pb.org_y) * inv_res;
         double f, dfdr, dfdc;
         bicubic(pb.map, bt.size_x, bt.size_y, gy, gx, f, dfdr, dfdc);
         const double r = prm.w_obstacle * f;
-        const double kx = prm.w_obstacle * dfdc / bt.resolution, ky = prm.w_obstacle * dfdr / bt.resolution;
+        const double kx = prm.w_obstacle * dfdc * inv_res, ky = prm.w_obstacle * dfdr * inv_res;
         const double cTh = 0.25 * (-kx * sT + ky * cT);
         cost += 0.5 * r * r;
         mXX += kx * kx; mXY += kx * ky; mXT += kx * cTh;
@@ -459,130 +496,114 @@ __device__ __noinline__ unsigned evaluate(const DevParams& prm, const DevBatch& 
         qX += kx * r; qY += ky * r; qT += cTh * r;
       }
 
-      // --- lane block -> parameter space: rows of D are dX/du, dY/du, dTheta/du, dlv/du --------------
-      double D0[P], D1[P], D2[P], D3[P];
+      // --- lane block -> parameter space. Column of v_b: (dX, dY, 0, [b == bj]); of w_b: (dX, dY, dTheta, 0) ----
+      acc[0] += cost;
+      double T0[P], T1[P], T2[P], T3[P];
       SMPC_UNROLL for (int b = 0; b < NB; ++b) {
-        D0[2 * b] = sd[4 * b + 0];
-        D1[2 * b] = sd[4 * b + 1];
-        D0[2 * b + 1] = sd[4 * b + 2];
-        D1[2 * b + 1] = sd[4 * b + 3];
-        D2[2 * b] = 0.0;
-        D2[2 * b + 1] = dt * (double)steps_in_block_before<NB>(j + 1, b, bl);
-        D3[2 * b] = (b == bj) ? 1.0 : 0.0;
-        D3[2 * b + 1] = 0.0;
+        const double xv = sd[4 * b + 0], yv = sd[4 * b + 1], xw = sd[4 * b + 2], yw = sd[4 * b + 3];
+        const double lb = (b == bj) ? 1.0 : 0.0, tw = tw_next[b];
+        T0[2 * b] = mXX * xv + mXY * yv + mXL * lb;
+        T1[2 * b] = mXY * xv + mYY * yv + mYL * lb;
+        T2[2 * b] = mXT * xv + mYT * yv + mTL * lb;
+        T3[2 * b] = mXL * xv + mYL * yv + mLL * lb;
+        T0[2 * b + 1] = mXX * xw + mXY * yw + mXT * tw;
+        T1[2 * b + 1] = mXY * xw + mYY * yw + mYT * tw;
+        T2[2 * b + 1] = mXT * xw + mYT * yw + mTT * tw;
+        T3[2 * b + 1] = mXL * xw + mYL * yw + mTL * tw;
+        acc[L::g(2 * b)] += qX * xv + qY * yv + qL * lb;
+        acc[L::g(2 * b + 1)] += qX * xw + qY * yw + qT * tw;
       }
-      SMPC_UNROLL for (int a = 0; a < P; ++a) {
-        const double t0 = mXX * D0[a] + mXY * D1[a] + mXT * D2[a] + mXL * D3[a];
-        const double t1 = mXY * D0[a] + mYY * D1[a] + mYT * D2[a] + mYL * D3[a];
-        const double t2 = mXT * D0[a] + mYT * D1[a] + mTT * D2[a] + mTL * D3[a];
-        const double t3 = mXL * D0[a] + mYL * D1[a] + mTL * D2[a] + mLL * D3[a];
-        g[a] += qX * D0[a] + qY * D1[a] + qT * D2[a] + qL * D3[a];
-        SMPC_UNROLL for (int b = 0; b <= a; ++b)
-          H[a * (a + 1) / 2 + b] += t0 * D0[b] + t1 * D1[b] + t2 * D2[b] + t3 * D3[b];
+      SMPC_UNROLL for (int b = 0; b < NB; ++b) {
+        const double xv = sd[4 * b + 0], yv = sd[4 * b + 1], xw = sd[4 * b + 2], yw = sd[4 * b + 3];
+        const double lb = (b == bj) ? 1.0 : 0.0, tw = tw_next[b];
+        SMPC_UNROLL for (int a = 2 * b; a < P; ++a) acc[L::h(a, 2 * b)] += xv * T0[a] + yv * T1[a] + lb * T3[a];
+        SMPC_UNROLL for (int a = 2 * b + 1; a < P; ++a) acc[L::h(a, 2 * b + 1)] += xw * T0[a] + yw * T1[a] + tw * T2[a];
       }
     }
   }
 
-  // warp all-reduce
-  cost = warp_sum(cost);
-  SMPC_UNROLL for (int c = 0; c < P; ++c) g[c] = warp_sum(g[c]);
-  SMPC_UNROLL for (int e = 0; e < NH; ++e) H[e] = warp_sum(H[e]);
+  // --- VelocityFeasibility (k=8): w ((v_i - v_{i-1})^2 + (w_i - w_{i-1})^2), 0 < i < ch/bl, on blocks i, i-1.
+  //     Parameter-space residuals: lane 0 adds them to its partial sums before the reduction.
+  if (lane == 0) {
+    SMPC_UNROLL for (int i = 1; i < NB; ++i) {
+      if (i < prm.n_bounded) {
+        const double dv = x[2 * i] - x[2 * i - 2], dw = x[2 * i + 1] - x[2 * i - 1];
+        const double r = prm.w_vf * dv * dv + prm.w_vf * dw * dw;
+        const double jv = 2.0 * prm.w_vf * dv, jw = 2.0 * prm.w_vf * dw;
+        acc[0] += 0.5 * r * r;
+        // row: [2i-2] = -jv, [2i-1] = -jw, [2i] = jv, [2i+1] = jw
+        const int p0 = 2 * i - 2, p1 = 2 * i - 1, p2 = 2 * i, p3 = 2 * i + 1;
+        acc[L::g(p0)] -= jv * r; acc[L::g(p1)] -= jw * r; acc[L::g(p2)] += jv * r; acc[L::g(p3)] += jw * r;
+        acc[L::h(p0, p0)] += jv * jv;
+        acc[L::h(p1, p0)] += jw * jv;
+        acc[L::h(p1, p1)] += jw * jw;
+        acc[L::h(p2, p0)] -= jv * jv;
+        acc[L::h(p2, p1)] -= jv * jw;
+        acc[L::h(p2, p2)] += jv * jv;
+        acc[L::h(p3, p0)] -= jw * jv;
+        acc[L::h(p3, p1)] -= jw * jw;
+        acc[L::h(p3, p2)] += jw * jv;
+        acc[L::h(p3, p3)] += jw * jw;
+      }
+    }
+  }
+
+  // warp reduction: lane l of group gI ends with the total of entry 32 gI + l and stores it
+  bool bad_res = false, bad_jac = false;
+  SMPC_UNROLL for (int gI = 0; gI < L::NG; ++gI) {
+    double v[32];
+    SMPC_UNROLL for (int k = 0; k < 32; ++k) v[k] = acc[32 * gI + k];
+    const double tot = warp_transpose_reduce32(v, lane);
+    const int e = 32 * gI + lane;
+    if (e < L::NE) {
+      out[e] = tot;
+      if (!isfinite(tot)) {
+        if (e == 0) bad_res = true; else bad_jac = true;
+      }
+    }
+  }
+  if (__any_sync(kFullMask, bad_res)) flags |= kResidualBad;
+  if (__any_sync(kFullMask, bad_jac)) flags |= kJacobianBad;
   flags = __reduce_or_sync(kFullMask, flags);
-
-  // --- VelocityFeasibility (k=8): w ((v_i - v_{i-1})^2 + (w_i - w_{i-1})^2), 0 < i < ch/bl, on blocks i, i-1 ----
-  SMPC_UNROLL for (int i = 1; i < NB; ++i) {
-    if (i < prm.n_bounded) {
-      const double dv = x[2 * i] - x[2 * i - 2], dw = x[2 * i + 1] - x[2 * i - 1];
-      const double r = prm.w_vf * dv * dv + prm.w_vf * dw * dw;
-      const double jv = 2.0 * prm.w_vf * dv, jw = 2.0 * prm.w_vf * dw;
-      cost += 0.5 * r * r;
-      // row: [2i-2] = -jv, [2i-1] = -jw, [2i] = jv, [2i+1] = jw
-      const int p0 = 2 * i - 2, p1 = 2 * i - 1, p2 = 2 * i, p3 = 2 * i + 1;
-      g[p0] -= jv * r; g[p1] -= jw * r; g[p2] += jv * r; g[p3] += jw * r;
-      H[p0 * (p0 + 1) / 2 + p0] += jv * jv;
-      H[p1 * (p1 + 1) / 2 + p0] += jw * jv;
-      H[p1 * (p1 + 1) / 2 + p1] += jw * jw;
-      H[p2 * (p2 + 1) / 2 + p0] -= jv * jv;
-      H[p2 * (p2 + 1) / 2 + p1] -= jv * jw;
-      H[p2 * (p2 + 1) / 2 + p2] += jv * jv;
-      H[p3 * (p3 + 1) / 2 + p0] -= jw * jv;
-      H[p3 * (p3 + 1) / 2 + p1] -= jw * jw;
-      H[p3 * (p3 + 1) / 2 + p2] += jw * jv;
-      H[p3 * (p3 + 1) / 2 + p3] += jw * jw;
-    }
-  }
-
-  out.cost = cost;
-  SMPC_UNROLL for (int c = 0; c < P; ++c) out.g[c] = g[c];
-  SMPC_UNROLL for (int e = 0; e < NH; ++e) out.H[e] = H[e];
-  if (!isfinite(cost)) flags |= kResidualBad;
-  bool jfin = true;
-  SMPC_UNROLL for (int c = 0; c < P; ++c) jfin = jfin && isfinite(g[c]) && isfinite(H[c * (c + 1) / 2 + c]);
-  if (!jfin) flags |= kJacobianBad;
+  __syncwarp();
   return flags;
 }
 
 // ---------------------------------------------------------------------------------------------------
 // Interpolating-polynomial minimiser of the Armijo line search (ceres polynomial.cc).
+// Ceres fits the polynomial with a pivoted LU and finds the critical points as companion-matrix eigenvalues;
+// the same polynomial is fitted here in closed form (Hermite data) and the roots of its derivative in closed
+// form too (quadratic: Ceres' own formula; quartic: Ferrari + Newton polish, Aberth-Ehrlich as the safety net).
 // Warp-uniform scalar code; called only when a trial step fails the sufficient-decrease test.
 // ---------------------------------------------------------------------------------------------------
 struct LsSample {
   double x, value, gradient;
-  bool value_ok, gradient_ok;
+  bool ok;
 };
 
-__device__ __forceinline__ double poly_eval(const double* c, int n, double x) {
-  double v = 0.0;
-  for (int i = 0; i < n; ++i) v = v * x + c[i];
-  return v;
+__device__ __forceinline__ double horner5(const double (&m)[6], double x) {
+  return m[0] + x * (m[1] + x * (m[2] + x * (m[3] + x * (m[4] + x * m[5]))));
 }
 
-// Real parts of the roots of c[0] x^deg + ... (deg <= 4), Aberth-Ehrlich iteration in complex double
-// for deg >= 3 (Ceres: eigenvalues of the companion matrix).
-static __device__ __noinline__ int poly_real_roots(const double* cin, int n, double* roots) {
-  int lead = 0;
-  while (lead + 1 < n && cin[lead] == 0.0) ++lead;
-  const double* c = cin + lead;
-  const int deg = n - lead - 1;
-  if (deg <= 0) return 0;
-  if (deg == 1) {
-    roots[0] = -c[1] / c[0];
-    return 1;
-  }
-  if (deg == 2) {
-    const double a = c[0], b = c[1], cc = c[2];
-    const double D = b * b - 4 * a * cc;
-    const double sD = sqrt(fabs(D));
-    if (D >= 0) {
-      if (b >= 0) {
-        roots[0] = (-b - sD) / (2.0 * a);
-        roots[1] = (2.0 * cc) / (-b - sD);
-      } else {
-        roots[0] = (2.0 * cc) / (-b + sD);
-        roots[1] = (-b + sD) / (2.0 * a);
-      }
-    } else {
-      roots[0] = roots[1] = -b / (2.0 * a);
-    }
-    return 2;
-  }
-  double m[5];
-  for (int i = 0; i <= deg; ++i) m[i] = c[i] / c[0];
+// Real parts of the 4 roots of c[0] + c[1] x + ... + c[4] x^4 by Aberth-Ehrlich (slow, robust).
+static __device__ __noinline__ void quartic_aberth(const double* c, double* re) {
+  double m[5];  // monic, highest first
+  for (int i = 0; i <= 4; ++i) m[i] = c[4 - i] / c[4];
   double radius = 0.0;
-  for (int i = 1; i <= deg; ++i) radius = fmax(radius, pow(fabs(m[i]), 1.0 / i));
+  for (int i = 1; i <= 4; ++i) radius = fmax(radius, pow(fabs(m[i]), 1.0 / i));
   radius = 2.0 * radius + 1e-300;
   double zr[4], zi[4];
-  for (int i = 0; i < deg; ++i) {
+  for (int i = 0; i < 4; ++i) {
     double s, co;
-    sincos(2.0 * M_PI * i / deg + 0.35, &s, &co);
+    sincos(2.0 * M_PI * i / 4 + 0.35, &s, &co);
     zr[i] = 0.7 * radius * co;
     zi[i] = 0.7 * radius * s;
   }
-  for (int it = 0; it < 200; ++it) {
+  for (int it = 0; it < 60; ++it) {
     double moved = 0.0;
-    for (int i = 0; i < deg; ++i) {
+    for (int i = 0; i < 4; ++i) {
       double pr = m[0], pi = 0.0, dr = 0.0, di = 0.0;
-      for (int j = 1; j <= deg; ++j) {
+      for (int j = 1; j <= 4; ++j) {
         const double ndr = dr * zr[i] - di * zi[i] + pr, ndi = dr * zi[i] + di * zr[i] + pi;
         const double npr = pr * zr[i] - pi * zi[i] + m[j], npi = pr * zi[i] + pi * zr[i];
         dr = ndr; di = ndi; pr = npr; pi = npi;
@@ -591,124 +612,234 @@ static __device__ __noinline__ int poly_real_roots(const double* cin, int n, dou
       const double dn = dr * dr + di * di;
       const double rr = (pr * dr + pi * di) / dn, ri = (pi * dr - pr * di) / dn;  // p / p'
       double sr = 0.0, si = 0.0;
-      for (int j = 0; j < deg; ++j) {
+      for (int j = 0; j < 4; ++j) {
         if (j == i) continue;
         const double er = zr[i] - zr[j], ei = zi[i] - zi[j];
         const double en = er * er + ei * ei;
         sr += er / en;
         si -= ei / en;
       }
-      const double qr = 1.0 - (rr * sr - ri * si), qi = -(rr * si + ri * sr);  // 1 - ratio*sum
+      const double qr = 1.0 - (rr * sr - ri * si), qi = -(rr * si + ri * sr);
       const double qn = qr * qr + qi * qi;
       const double stepr = (rr * qr + ri * qi) / qn, stepi = (ri * qr - rr * qi) / qn;
       zr[i] -= stepr;
       zi[i] -= stepi;
-      moved = fmax(moved, sqrt(stepr * stepr + stepi * stepi) / (sqrt(zr[i] * zr[i] + zi[i] * zi[i]) + 1e-300));
+      moved = fmax(moved, (fabs(stepr) + fabs(stepi)) / (fabs(zr[i]) + fabs(zi[i]) + 1e-300));
     }
-    if (moved < 1e-15) break;
+    if (moved < 1e-13) break;
   }
-  for (int i = 0; i < deg; ++i) roots[i] = zr[i];
-  return deg;
+  for (int i = 0; i < 4; ++i) re[i] = zr[i];
 }
 
-// Fit the polynomial through ns (<= 3) samples (values + gradients) with a full-pivot LU, minimise it on [lo, hi].
-static __device__ __noinline__ double interpolating_poly_min(const LsSample* s, int ns, double lo, double hi) {
-  int nc = 0;
-  for (int i = 0; i < ns; ++i) nc += (s[i].value_ok ? 1 : 0) + (s[i].gradient_ok ? 1 : 0);
-  const int degree = nc - 1;
-  double a[6][6], rhs[6], poly[6];
-  int colperm[6];
-  for (int i = 0; i < 6; ++i) {
-    rhs[i] = 0.0;
-    colperm[i] = i;
-    for (int j = 0; j < 6; ++j) a[i][j] = 0.0;
+// Real parts of the roots of c[0] + c[1] x + c[2] x^2 + c[3] x^3 + c[4] x^4 (c[4] != 0). Returns 4.
+__device__ __forceinline__ int quartic_real_parts(const double (&c)[5], double (&re)[4]) {
+  const double inv = 1.0 / c[4];
+  const double a = c[3] * inv, b = c[2] * inv, cc = c[1] * inv, d = c[0] * inv;
+  const double a2 = a * a;
+  const double p = b - 0.375 * a2;
+  const double q = cc - 0.5 * a * b + 0.125 * a2 * a;
+  const double r = d - 0.25 * a * cc + 0.0625 * a2 * b - (3.0 / 256.0) * a2 * a2;
+  double yr[4], yi[4];
+  bool ok = true;
+  if (q == 0.0) {
+    // biquadratic: w^2 + p w + r = 0, y = +-sqrt(w)
+    const double disc = p * p - 4.0 * r;
+    double wr[2], wi[2];
+    if (disc >= 0.0) {
+      const double sq = sqrt(disc);
+      wr[0] = 0.5 * (-p + sq); wr[1] = 0.5 * (-p - sq);
+      wi[0] = wi[1] = 0.0;
+    } else {
+      wr[0] = wr[1] = -0.5 * p;
+      wi[0] = 0.5 * sqrt(-disc); wi[1] = -wi[0];
+    }
+    for (int k = 0; k < 2; ++k) {  // principal complex square root
+      const double mod = sqrt(wr[k] * wr[k] + wi[k] * wi[k]);
+      const double sr = sqrt(fmax(0.5 * (mod + wr[k]), 0.0));
+      double si = sqrt(fmax(0.5 * (mod - wr[k]), 0.0));
+      if (wi[k] < 0.0) si = -si;
+      yr[2 * k] = sr; yi[2 * k] = si;
+      yr[2 * k + 1] = -sr; yi[2 * k + 1] = -si;
+    }
+  } else {
+    // resolvent cubic z^3 + 2p z^2 + (p^2 - 4r) z - q^2 = 0: largest real root (positive)
+    const double A = 2.0 * p, B = p * p - 4.0 * r, C = -q * q;
+    const double Pd = B - A * A * (1.0 / 3.0);
+    const double Qd = (2.0 / 27.0) * A * A * A - (1.0 / 3.0) * A * B + C;
+    const double disc = 0.25 * Qd * Qd + (1.0 / 27.0) * Pd * Pd * Pd;
+    double t;
+    if (disc > 0.0) {
+      const double sq = sqrt(disc);
+      const double u = cbrt((-0.5 * Qd >= 0.0) ? (-0.5 * Qd + sq) : (-0.5 * Qd - sq));
+      t = (u != 0.0) ? (u - Pd / (3.0 * u)) : 0.0;
+    } else {
+      const double mm = 2.0 * sqrt(fmax(-Pd * (1.0 / 3.0), 0.0));
+      const double arg = (mm > 0.0) ? fmin(fmax(3.0 * Qd / (Pd * mm), -1.0), 1.0) : 0.0;
+      t = mm * cos(acos(arg) * (1.0 / 3.0));
+    }
+    double z = t - A * (1.0 / 3.0);
+    SMPC_UNROLL for (int it = 0; it < 3; ++it) {  // Newton polish on the resolvent
+      const double f = ((z + A) * z + B) * z + C;
+      const double fp = (3.0 * z + 2.0 * A) * z + B;
+      if (fp != 0.0) z -= f / fp;
+    }
+    if (!(z > 0.0) || !isfinite(z)) ok = false;
+    const double s = sqrt(fmax(z, 0.0));
+    const double qs = (s > 0.0) ? q / s : 0.0;
+    const double u = 0.5 * (p + z - qs), v = 0.5 * (p + z + qs);
+    // y^2 + s y + u = 0 and y^2 - s y + v = 0
+    const double d1 = s * s - 4.0 * u, d2 = s * s - 4.0 * v;
+    if (d1 >= 0.0) {
+      const double sq = sqrt(d1);
+      yr[0] = 0.5 * (-s + sq); yr[1] = 0.5 * (-s - sq); yi[0] = yi[1] = 0.0;
+    } else {
+      yr[0] = yr[1] = -0.5 * s; yi[0] = 0.5 * sqrt(-d1); yi[1] = -yi[0];
+    }
+    if (d2 >= 0.0) {
+      const double sq = sqrt(d2);
+      yr[2] = 0.5 * (s + sq); yr[3] = 0.5 * (s - sq); yi[2] = yi[3] = 0.0;
+    } else {
+      yr[2] = yr[3] = 0.5 * s; yi[2] = 0.5 * sqrt(-d2); yi[3] = -yi[2];
+    }
   }
-  int row = 0;
-  for (int i = 0; i < ns; ++i) {
-    if (s[i].value_ok) {
-      for (int j = 0; j <= degree; ++j) a[row][j] = pow(s[i].x, (double)(degree - j));
-      rhs[row++] = s[i].value;
-    }
-    if (s[i].gradient_ok) {
-      for (int j = 0; j < degree; ++j) a[row][j] = (degree - j) * pow(s[i].x, (double)(degree - j - 1));
-      rhs[row++] = s[i].gradient;
-    }
-  }
-  for (int k = 0; k < nc; ++k) {
-    int pr = k, pc = k;
-    double best = -1.0;
-    for (int i = k; i < nc; ++i)
-      for (int j = k; j < nc; ++j)
-        if (fabs(a[i][j]) > best) {
-          best = fabs(a[i][j]);
-          pr = i;
-          pc = j;
-        }
-    if (best == 0.0) break;
-    for (int j = 0; j < nc; ++j) {
-      const double t = a[k][j]; a[k][j] = a[pr][j]; a[pr][j] = t;
-    }
-    { const double t = rhs[k]; rhs[k] = rhs[pr]; rhs[pr] = t; }
-    if (pc != k) {
-      for (int i = 0; i < nc; ++i) {
-        const double t = a[i][k]; a[i][k] = a[i][pc]; a[i][pc] = t;
+  // back to x, complex Newton polish on the monic quartic, residual check
+  const double shift = 0.25 * a;
+  SMPC_UNROLL for (int k = 0; k < 4; ++k) {
+    double xr = yr[k] - shift, xi = yi[k];
+    double res = 0.0, scale = 0.0;
+    SMPC_UNROLL for (int it = 0; it < 3; ++it) {
+      // p(x) and p'(x) by Horner, complex
+      double pr = 1.0, pi = 0.0, dr = 0.0, di = 0.0;
+      const double co[4] = {a, b, cc, d};
+      SMPC_UNROLL for (int j = 0; j < 4; ++j) {
+        const double ndr = dr * xr - di * xi + pr, ndi = dr * xi + di * xr + pi;
+        const double npr = pr * xr - pi * xi + co[j], npi = pr * xi + pi * xr;
+        dr = ndr; di = ndi; pr = npr; pi = npi;
       }
-      const int t = colperm[k]; colperm[k] = colperm[pc]; colperm[pc] = t;
+      res = fabs(pr) + fabs(pi);
+      if (it == 2) break;
+      const double dn = dr * dr + di * di;
+      if (dn > 0.0) {
+        xr -= (pr * dr + pi * di) / dn;
+        xi -= (pi * dr - pr * di) / dn;
+      }
     }
-    for (int i = k + 1; i < nc; ++i) {
-      const double f = a[i][k] / a[k][k];
-      if (f == 0.0) continue;
-      for (int j = k; j < nc; ++j) a[i][j] -= f * a[k][j];
-      rhs[i] -= f * rhs[k];
-    }
+    const double ax = fabs(xr) + fabs(xi);
+    scale = fabs(d) + ax * (fabs(cc) + ax * (fabs(b) + ax * (fabs(a) + ax)));
+    if (!(res <= 1e-9 * scale + 1e-300)) ok = false;
+    re[k] = xr;
   }
-  double y[6];
-  for (int i = nc - 1; i >= 0; --i) {
-    double v = rhs[i];
-    for (int j = i + 1; j < nc; ++j) v -= a[i][j] * y[j];
-    y[i] = (a[i][i] != 0.0) ? v / a[i][i] : 0.0;
-  }
-  for (int i = 0; i < nc; ++i) poly[colperm[i]] = y[i];
+  if (!ok) quartic_aberth(c, re);
+  return 4;
+}
 
-  double ox = (lo + hi) / 2.0;
-  double ov = poly_eval(poly, nc, ox);
-  const double vlo = poly_eval(poly, nc, lo);
+// Minimiser on [lo, hi] of the cubic through (0, f0, g0), (t, f1, g1).
+__device__ __forceinline__ double cubic_interp_min(double f0, double g0, double t, double f1, double g1, double lo,
+                                                   double hi) {
+  const double A = f1 - f0 - g0 * t, Bv = g1 - g0;
+  const double inv_t = 1.0 / t;
+  const double a = (Bv * t - 2.0 * A) * inv_t * inv_t * inv_t;
+  const double b = (3.0 * A - Bv * t) * inv_t * inv_t;
+  auto pv = [&](double x) { return f0 + x * (g0 + x * (b + x * a)); };
+  double ox = (lo + hi) / 2.0, ov = pv(ox);
+  const double vlo = pv(lo);
   if (vlo < ov) { ov = vlo; ox = lo; }
-  const double vhi = poly_eval(poly, nc, hi);
+  const double vhi = pv(hi);
   if (vhi < ov) { ov = vhi; ox = hi; }
-  if (nc > 2) {
-    double der[5], roots[4];
-    for (int j = 0; j < degree; ++j) der[j] = (degree - j) * poly[j];
-    const int nr = poly_real_roots(der, degree, roots);
-    for (int i = 0; i < nr; ++i) {
-      if (roots[i] < lo || roots[i] > hi) continue;
-      const double v = poly_eval(poly, nc, roots[i]);
-      if (v < ov) { ov = v; ox = roots[i]; }
+  // critical points: roots of 3a x^2 + 2b x + g0 (leading zeros removed as Ceres does)
+  const double qa = 3.0 * a, qb = 2.0 * b, qc = g0;
+  double r0 = NAN, r1 = NAN;
+  if (qa != 0.0) {
+    const double D = qb * qb - 4.0 * qa * qc;
+    const double sD = sqrt(fabs(D));
+    if (D >= 0.0) {
+      if (qb >= 0.0) {
+        r0 = (-qb - sD) / (2.0 * qa);
+        r1 = (2.0 * qc) / (-qb - sD);
+      } else {
+        r0 = (2.0 * qc) / (-qb + sD);
+        r1 = (-qb + sD) / (2.0 * qa);
+      }
+    } else {
+      r0 = r1 = -qb / (2.0 * qa);
     }
+  } else if (qb != 0.0) {
+    r0 = -qc / qb;
   }
-  for (int i = 0; i < ns; ++i) {
-    if (s[i].x < lo || s[i].x > hi) continue;
-    const double v = poly_eval(poly, nc, s[i].x);
-    if (v < ov) { ov = v; ox = s[i].x; }
+  if (r0 >= lo && r0 <= hi) {
+    const double v = pv(r0);
+    if (v < ov) { ov = v; ox = r0; }
+  }
+  if (r1 >= lo && r1 <= hi) {
+    const double v = pv(r1);
+    if (v < ov) { ov = v; ox = r1; }
   }
   return ox;
 }
 
+// Minimiser on [lo, hi] of the quintic through (0, f0, g0), (t1, f1, g1), (t2, f2, g2), 0 < t1 < t2.
+__device__ __forceinline__ double quintic_interp_min(double f0, double g0, double t1, double f1, double g1, double t2,
+                                                     double f2, double g2, double lo, double hi) {
+  // work in xi = x / t2: nodes 0, tau, 1 (Hermite divided differences), then expand to monomials
+  const double tau = t1 / t2;
+  const double d0 = g0 * t2, d1 = g1 * t2, d2 = g2 * t2;
+  const double inv_tau = 1.0 / tau, inv_om = 1.0 / (1.0 - tau);
+  const double e01 = (f1 - f0) * inv_tau, e12 = (f2 - f1) * inv_om;
+  const double s0 = (e01 - d0) * inv_tau, s1 = (d1 - e01) * inv_tau, s2 = (e12 - d1) * inv_om, s3 = (d2 - e12) * inv_om;
+  const double h0 = (s1 - s0) * inv_tau, h1 = (s2 - s1), h2 = (s3 - s2) * inv_om;
+  const double k0 = h1 - h0, k1 = h2 - h1;
+  const double c5 = k1 - k0;
+  const double c0 = f0, c1 = d0, c2 = s0, c3 = h0, c4 = k0;
+  const double tau2 = tau * tau;
+  double m[6];
+  m[5] = c5;
+  m[4] = c4 - (2.0 * tau + 1.0) * c5;
+  m[3] = c3 - 2.0 * tau * c4 + (tau2 + 2.0 * tau) * c5;
+  m[2] = c2 - tau * c3 + tau2 * c4 - tau2 * c5;
+  m[1] = c1;
+  m[0] = c0;
+  const double xlo = lo / t2, xhi = hi / t2;
+  double ox = (xlo + xhi) / 2.0, ov = horner5(m, ox);
+  const double vlo = horner5(m, xlo);
+  if (vlo < ov) { ov = vlo; ox = xlo; }
+  const double vhi = horner5(m, xhi);
+  if (vhi < ov) { ov = vhi; ox = xhi; }
+  const double dq[5] = {m[1], 2.0 * m[2], 3.0 * m[3], 4.0 * m[4], 5.0 * m[5]};
+  double roots[4];
+  int nr = 0;
+  if (dq[4] != 0.0) {
+    nr = quartic_real_parts(dq, roots);
+  } else if (dq[3] != 0.0) {
+    // exactly-zero leading coefficient (never seen on real data): x * cubic has the cubic's roots plus 0,
+    // and 0 lies outside [xlo, xhi]
+    const double dq2[5] = {0.0, dq[0], dq[1], dq[2], dq[3]};
+    quartic_aberth(dq2, roots);
+    nr = 4;
+  } else if (dq[2] != 0.0) {
+    const double dq2[5] = {0.0, 0.0, dq[0], dq[1], dq[2]};
+    quartic_aberth(dq2, roots);
+    nr = 4;
+  } else if (dq[1] != 0.0) {
+    roots[0] = -dq[0] / dq[1];
+    nr = 1;
+  }
+  for (int i = 0; i < nr; ++i) {
+    if (roots[i] >= xlo && roots[i] <= xhi) {
+      const double v = horner5(m, roots[i]);
+      if (v < ov) { ov = v; ox = roots[i]; }
+    }
+  }
+  return ox * t2;
+}
+
 // Box projection of ParameterBlock::Plus: only the first n_bounded blocks carry bounds
 // (reference src/optimizer.cpp:373-379: v in [0, 0.6], w in [-1.4, 1.4]).
-template <int NB>
-__device__ __forceinline__ void plus_project(const double (&x)[2 * NB], const double (&d)[2 * NB], double t, int n_bounded,
-                                             double (&out)[2 * NB]) {
-  SMPC_UNROLL for (int b = 0; b < NB; ++b) {
-    double v = x[2 * b] + t * d[2 * b];
-    double w = x[2 * b + 1] + t * d[2 * b + 1];
-    if (b < n_bounded) {
-      v = fmin(fmax(v, 0.0), 0.6);
-      w = fmin(fmax(w, -1.4), 1.4);
-    }
-    out[2 * b] = v;
-    out[2 * b + 1] = w;
+__device__ __forceinline__ double project_param(double v, int c, int n_bounded) {
+  if ((c >> 1) < n_bounded) {
+    if (c & 1) return fmin(fmax(v, -1.4), 1.4);
+    return fmin(fmax(v, 0.0), 0.6);
   }
+  return v;
 }
 
 enum Termination {
@@ -727,255 +858,286 @@ struct SolveOut {
 };
 
 // ---------------------------------------------------------------------------------------------------
-// ceres::Solve restated, warp-uniform. x: in = seed block values, out = solution
-// (left at the projected seed when the solution is not usable).
+// ceres::Solve restated, warp-uniform, as a state machine around ONE evaluation site:
+// every trial point (iteration zero, each line-search sample, the un-shortened step after a failed line search)
+// gets a full evaluation, so an accepted point needs no second pass — its cost is the candidate cost and its
+// J^T J / J^T r are the next iterate's. ws: this warp's shared-memory state (Layout<NB>); ws[kX..] holds the seed
+// on entry and the solution on exit (the seed again when the solution is not usable).
 // ---------------------------------------------------------------------------------------------------
 template <int NB>
-__device__ void solve_problem(const DevParams& prm, const DevBatch& bt, const Prob& pb,
-                              const double (&aa_target)[kMaxChunks], double (&x)[2 * NB], int lane, SolveOut& so) {
-  constexpr int P = 2 * NB;
-  constexpr int NH = P * (P + 1) / 2;
+__device__ __forceinline__ void solve_problem(const DevParams& prm, const DevBatch& bt, const Prob& pb,
+                                              const double (&aa_target)[kMaxChunks], double* ws, int lane,
+                                              SolveOut& so) {
+  using L = Layout<NB>;
+  constexpr int P = L::P;
   const int nbd = prm.n_bounded;
-  so.n_jac = 0;
-  so.n_cost = 0;
+  double* xs = ws + L::kX;
+  double* best = ws + L::kBest;
+  double* scale = ws + L::kScale;
+  double* diag = ws + L::kDiag;
+  double* delta = ws + L::kDelta;
+  double* cand = ws + L::kCand;
+  double* cur = ws + L::kBuf0;    // normal equations at x
+  double* trial = ws + L::kBuf1;  // normal equations at the trial point
 
-  double zero[P], x_seed[P];
-  SMPC_UNROLL for (int c = 0; c < P; ++c) {
-    zero[c] = 0.0;
-    x_seed[c] = x[c];
+  // IterationZero: project the start point onto the box
+  if (lane < P) {
+    const double v = xs[lane];
+    best[lane] = v;
+    cand[lane] = project_param(v, lane, nbd);
   }
-  {
-    double xp[P];
-    plus_project<NB>(x, zero, 0.0, nbd, xp);  // IterationZero: project the start point
-    SMPC_UNROLL for (int c = 0; c < P; ++c) x[c] = xp[c];
-  }
-  double best[P];
-  SMPC_UNROLL for (int c = 0; c < P; ++c) best[c] = x[c];
+  __syncwarp();
 
-  Normal<NB> cur;  // normal equations at x
-  unsigned fl = evaluate<NB>(prm, bt, pb, aa_target, x, lane, cur);
-  ++so.n_jac;
-  so.cost_initial = cur.cost;
-  so.cost_final = cur.cost;
-  so.iterations = 0;
-  if (fl) {
-    so.termination = kFailEvaluation;
-    SMPC_UNROLL for (int c = 0; c < P; ++c) x[c] = x_seed[c];
-    return;
-  }
-  double x_cost = cur.cost;
-  double scale[P];
-  SMPC_UNROLL for (int c = 0; c < P; ++c) scale[c] = 1.0 / (1.0 + sqrt(cur.H[c * (c + 1) / 2 + c]));
-
-  auto grad_max_norm = [&](const double (&xx)[P], const double (&gg)[P]) {
-    double neg[P], proj[P];
-    SMPC_UNROLL for (int c = 0; c < P; ++c) neg[c] = -gg[c];
-    plus_project<NB>(xx, neg, 1.0, nbd, proj);
-    double m = 0.0;
-    SMPC_UNROLL for (int c = 0; c < P; ++c) m = fmax(m, fabs(xx[c] - proj[c]));
-    return m;
-  };
-  double gmax = grad_max_norm(x, cur.g);
-  double x_norm = 0.0;
-  SMPC_UNROLL for (int c = 0; c < P; ++c) x_norm += x[c] * x[c];
-  x_norm = sqrt(x_norm);
-
-  double radius = 1e4, decrease_factor = 2.0, minimum_cost = DBL_MAX;
-  bool reuse_diagonal = false, it_successful = true, any_success = false;
-  int n_invalid = 0, iteration = 0;
-  double it_cost = x_cost;
-  double diag[P];
-  SMPC_UNROLL for (int c = 0; c < P; ++c) diag[c] = 1.0;
+  enum Phase { kInit = 0, kLineSearch = 1, kFullStep = 2 };
+  int phase = kInit;
   int term = kNoConvergence;
-  Normal<NB> trial;
+  int iteration = 0, n_invalid = 0, n_eval = 0, ls_iters = 0;
+  double x_cost = 0.0, x_norm = 0.0, gmax = 0.0, radius = 1e4, decrease_factor = 2.0, minimum_cost = DBL_MAX;
+  double it_cost = 0.0, cost_initial = 0.0, cost_final = 0.0, model_cost_change = 0.0, g0 = 0.0, dmax = 0.0, t = 1.0;
+  bool reuse_diagonal = false, it_successful = true, any_success = false;
+  LsSample prev{0.0, 0.0, 0.0, false};
 
   for (;;) {
-    // FinalizeIterationAndCheckIfMinimizerCanContinue
-    if (it_successful && x_cost < minimum_cost) {
-      minimum_cost = x_cost;
-      SMPC_UNROLL for (int c = 0; c < P; ++c) best[c] = x[c];
-    }
-    so.cost_final = fmin(so.cost_final, it_cost);
-    if (iteration >= prm.max_iterations) { term = kNoConvergence; break; }
-    if (it_successful && gmax <= prm.gradient_tol) { term = kConvGradient; break; }
-    if (radius <= 1e-32) { term = kConvRadius; break; }
-    ++iteration;
+    const unsigned fl = evaluate<NB>(prm, bt, pb, aa_target, cand, lane, trial);
+    ++n_eval;
+    const double t_cost = trial[0];
+    bool take_step = false;  // proceed to accept/reject with `cand`
 
-    // LevenbergMarquardtStrategy::ComputeStep on the column-scaled normal equations
-    if (!reuse_diagonal) {
-      SMPC_UNROLL for (int c = 0; c < P; ++c)
-        diag[c] = fmin(fmax(scale[c] * scale[c] * cur.H[c * (c + 1) / 2 + c], 1e-6), 1e32);
+    if (phase == kInit) {
+      cost_initial = cost_final = t_cost;
+      if (fl) {
+        term = kFailEvaluation;
+        break;
+      }
+      // x <- projected seed; cur <- trial; Jacobi scaling from the column norms (= sqrt of diag(J^T J))
+      if (lane < P) {
+        xs[lane] = cand[lane];
+        scale[lane] = 1.0 / (1.0 + sqrt(trial[L::h(lane, lane)]));
+      }
+      __syncwarp();
+      { double* tmp = cur; cur = trial; trial = tmp; }
+      x_cost = t_cost;
+      it_cost = x_cost;
+      it_successful = true;
+    } else if (phase == kLineSearch) {
+      // Armijo sufficient decrease at step t along delta (projected)
+      const bool sample_ok = (fl == 0);
+      double gd = 0.0;
+      SMPC_UNROLL for (int c = 0; c < P; ++c) gd += delta[c] * trial[L::g(c)];
+      if (sample_ok && !(t_cost > x_cost + 1e-4 * g0 * t)) {
+        take_step = true;  // success: delta <- t * delta, candidate = this trial point
+      } else {
+        ++ls_iters;
+        bool ls_failed = ls_iters >= 20;
+        double t_new = t;
+        if (!ls_failed) {
+          const double lo = 1e-3 * t, hi = 0.6 * t;
+          if (!sample_ok) {
+            t_new = fmin(fmax(t * 0.5, lo), hi);
+          } else if (prev.ok) {
+            t_new = quintic_interp_min(x_cost, g0, t, t_cost, gd, prev.x, prev.value, prev.gradient, lo, hi);
+          } else {
+            t_new = cubic_interp_min(x_cost, g0, t, t_cost, gd, lo, hi);
+          }
+          if (t_new * dmax < 1e-9) ls_failed = true;
+        }
+        if (!ls_failed) {
+          prev = LsSample{t, t_cost, gd, sample_ok};
+          t = t_new;
+          if (lane < P) cand[lane] = project_param(xs[lane] + t * delta[lane], lane, nbd);
+          __syncwarp();
+          continue;  // evaluate the next line-search sample
+        }
+        // line search failed: the un-shortened TR step is the candidate (delta unchanged)
+        if (t != 1.0) {
+          t = 1.0;
+          if (lane < P) cand[lane] = project_param(xs[lane] + delta[lane], lane, nbd);
+          __syncwarp();
+          phase = kFullStep;
+          continue;
+        }
+        take_step = true;  // t is still 1: this trial IS Plus(x, delta)
+      }
+    } else {  // kFullStep: evaluation of Plus(x, delta) after a failed line search
+      take_step = true;
     }
-    reuse_diagonal = true;
-    double Lc[NH], rhs[P], step[P];
-    SMPC_UNROLL for (int a = 0; a < P; ++a) {
-      rhs[a] = scale[a] * cur.g[a];
-      SMPC_UNROLL for (int b = 0; b <= a; ++b) Lc[a * (a + 1) / 2 + b] = scale[a] * scale[b] * cur.H[a * (a + 1) / 2 + b];
-      const double lm = sqrt(diag[a] / radius);
-      Lc[a * (a + 1) / 2 + a] += lm * lm;
-    }
-    bool step_ok = true;
-    SMPC_UNROLL for (int jc = 0; jc < P; ++jc) {  // Cholesky, in place, lower triangle
-      double d = Lc[jc * (jc + 1) / 2 + jc];
-      SMPC_UNROLL for (int k = 0; k < jc; ++k) d -= Lc[jc * (jc + 1) / 2 + k] * Lc[jc * (jc + 1) / 2 + k];
-      if (!(d > 0.0)) step_ok = false;
-      d = sqrt(d);
-      Lc[jc * (jc + 1) / 2 + jc] = d;
-      const double inv_d = 1.0 / d;
-      SMPC_UNROLL for (int i = jc + 1; i < P; ++i) {
-        double s = Lc[i * (i + 1) / 2 + jc];
-        SMPC_UNROLL for (int k = 0; k < jc; ++k) s -= Lc[i * (i + 1) / 2 + k] * Lc[jc * (jc + 1) / 2 + k];
-        Lc[i * (i + 1) / 2 + jc] = s * inv_d;
+
+    if (take_step) {
+      const double cand_cost = (fl & kResidualBad) ? DBL_MAX : t_cost;
+      const bool tol_armed = (prm.ceres_compat < 210) || any_success;
+      double step_norm = 0.0;
+      SMPC_UNROLL for (int c = 0; c < P; ++c) {
+        const double dd = xs[c] - cand[c];
+        step_norm += dd * dd;
+      }
+      step_norm = sqrt(step_norm);
+      if (tol_armed && step_norm <= prm.param_tol * (x_norm + prm.param_tol)) {
+        --iteration;
+        term = kConvParameter;
+        break;
+      }
+      const double cost_change = x_cost - cand_cost;
+      if (tol_armed && fabs(cost_change) <= prm.fn_tol * x_cost) {
+        --iteration;
+        term = kConvFunction;
+        break;
+      }
+      const double rho = (cand_cost >= DBL_MAX) ? -DBL_MAX : cost_change / model_cost_change;
+      if (rho > 1e-3) {  // HandleSuccessfulStep
+        if (fl & kJacobianBad) {
+          --iteration;
+          term = kFailEvaluation;
+          break;
+        }
+        __syncwarp();
+        if (lane < P) xs[lane] = cand[lane];
+        __syncwarp();
+        { double* tmp = cur; cur = trial; trial = tmp; }
+        x_cost = cand_cost;
+        any_success = true;
+        it_successful = true;
+        it_cost = x_cost;
+        const double qq = 2.0 * rho - 1.0;
+        radius = fmin(1e16, radius / fmax(1.0 / 3.0, 1.0 - qq * qq * qq));
+        decrease_factor = 2.0;
+        reuse_diagonal = false;
+      } else {
+        it_successful = false;
+        it_cost = cand_cost;
+        radius = radius / decrease_factor;
+        decrease_factor *= 2.0;
+        reuse_diagonal = true;
       }
     }
-    SMPC_UNROLL for (int i = 0; i < P; ++i) {  // forward substitution
-      double s = rhs[i];
-      SMPC_UNROLL for (int k = 0; k < i; ++k) s -= Lc[i * (i + 1) / 2 + k] * step[k];
-      step[i] = s / Lc[i * (i + 1) / 2 + i];
+
+    // ---- a new outer iteration starts here (after iteration zero or after accept / reject) ----
+    if (it_successful) {  // x changed: refresh |x| and the projected-gradient max norm
+      double xn = 0.0, gm = 0.0;
+      SMPC_UNROLL for (int c = 0; c < P; ++c) {
+        const double xv = xs[c];
+        xn += xv * xv;
+        gm = fmax(gm, fabs(xv - project_param(xv - cur[L::g(c)], c, nbd)));
+      }
+      x_norm = sqrt(xn);
+      gmax = gm;
     }
-    SMPC_UNROLL for (int i = P - 1; i >= 0; --i) {  // back substitution
-      double s = step[i];
-      SMPC_UNROLL for (int k = i + 1; k < P; ++k) s -= Lc[k * (k + 1) / 2 + i] * step[k];
-      step[i] = s / Lc[i * (i + 1) / 2 + i];
-    }
-    SMPC_UNROLL for (int c = 0; c < P; ++c) {
-      step_ok = step_ok && isfinite(step[c]);
-      step[c] = -step[c];
-    }
-    // model_cost_change = -(Js s)'(r + Js s / 2) = -s'(Js' r) - s'(Js' Js) s / 2
-    double model_cost_change = 0.0;
-    if (step_ok) {
+    bool stop = false;
+    for (;;) {
+      // FinalizeIterationAndCheckIfMinimizerCanContinue
+      if (it_successful && x_cost < minimum_cost) {
+        minimum_cost = x_cost;
+        __syncwarp();
+        if (lane < P) best[lane] = xs[lane];
+        __syncwarp();
+      }
+      cost_final = fmin(cost_final, it_cost);
+      if (iteration >= prm.max_iterations) { term = kNoConvergence; stop = true; break; }
+      if (it_successful && gmax <= prm.gradient_tol) { term = kConvGradient; stop = true; break; }
+      if (radius <= 1e-32) { term = kConvRadius; stop = true; break; }
+      ++iteration;
+
+      // LevenbergMarquardtStrategy::ComputeStep on the column-scaled normal equations
+      __syncwarp();
+      if (!reuse_diagonal && lane < P) {
+        const double sc = scale[lane];
+        diag[lane] = fmin(fmax(sc * sc * cur[L::h(lane, lane)], 1e-6), 1e32);
+      }
+      __syncwarp();
+      reuse_diagonal = true;
+      double sc[P], Lc[L::NH], step[P];
+      SMPC_UNROLL for (int c = 0; c < P; ++c) sc[c] = scale[c];
+      SMPC_UNROLL for (int a = 0; a < P; ++a) {
+        SMPC_UNROLL for (int b = 0; b <= a; ++b) Lc[a * (a + 1) / 2 + b] = sc[a] * sc[b] * cur[L::h(a, b)];
+        const double lm = sqrt(diag[a] / radius);
+        Lc[a * (a + 1) / 2 + a] += lm * lm;
+      }
+      bool step_ok = true;
+      SMPC_UNROLL for (int jc = 0; jc < P; ++jc) {  // Cholesky, in place, lower triangle
+        double d = Lc[jc * (jc + 1) / 2 + jc];
+        SMPC_UNROLL for (int k = 0; k < jc; ++k) d -= Lc[jc * (jc + 1) / 2 + k] * Lc[jc * (jc + 1) / 2 + k];
+        if (!(d > 0.0)) step_ok = false;
+        const double inv_d = rsqrt(d);
+        Lc[jc * (jc + 1) / 2 + jc] = inv_d;  // store 1/L_jj
+        SMPC_UNROLL for (int i = jc + 1; i < P; ++i) {
+          double s = Lc[i * (i + 1) / 2 + jc];
+          SMPC_UNROLL for (int k = 0; k < jc; ++k) s -= Lc[i * (i + 1) / 2 + k] * Lc[jc * (jc + 1) / 2 + k];
+          Lc[i * (i + 1) / 2 + jc] = s * inv_d;
+        }
+      }
+      SMPC_UNROLL for (int i = 0; i < P; ++i) {  // forward substitution
+        double s = sc[i] * cur[L::g(i)];
+        SMPC_UNROLL for (int k = 0; k < i; ++k) s -= Lc[i * (i + 1) / 2 + k] * step[k];
+        step[i] = s * Lc[i * (i + 1) / 2 + i];
+      }
+      SMPC_UNROLL for (int i = P - 1; i >= 0; --i) {  // back substitution
+        double s = step[i];
+        SMPC_UNROLL for (int k = i + 1; k < P; ++k) s -= Lc[k * (k + 1) / 2 + i] * step[k];
+        step[i] = s * Lc[i * (i + 1) / 2 + i];
+      }
+      SMPC_UNROLL for (int c = 0; c < P; ++c) {
+        step_ok = step_ok && isfinite(step[c]);
+        step[c] = -step[c];
+      }
+      // model_cost_change = -(Js s)'(r + Js s / 2) = -s'(Js' r) - s'(Js' Js) s / 2
       double lin = 0.0, quad = 0.0;
       SMPC_UNROLL for (int a = 0; a < P; ++a) {
-        lin += step[a] * scale[a] * cur.g[a];
+        const double sa = sc[a] * step[a];
+        lin += sa * cur[L::g(a)];
         double rowv = 0.0;
-        SMPC_UNROLL for (int b = 0; b < P; ++b) {
-          const int hi = a > b ? a : b, lo = a > b ? b : a;
-          rowv += scale[a] * scale[b] * cur.H[hi * (hi + 1) / 2 + lo] * step[b];
-        }
-        quad += step[a] * rowv;
+        SMPC_UNROLL for (int b = 0; b < a; ++b) rowv += cur[L::h(a, b)] * (sc[b] * step[b]);
+        quad += sa * (2.0 * rowv + cur[L::h(a, a)] * sa);
       }
       model_cost_change = -lin - 0.5 * quad;
-    }
-    const bool valid = step_ok && (model_cost_change > 0.0);
-    if (!valid) {  // HandleInvalidStep
+      const bool valid = step_ok && (model_cost_change > 0.0);
+      if (valid) {
+        n_invalid = 0;
+        g0 = 0.0;
+        dmax = 0.0;
+        SMPC_UNROLL for (int c = 0; c < P; ++c) {
+          const double dl = step[c] * sc[c];
+          g0 += cur[L::g(c)] * dl;
+          dmax = fmax(dmax, fabs(dl));
+          step[c] = dl;
+        }
+        __syncwarp();
+        if (lane < P) {
+          double dl = step[0];
+          SMPC_UNROLL for (int c = 1; c < P; ++c) dl = (lane == c) ? step[c] : dl;
+          delta[lane] = dl;
+          cand[lane] = project_param(xs[lane] + dl, lane, nbd);
+        }
+        __syncwarp();
+        break;
+      }
+      // HandleInvalidStep
       if (++n_invalid >= 5) {
         --iteration;
         term = kFailInvalidSteps;
+        stop = true;
         break;
       }
       radius /= decrease_factor;
       decrease_factor *= 2.0;
       it_successful = false;
       it_cost = x_cost;
-      continue;
     }
-    n_invalid = 0;
-    double delta[P];
-    SMPC_UNROLL for (int c = 0; c < P; ++c) delta[c] = step[c] * scale[c];
-
-    // DoLineSearch: projected Armijo with cubic interpolation. Every trial point gets a full evaluation so
-    // that an accepted point needs no second pass (its cost is the candidate cost, its J^T J the next iterate's).
-    double g0 = 0.0, dmax = 0.0;
-    SMPC_UNROLL for (int c = 0; c < P; ++c) {
-      g0 += cur.g[c] * delta[c];
-      dmax = fmax(dmax, fabs(delta[c]));
-    }
-    LsSample smp[3];  // [0] initial, [1] current, [2] previous
-    smp[0] = {0.0, x_cost, g0, true, true};
-    smp[2] = {0.0, 0.0, 0.0, false, false};
-    double cand[P];
-    double t = 1.0;
-    int ls_iters = 0;
-    bool ls_success = false;
-    unsigned tfl = 0;
-    for (;;) {
-      plus_project<NB>(x, delta, t, nbd, cand);
-      tfl = evaluate<NB>(prm, bt, pb, aa_target, cand, lane, trial);
-      ++so.n_jac;
-      smp[1] = {t, trial.cost, 0.0, false, false};
-      if (!(tfl & kResidualBad) && !(tfl & kJacobianBad)) {
-        smp[1].value_ok = true;
-        double gd = 0.0;
-        SMPC_UNROLL for (int c = 0; c < P; ++c) gd += delta[c] * trial.g[c];
-        smp[1].gradient = gd;
-        smp[1].gradient_ok = isfinite(gd);
-      }
-      if (smp[1].value_ok && !(smp[1].value > x_cost + 1e-4 * g0 * t)) {
-        ls_success = true;
-        break;
-      }
-      ++ls_iters;
-      if (ls_iters >= 20) break;
-      const double lo = 1e-3 * t, hi = 0.6 * t;
-      double t_new;
-      if (!smp[1].value_ok) {
-        t_new = fmin(fmax(t * 0.5, lo), hi);
-      } else {
-        t_new = interpolating_poly_min(smp, smp[2].value_ok ? 3 : 2, lo, hi);
-      }
-      if (t_new * dmax < 1e-9) break;
-      smp[2] = smp[1];
-      t = t_new;
-    }
-    if (!ls_success && t != 1.0) {
-      // line search failed: the TR step is kept as is (delta unchanged) -> candidate = Plus(x, delta)
-      plus_project<NB>(x, delta, 1.0, nbd, cand);
-      tfl = evaluate<NB>(prm, bt, pb, aa_target, cand, lane, trial);
-      ++so.n_jac;
-    }
-    double cand_cost;
-    cand_cost = (tfl & kResidualBad) ? DBL_MAX : trial.cost;
-
-    const bool tol_armed = (prm.ceres_compat < 210) || any_success;
-    double step_norm = 0.0;
-    SMPC_UNROLL for (int c = 0; c < P; ++c) step_norm += (x[c] - cand[c]) * (x[c] - cand[c]);
-    step_norm = sqrt(step_norm);
-    if (tol_armed && step_norm <= prm.param_tol * (x_norm + prm.param_tol)) {
-      --iteration;
-      term = kConvParameter;
-      break;
-    }
-    const double cost_change = x_cost - cand_cost;
-    if (tol_armed && fabs(cost_change) <= prm.fn_tol * x_cost) {
-      --iteration;
-      term = kConvFunction;
-      break;
-    }
-    const double rho = (cand_cost >= DBL_MAX) ? -DBL_MAX : (x_cost - cand_cost) / model_cost_change;
-    if (rho > 1e-3) {  // HandleSuccessfulStep
-      if (tfl & kJacobianBad) {
-        --iteration;
-        term = kFailEvaluation;
-        break;
-      }
-      SMPC_UNROLL for (int c = 0; c < P; ++c) x[c] = cand[c];
-      x_norm = 0.0;
-      SMPC_UNROLL for (int c = 0; c < P; ++c) x_norm += x[c] * x[c];
-      x_norm = sqrt(x_norm);
-      cur = trial;
-      x_cost = cur.cost;
-      gmax = grad_max_norm(x, cur.g);
-      any_success = true;
-      it_successful = true;
-      it_cost = x_cost;
-      const double q = 2.0 * rho - 1.0;
-      radius = radius / fmax(1.0 / 3.0, 1.0 - q * q * q);
-      radius = fmin(1e16, radius);
-      decrease_factor = 2.0;
-      reuse_diagonal = false;
-    } else {
-      it_successful = false;
-      it_cost = cand_cost;
-      radius = radius / decrease_factor;
-      decrease_factor *= 2.0;
-      reuse_diagonal = true;
-    }
+    if (stop) break;
+    phase = kLineSearch;
+    t = 1.0;
+    ls_iters = 0;
+    prev.ok = false;
   }
+
   so.termination = term;
   so.iterations = iteration;
-  const bool usable = term <= kNoConvergence;  // Solver::Summary::IsSolutionUsable
-  SMPC_UNROLL for (int c = 0; c < P; ++c) x[c] = usable ? best[c] : x_seed[c];
+  so.cost_initial = cost_initial;
+  so.cost_final = cost_final;
+  so.n_jac = n_eval;
+  so.n_cost = 0;
+  // solution = best accepted iterate (the caller substitutes the seed when the termination is not usable)
+  __syncwarp();
+  if (lane < P) xs[lane] = best[lane];
+  __syncwarp();
 }
 
 // Load the warp-uniform problem view.

@@ -14,8 +14,11 @@ constexpr int kThreads = kWarpsPerCta * 32;
 
 template <int NB>
 __global__ void __launch_bounds__(kThreads) smpc_solve_kernel(DevParams prm, DevBatch bt, DevResult rs, int* queue) {
+  using L = Layout<NB>;
   constexpr int P = 2 * NB;
+  __shared__ double smem[kWarpsPerCta * L::kTotal];
   const int lane = threadIdx.x & 31;
+  double* ws = smem + (threadIdx.x >> 5) * L::kTotal;
   for (;;) {
     int b = 0;
     if (lane == 0) b = atomicAdd(queue, 1);
@@ -26,11 +29,15 @@ __global__ void __launch_bounds__(kThreads) smpc_solve_kernel(DevParams prm, Dev
     load_problem(bt, b, pb);
     double aa_target[kMaxChunks];
     agent_angle_setup(prm, bt, pb, lane, aa_target);
-    double x[P];
-    SMPC_UNROLL for (int c = 0; c < P; ++c) x[c] = __ldg(bt.u0 + (size_t)b * P + c);
+    __syncwarp();
+    if (lane < P) ws[L::kX + lane] = __ldg(bt.u0 + (size_t)b * P + lane);
+    __syncwarp();
 
     SolveOut so;
-    solve_problem<NB>(prm, bt, pb, aa_target, x, lane, so);
+    solve_problem<NB>(prm, bt, pb, aa_target, ws, lane, so);
+    const bool usable = so.termination <= kNoConvergence;  // Solver::Summary::IsSolutionUsable
+    double x[P];
+    SMPC_UNROLL for (int c = 0; c < P; ++c) x[c] = usable ? ws[L::kX + c] : __ldg(bt.u0 + (size_t)b * P + c);
 
     if (lane == 0) {
       if (rs.u) {
@@ -40,7 +47,7 @@ __global__ void __launch_bounds__(kThreads) smpc_solve_kernel(DevParams prm, Dev
       if (rs.cost_final) rs.cost_final[b] = so.cost_final;
       if (rs.iterations) rs.iterations[b] = so.iterations;
       if (rs.termination) rs.termination[b] = so.termination;
-      if (rs.usable) rs.usable[b] = (so.termination <= kNoConvergence) ? 1 : 0;
+      if (rs.usable) rs.usable[b] = usable ? 1 : 0;
       if (rs.n_evals) {
         rs.n_evals[2 * b] = so.n_jac;
         rs.n_evals[2 * b + 1] = so.n_cost;
@@ -102,9 +109,11 @@ __global__ void __launch_bounds__(kThreads) smpc_solve_kernel(DevParams prm, Dev
 
 template <int NB>
 __global__ void __launch_bounds__(kThreads) smpc_eval_kernel(DevParams prm, DevBatch bt, const double* xin, DevEvalOut eo) {
+  using L = Layout<NB>;
   constexpr int P = 2 * NB;
-  constexpr int NH = P * (P + 1) / 2;
+  __shared__ double smem[kWarpsPerCta * L::kTotal];
   const int lane = threadIdx.x & 31;
+  double* ws = smem + (threadIdx.x >> 5) * L::kTotal;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int n_warps = (gridDim.x * blockDim.x) >> 5;
   for (int b = warp; b < bt.B; b += n_warps) {
@@ -112,21 +121,29 @@ __global__ void __launch_bounds__(kThreads) smpc_eval_kernel(DevParams prm, DevB
     load_problem(bt, b, pb);
     double aa_target[kMaxChunks];
     agent_angle_setup(prm, bt, pb, lane, aa_target);
-    double x[P];
-    SMPC_UNROLL for (int c = 0; c < P; ++c) x[c] = __ldg(xin + (size_t)b * P + c);
-    Normal<NB> nrm;
-    const unsigned fl = evaluate<NB>(prm, bt, pb, aa_target, x, lane, nrm);
+    __syncwarp();
+    if (lane < P) ws[L::kCand + lane] = __ldg(xin + (size_t)b * P + lane);
+    __syncwarp();
+    const unsigned fl = evaluate<NB>(prm, bt, pb, aa_target, ws + L::kCand, lane, ws + L::kBuf0);
     if (lane == 0) {
-      if (eo.cost) eo.cost[b] = nrm.cost;
+      if (eo.cost) eo.cost[b] = ws[L::kBuf0];
       if (eo.ok) eo.ok[b] = (fl == 0) ? 1 : 0;
-      if (eo.grad) {
-        SMPC_UNROLL for (int c = 0; c < P; ++c) eo.grad[(size_t)b * P + c] = nrm.g[c];
-      }
-      if (eo.hess) {
-        SMPC_UNROLL for (int e = 0; e < NH; ++e) eo.hess[(size_t)b * NH + e] = nrm.H[e];
-      }
     }
+    if (eo.grad && lane < P) eo.grad[(size_t)b * P + lane] = ws[L::kBuf0 + 1 + lane];
+    if (eo.hess)
+      for (int e = lane; e < L::NH; e += 32) eo.hess[(size_t)b * L::NH + e] = ws[L::kBuf0 + 1 + P + e];
+    __syncwarp();
   }
+}
+
+// Line-search polynomial minimiser exposed for unit tests: rows of (lo, hi, f0, g0, t1, f1, g1, t2, f2, g2);
+// t2 <= 0 selects the two-sample (cubic) case.
+__global__ void smpc_polymin_kernel(int n, const double* __restrict__ in, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* r = in + (size_t)i * 10;
+  out[i] = (r[7] > 0.0) ? quintic_interp_min(r[2], r[3], r[4], r[5], r[6], r[7], r[8], r[9], r[0], r[1])
+                        : cubic_interp_min(r[2], r[3], r[4], r[5], r[6], r[0], r[1]);
 }
 
 // One CTA per robot: arg-min of cost_final over its n_starts consecutive solves (usable ones only; ties -> lowest index).
@@ -247,6 +264,11 @@ cudaError_t launch_argmin(int n_robots, int n_starts, int n_blocks, const double
 }
 
 int max_supported_blocks() { return 6; }
+
+cudaError_t launch_polymin(int n, const double* in, double* out, cudaStream_t stream) {
+  smpc_polymin_kernel<<<(n + 127) / 128, 128, 0, stream>>>(n, in, out);
+  return cudaGetLastError();
+}
 
 // DFMA-saturating microbenchmark: 8 independent FMA chains per thread (roofline denominator, "of measured").
 __global__ void __launch_bounds__(256) smpc_dfma_peak_kernel(double* sink, int iters, double a, double b) {

@@ -141,6 +141,14 @@ class Optimizer:
         self._need()
         return float(_lib.lib().smpc_last_kernel_ms(self._h))
 
+    def debug_polymin(self, rows: np.ndarray) -> np.ndarray:
+        """Line-search polynomial minimiser on rows of (lo, hi, f0, g0, t1, f1, g1, t2, f2, g2) (unit tests)."""
+        self._need()
+        rows = np.ascontiguousarray(rows, dtype=np.float64).reshape(-1, 10)
+        out = np.zeros(rows.shape[0])
+        _lib.check(_lib.lib().smpc_debug_polymin(self._h, rows.shape[0], rows.ctypes.data, out.ctypes.data))
+        return out
+
     def measure_fp64_peak(self) -> float:
         """TFLOP/s of a DFMA-saturating microbenchmark on this GPU (roofline denominator)."""
         self._need()

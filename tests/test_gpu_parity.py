@@ -174,3 +174,33 @@ def test_multistart_argmin(make_opt):
     assert np.array_equal(best_index.cpu().numpy(), want)
     assert np.array_equal(best_cost.cpu().numpy(), c.min(axis=1))
     assert np.array_equal(best_u.cpu().numpy(), got["u"][want])
+
+
+def test_line_search_polynomial_minimiser_matches_oracle(oracle, make_opt):
+    """Closed-form cubic / quintic Hermite minimiser on the GPU vs the oracle's polynomial.cc restatement
+    (pivoted LU fit + root finding) on random line-search-like samples."""
+    opt = make_opt(sc.make_params("obst_only"))
+    rng = np.random.default_rng(3)
+    rows, want = [], []
+    for k in range(400):
+        f0 = rng.uniform(1.0, 100.0)
+        g0 = -rng.uniform(0.1, 50.0)
+        t2 = rng.uniform(0.05, 1.0)
+        f2 = f0 + rng.uniform(0.0, 50.0)
+        g2 = rng.uniform(-20.0, 200.0)
+        if k % 2 == 0:  # two samples: cubic
+            lo, hi = 1e-3 * t2, 0.6 * t2
+            rows.append([lo, hi, f0, g0, t2, f2, g2, 0.0, 0.0, 0.0])
+            want.append(oracle.poly_min([[0, f0, g0, 1, 1], [t2, f2, g2, 1, 1]], lo, hi))
+        else:  # three samples: quintic; current step t1 inside [1e-3, 0.6] * previous
+            t1 = t2 * rng.uniform(1e-3, 0.6)
+            f1 = f0 + rng.uniform(-0.5, 5.0) * t1
+            g1 = rng.uniform(-30.0, 60.0)
+            lo, hi = 1e-3 * t1, 0.6 * t1
+            rows.append([lo, hi, f0, g0, t1, f1, g1, t2, f2, g2])
+            want.append(oracle.poly_min([[0, f0, g0, 1, 1], [t1, f1, g1, 1, 1], [t2, f2, g2, 1, 1]], lo, hi))
+    got = opt.debug_polymin(np.array(rows))
+    want = np.array(want)
+    rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-300)
+    assert np.quantile(rel, 0.99) < 1e-8, rel.max()
+    assert (rel < 1e-6).mean() > 0.995
