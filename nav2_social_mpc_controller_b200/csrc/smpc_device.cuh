@@ -277,13 +277,27 @@ __device__ __forceinline__ double wrap_angle(double a) {
 // Full evaluation at block values xs[P] (shared memory): cost = 1/2 sum r^2, g = J^T r, H = J^T J, written to
 // out[NE] (shared memory). Residual set and order of reference src/optimizer.cpp:251-371.
 // ---------------------------------------------------------------------------------------------------
+// Per-lane constants of the horizon discretisation (batch-uniform S, bl): the block of the lane's step and
+// d theta_j / d w_b = dt * #{steps before j in block b}. Hoisted out of the solve (single-chunk case, S <= 32).
 template <int NB>
+struct LaneConst {
+  int bj;
+  double tau[NB];
+};
+
+template <int NB>
+__device__ __forceinline__ void lane_setup(int j, int bl, double dt, LaneConst<NB>& lc) {
+  lc.bj = min(j / bl, NB - 1);
+  SMPC_UNROLL for (int b = 0; b < NB; ++b) lc.tau[b] = dt * (double)steps_in_block_before<NB>(j, b, bl);
+}
+
+template <int NB, bool MULTI>
 __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatch& bt, const Prob& pb,
-                                             const double (&aa_target)[kMaxChunks], const double* xs, int lane,
-                                             double* out) {
+                                             const double (&aa_target)[kMaxChunks], const LaneConst<NB>& lc0,
+                                             const double* xs, int lane, double* out) {
   using L = Layout<NB>;
   constexpr int P = L::P;
-  const int S = bt.S, bl = prm.bl, ch = prm.ch;
+  const int S = bt.S, ch = prm.ch;
   const double dt = bt.dt;
   const int stride = S + 1;
   const double inv_res = 1.0 / bt.resolution;
@@ -295,26 +309,29 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
   SMPC_UNROLL for (int e = 0; e < L::NEP; ++e) acc[e] = 0.0;
   unsigned flags = 0;
 
-  // carries of the inclusive scans between 32-step chunks (dead code when S <= 32)
+  // carries of the inclusive scans between 32-step chunks (only instantiated when S > 32)
   double carry_x = pb.x0, carry_y = pb.y0;
-  double carry_d[4 * NB];
-  SMPC_UNROLL for (int e = 0; e < 4 * NB; ++e) carry_d[e] = 0.0;
+  double carry_d[MULTI ? 4 * NB : 1];
+  if (MULTI) {
+    SMPC_UNROLL for (int e = 0; e < 4 * NB; ++e) carry_d[e] = 0.0;
+  }
 
 #pragma unroll 1
-  for (int chunk = 0; chunk * 32 < S; ++chunk) {
+  for (int chunk = 0; chunk * 32 < (MULTI ? S : 1); ++chunk) {
     const int j = chunk * 32 + lane;
     const bool act = j < S;
-    const int bj = min(j / bl, NB - 1);
+    LaneConst<NB> lcm;
+    if (MULTI) lane_setup<NB>(j, prm.bl, dt, lcm);
+    const LaneConst<NB>& lc = MULTI ? lcm : lc0;
+    const int bj = lc.bj;
     double vj = x[0], wj = x[1];
     double th = pb.yaw0;  // heading before step j
-    double tw_next[NB];   // d Theta_j / d w_b (heading after step j)
     SMPC_UNROLL for (int b = 0; b < NB; ++b) {
       if (b == bj) {
         vj = x[2 * b];
         wj = x[2 * b + 1];
       }
-      th += x[2 * b + 1] * (dt * (double)steps_in_block_before<NB>(j, b, bl));
-      tw_next[b] = dt * (double)steps_in_block_before<NB>(j + 1, b, bl);
+      th += x[2 * b + 1] * lc.tau[b];
     }
     double sn, cs;
     sincos(th, &sn, &cs);
@@ -325,36 +342,41 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
     double sx = aj, sy = bjv;
     double sd[4 * NB];
     SMPC_UNROLL for (int b = 0; b < NB; ++b) {
-      const double tau = dt * (double)steps_in_block_before<NB>(j, b, bl);  // d theta_j / d w_b
-      sd[4 * b + 0] = (b == bj) ? cdt : 0.0;                                // dX/dv_b
-      sd[4 * b + 1] = (b == bj) ? sdt : 0.0;                                // dY/dv_b
-      sd[4 * b + 2] = -bjv * tau;                                           // dX/dw_b
-      sd[4 * b + 3] = aj * tau;                                             // dY/dw_b
+      sd[4 * b + 0] = (b == bj) ? cdt : 0.0;  // dX/dv_b
+      sd[4 * b + 1] = (b == bj) ? sdt : 0.0;  // dY/dv_b
+      sd[4 * b + 2] = -bjv * lc.tau[b];       // dX/dw_b
+      sd[4 * b + 3] = aj * lc.tau[b];         // dY/dw_b
     }
     SMPC_UNROLL for (int d = 1; d < 32; d <<= 1) {
       const double tx = __shfl_up_sync(kFullMask, sx, d);
       const double ty = __shfl_up_sync(kFullMask, sy, d);
-      const bool on = lane >= d;
-      sx += on ? tx : 0.0;
-      sy += on ? ty : 0.0;
+      if (lane >= d) {
+        sx += tx;
+        sy += ty;
+      }
       SMPC_UNROLL for (int e = 0; e < 4 * NB; ++e) {
         const double t = __shfl_up_sync(kFullMask, sd[e], d);
-        sd[e] += on ? t : 0.0;
+        if (lane >= d) sd[e] += t;
       }
     }
     const double X = carry_x + sx, Y = carry_y + sy;
-    if (S > 32) {
+    if (MULTI) {
       SMPC_UNROLL for (int e = 0; e < 4 * NB; ++e) sd[e] += carry_d[e];
       carry_x = __shfl_sync(kFullMask, X, 31);
       carry_y = __shfl_sync(kFullMask, Y, 31);
       SMPC_UNROLL for (int e = 0; e < 4 * NB; ++e) carry_d[e] = __shfl_sync(kFullMask, sd[e], 31);
     }
+    // heading after step j = heading before step j+1: take lane j+1's sin/cos when that lane exists
+    double sT, cT;
+    const double Th = th + wj * dt;
+    if (!MULTI && S <= 31) {
+      sT = __shfl_down_sync(kFullMask, sn, 1);
+      cT = __shfl_down_sync(kFullMask, cs, 1);
+    } else {
+      sincos(Th, &sT, &cT);
+    }
 
     if (act) {
-      const double Th = th + wj * dt;  // heading after step j
-      double sT, cT;
-      sincos(Th, &sT, &cT);
-
       // per-lane Gauss-Newton block wrt (X, Y, Theta, lv): M = sum c c^T (10 entries), q = sum c r
       double mXX = 0, mXY = 0, mXT = 0, mXL = 0, mYY = 0, mYT = 0, mYL = 0, mTT = 0, mTL = 0, mLL = 0;
       double qX = 0, qY = 0, qT = 0, qL = 0;
@@ -496,28 +518,42 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
         qX += kx * r; qY += ky * r; qT += cTh * r;
       }
 
-      // --- lane block -> parameter space. Column of v_b: (dX, dY, 0, [b == bj]); of w_b: (dX, dY, dTheta, 0) ----
+      // --- lane block -> parameter space, one column at a time (T = M D[:,a] is never stored).
+      //     Column of v_b: (dX, dY, 0, [b == bj]); of w_b: (dX, dY, dTheta, 0). ------------------------------
       acc[0] += cost;
-      double T0[P], T1[P], T2[P], T3[P];
-      SMPC_UNROLL for (int b = 0; b < NB; ++b) {
-        const double xv = sd[4 * b + 0], yv = sd[4 * b + 1], xw = sd[4 * b + 2], yw = sd[4 * b + 3];
-        const double lb = (b == bj) ? 1.0 : 0.0, tw = tw_next[b];
-        T0[2 * b] = mXX * xv + mXY * yv + mXL * lb;
-        T1[2 * b] = mXY * xv + mYY * yv + mYL * lb;
-        T2[2 * b] = mXT * xv + mYT * yv + mTL * lb;
-        T3[2 * b] = mXL * xv + mYL * yv + mLL * lb;
-        T0[2 * b + 1] = mXX * xw + mXY * yw + mXT * tw;
-        T1[2 * b + 1] = mXY * xw + mYY * yw + mYT * tw;
-        T2[2 * b + 1] = mXT * xw + mYT * yw + mTT * tw;
-        T3[2 * b + 1] = mXL * xw + mYL * yw + mTL * tw;
-        acc[L::g(2 * b)] += qX * xv + qY * yv + qL * lb;
-        acc[L::g(2 * b + 1)] += qX * xw + qY * yw + qT * tw;
-      }
-      SMPC_UNROLL for (int b = 0; b < NB; ++b) {
-        const double xv = sd[4 * b + 0], yv = sd[4 * b + 1], xw = sd[4 * b + 2], yw = sd[4 * b + 3];
-        const double lb = (b == bj) ? 1.0 : 0.0, tw = tw_next[b];
-        SMPC_UNROLL for (int a = 2 * b; a < P; ++a) acc[L::h(a, 2 * b)] += xv * T0[a] + yv * T1[a] + lb * T3[a];
-        SMPC_UNROLL for (int a = 2 * b + 1; a < P; ++a) acc[L::h(a, 2 * b + 1)] += xw * T0[a] + yw * T1[a] + tw * T2[a];
+      SMPC_UNROLL for (int ba = 0; ba < NB; ++ba) {
+        const double la = (ba == bj) ? 1.0 : 0.0;
+        const double twa = lc.tau[ba] + ((ba == bj) ? dt : 0.0);  // d Theta_j / d w_ba (heading after step j)
+        {  // column a = 2 ba (v_ba)
+          const double xv = sd[4 * ba + 0], yv = sd[4 * ba + 1];
+          const double t0 = mXX * xv + mXY * yv + mXL * la;
+          const double t1 = mXY * xv + mYY * yv + mYL * la;
+          const double t2 = mXT * xv + mYT * yv + mTL * la;
+          const double t3 = mXL * xv + mYL * yv + mLL * la;
+          acc[L::g(2 * ba)] += qX * xv + qY * yv + qL * la;
+          SMPC_UNROLL for (int bb = 0; bb <= ba; ++bb) {
+            const double lb = (bb == bj) ? 1.0 : 0.0;
+            acc[L::h(2 * ba, 2 * bb)] += sd[4 * bb + 0] * t0 + sd[4 * bb + 1] * t1 + lb * t3;
+            if (bb < ba) {
+              const double twb = lc.tau[bb] + ((bb == bj) ? dt : 0.0);
+              acc[L::h(2 * ba, 2 * bb + 1)] += sd[4 * bb + 2] * t0 + sd[4 * bb + 3] * t1 + twb * t2;
+            }
+          }
+        }
+        {  // column a = 2 ba + 1 (w_ba)
+          const double xw = sd[4 * ba + 2], yw = sd[4 * ba + 3];
+          const double t0 = mXX * xw + mXY * yw + mXT * twa;
+          const double t1 = mXY * xw + mYY * yw + mYT * twa;
+          const double t2 = mXT * xw + mYT * yw + mTT * twa;
+          const double t3 = mXL * xw + mYL * yw + mTL * twa;
+          acc[L::g(2 * ba + 1)] += qX * xw + qY * yw + qT * twa;
+          SMPC_UNROLL for (int bb = 0; bb <= ba; ++bb) {
+            const double lb = (bb == bj) ? 1.0 : 0.0;
+            const double twb = lc.tau[bb] + ((bb == bj) ? dt : 0.0);
+            acc[L::h(2 * ba + 1, 2 * bb)] += sd[4 * bb + 0] * t0 + sd[4 * bb + 1] * t1 + lb * t3;
+            acc[L::h(2 * ba + 1, 2 * bb + 1)] += sd[4 * bb + 2] * t0 + sd[4 * bb + 3] * t1 + twb * t2;
+          }
+        }
       }
     }
   }
@@ -632,7 +668,7 @@ static __device__ __noinline__ void quartic_aberth(const double* c, double* re) 
 }
 
 // Real parts of the roots of c[0] + c[1] x + c[2] x^2 + c[3] x^3 + c[4] x^4 (c[4] != 0). Returns 4.
-__device__ __forceinline__ int quartic_real_parts(const double (&c)[5], double (&re)[4]) {
+__device__ __forceinline__ int quartic_real_parts(const double (&c)[5], double xlo, double xhi, double (&re)[4]) {
   const double inv = 1.0 / c[4];
   const double a = c[3] * inv, b = c[2] * inv, cc = c[1] * inv, d = c[0] * inv;
   const double a2 = a * a;
@@ -702,31 +738,36 @@ __device__ __forceinline__ int quartic_real_parts(const double (&c)[5], double (
       yr[2] = yr[3] = 0.5 * s; yi[2] = 0.5 * sqrt(-d2); yi[3] = -yi[2];
     }
   }
-  // back to x, complex Newton polish on the monic quartic, residual check
+  // back to x. Only roots whose real part can land in [xlo, xhi] matter to the caller: those get a complex
+  // Newton polish on the monic quartic; the others only get a residual check (a wrong factorisation must not
+  // hide an in-range root).
   const double shift = 0.25 * a;
+  const double margin = 0.05 * (xhi - xlo) + 1e-3 * fabs(xhi);
+  const double co[4] = {a, b, cc, d};
   SMPC_UNROLL for (int k = 0; k < 4; ++k) {
     double xr = yr[k] - shift, xi = yi[k];
-    double res = 0.0, scale = 0.0;
-    SMPC_UNROLL for (int it = 0; it < 3; ++it) {
-      // p(x) and p'(x) by Horner, complex
-      double pr = 1.0, pi = 0.0, dr = 0.0, di = 0.0;
-      const double co[4] = {a, b, cc, d};
+    const bool near = (xr >= xlo - margin) && (xr <= xhi + margin);
+    double res = 0.0;
+    const int n_it = near ? 3 : 1;
+    for (int it = 0; it < n_it; ++it) {
+      double pr = 1.0, pi = 0.0, dr = 0.0, di = 0.0;  // p(x) and p'(x) by Horner, complex
       SMPC_UNROLL for (int j = 0; j < 4; ++j) {
         const double ndr = dr * xr - di * xi + pr, ndi = dr * xi + di * xr + pi;
         const double npr = pr * xr - pi * xi + co[j], npi = pr * xi + pi * xr;
         dr = ndr; di = ndi; pr = npr; pi = npi;
       }
       res = fabs(pr) + fabs(pi);
-      if (it == 2) break;
+      if (it == n_it - 1) break;
       const double dn = dr * dr + di * di;
       if (dn > 0.0) {
-        xr -= (pr * dr + pi * di) / dn;
-        xi -= (pi * dr - pr * di) / dn;
+        const double idn = 1.0 / dn;
+        xr -= (pr * dr + pi * di) * idn;
+        xi -= (pi * dr - pr * di) * idn;
       }
     }
     const double ax = fabs(xr) + fabs(xi);
-    scale = fabs(d) + ax * (fabs(cc) + ax * (fabs(b) + ax * (fabs(a) + ax)));
-    if (!(res <= 1e-9 * scale + 1e-300)) ok = false;
+    const double scale = fabs(d) + ax * (fabs(cc) + ax * (fabs(b) + ax * (fabs(a) + ax)));
+    if (!(res <= (near ? 1e-10 : 1e-6) * scale + 1e-300)) ok = false;
     re[k] = xr;
   }
   if (!ok) quartic_aberth(c, re);
@@ -808,7 +849,7 @@ __device__ __forceinline__ double quintic_interp_min(double f0, double g0, doubl
   double roots[4];
   int nr = 0;
   if (dq[4] != 0.0) {
-    nr = quartic_real_parts(dq, roots);
+    nr = quartic_real_parts(dq, xlo, xhi, roots);
   } else if (dq[3] != 0.0) {
     // exactly-zero leading coefficient (never seen on real data): x * cubic has the cubic's roots plus 0,
     // and 0 lies outside [xlo, xhi]
@@ -864,10 +905,10 @@ struct SolveOut {
 // J^T J / J^T r are the next iterate's. ws: this warp's shared-memory state (Layout<NB>); ws[kX..] holds the seed
 // on entry and the solution on exit (the seed again when the solution is not usable).
 // ---------------------------------------------------------------------------------------------------
-template <int NB>
+template <int NB, bool MULTI>
 __device__ __forceinline__ void solve_problem(const DevParams& prm, const DevBatch& bt, const Prob& pb,
-                                              const double (&aa_target)[kMaxChunks], double* ws, int lane,
-                                              SolveOut& so) {
+                                              const double (&aa_target)[kMaxChunks], const LaneConst<NB>& lc,
+                                              double* ws, int lane, SolveOut& so) {
   using L = Layout<NB>;
   constexpr int P = L::P;
   const int nbd = prm.n_bounded;
@@ -898,7 +939,7 @@ __device__ __forceinline__ void solve_problem(const DevParams& prm, const DevBat
   LsSample prev{0.0, 0.0, 0.0, false};
 
   for (;;) {
-    const unsigned fl = evaluate<NB>(prm, bt, pb, aa_target, cand, lane, trial);
+    const unsigned fl = evaluate<NB, MULTI>(prm, bt, pb, aa_target, lc, cand, lane, trial);
     ++n_eval;
     const double t_cost = trial[0];
     bool take_step = false;  // proceed to accept/reject with `cand`
@@ -1045,11 +1086,11 @@ __device__ __forceinline__ void solve_problem(const DevParams& prm, const DevBat
       __syncwarp();
       reuse_diagonal = true;
       double sc[P], Lc[L::NH], step[P];
+      const double inv_radius = 1.0 / radius;
       SMPC_UNROLL for (int c = 0; c < P; ++c) sc[c] = scale[c];
       SMPC_UNROLL for (int a = 0; a < P; ++a) {
         SMPC_UNROLL for (int b = 0; b <= a; ++b) Lc[a * (a + 1) / 2 + b] = sc[a] * sc[b] * cur[L::h(a, b)];
-        const double lm = sqrt(diag[a] / radius);
-        Lc[a * (a + 1) / 2 + a] += lm * lm;
+        Lc[a * (a + 1) / 2 + a] += diag[a] * inv_radius;  // (sqrt(diag / radius))^2 of the LM strategy
       }
       bool step_ok = true;
       SMPC_UNROLL for (int jc = 0; jc < P; ++jc) {  // Cholesky, in place, lower triangle

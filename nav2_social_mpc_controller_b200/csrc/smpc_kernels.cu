@@ -11,14 +11,19 @@ namespace smpc {
 
 constexpr int kWarpsPerCta = 4;
 constexpr int kThreads = kWarpsPerCta * 32;
+#ifndef SMPC_MIN_CTAS
+#define SMPC_MIN_CTAS 4
+#endif
 
-template <int NB>
-__global__ void __launch_bounds__(kThreads) smpc_solve_kernel(DevParams prm, DevBatch bt, DevResult rs, int* queue) {
+template <int NB, bool MULTI>
+__global__ void __launch_bounds__(kThreads, SMPC_MIN_CTAS) smpc_solve_kernel(DevParams prm, DevBatch bt, DevResult rs, int* queue) {
   using L = Layout<NB>;
   constexpr int P = 2 * NB;
   __shared__ double smem[kWarpsPerCta * L::kTotal];
   const int lane = threadIdx.x & 31;
   double* ws = smem + (threadIdx.x >> 5) * L::kTotal;
+  LaneConst<NB> lc;
+  lane_setup<NB>(lane, prm.bl, bt.dt, lc);
   for (;;) {
     int b = 0;
     if (lane == 0) b = atomicAdd(queue, 1);
@@ -34,7 +39,7 @@ __global__ void __launch_bounds__(kThreads) smpc_solve_kernel(DevParams prm, Dev
     __syncwarp();
 
     SolveOut so;
-    solve_problem<NB>(prm, bt, pb, aa_target, ws, lane, so);
+    solve_problem<NB, MULTI>(prm, bt, pb, aa_target, lc, ws, lane, so);
     const bool usable = so.termination <= kNoConvergence;  // Solver::Summary::IsSolutionUsable
     double x[P];
     SMPC_UNROLL for (int c = 0; c < P; ++c) x[c] = usable ? ws[L::kX + c] : __ldg(bt.u0 + (size_t)b * P + c);
@@ -114,6 +119,8 @@ __global__ void __launch_bounds__(kThreads) smpc_eval_kernel(DevParams prm, DevB
   __shared__ double smem[kWarpsPerCta * L::kTotal];
   const int lane = threadIdx.x & 31;
   double* ws = smem + (threadIdx.x >> 5) * L::kTotal;
+  LaneConst<NB> lc;
+  lane_setup<NB>(lane, prm.bl, bt.dt, lc);
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int n_warps = (gridDim.x * blockDim.x) >> 5;
   for (int b = warp; b < bt.B; b += n_warps) {
@@ -124,7 +131,8 @@ __global__ void __launch_bounds__(kThreads) smpc_eval_kernel(DevParams prm, DevB
     __syncwarp();
     if (lane < P) ws[L::kCand + lane] = __ldg(xin + (size_t)b * P + lane);
     __syncwarp();
-    const unsigned fl = evaluate<NB>(prm, bt, pb, aa_target, ws + L::kCand, lane, ws + L::kBuf0);
+    const unsigned fl = (bt.S > 32) ? evaluate<NB, true>(prm, bt, pb, aa_target, lc, ws + L::kCand, lane, ws + L::kBuf0)
+                                    : evaluate<NB, false>(prm, bt, pb, aa_target, lc, ws + L::kCand, lane, ws + L::kBuf0);
     if (lane == 0) {
       if (eo.cost) eo.cost[b] = ws[L::kBuf0];
       if (eo.ok) eo.ok[b] = (fl == 0) ? 1 : 0;
@@ -209,8 +217,10 @@ __global__ void smpc_argmin_kernel(int n_starts, int n_blocks, const double* __r
 template <int NB>
 static cudaError_t launch_solve_nb(const DevParams& prm, const DevBatch& bt, const DevResult& rs, int* queue, int n_sm,
                                    cudaStream_t stream) {
+  const bool multi = bt.S > 32;
   int ctas_per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, smpc_solve_kernel<NB>, kThreads, 0);
+  cudaError_t e = multi ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, smpc_solve_kernel<NB, true>, kThreads, 0)
+                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, smpc_solve_kernel<NB, false>, kThreads, 0);
   if (e != cudaSuccess) return e;
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   // persistent grid: a multiple of the SM count, never more warps than problems
@@ -218,7 +228,10 @@ static cudaError_t launch_solve_nb(const DevParams& prm, const DevBatch& bt, con
   long long grid = (long long)n_sm * ctas_per_sm;
   if (want_ctas < grid) grid = want_ctas;
   if (grid < 1) grid = 1;
-  smpc_solve_kernel<NB><<<(unsigned)grid, kThreads, 0, stream>>>(prm, bt, rs, queue);
+  if (multi)
+    smpc_solve_kernel<NB, true><<<(unsigned)grid, kThreads, 0, stream>>>(prm, bt, rs, queue);
+  else
+    smpc_solve_kernel<NB, false><<<(unsigned)grid, kThreads, 0, stream>>>(prm, bt, rs, queue);
   return cudaGetLastError();
 }
 
