@@ -34,7 +34,7 @@ PARAM_SETS = {
                    agent_angle_w=40.0, velocity_feasibility_w=5.0, goal_align_w=10.0, obstacle_w=0.15,
                    proxemics_w=100.0),
     "params_yaml": dict(time_step=0.05, max_time=2.0, control_horizon=20, parameter_block_length=4,
-                        lookahead_dist=1.0, current_cmds_w=0.5, distance_w=50.0, socialwork_w=700.0,
+                        lookahead_dist=1.0, discretization=2, transform_tolerance=0.3, current_cmds_w=0.5, distance_w=50.0, socialwork_w=700.0,
                         velocity_w=8.0, angle_w=180.0, agent_angle_w=0.0, velocity_feasibility_w=5.0,
                         goal_align_w=8.0, obstacle_w=0.2),
     "obst_only": dict(time_step=0.05, max_time=1.5, control_horizon=18, parameter_block_length=6,
