@@ -197,6 +197,11 @@ int smpc_multistart_argmin_device(smpc_handle* h, int n_robots, int n_starts, in
                                   const uint8_t* usable, const double* u, int32_t* best_index, double* best_cost,
                                   double* best_u, void* stream);
 
+/* Work mapping: lanes of a warp that cooperate on one problem (4, 8, 16, 32; 0 = choose from the batch size:
+ * 32 for single solves / lowest latency, 4 for large batches / highest throughput). Results do not depend on it
+ * beyond floating-point summation order. */
+int smpc_set_group(smpc_handle* h, int lanes_per_problem);
+
 /* Device-time (ms) of the solve kernel of the last *_device / host solve call,
  * measured with CUDA events on the launching stream; < 0 if unavailable.
  * Synchronises the stream. */

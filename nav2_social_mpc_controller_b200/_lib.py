@@ -59,6 +59,8 @@ def lib():
     L.smpc_launch_count.restype = C.c_longlong
     L.smpc_measure_fp64_peak.argtypes = [C.c_void_p, P(C.c_double)]
     L.smpc_measure_fp64_peak.restype = C.c_int
+    L.smpc_set_group.argtypes = [C.c_void_p, C.c_int]
+    L.smpc_set_group.restype = C.c_int
     L.smpc_debug_polymin.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.smpc_debug_polymin.restype = C.c_int
     if L.smpc_abi_version() != abi.SMPC_ABI_VERSION:
@@ -76,5 +78,5 @@ EXPORTED_SYMBOLS = (
     "smpc_abi_version", "smpc_last_error", "smpc_params_default", "smpc_params_from_yaml", "smpc_problem_dims",
     "smpc_create", "smpc_destroy", "smpc_solve_batch", "smpc_solve_batch_device", "smpc_eval_batch_device",
     "smpc_eval_batch", "smpc_multistart_argmin_device", "smpc_last_kernel_ms", "smpc_launch_count",
-    "smpc_measure_fp64_peak", "smpc_debug_polymin",
+    "smpc_measure_fp64_peak", "smpc_debug_polymin", "smpc_set_group",
 )

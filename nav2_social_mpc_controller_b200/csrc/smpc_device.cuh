@@ -1,6 +1,6 @@
 // smpc_device.cuh — device-side social-MPC solver for sm_100a (B200), FP64 CUDA cores.
 //
-// One WARP solves one MPC problem: lane j owns horizon step j (steps j, j+32 when S > 32).
+// A GROUP of G lanes (4, 8, 16 or 32) solves one MPC problem: lane gl owns horizon steps gl, gl+G, ...
 //   * rollout: heading in closed form from the block-held angular rates, positions by warp inclusive
 //     scans; forward sensitivities dX/du, dY/du by the same scans (reference update_state.hpp:37-63
 //     re-rolls-out 0..i inside every functor, O(S^2); here it is one O(S) pass per evaluation).
@@ -22,7 +22,7 @@
 namespace smpc {
 
 constexpr unsigned kFullMask = 0xffffffffu;
-constexpr int kMaxChunks = 2;  // S <= 64 steps (the reference parameter sets give 13, 28, 38)
+constexpr int kMaxSteps = 64;  // S <= 64 steps (the reference parameter sets give 13, 28, 38)
 
 struct DevParams {
   double w_distance, w_social, w_velocity, w_angle, w_agent_angle, w_prox, w_vf, w_obstacle, w_goal;
@@ -231,42 +231,45 @@ __device__ __forceinline__ double agent_angle_target(const DevBatch& bt, const P
 }
 #define SMPC_UNROLL _Pragma("unroll")
 
-// Per-warp shared-memory state of one solve. Buffers hold [cost, g[P], H[NH]] (H row-major lower triangle,
+// ---------------------------------------------------------------------------------------------------
+// Work mapping: a GROUP of G lanes (G = 4, 8, 16 or 32) solves one problem, so a warp holds 32/G problems.
+// Lane gl of the group owns horizon steps gl, gl+G, gl+2G, ... ("chunks" of G consecutive steps are scanned
+// across the group, carries go through shared memory). G = 32 is the latency mapping (one step per lane);
+// small G is the throughput mapping: the warp-uniform part of the solver (LM step, line-search polynomials)
+// and the scan / reduction overheads are then shared by 32/G problems instead of being replicated 32 times.
+// ---------------------------------------------------------------------------------------------------
+
+// Per-group shared-memory state. Buffers hold [cost, g[P], H[NH]] (H row-major lower triangle,
 // H[a(a+1)/2 + b], a >= b) of the current iterate and of the trial point; the LM vectors follow.
 template <int NB>
 struct Layout {
   static constexpr int P = 2 * NB;
   static constexpr int NH = P * (P + 1) / 2;
   static constexpr int NE = 1 + P + NH;
-  static constexpr int NG = (NE + 31) / 32;
-  static constexpr int NEP = NG * 32;
+  static constexpr int NC = 4 + 4 * NB;  // scan carries: X, Y, sin, cos of the heading, 4 NB sensitivities
   static constexpr int kBuf0 = 0;
-  static constexpr int kBuf1 = NEP;
-  static constexpr int kX = 2 * NEP;
+  static constexpr int kBuf1 = NE;
+  static constexpr int kX = 2 * NE;
   static constexpr int kBest = kX + P;
   static constexpr int kScale = kBest + P;
   static constexpr int kDiag = kScale + P;
   static constexpr int kDelta = kDiag + P;
   static constexpr int kCand = kDelta + P;
-  static constexpr int kTotal = kCand + P;
+  static constexpr int kCarry = kCand + P;
+  static constexpr int kAa = kCarry + NC;  // agent-angle steering target per step [S]
+  __host__ __device__ static constexpr int total(int S) { return ((kAa + S) | 1); }  // odd stride: no bank conflicts
   __host__ __device__ static constexpr int g(int c) { return 1 + c; }
   __host__ __device__ static constexpr int h(int a, int b) { return 1 + P + a * (a + 1) / 2 + b; }
 };
 
-// Sum 32 per-lane values across the warp so that lane l ends with the total of v[l]:
-// 31 exchanges instead of the 160 of a butterfly all-reduce, and one live register at the end.
-__device__ __forceinline__ double warp_transpose_reduce32(double (&v)[32], int lane) {
-  SMPC_UNROLL for (int r = 0; r < 5; ++r) {
-    const int d = 16 >> r;
-    const bool up = (lane & d) != 0;
-    SMPC_UNROLL for (int k = 0; k < d; ++k) {
-      const double send = up ? v[k] : v[k + d];
-      const double keep = up ? v[k + d] : v[k];
-      v[k] = keep + __shfl_xor_sync(kFullMask, send, d);
-    }
+template <int G>
+struct Group {
+  static constexpr int kLog2 = (G == 32) ? 5 : (G == 16) ? 4 : (G == 8) ? 3 : (G == 4) ? 2 : (G == 2) ? 1 : 0;
+  static constexpr int kPerWarp = 32 / G;
+  __device__ static __forceinline__ unsigned mask(int lane) {
+    return (G == 32) ? kFullMask : (((1u << G) - 1u) << (lane & ~(G - 1)));
   }
-  return v[0];
-}
+};
 
 __device__ __forceinline__ double wrap_angle(double a) {
   // atan2(sin a, cos a) of the reference critics, evaluated as a - 2 pi round(a / 2 pi) (|difference| ~ 1 ulp of pi)
@@ -274,67 +277,62 @@ __device__ __forceinline__ double wrap_angle(double a) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Full evaluation at block values xs[P] (shared memory): cost = 1/2 sum r^2, g = J^T r, H = J^T J, written to
-// out[NE] (shared memory). Residual set and order of reference src/optimizer.cpp:251-371.
+// Full evaluation at block values xs[P] (group shared memory): cost = 1/2 sum r^2, g = J^T r, H = J^T J,
+// written to out[NE] (group shared memory). Residual set and order of reference src/optimizer.cpp:251-371
+// (SURVEY Appendix D). Must be called by all 32 lanes of the warp (scans use full-mask shuffles of width G);
+// `live` = this group holds a problem.
 // ---------------------------------------------------------------------------------------------------
-// Per-lane constants of the horizon discretisation (batch-uniform S, bl): the block of the lane's step and
-// d theta_j / d w_b = dt * #{steps before j in block b}. Hoisted out of the solve (single-chunk case, S <= 32).
-template <int NB>
-struct LaneConst {
-  int bj;
-  double tau[NB];
-};
-
-template <int NB>
-__device__ __forceinline__ void lane_setup(int j, int bl, double dt, LaneConst<NB>& lc) {
-  lc.bj = min(j / bl, NB - 1);
-  SMPC_UNROLL for (int b = 0; b < NB; ++b) lc.tau[b] = dt * (double)steps_in_block_before<NB>(j, b, bl);
-}
-
-template <int NB, bool MULTI>
-__device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatch& bt, const Prob& pb,
-                                             const double (&aa_target)[kMaxChunks], const LaneConst<NB>& lc0,
-                                             const double* xs, int lane, double* out) {
+template <int NB, int G>
+__device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatch& bt, const Prob& pb, bool live,
+                                             double* ws, const double* xs, int lane, double* out) {
   using L = Layout<NB>;
   constexpr int P = L::P;
-  const int S = bt.S, ch = prm.ch;
+  const int gl = lane & (G - 1);
+  const unsigned gmask = Group<G>::mask(lane);
+  const int S = bt.S, ch = prm.ch, bl = prm.bl;
   const double dt = bt.dt;
   const int stride = S + 1;
   const double inv_res = 1.0 / bt.resolution;
+  double* carry = ws + L::kCarry;
+  const double* aa = ws + L::kAa;
 
   double x[P];
   SMPC_UNROLL for (int c = 0; c < P; ++c) x[c] = xs[c];
 
-  double acc[L::NEP];  // [cost, g, H] partial sums of this lane
-  SMPC_UNROLL for (int e = 0; e < L::NEP; ++e) acc[e] = 0.0;
+  double acc[L::NE];  // [cost, g, H] partial sums of this lane
+  SMPC_UNROLL for (int e = 0; e < L::NE; ++e) acc[e] = 0.0;
   unsigned flags = 0;
 
-  // carries of the inclusive scans between 32-step chunks (only instantiated when S > 32)
-  double carry_x = pb.x0, carry_y = pb.y0;
-  double carry_d[MULTI ? 4 * NB : 1];
-  if (MULTI) {
-    SMPC_UNROLL for (int e = 0; e < 4 * NB; ++e) carry_d[e] = 0.0;
-  }
+  // heading before the group's first step: sin / cos of yaw0, then carried from chunk to chunk
+  double s0, c0;
+  sincos(pb.yaw0, &s0, &c0);
 
 #pragma unroll 1
-  for (int chunk = 0; chunk * 32 < (MULTI ? S : 1); ++chunk) {
-    const int j = chunk * 32 + lane;
-    const bool act = j < S;
-    LaneConst<NB> lcm;
-    if (MULTI) lane_setup<NB>(j, prm.bl, dt, lcm);
-    const LaneConst<NB>& lc = MULTI ? lcm : lc0;
-    const int bj = lc.bj;
+  for (int base = 0; base < S; base += G) {
+    const int j = base + gl;
+    const bool act = live && (j < S);
+    const int bj = min(j / bl, NB - 1);
     double vj = x[0], wj = x[1];
-    double th = pb.yaw0;  // heading before step j
+    double Th = pb.yaw0;  // heading AFTER step j = yaw0 + sum_b w_b dt #{steps <= j in block b}
+    double tau[NB];       // d theta_j / d w_b (heading before step j)
     SMPC_UNROLL for (int b = 0; b < NB; ++b) {
       if (b == bj) {
         vj = x[2 * b];
         wj = x[2 * b + 1];
       }
-      th += x[2 * b + 1] * lc.tau[b];
+      tau[b] = dt * (double)steps_in_block_before<NB>(j, b, bl);
+      Th += x[2 * b + 1] * (dt * (double)steps_in_block_before<NB>(j + 1, b, bl));
     }
-    double sn, cs;
-    sincos(th, &sn, &cs);
+    // one sincos per step: lane j evaluates the heading after its step; the heading before it is the
+    // previous lane's (the previous chunk's last lane / yaw0 for the group's first lane)
+    double sT, cT;
+    sincos(Th, &sT, &cT);
+    double sn = __shfl_up_sync(kFullMask, sT, 1, G);
+    double cs = __shfl_up_sync(kFullMask, cT, 1, G);
+    if (gl == 0) {
+      sn = (base == 0) ? s0 : carry[2];
+      cs = (base == 0) ? c0 : carry[3];
+    }
     const double cdt = act ? cs * dt : 0.0, sdt = act ? sn * dt : 0.0;
     const double aj = vj * cdt, bjv = vj * sdt;
 
@@ -344,36 +342,40 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
     SMPC_UNROLL for (int b = 0; b < NB; ++b) {
       sd[4 * b + 0] = (b == bj) ? cdt : 0.0;  // dX/dv_b
       sd[4 * b + 1] = (b == bj) ? sdt : 0.0;  // dY/dv_b
-      sd[4 * b + 2] = -bjv * lc.tau[b];       // dX/dw_b
-      sd[4 * b + 3] = aj * lc.tau[b];         // dY/dw_b
+      sd[4 * b + 2] = -bjv * tau[b];          // dX/dw_b
+      sd[4 * b + 3] = aj * tau[b];            // dY/dw_b
     }
-    SMPC_UNROLL for (int d = 1; d < 32; d <<= 1) {
-      const double tx = __shfl_up_sync(kFullMask, sx, d);
-      const double ty = __shfl_up_sync(kFullMask, sy, d);
-      if (lane >= d) {
+    SMPC_UNROLL for (int d = 1; d < G; d <<= 1) {
+      const double tx = __shfl_up_sync(kFullMask, sx, d, G);
+      const double ty = __shfl_up_sync(kFullMask, sy, d, G);
+      if (gl >= d) {
         sx += tx;
         sy += ty;
       }
       SMPC_UNROLL for (int e = 0; e < 4 * NB; ++e) {
-        const double t = __shfl_up_sync(kFullMask, sd[e], d);
-        if (lane >= d) sd[e] += t;
+        const double t = __shfl_up_sync(kFullMask, sd[e], d, G);
+        if (gl >= d) sd[e] += t;
       }
     }
-    const double X = carry_x + sx, Y = carry_y + sy;
-    if (MULTI) {
-      SMPC_UNROLL for (int e = 0; e < 4 * NB; ++e) sd[e] += carry_d[e];
-      carry_x = __shfl_sync(kFullMask, X, 31);
-      carry_y = __shfl_sync(kFullMask, Y, 31);
-      SMPC_UNROLL for (int e = 0; e < 4 * NB; ++e) carry_d[e] = __shfl_sync(kFullMask, sd[e], 31);
-    }
-    // heading after step j = heading before step j+1: take lane j+1's sin/cos when that lane exists
-    double sT, cT;
-    const double Th = th + wj * dt;
-    if (!MULTI && S <= 31) {
-      sT = __shfl_down_sync(kFullMask, sn, 1);
-      cT = __shfl_down_sync(kFullMask, cs, 1);
+    double X, Y;
+    if (base == 0) {
+      X = pb.x0 + sx;
+      Y = pb.y0 + sy;
     } else {
-      sincos(Th, &sT, &cT);
+      X = carry[0] + sx;
+      Y = carry[1] + sy;
+      SMPC_UNROLL for (int e = 0; e < 4 * NB; ++e) sd[e] += carry[4 + e];
+    }
+    if (base + G < S) {  // hand the inclusive totals to the next chunk
+      __syncwarp(gmask);
+      if (gl == G - 1) {
+        carry[0] = X;
+        carry[1] = Y;
+        carry[2] = sT;
+        carry[3] = cT;
+        SMPC_UNROLL for (int e = 0; e < 4 * NB; ++e) carry[4 + e] = sd[e];
+      }
+      __syncwarp(gmask);
     }
 
     if (act) {
@@ -384,7 +386,7 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
 
       if (pb.has_people) {
         // --- AgentAngle (k=0): w * wrap(Theta - target)^2 ------------------------------------------
-        const double tgt = aa_target[chunk & (kMaxChunks - 1)];
+        const double tgt = aa[j];
         if (tgt == tgt) {
           const double del = wrap_angle(Th - tgt);
           const double r = prm.w_agent_angle * (del * del);
@@ -420,20 +422,25 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
             double sa, ca;
             sincos(ayaw, &sa, &ca);
             const double avx = alv * ca, avy = alv * sa;
-            PairOut po;
-            if (valid) {  // robot <- agent k
-              social_pair(ddx, ddy, rvx - avx, rvy - avy, po);
-              Frx += po.fx;
-              Fry += po.fy;
-              SMPC_UNROLL for (int c = 0; c < 4; ++c) {
-                JFx[c] += po.dfx[c];
-                JFy[c] += po.dfy[c];
+            // role 0: agent k (also a padded one) <- robot (d and w change sign);
+            // role 1: robot <- agent k (valid agents only). One inlined call site keeps the code small.
+#pragma unroll 1
+            for (int role = 0; role < (valid ? 2 : 1); ++role) {
+              const double sg = role ? 1.0 : -1.0;
+              PairOut po;
+              social_pair(sg * ddx, sg * ddy, sg * (rvx - avx), sg * (rvy - avy), po);
+              if (role) {
+                Frx += po.fx;
+                Fry += po.fy;
+                SMPC_UNROLL for (int c = 0; c < 4; ++c) {
+                  JFx[c] += po.dfx[c];
+                  JFy[c] += po.dfy[c];
+                }
+              } else {
+                wp += po.fx * po.fx + po.fy * po.fy;
+                SMPC_UNROLL for (int c = 0; c < 4; ++c) G4[c] -= 2.0 * (po.fx * po.dfx[c] + po.fy * po.dfy[c]);
               }
             }
-            // agent k (also a padded one) <- robot: d and w change sign
-            social_pair(-ddx, -ddy, avx - rvx, avy - rvy, po);
-            wp += po.fx * po.fx + po.fy * po.fy;
-            SMPC_UNROLL for (int c = 0; c < 4; ++c) G4[c] -= 2.0 * (po.fx * po.dfx[c] + po.fy * po.dfy[c]);
           }
         }
         if (do_social) {
@@ -494,7 +501,7 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
         qX += cX * r; qY += cY * r;
       }
       {
-        const double ex = X - __ldg(pb.px + j + 1), ey = Y - __ldg(pb.py + j + 1);
+        const double ex = X - __ldg(pb.px + j + 1), ey = Y - __ldg(pb.px + stride + j + 1);
         const double q2 = ex * ex + ey * ey;
         const double r = prm.w_angle * q2 * q2;
         const double k = 4.0 * prm.w_angle * q2;
@@ -523,7 +530,7 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
       acc[0] += cost;
       SMPC_UNROLL for (int ba = 0; ba < NB; ++ba) {
         const double la = (ba == bj) ? 1.0 : 0.0;
-        const double twa = lc.tau[ba] + ((ba == bj) ? dt : 0.0);  // d Theta_j / d w_ba (heading after step j)
+        const double twa = tau[ba] + ((ba == bj) ? dt : 0.0);  // d Theta_j / d w_ba (heading after step j)
         {  // column a = 2 ba (v_ba)
           const double xv = sd[4 * ba + 0], yv = sd[4 * ba + 1];
           const double t0 = mXX * xv + mXY * yv + mXL * la;
@@ -535,7 +542,7 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
             const double lb = (bb == bj) ? 1.0 : 0.0;
             acc[L::h(2 * ba, 2 * bb)] += sd[4 * bb + 0] * t0 + sd[4 * bb + 1] * t1 + lb * t3;
             if (bb < ba) {
-              const double twb = lc.tau[bb] + ((bb == bj) ? dt : 0.0);
+              const double twb = tau[bb] + ((bb == bj) ? dt : 0.0);
               acc[L::h(2 * ba, 2 * bb + 1)] += sd[4 * bb + 2] * t0 + sd[4 * bb + 3] * t1 + twb * t2;
             }
           }
@@ -549,7 +556,7 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
           acc[L::g(2 * ba + 1)] += qX * xw + qY * yw + qT * twa;
           SMPC_UNROLL for (int bb = 0; bb <= ba; ++bb) {
             const double lb = (bb == bj) ? 1.0 : 0.0;
-            const double twb = lc.tau[bb] + ((bb == bj) ? dt : 0.0);
+            const double twb = tau[bb] + ((bb == bj) ? dt : 0.0);
             acc[L::h(2 * ba + 1, 2 * bb)] += sd[4 * bb + 0] * t0 + sd[4 * bb + 1] * t1 + lb * t3;
             acc[L::h(2 * ba + 1, 2 * bb + 1)] += sd[4 * bb + 2] * t0 + sd[4 * bb + 3] * t1 + twb * t2;
           }
@@ -559,8 +566,8 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
   }
 
   // --- VelocityFeasibility (k=8): w ((v_i - v_{i-1})^2 + (w_i - w_{i-1})^2), 0 < i < ch/bl, on blocks i, i-1.
-  //     Parameter-space residuals: lane 0 adds them to its partial sums before the reduction.
-  if (lane == 0) {
+  //     Parameter-space residuals: the group's first lane adds them to its partial sums before the reduction.
+  if (gl == 0 && live) {
     SMPC_UNROLL for (int i = 1; i < NB; ++i) {
       if (i < prm.n_bounded) {
         const double dv = x[2 * i] - x[2 * i - 2], dw = x[2 * i + 1] - x[2 * i - 1];
@@ -584,24 +591,40 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
     }
   }
 
-  // warp reduction: lane l of group gI ends with the total of entry 32 gI + l and stores it
+  // group reduction. Halving exchange: after round r each lane keeps half of its entries summed with its
+  // partner's; after log2(G) rounds lane gl owns the group totals of entries e == gl (mod G) ... in the
+  // bit order of the exchange, and stores them. Entry count is padded with zeros to a multiple of G.
+  constexpr int NEP = ((L::NE + G - 1) / G) * G;
+  double v[NEP];
+  SMPC_UNROLL for (int e = 0; e < NEP; ++e) v[e] = (e < L::NE) ? acc[e] : 0.0;
+  {
+    int n = NEP;
+    SMPC_UNROLL for (int d = G / 2; d >= 1; d >>= 1) {
+      n >>= 1;
+      const bool up = (gl & d) != 0;
+      SMPC_UNROLL for (int k = 0; k < n; ++k) {
+        const double send = up ? v[k] : v[k + n];
+        const double keep = up ? v[k + n] : v[k];
+        v[k] = keep + __shfl_xor_sync(kFullMask, send, d, G);
+      }
+    }
+  }
+  // after the exchange lane gl holds, in v[k], the total of entry (NEP / G) * gl + k
   bool bad_res = false, bad_jac = false;
-  SMPC_UNROLL for (int gI = 0; gI < L::NG; ++gI) {
-    double v[32];
-    SMPC_UNROLL for (int k = 0; k < 32; ++k) v[k] = acc[32 * gI + k];
-    const double tot = warp_transpose_reduce32(v, lane);
-    const int e = 32 * gI + lane;
+  constexpr int PER = NEP / G;
+  SMPC_UNROLL for (int k = 0; k < PER; ++k) {
+    const int e = PER * gl + k;
     if (e < L::NE) {
-      out[e] = tot;
-      if (!isfinite(tot)) {
+      out[e] = v[k];
+      if (!isfinite(v[k])) {
         if (e == 0) bad_res = true; else bad_jac = true;
       }
     }
   }
-  if (__any_sync(kFullMask, bad_res)) flags |= kResidualBad;
-  if (__any_sync(kFullMask, bad_jac)) flags |= kJacobianBad;
-  flags = __reduce_or_sync(kFullMask, flags);
-  __syncwarp();
+  if (__any_sync(gmask, bad_res)) flags |= kResidualBad;
+  if (__any_sync(gmask, bad_jac)) flags |= kJacobianBad;
+  flags = __reduce_or_sync(gmask, flags);
+  __syncwarp(gmask);
   return flags;
 }
 
@@ -893,24 +916,110 @@ enum Termination {
   kFailEvaluation = 6
 };
 
-struct SolveOut {
-  double cost_initial, cost_final;
-  int iterations, termination, n_jac, n_cost;
-};
+// Load the group-uniform problem view.
+__device__ __forceinline__ void load_problem(const DevBatch& bt, int b, Prob& pb) {
+  const int S = bt.S;
+  pb.x0 = __ldg(bt.pose0 + 3 * (size_t)b);
+  pb.y0 = __ldg(bt.pose0 + 3 * (size_t)b + 1);
+  pb.yaw0 = __ldg(bt.pose0 + 3 * (size_t)b + 2);
+  pb.goal_yaw = __ldg(bt.goal_yaw + b);
+  pb.px = bt.path_xy + (size_t)b * 2 * (S + 1);
+  pb.py = pb.px + (S + 1);
+  pb.fin_x = __ldg(pb.px + S);
+  pb.fin_y = __ldg(pb.py + S);
+  pb.agents = (bt.A > 0 && bt.agents) ? bt.agents + (size_t)b * bt.A * 6 * (S + 1) : nullptr;
+  pb.has_people = (bt.has_people != nullptr) && (bt.has_people[b] != 0);
+  const int mi = bt.costmap_index ? __ldg(bt.costmap_index + b) : (b % bt.M);
+  pb.map = bt.costmaps + (size_t)mi * bt.size_x * bt.size_y;
+  pb.org_x = __ldg(bt.costmap_origin + 2 * mi);
+  pb.org_y = __ldg(bt.costmap_origin + 2 * mi + 1);
+}
+
+// Agent-angle steering targets of every step -> group shared memory (once per problem).
+template <int NB, int G>
+__device__ __forceinline__ void agent_angle_setup(const DevBatch& bt, const Prob& pb, int lane, double* ws) {
+  using L = Layout<NB>;
+  const int gl = lane & (G - 1);
+  for (int j = gl; j < bt.S; j += G) {
+    double tgt = NAN;
+    if (pb.has_people && bt.A > 0 && pb.agents != nullptr) tgt = agent_angle_target(bt, pb, j + 1);
+    ws[L::kAa + j] = tgt;
+  }
+}
+
+// Post-solve expansion (reference src/optimizer.cpp:390-446): cmds[S+1] hold block min(i/bl, NB-1) for i < ch
+// and the last block afterwards; the path is the Euler rollout of those cmds from pose0 (pose0 excluded).
+template <int NB, int G>
+__device__ __forceinline__ void expand_outputs(const DevParams& prm, const DevBatch& bt, const DevResult& rs,
+                                               const Prob& pb, int b, const double (&x)[2 * NB], int lane) {
+  const int gl = lane & (G - 1);
+  const unsigned gmask = Group<G>::mask(lane);
+  const int S = bt.S;
+  double s0, c0;
+  sincos(pb.yaw0 * 0.5, &s0, &c0);
+  const double yaw_rt = atan2(2.0 * (c0 * s0), c0 * c0 - s0 * s0);  // evolving_poses[0] went through setRPY/getYaw
+  double carry_x = pb.x0, carry_y = pb.y0;
+  for (int base = 0; base <= S; base += G) {
+    const int i = base + gl;
+    const bool act = i <= S;
+    const int bi = (i < prm.ch) ? min(i / prm.bl, NB - 1) : NB - 1;
+    double v = x[0], w = x[1];
+    double th = yaw_rt, th_next = yaw_rt;
+    SMPC_UNROLL for (int bb = 0; bb < NB; ++bb) {
+      if (bb == bi) {
+        v = x[2 * bb];
+        w = x[2 * bb + 1];
+      }
+      th += x[2 * bb + 1] * (bt.dt * (double)steps_in_block_before<NB>(i, bb, prm.bl));
+      th_next += x[2 * bb + 1] * (bt.dt * (double)steps_in_block_before<NB>(i + 1, bb, prm.bl));
+    }
+    if (act && rs.cmds) {
+      rs.cmds[((size_t)b * (S + 1) + i) * 2] = v;
+      rs.cmds[((size_t)b * (S + 1) + i) * 2 + 1] = w;
+    }
+    if (rs.path) {
+      double sn, cs;
+      sincos(th, &sn, &cs);
+      double sx = act ? v * cs * bt.dt : 0.0, sy = act ? v * sn * bt.dt : 0.0;
+      SMPC_UNROLL for (int d = 1; d < G; d <<= 1) {
+        const double tx = __shfl_up_sync(gmask, sx, d, G), ty = __shfl_up_sync(gmask, sy, d, G);
+        if (gl >= d) {
+          sx += tx;
+          sy += ty;
+        }
+      }
+      const double X = carry_x + sx, Y = carry_y + sy;
+      carry_x = __shfl_sync(gmask, X, G - 1, G);
+      carry_y = __shfl_sync(gmask, Y, G - 1, G);
+      if (act) {
+        double sh, chh;
+        sincos(th_next * 0.5, &sh, &chh);
+        double* o = rs.path + ((size_t)b * (S + 1) + i) * 3;
+        o[0] = X;
+        o[1] = Y;
+        o[2] = atan2(2.0 * (chh * sh), chh * chh - sh * sh);  // tf2 setRPY -> getYaw
+      }
+    }
+  }
+}
 
 // ---------------------------------------------------------------------------------------------------
-// ceres::Solve restated, warp-uniform, as a state machine around ONE evaluation site:
-// every trial point (iteration zero, each line-search sample, the un-shortened step after a failed line search)
-// gets a full evaluation, so an accepted point needs no second pass — its cost is the candidate cost and its
-// J^T J / J^T r are the next iterate's. ws: this warp's shared-memory state (Layout<NB>); ws[kX..] holds the seed
-// on entry and the solution on exit (the seed again when the solution is not usable).
+// ceres::Solve restated as a per-group state machine around ONE evaluation site.
+// Every trial point (iteration zero, each line-search sample, the un-shortened step after a failed line search)
+// gets a full evaluation, so an accepted point needs no second pass: its cost is the candidate cost and its
+// J^T J / J^T r are the next iterate's. Groups of a warp run different problems in different phases; they meet
+// at the evaluation (warp-convergent) and diverge only in the short scalar phase logic. A group that finishes
+// its problem writes the results and pulls the next problem from the atomic queue.
 // ---------------------------------------------------------------------------------------------------
-template <int NB, bool MULTI>
-__device__ __forceinline__ void solve_problem(const DevParams& prm, const DevBatch& bt, const Prob& pb,
-                                              const double (&aa_target)[kMaxChunks], const LaneConst<NB>& lc,
-                                              double* ws, int lane, SolveOut& so) {
+enum Phase { kFetch = 0, kInit = 1, kLineSearch = 2, kFullStep = 3 };
+
+template <int NB, int G>
+__device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch& bt, const DevResult& rs, int* queue,
+                                           double* ws, int lane) {
   using L = Layout<NB>;
   constexpr int P = L::P;
+  const int gl = lane & (G - 1);
+  const unsigned gmask = Group<G>::mask(lane);
   const int nbd = prm.n_bounded;
   double* xs = ws + L::kX;
   double* best = ws + L::kBest;
@@ -921,16 +1030,15 @@ __device__ __forceinline__ void solve_problem(const DevParams& prm, const DevBat
   double* cur = ws + L::kBuf0;    // normal equations at x
   double* trial = ws + L::kBuf1;  // normal equations at the trial point
 
-  // IterationZero: project the start point onto the box
-  if (lane < P) {
-    const double v = xs[lane];
-    best[lane] = v;
-    cand[lane] = project_param(v, lane, nbd);
-  }
-  __syncwarp();
+  Prob pb;
+  pb.x0 = pb.y0 = pb.yaw0 = pb.goal_yaw = pb.fin_x = pb.fin_y = pb.org_x = pb.org_y = 0.0;
+  pb.px = pb.py = pb.agents = nullptr;
+  pb.map = nullptr;
+  pb.has_people = false;
+  int b = -1;
+  bool live = false, exhausted = false;
 
-  enum Phase { kInit = 0, kLineSearch = 1, kFullStep = 2 };
-  int phase = kInit;
+  int phase = kFetch;
   int term = kNoConvergence;
   int iteration = 0, n_invalid = 0, n_eval = 0, ls_iters = 0;
   double x_cost = 0.0, x_norm = 0.0, gmax = 0.0, radius = 1e4, decrease_factor = 2.0, minimum_cost = DBL_MAX;
@@ -939,27 +1047,64 @@ __device__ __forceinline__ void solve_problem(const DevParams& prm, const DevBat
   LsSample prev{0.0, 0.0, 0.0, false};
 
   for (;;) {
-    const unsigned fl = evaluate<NB, MULTI>(prm, bt, pb, aa_target, lc, cand, lane, trial);
+    if (phase == kFetch && !exhausted) {
+      int nb_ = 0;
+      if (gl == 0) nb_ = atomicAdd(queue, 1);
+      nb_ = __shfl_sync(gmask, nb_, 0, G);
+      if (nb_ >= bt.B) {
+        exhausted = true;
+        live = false;
+      } else {
+        b = nb_;
+        live = true;
+        load_problem(bt, b, pb);
+        __syncwarp(gmask);
+        agent_angle_setup<NB, G>(bt, pb, lane, ws);
+        // IterationZero: project the start point onto the box
+        for (int c = gl; c < P; c += G) {
+          const double v = __ldg(bt.u0 + (size_t)b * P + c);
+          xs[c] = v;
+          best[c] = v;
+          cand[c] = project_param(v, c, nbd);
+        }
+        __syncwarp(gmask);
+        phase = kInit;
+        term = kNoConvergence;
+        iteration = 0; n_invalid = 0; n_eval = 0; ls_iters = 0;
+        x_cost = 0.0; x_norm = 0.0; gmax = 0.0; radius = 1e4; decrease_factor = 2.0; minimum_cost = DBL_MAX;
+        it_cost = 0.0; cost_initial = 0.0; cost_final = 0.0; model_cost_change = 0.0; g0 = 0.0; dmax = 0.0; t = 1.0;
+        reuse_diagonal = false; it_successful = true; any_success = false;
+        prev.ok = false;
+        cur = ws + L::kBuf0;
+        trial = ws + L::kBuf1;
+      }
+    }
+    if (__all_sync(kFullMask, exhausted)) break;
+
+    const unsigned fl = evaluate<NB, G>(prm, bt, pb, live, ws, cand, lane, trial);
+    if (!live) continue;
     ++n_eval;
     const double t_cost = trial[0];
     bool take_step = false;  // proceed to accept/reject with `cand`
+    bool finished = false;   // the solve of this problem has terminated
 
     if (phase == kInit) {
       cost_initial = cost_final = t_cost;
       if (fl) {
         term = kFailEvaluation;
-        break;
+        finished = true;
+      } else {
+        // x <- projected seed; cur <- trial; Jacobi scaling from the column norms (= sqrt of diag(J^T J))
+        for (int c = gl; c < P; c += G) {
+          xs[c] = cand[c];
+          scale[c] = 1.0 / (1.0 + sqrt(trial[L::h(0, 0) + c * (c + 1) / 2 + c]));
+        }
+        __syncwarp(gmask);
+        { double* tmp = cur; cur = trial; trial = tmp; }
+        x_cost = t_cost;
+        it_cost = x_cost;
+        it_successful = true;
       }
-      // x <- projected seed; cur <- trial; Jacobi scaling from the column norms (= sqrt of diag(J^T J))
-      if (lane < P) {
-        xs[lane] = cand[lane];
-        scale[lane] = 1.0 / (1.0 + sqrt(trial[L::h(lane, lane)]));
-      }
-      __syncwarp();
-      { double* tmp = cur; cur = trial; trial = tmp; }
-      x_cost = t_cost;
-      it_cost = x_cost;
-      it_successful = true;
     } else if (phase == kLineSearch) {
       // Armijo sufficient decrease at step t along delta (projected)
       const bool sample_ok = (fl == 0);
@@ -985,15 +1130,17 @@ __device__ __forceinline__ void solve_problem(const DevParams& prm, const DevBat
         if (!ls_failed) {
           prev = LsSample{t, t_cost, gd, sample_ok};
           t = t_new;
-          if (lane < P) cand[lane] = project_param(xs[lane] + t * delta[lane], lane, nbd);
-          __syncwarp();
+          __syncwarp(gmask);
+          for (int c = gl; c < P; c += G) cand[c] = project_param(xs[c] + t * delta[c], c, nbd);
+          __syncwarp(gmask);
           continue;  // evaluate the next line-search sample
         }
         // line search failed: the un-shortened TR step is the candidate (delta unchanged)
         if (t != 1.0) {
           t = 1.0;
-          if (lane < P) cand[lane] = project_param(xs[lane] + delta[lane], lane, nbd);
-          __syncwarp();
+          __syncwarp(gmask);
+          for (int c = gl; c < P; c += G) cand[c] = project_param(xs[c] + delta[c], c, nbd);
+          __syncwarp(gmask);
           phase = kFullStep;
           continue;
         }
@@ -1012,201 +1159,192 @@ __device__ __forceinline__ void solve_problem(const DevParams& prm, const DevBat
         step_norm += dd * dd;
       }
       step_norm = sqrt(step_norm);
+      const double cost_change = x_cost - cand_cost;
       if (tol_armed && step_norm <= prm.param_tol * (x_norm + prm.param_tol)) {
         --iteration;
         term = kConvParameter;
-        break;
-      }
-      const double cost_change = x_cost - cand_cost;
-      if (tol_armed && fabs(cost_change) <= prm.fn_tol * x_cost) {
+        finished = true;
+      } else if (tol_armed && fabs(cost_change) <= prm.fn_tol * x_cost) {
         --iteration;
         term = kConvFunction;
-        break;
-      }
-      const double rho = (cand_cost >= DBL_MAX) ? -DBL_MAX : cost_change / model_cost_change;
-      if (rho > 1e-3) {  // HandleSuccessfulStep
-        if (fl & kJacobianBad) {
-          --iteration;
-          term = kFailEvaluation;
-          break;
-        }
-        __syncwarp();
-        if (lane < P) xs[lane] = cand[lane];
-        __syncwarp();
-        { double* tmp = cur; cur = trial; trial = tmp; }
-        x_cost = cand_cost;
-        any_success = true;
-        it_successful = true;
-        it_cost = x_cost;
-        const double qq = 2.0 * rho - 1.0;
-        radius = fmin(1e16, radius / fmax(1.0 / 3.0, 1.0 - qq * qq * qq));
-        decrease_factor = 2.0;
-        reuse_diagonal = false;
+        finished = true;
       } else {
-        it_successful = false;
-        it_cost = cand_cost;
-        radius = radius / decrease_factor;
-        decrease_factor *= 2.0;
-        reuse_diagonal = true;
+        const double rho = (cand_cost >= DBL_MAX) ? -DBL_MAX : cost_change / model_cost_change;
+        if (rho > 1e-3) {  // HandleSuccessfulStep
+          if (fl & kJacobianBad) {
+            --iteration;
+            term = kFailEvaluation;
+            finished = true;
+          } else {
+            __syncwarp(gmask);
+            for (int c = gl; c < P; c += G) xs[c] = cand[c];
+            __syncwarp(gmask);
+            { double* tmp = cur; cur = trial; trial = tmp; }
+            x_cost = cand_cost;
+            any_success = true;
+            it_successful = true;
+            it_cost = x_cost;
+            const double qq = 2.0 * rho - 1.0;
+            radius = fmin(1e16, radius / fmax(1.0 / 3.0, 1.0 - qq * qq * qq));
+            decrease_factor = 2.0;
+            reuse_diagonal = false;
+          }
+        } else {
+          it_successful = false;
+          it_cost = cand_cost;
+          radius = radius / decrease_factor;
+          decrease_factor *= 2.0;
+          reuse_diagonal = true;
+        }
       }
     }
 
     // ---- a new outer iteration starts here (after iteration zero or after accept / reject) ----
-    if (it_successful) {  // x changed: refresh |x| and the projected-gradient max norm
-      double xn = 0.0, gm = 0.0;
-      SMPC_UNROLL for (int c = 0; c < P; ++c) {
-        const double xv = xs[c];
-        xn += xv * xv;
-        gm = fmax(gm, fabs(xv - project_param(xv - cur[L::g(c)], c, nbd)));
-      }
-      x_norm = sqrt(xn);
-      gmax = gm;
-    }
-    bool stop = false;
-    for (;;) {
-      // FinalizeIterationAndCheckIfMinimizerCanContinue
-      if (it_successful && x_cost < minimum_cost) {
-        minimum_cost = x_cost;
-        __syncwarp();
-        if (lane < P) best[lane] = xs[lane];
-        __syncwarp();
-      }
-      cost_final = fmin(cost_final, it_cost);
-      if (iteration >= prm.max_iterations) { term = kNoConvergence; stop = true; break; }
-      if (it_successful && gmax <= prm.gradient_tol) { term = kConvGradient; stop = true; break; }
-      if (radius <= 1e-32) { term = kConvRadius; stop = true; break; }
-      ++iteration;
-
-      // LevenbergMarquardtStrategy::ComputeStep on the column-scaled normal equations
-      __syncwarp();
-      if (!reuse_diagonal && lane < P) {
-        const double sc = scale[lane];
-        diag[lane] = fmin(fmax(sc * sc * cur[L::h(lane, lane)], 1e-6), 1e32);
-      }
-      __syncwarp();
-      reuse_diagonal = true;
-      double sc[P], Lc[L::NH], step[P];
-      const double inv_radius = 1.0 / radius;
-      SMPC_UNROLL for (int c = 0; c < P; ++c) sc[c] = scale[c];
-      SMPC_UNROLL for (int a = 0; a < P; ++a) {
-        SMPC_UNROLL for (int b = 0; b <= a; ++b) Lc[a * (a + 1) / 2 + b] = sc[a] * sc[b] * cur[L::h(a, b)];
-        Lc[a * (a + 1) / 2 + a] += diag[a] * inv_radius;  // (sqrt(diag / radius))^2 of the LM strategy
-      }
-      bool step_ok = true;
-      SMPC_UNROLL for (int jc = 0; jc < P; ++jc) {  // Cholesky, in place, lower triangle
-        double d = Lc[jc * (jc + 1) / 2 + jc];
-        SMPC_UNROLL for (int k = 0; k < jc; ++k) d -= Lc[jc * (jc + 1) / 2 + k] * Lc[jc * (jc + 1) / 2 + k];
-        if (!(d > 0.0)) step_ok = false;
-        const double inv_d = rsqrt(d);
-        Lc[jc * (jc + 1) / 2 + jc] = inv_d;  // store 1/L_jj
-        SMPC_UNROLL for (int i = jc + 1; i < P; ++i) {
-          double s = Lc[i * (i + 1) / 2 + jc];
-          SMPC_UNROLL for (int k = 0; k < jc; ++k) s -= Lc[i * (i + 1) / 2 + k] * Lc[jc * (jc + 1) / 2 + k];
-          Lc[i * (i + 1) / 2 + jc] = s * inv_d;
-        }
-      }
-      SMPC_UNROLL for (int i = 0; i < P; ++i) {  // forward substitution
-        double s = sc[i] * cur[L::g(i)];
-        SMPC_UNROLL for (int k = 0; k < i; ++k) s -= Lc[i * (i + 1) / 2 + k] * step[k];
-        step[i] = s * Lc[i * (i + 1) / 2 + i];
-      }
-      SMPC_UNROLL for (int i = P - 1; i >= 0; --i) {  // back substitution
-        double s = step[i];
-        SMPC_UNROLL for (int k = i + 1; k < P; ++k) s -= Lc[k * (k + 1) / 2 + i] * step[k];
-        step[i] = s * Lc[i * (i + 1) / 2 + i];
-      }
-      SMPC_UNROLL for (int c = 0; c < P; ++c) {
-        step_ok = step_ok && isfinite(step[c]);
-        step[c] = -step[c];
-      }
-      // model_cost_change = -(Js s)'(r + Js s / 2) = -s'(Js' r) - s'(Js' Js) s / 2
-      double lin = 0.0, quad = 0.0;
-      SMPC_UNROLL for (int a = 0; a < P; ++a) {
-        const double sa = sc[a] * step[a];
-        lin += sa * cur[L::g(a)];
-        double rowv = 0.0;
-        SMPC_UNROLL for (int b = 0; b < a; ++b) rowv += cur[L::h(a, b)] * (sc[b] * step[b]);
-        quad += sa * (2.0 * rowv + cur[L::h(a, a)] * sa);
-      }
-      model_cost_change = -lin - 0.5 * quad;
-      const bool valid = step_ok && (model_cost_change > 0.0);
-      if (valid) {
-        n_invalid = 0;
-        g0 = 0.0;
-        dmax = 0.0;
+    if (!finished) {
+      if (it_successful) {  // x changed: refresh |x| and the projected-gradient max norm
+        double xn = 0.0, gm = 0.0;
         SMPC_UNROLL for (int c = 0; c < P; ++c) {
-          const double dl = step[c] * sc[c];
-          g0 += cur[L::g(c)] * dl;
-          dmax = fmax(dmax, fabs(dl));
-          step[c] = dl;
+          const double xv = xs[c];
+          xn += xv * xv;
+          gm = fmax(gm, fabs(xv - project_param(xv - cur[L::g(c)], c, nbd)));
         }
-        __syncwarp();
-        if (lane < P) {
-          double dl = step[0];
-          SMPC_UNROLL for (int c = 1; c < P; ++c) dl = (lane == c) ? step[c] : dl;
-          delta[lane] = dl;
-          cand[lane] = project_param(xs[lane] + dl, lane, nbd);
+        x_norm = sqrt(xn);
+        gmax = gm;
+      }
+      for (;;) {
+        // FinalizeIterationAndCheckIfMinimizerCanContinue
+        if (it_successful && x_cost < minimum_cost) {
+          minimum_cost = x_cost;
+          __syncwarp(gmask);
+          for (int c = gl; c < P; c += G) best[c] = xs[c];
+          __syncwarp(gmask);
         }
-        __syncwarp();
-        break;
+        cost_final = fmin(cost_final, it_cost);
+        if (iteration >= prm.max_iterations) { term = kNoConvergence; finished = true; break; }
+        if (it_successful && gmax <= prm.gradient_tol) { term = kConvGradient; finished = true; break; }
+        if (radius <= 1e-32) { term = kConvRadius; finished = true; break; }
+        ++iteration;
+
+        // LevenbergMarquardtStrategy::ComputeStep on the column-scaled normal equations
+        __syncwarp(gmask);
+        if (!reuse_diagonal) {
+          for (int c = gl; c < P; c += G) {
+            const double scv = scale[c];
+            diag[c] = fmin(fmax(scv * scv * cur[L::h(0, 0) + c * (c + 1) / 2 + c], 1e-6), 1e32);
+          }
+        }
+        __syncwarp(gmask);
+        reuse_diagonal = true;
+        double sc[P], Lc[L::NH], step[P];
+        const double inv_radius = 1.0 / radius;
+        SMPC_UNROLL for (int c = 0; c < P; ++c) sc[c] = scale[c];
+        SMPC_UNROLL for (int a = 0; a < P; ++a) {
+          SMPC_UNROLL for (int bq = 0; bq <= a; ++bq) Lc[a * (a + 1) / 2 + bq] = sc[a] * sc[bq] * cur[L::h(a, bq)];
+          Lc[a * (a + 1) / 2 + a] += diag[a] * inv_radius;  // (sqrt(diag / radius))^2 of the LM strategy
+        }
+        bool step_ok = true;
+        SMPC_UNROLL for (int jc = 0; jc < P; ++jc) {  // Cholesky, in place, lower triangle
+          double d = Lc[jc * (jc + 1) / 2 + jc];
+          SMPC_UNROLL for (int k = 0; k < jc; ++k) d -= Lc[jc * (jc + 1) / 2 + k] * Lc[jc * (jc + 1) / 2 + k];
+          if (!(d > 0.0)) step_ok = false;
+          const double inv_d = rsqrt(d);
+          Lc[jc * (jc + 1) / 2 + jc] = inv_d;  // store 1/L_jj
+          SMPC_UNROLL for (int i = jc + 1; i < P; ++i) {
+            double s = Lc[i * (i + 1) / 2 + jc];
+            SMPC_UNROLL for (int k = 0; k < jc; ++k) s -= Lc[i * (i + 1) / 2 + k] * Lc[jc * (jc + 1) / 2 + k];
+            Lc[i * (i + 1) / 2 + jc] = s * inv_d;
+          }
+        }
+        SMPC_UNROLL for (int i = 0; i < P; ++i) {  // forward substitution
+          double s = sc[i] * cur[L::g(i)];
+          SMPC_UNROLL for (int k = 0; k < i; ++k) s -= Lc[i * (i + 1) / 2 + k] * step[k];
+          step[i] = s * Lc[i * (i + 1) / 2 + i];
+        }
+        SMPC_UNROLL for (int i = P - 1; i >= 0; --i) {  // back substitution
+          double s = step[i];
+          SMPC_UNROLL for (int k = i + 1; k < P; ++k) s -= Lc[k * (k + 1) / 2 + i] * step[k];
+          step[i] = s * Lc[i * (i + 1) / 2 + i];
+        }
+        SMPC_UNROLL for (int c = 0; c < P; ++c) {
+          step_ok = step_ok && isfinite(step[c]);
+          step[c] = -step[c];
+        }
+        // model_cost_change = -(Js s)'(r + Js s / 2) = -s'(Js' r) - s'(Js' Js) s / 2
+        double lin = 0.0, quad = 0.0;
+        SMPC_UNROLL for (int a = 0; a < P; ++a) {
+          const double sa = sc[a] * step[a];
+          lin += sa * cur[L::g(a)];
+          double rowv = 0.0;
+          SMPC_UNROLL for (int bq = 0; bq < a; ++bq) rowv += cur[L::h(a, bq)] * (sc[bq] * step[bq]);
+          quad += sa * (2.0 * rowv + cur[L::h(a, a)] * sa);
+        }
+        model_cost_change = -lin - 0.5 * quad;
+        const bool valid = step_ok && (model_cost_change > 0.0);
+        if (valid) {
+          n_invalid = 0;
+          g0 = 0.0;
+          dmax = 0.0;
+          SMPC_UNROLL for (int c = 0; c < P; ++c) {
+            const double dl = step[c] * sc[c];
+            g0 += cur[L::g(c)] * dl;
+            dmax = fmax(dmax, fabs(dl));
+            step[c] = dl;
+          }
+          __syncwarp(gmask);
+          if (gl == 0) {
+            SMPC_UNROLL for (int c = 0; c < P; ++c) {
+              delta[c] = step[c];
+              cand[c] = project_param(xs[c] + step[c], c, nbd);
+            }
+          }
+          __syncwarp(gmask);
+          break;
+        }
+        // HandleInvalidStep
+        if (++n_invalid >= 5) {
+          --iteration;
+          term = kFailInvalidSteps;
+          finished = true;
+          break;
+        }
+        radius /= decrease_factor;
+        decrease_factor *= 2.0;
+        it_successful = false;
+        it_cost = x_cost;
       }
-      // HandleInvalidStep
-      if (++n_invalid >= 5) {
-        --iteration;
-        term = kFailInvalidSteps;
-        stop = true;
-        break;
+      if (!finished) {
+        phase = kLineSearch;
+        t = 1.0;
+        ls_iters = 0;
+        prev.ok = false;
       }
-      radius /= decrease_factor;
-      decrease_factor *= 2.0;
-      it_successful = false;
-      it_cost = x_cost;
     }
-    if (stop) break;
-    phase = kLineSearch;
-    t = 1.0;
-    ls_iters = 0;
-    prev.ok = false;
-  }
 
-  so.termination = term;
-  so.iterations = iteration;
-  so.cost_initial = cost_initial;
-  so.cost_final = cost_final;
-  so.n_jac = n_eval;
-  so.n_cost = 0;
-  // solution = best accepted iterate (the caller substitutes the seed when the termination is not usable)
-  __syncwarp();
-  if (lane < P) xs[lane] = best[lane];
-  __syncwarp();
-}
-
-// Load the warp-uniform problem view.
-__device__ __forceinline__ void load_problem(const DevBatch& bt, int b, Prob& pb) {
-  const int S = bt.S;
-  pb.x0 = __ldg(bt.pose0 + 3 * (size_t)b);
-  pb.y0 = __ldg(bt.pose0 + 3 * (size_t)b + 1);
-  pb.yaw0 = __ldg(bt.pose0 + 3 * (size_t)b + 2);
-  pb.goal_yaw = __ldg(bt.goal_yaw + b);
-  pb.px = bt.path_xy + (size_t)b * 2 * (S + 1);
-  pb.py = pb.px + (S + 1);
-  pb.fin_x = __ldg(pb.px + S);
-  pb.fin_y = __ldg(pb.py + S);
-  pb.agents = (bt.A > 0 && bt.agents) ? bt.agents + (size_t)b * bt.A * 6 * (S + 1) : nullptr;
-  pb.has_people = (bt.has_people != nullptr) && (bt.has_people[b] != 0);
-  const int mi = bt.costmap_index ? __ldg(bt.costmap_index + b) : (b % bt.M);
-  pb.map = bt.costmaps + (size_t)mi * bt.size_x * bt.size_y;
-  pb.org_x = __ldg(bt.costmap_origin + 2 * mi);
-  pb.org_y = __ldg(bt.costmap_origin + 2 * mi + 1);
-}
-
-__device__ __forceinline__ void agent_angle_setup(const DevParams& prm, const DevBatch& bt, const Prob& pb, int lane,
-                                                  double (&aa_target)[kMaxChunks]) {
-#pragma unroll
-  for (int c = 0; c < kMaxChunks; ++c) {
-    aa_target[c] = NAN;
-    const int j = c * 32 + lane;
-    if (pb.has_people && j < bt.S && bt.A > 0 && pb.agents != nullptr) aa_target[c] = agent_angle_target(bt, pb, j + 1);
+    if (finished) {
+      // results. Solution = best accepted iterate when usable (Solver::Summary::IsSolutionUsable), else the seed.
+      const bool usable = term <= kNoConvergence;
+      __syncwarp(gmask);
+      double x[P];
+      SMPC_UNROLL for (int c = 0; c < P; ++c) x[c] = usable ? best[c] : __ldg(bt.u0 + (size_t)b * P + c);
+      if (gl == 0) {
+        if (rs.u) {
+          SMPC_UNROLL for (int c = 0; c < P; ++c) rs.u[(size_t)b * P + c] = x[c];
+        }
+        if (rs.cost_initial) rs.cost_initial[b] = cost_initial;
+        if (rs.cost_final) rs.cost_final[b] = cost_final;
+        if (rs.iterations) rs.iterations[b] = iteration;
+        if (rs.termination) rs.termination[b] = term;
+        if (rs.usable) rs.usable[b] = usable ? 1 : 0;
+        if (rs.n_evals) {
+          rs.n_evals[2 * b] = n_eval;
+          rs.n_evals[2 * b + 1] = 0;
+        }
+      }
+      if (rs.cmds || rs.path) expand_outputs<NB, G>(prm, bt, rs, pb, b, x, lane);
+      __syncwarp(gmask);
+      phase = kFetch;
+      live = false;
+    }
   }
 }
 

@@ -79,6 +79,7 @@ struct smpc_handle {
   bool timed = false;
   int* queue = nullptr;
   long long launches = 0;
+  int forced_group = 0;  // 0 = pick lanes-per-problem from the batch size; SMPC_GROUP env / smpc_set_group override
   std::mutex mu;
   // staging for the host-buffer entry points
   DeviceBuffer in_buf, out_buf;
@@ -105,7 +106,7 @@ int make_dev_params(const smpc_params& p, int S, smpc::DevParams* d) {
   if (d->nb > smpc::max_supported_blocks())
     return fail(SMPC_ERR_UNSUPPORTED, "more than " + std::to_string(smpc::max_supported_blocks()) +
                                           " parameter blocks are not built into this libsmpc.so");
-  if (S > 32 * smpc::kMaxChunks) return fail(SMPC_ERR_UNSUPPORTED, "n_steps > 64 is not supported");
+  if (S > smpc::kMaxSteps) return fail(SMPC_ERR_UNSUPPORTED, "n_steps > 64 is not supported");
   d->w_distance = p.distance_w;
   d->w_social = p.socialwork_w;
   d->w_velocity = p.velocity_w;
@@ -385,7 +386,17 @@ int smpc_create(const smpc_params* p, int device, smpc_handle** out) {
     smpc_destroy(h);
     return cuda_fail(e, "smpc_create resources");
   }
+  if (const char* env = std::getenv("SMPC_GROUP")) h->forced_group = std::atoi(env);
   *out = h;
+  return SMPC_OK;
+}
+
+int smpc_set_group(smpc_handle* h, int lanes_per_problem) {
+  if (!h) return fail(SMPC_ERR_ARGUMENT, "handle is NULL");
+  if (lanes_per_problem != 0 && lanes_per_problem != 4 && lanes_per_problem != 8 && lanes_per_problem != 16 &&
+      lanes_per_problem != 32)
+    return fail(SMPC_ERR_ARGUMENT, "lanes_per_problem must be 0 (auto), 4, 8, 16 or 32");
+  h->forced_group = lanes_per_problem;
   return SMPC_OK;
 }
 
@@ -417,7 +428,7 @@ static int solve_device_locked(smpc_handle* h, const smpc_batch* in, smpc_result
   SMPC_CUDA(cudaSetDevice(h->device));
   SMPC_CUDA(cudaMemsetAsync(h->queue, 0, sizeof(int), stream));
   SMPC_CUDA(cudaEventRecord(h->ev0, stream));
-  SMPC_CUDA(smpc::launch_solve(prm, bt, rs, h->queue, h->n_sm, stream));
+  SMPC_CUDA(smpc::launch_solve(prm, bt, rs, h->queue, h->n_sm, h->forced_group, stream));
   SMPC_CUDA(cudaEventRecord(h->ev1, stream));
   h->timed = true;
   h->launches += 1;
@@ -511,7 +522,7 @@ int smpc_eval_batch_device(smpc_handle* h, const smpc_batch* in, const double* x
   smpc::DevEvalOut eo{out->cost, out->grad, out->hess, out->ok};
   SMPC_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
-  SMPC_CUDA(smpc::launch_eval(prm, bt, x, eo, h->n_sm, st));
+  SMPC_CUDA(smpc::launch_eval(prm, bt, x, eo, h->n_sm, h->forced_group, st));
   h->launches += 1;
   return SMPC_OK;
 }

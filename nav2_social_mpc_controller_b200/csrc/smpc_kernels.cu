@@ -15,132 +15,53 @@ constexpr int kThreads = kWarpsPerCta * 32;
 #define SMPC_MIN_CTAS 4
 #endif
 
-template <int NB, bool MULTI>
+template <int NB, int G>
 __global__ void __launch_bounds__(kThreads, SMPC_MIN_CTAS) smpc_solve_kernel(DevParams prm, DevBatch bt, DevResult rs, int* queue) {
-  using L = Layout<NB>;
-  constexpr int P = 2 * NB;
-  __shared__ double smem[kWarpsPerCta * L::kTotal];
+  extern __shared__ double smem[];
   const int lane = threadIdx.x & 31;
-  double* ws = smem + (threadIdx.x >> 5) * L::kTotal;
-  LaneConst<NB> lc;
-  lane_setup<NB>(lane, prm.bl, bt.dt, lc);
-  for (;;) {
-    int b = 0;
-    if (lane == 0) b = atomicAdd(queue, 1);
-    b = __shfl_sync(kFullMask, b, 0);
-    if (b >= bt.B) break;
-
-    Prob pb;
-    load_problem(bt, b, pb);
-    double aa_target[kMaxChunks];
-    agent_angle_setup(prm, bt, pb, lane, aa_target);
-    __syncwarp();
-    if (lane < P) ws[L::kX + lane] = __ldg(bt.u0 + (size_t)b * P + lane);
-    __syncwarp();
-
-    SolveOut so;
-    solve_problem<NB, MULTI>(prm, bt, pb, aa_target, lc, ws, lane, so);
-    const bool usable = so.termination <= kNoConvergence;  // Solver::Summary::IsSolutionUsable
-    double x[P];
-    SMPC_UNROLL for (int c = 0; c < P; ++c) x[c] = usable ? ws[L::kX + c] : __ldg(bt.u0 + (size_t)b * P + c);
-
-    if (lane == 0) {
-      if (rs.u) {
-        SMPC_UNROLL for (int c = 0; c < P; ++c) rs.u[(size_t)b * P + c] = x[c];
-      }
-      if (rs.cost_initial) rs.cost_initial[b] = so.cost_initial;
-      if (rs.cost_final) rs.cost_final[b] = so.cost_final;
-      if (rs.iterations) rs.iterations[b] = so.iterations;
-      if (rs.termination) rs.termination[b] = so.termination;
-      if (rs.usable) rs.usable[b] = usable ? 1 : 0;
-      if (rs.n_evals) {
-        rs.n_evals[2 * b] = so.n_jac;
-        rs.n_evals[2 * b + 1] = so.n_cost;
-      }
-    }
-    // Post-solve expansion (reference src/optimizer.cpp:390-446): cmds[S+1] hold block min(i/bl, NB-1) for
-    // i < ch and the last block afterwards; the path is the Euler rollout of those cmds from pose0.
-    if (rs.cmds || rs.path) {
-      const int S = bt.S;
-      double s0, c0;
-      sincos(pb.yaw0 * 0.5, &s0, &c0);
-      const double yaw_rt = atan2(2.0 * (c0 * s0), c0 * c0 - s0 * s0);  // evolving_poses[0] went through setRPY/getYaw
-      double carry_x = pb.x0, carry_y = pb.y0;
-      for (int base = 0; base <= S; base += 32) {
-        const int i = base + lane;
-        const bool act = i <= S;
-        const int bi = (i < prm.ch) ? min(i / prm.bl, NB - 1) : NB - 1;
-        double v = x[0], w = x[1];
-        double th = yaw_rt, th_next = yaw_rt;
-        SMPC_UNROLL for (int bb = 0; bb < NB; ++bb) {
-          if (bb == bi) {
-            v = x[2 * bb];
-            w = x[2 * bb + 1];
-          }
-          th += x[2 * bb + 1] * (bt.dt * (double)steps_in_block_before<NB>(i, bb, prm.bl));
-          th_next += x[2 * bb + 1] * (bt.dt * (double)steps_in_block_before<NB>(i + 1, bb, prm.bl));
-        }
-        if (act && rs.cmds) {
-          rs.cmds[((size_t)b * (S + 1) + i) * 2] = v;
-          rs.cmds[((size_t)b * (S + 1) + i) * 2 + 1] = w;
-        }
-        if (rs.path) {
-          double sn, cs;
-          sincos(th, &sn, &cs);
-          double sx = act ? v * cs * bt.dt : 0.0, sy = act ? v * sn * bt.dt : 0.0;
-          SMPC_UNROLL for (int d = 1; d < 32; d <<= 1) {
-            const double tx = __shfl_up_sync(kFullMask, sx, d), ty = __shfl_up_sync(kFullMask, sy, d);
-            if (lane >= d) {
-              sx += tx;
-              sy += ty;
-            }
-          }
-          const double X = carry_x + sx, Y = carry_y + sy;
-          carry_x = __shfl_sync(kFullMask, X, 31);
-          carry_y = __shfl_sync(kFullMask, Y, 31);
-          if (act) {
-            double sh, chh;
-            sincos(th_next * 0.5, &sh, &chh);
-            double* o = rs.path + ((size_t)b * (S + 1) + i) * 3;
-            o[0] = X;
-            o[1] = Y;
-            o[2] = atan2(2.0 * (chh * sh), chh * chh - sh * sh);  // tf2 setRPY -> getYaw
-          }
-        }
-      }
-    }
-  }
+  const int group_in_cta = threadIdx.x / G;
+  double* ws = smem + (size_t)group_in_cta * Layout<NB>::total(bt.S);
+  solve_loop<NB, G>(prm, bt, rs, queue, ws, lane);
 }
 
-template <int NB>
+template <int NB, int G>
 __global__ void __launch_bounds__(kThreads) smpc_eval_kernel(DevParams prm, DevBatch bt, const double* xin, DevEvalOut eo) {
   using L = Layout<NB>;
   constexpr int P = 2 * NB;
-  __shared__ double smem[kWarpsPerCta * L::kTotal];
+  extern __shared__ double smem[];
   const int lane = threadIdx.x & 31;
-  double* ws = smem + (threadIdx.x >> 5) * L::kTotal;
-  LaneConst<NB> lc;
-  lane_setup<NB>(lane, prm.bl, bt.dt, lc);
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int n_warps = (gridDim.x * blockDim.x) >> 5;
-  for (int b = warp; b < bt.B; b += n_warps) {
+  const int gl = lane & (G - 1);
+  const unsigned gmask = Group<G>::mask(lane);
+  const int group_in_cta = threadIdx.x / G;
+  double* ws = smem + (size_t)group_in_cta * L::total(bt.S);
+  const int groups_per_cta = kThreads / G;
+  const int n_groups = gridDim.x * groups_per_cta;
+  for (int base = blockIdx.x * groups_per_cta; base < bt.B; base += n_groups) {
+    const int b = base + group_in_cta;
+    const bool live = b < bt.B;
     Prob pb;
-    load_problem(bt, b, pb);
-    double aa_target[kMaxChunks];
-    agent_angle_setup(prm, bt, pb, lane, aa_target);
-    __syncwarp();
-    if (lane < P) ws[L::kCand + lane] = __ldg(xin + (size_t)b * P + lane);
-    __syncwarp();
-    const unsigned fl = (bt.S > 32) ? evaluate<NB, true>(prm, bt, pb, aa_target, lc, ws + L::kCand, lane, ws + L::kBuf0)
-                                    : evaluate<NB, false>(prm, bt, pb, aa_target, lc, ws + L::kCand, lane, ws + L::kBuf0);
-    if (lane == 0) {
-      if (eo.cost) eo.cost[b] = ws[L::kBuf0];
-      if (eo.ok) eo.ok[b] = (fl == 0) ? 1 : 0;
+    pb.x0 = pb.y0 = pb.yaw0 = pb.goal_yaw = pb.fin_x = pb.fin_y = pb.org_x = pb.org_y = 0.0;
+    pb.px = pb.py = pb.agents = nullptr;
+    pb.map = nullptr;
+    pb.has_people = false;
+    if (live) {
+      load_problem(bt, b, pb);
+      agent_angle_setup<NB, G>(bt, pb, lane, ws);
+      for (int c = gl; c < P; c += G) ws[L::kCand + c] = __ldg(xin + (size_t)b * P + c);
     }
-    if (eo.grad && lane < P) eo.grad[(size_t)b * P + lane] = ws[L::kBuf0 + 1 + lane];
-    if (eo.hess)
-      for (int e = lane; e < L::NH; e += 32) eo.hess[(size_t)b * L::NH + e] = ws[L::kBuf0 + 1 + P + e];
-    __syncwarp();
+    __syncwarp(gmask);
+    const unsigned fl = evaluate<NB, G>(prm, bt, pb, live, ws, ws + L::kCand, lane, ws + L::kBuf0);
+    if (live) {
+      if (gl == 0) {
+        if (eo.cost) eo.cost[b] = ws[L::kBuf0];
+        if (eo.ok) eo.ok[b] = (fl == 0) ? 1 : 0;
+      }
+      if (eo.grad)
+        for (int c = gl; c < P; c += G) eo.grad[(size_t)b * P + c] = ws[L::kBuf0 + 1 + c];
+      if (eo.hess)
+        for (int e = gl; e < L::NH; e += G) eo.hess[(size_t)b * L::NH + e] = ws[L::kBuf0 + 1 + P + e];
+    }
+    __syncwarp(gmask);
   }
 }
 
@@ -214,36 +135,72 @@ __global__ void smpc_argmin_kernel(int n_starts, int n_blocks, const double* __r
 // -------------------------------------------------------------------------------------------------------
 // launchers
 // -------------------------------------------------------------------------------------------------------
-template <int NB>
-static cudaError_t launch_solve_nb(const DevParams& prm, const DevBatch& bt, const DevResult& rs, int* queue, int n_sm,
+// Lanes per problem: the throughput mapping (G = 4) once the batch alone fills the GPU with warps, wider groups
+// for smaller batches so that every SM sub-partition still has several warps, G = 32 for single-digit batches
+// (lowest latency per solve).
+static int pick_group(int B, int n_sm, int forced) {
+  if (forced == 4 || forced == 8 || forced == 16 || forced == 32) return forced;
+  const long long target_warps = (long long)n_sm * 4 * 4;  // >= 4 warps per SM sub-partition
+  for (int g = 4; g < 32; g <<= 1)
+    if ((long long)B * g / 32 >= target_warps) return g;
+  return 32;
+}
+
+template <int NB, int G>
+static cudaError_t launch_solve_ng(const DevParams& prm, const DevBatch& bt, const DevResult& rs, int* queue, int n_sm,
                                    cudaStream_t stream) {
-  const bool multi = bt.S > 32;
-  int ctas_per_sm = 0;
-  cudaError_t e = multi ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, smpc_solve_kernel<NB, true>, kThreads, 0)
-                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, smpc_solve_kernel<NB, false>, kThreads, 0);
+  const size_t smem = sizeof(double) * (kThreads / G) * Layout<NB>::total(bt.S);
+  cudaError_t e = cudaFuncSetAttribute(smpc_solve_kernel<NB, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  if (ctas_per_sm < 1) ctas_per_sm = 1;
-  // persistent grid: a multiple of the SM count, never more warps than problems
-  long long want_ctas = ((long long)bt.B + kWarpsPerCta - 1) / kWarpsPerCta;
+  int ctas_per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, smpc_solve_kernel<NB, G>, kThreads, smem);
+  if (e != cudaSuccess) return e;
+  if (ctas_per_sm < 1) return cudaErrorLaunchOutOfResources;
+  // persistent grid: a multiple of the SM count, never more groups than problems
+  const int groups_per_cta = kThreads / G;
+  long long want_ctas = ((long long)bt.B + groups_per_cta - 1) / groups_per_cta;
   long long grid = (long long)n_sm * ctas_per_sm;
   if (want_ctas < grid) grid = want_ctas;
   if (grid < 1) grid = 1;
-  if (multi)
-    smpc_solve_kernel<NB, true><<<(unsigned)grid, kThreads, 0, stream>>>(prm, bt, rs, queue);
-  else
-    smpc_solve_kernel<NB, false><<<(unsigned)grid, kThreads, 0, stream>>>(prm, bt, rs, queue);
+  smpc_solve_kernel<NB, G><<<(unsigned)grid, kThreads, smem, stream>>>(prm, bt, rs, queue);
+  return cudaGetLastError();
+}
+
+template <int NB>
+static cudaError_t launch_solve_nb(const DevParams& prm, const DevBatch& bt, const DevResult& rs, int* queue, int n_sm,
+                                   int forced_group, cudaStream_t stream) {
+  switch (pick_group(bt.B, n_sm, forced_group)) {
+    case 4: return launch_solve_ng<NB, 4>(prm, bt, rs, queue, n_sm, stream);
+    case 8: return launch_solve_ng<NB, 8>(prm, bt, rs, queue, n_sm, stream);
+    case 16: return launch_solve_ng<NB, 16>(prm, bt, rs, queue, n_sm, stream);
+    default: return launch_solve_ng<NB, 32>(prm, bt, rs, queue, n_sm, stream);
+  }
+}
+
+template <int NB, int G>
+static cudaError_t launch_eval_ng(const DevParams& prm, const DevBatch& bt, const double* x, const DevEvalOut& eo, int n_sm,
+                                  cudaStream_t stream) {
+  const size_t smem = sizeof(double) * (kThreads / G) * Layout<NB>::total(bt.S);
+  cudaError_t e = cudaFuncSetAttribute(smpc_eval_kernel<NB, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int groups_per_cta = kThreads / G;
+  long long want_ctas = ((long long)bt.B + groups_per_cta - 1) / groups_per_cta;
+  long long grid = (long long)n_sm * 4;
+  if (want_ctas < grid) grid = want_ctas;
+  if (grid < 1) grid = 1;
+  smpc_eval_kernel<NB, G><<<(unsigned)grid, kThreads, smem, stream>>>(prm, bt, x, eo);
   return cudaGetLastError();
 }
 
 template <int NB>
 static cudaError_t launch_eval_nb(const DevParams& prm, const DevBatch& bt, const double* x, const DevEvalOut& eo, int n_sm,
-                                  cudaStream_t stream) {
-  long long want_ctas = ((long long)bt.B + kWarpsPerCta - 1) / kWarpsPerCta;
-  long long grid = (long long)n_sm * 8;
-  if (want_ctas < grid) grid = want_ctas;
-  if (grid < 1) grid = 1;
-  smpc_eval_kernel<NB><<<(unsigned)grid, kThreads, 0, stream>>>(prm, bt, x, eo);
-  return cudaGetLastError();
+                                  int forced_group, cudaStream_t stream) {
+  switch (pick_group(bt.B, n_sm, forced_group)) {
+    case 4: return launch_eval_ng<NB, 4>(prm, bt, x, eo, n_sm, stream);
+    case 8: return launch_eval_ng<NB, 8>(prm, bt, x, eo, n_sm, stream);
+    case 16: return launch_eval_ng<NB, 16>(prm, bt, x, eo, n_sm, stream);
+    default: return launch_eval_ng<NB, 32>(prm, bt, x, eo, n_sm, stream);
+  }
 }
 
 #define SMPC_DISPATCH_NB(FN, ...)                  \
@@ -258,13 +215,13 @@ static cudaError_t launch_eval_nb(const DevParams& prm, const DevBatch& bt, cons
   }
 
 cudaError_t launch_solve(const DevParams& prm, const DevBatch& bt, const DevResult& rs, int* queue, int n_sm,
-                         cudaStream_t stream) {
-  SMPC_DISPATCH_NB(launch_solve_nb, prm, bt, rs, queue, n_sm, stream)
+                         int forced_group, cudaStream_t stream) {
+  SMPC_DISPATCH_NB(launch_solve_nb, prm, bt, rs, queue, n_sm, forced_group, stream)
 }
 
 cudaError_t launch_eval(const DevParams& prm, const DevBatch& bt, const double* x, const DevEvalOut& eo, int n_sm,
-                        cudaStream_t stream) {
-  SMPC_DISPATCH_NB(launch_eval_nb, prm, bt, x, eo, n_sm, stream)
+                        int forced_group, cudaStream_t stream) {
+  SMPC_DISPATCH_NB(launch_eval_nb, prm, bt, x, eo, n_sm, forced_group, stream)
 }
 
 cudaError_t launch_argmin(int n_robots, int n_starts, int n_blocks, const double* cost_final, const uint8_t* usable,

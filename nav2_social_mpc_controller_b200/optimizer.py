@@ -137,6 +137,11 @@ class Optimizer:
             self._h, n_robots, n_starts, n_blocks, p(cost_final), p(usable), p(u), p(best_index), p(best_cost),
             p(best_u), C.c_void_p(stream) if stream else None))
 
+    def set_group(self, lanes_per_problem: int) -> None:
+        """Lanes per problem (0 = auto, 4, 8, 16, 32): throughput vs latency mapping of the solve kernel."""
+        self._need()
+        _lib.check(_lib.lib().smpc_set_group(self._h, lanes_per_problem))
+
     def last_kernel_ms(self) -> float:
         self._need()
         return float(_lib.lib().smpc_last_kernel_ms(self._h))

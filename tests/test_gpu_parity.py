@@ -204,3 +204,42 @@ def test_line_search_polynomial_minimiser_matches_oracle(oracle, make_opt):
     rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-300)
     assert np.quantile(rel, 0.99) < 1e-8, rel.max()
     assert (rel < 1e-6).mean() > 0.995
+
+
+@pytest.mark.parametrize("group", [4, 8, 16, 32])
+@pytest.mark.parametrize("name", ["readme", "params_yaml", "soc_work_obst"])
+def test_every_lane_mapping_matches_oracle(oracle, make_opt, group, name):
+    """The lanes-per-problem mapping (4/8/16/32) only changes summation order: eval and solve parity for each,
+    on S = 13 (less than one chunk at G = 16/32), S = 28 and S = 38 (two chunks at G = 32)."""
+    from nav2_social_mpc_controller_b200.optimizer import hess_to_dense
+    batch = sc.single(name)
+    opt = make_opt(batch.params)
+    opt.set_group(group)
+    try:
+        P = 2 * batch.n_blocks
+        x = batch.arrays["u0"].reshape(1, P) + 0.01
+        got = opt.eval_batch(batch, x)
+        e = oracle.evaluate(batch, 0, x[0])
+        assert got["cost"][0] == pytest.approx(e["cost"], rel=1e-11)
+        H_ref = e["jac"].T @ e["jac"]
+        assert np.abs(hess_to_dense(got["hess"], P)[0] - H_ref).max() <= 1e-9 * np.abs(H_ref).max()
+        assert np.abs(got["grad"][0] - e["grad"]).max() <= 1e-9 * np.abs(e["grad"]).max()
+        r = _compare_solves(oracle, opt, batch)
+        assert r["ok"].all() and r["same_term"].all() and r["same_iters"].all(), (r["du"], r["dc"])
+        assert np.abs(r["got"]["cmds"] - r["ref"]["cmds"]).max() <= U_ATOL
+    finally:
+        opt.set_group(0)
+
+
+@pytest.mark.parametrize("group", [4, 8, 32])
+def test_mixed_batch_with_refill(oracle, make_opt, group):
+    """More problems than resident groups of one CTA row, uneven iteration counts: the per-group queue refill
+    must keep every problem's result independent of its neighbours in the warp."""
+    batch = sc.crowd(B=160, A=3, config_id=12, n_valid=2)
+    opt = make_opt(batch.params)
+    opt.set_group(group)
+    try:
+        r = _compare_solves(oracle, opt, batch)
+        assert r["ok"].mean() >= 0.95, (group, r["ok"].mean(), r["du"].max(), r["dc"].max())
+    finally:
+        opt.set_group(0)
