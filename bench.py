@@ -44,13 +44,21 @@ WORKLOADS = {
                                  "crowd scenarios, 20 agents, S=28, P=6, 256 shared costmaps", False),
     "soc_work_obst_x16384_A3": (lambda: sc.crowd(B=16384, A=3, config_id=6), "soc_work_obst params, 16384 crowd "
                                 "scenarios with the reference's 3 agents, S=28, P=6", False),
+    "obst_only_x65536": (lambda: sc.corridor(B=65536, unique_maps=False, config_id=22), "obst_only params, 65536 corridor "
+                         "scenarios, 256 shared costmaps (throughput-mode check)", False),
+    "soc_work_obst_x65536_A3": (lambda: sc.crowd(B=65536, A=3, config_id=23), "soc_work_obst params, 65536 crowd "
+                                "scenarios with the reference's 3 agents", False),
     "multistart_256x1024": (lambda: sc.multistart(256, 1024), "BASELINE configs[3]: 1024 perturbed starts x 256 robots, "
                             "A=3, per-robot arg-min", False),
     "crowd_x131072_A50": (lambda: sc.crowd(B=131072, A=50, config_id=5), "BASELINE configs[4] slice: 131072 problems, "
                           "50 agents (per-GPU shard of the 10^6 sweep)", False),
 }
 CPU_SAMPLE = {"obst_only_x4096": 768, "soc_work_obst_x65536_A20": 96, "soc_work_obst_x16384_A3": 256,
-              "multistart_256x1024": 256, "crowd_x131072_A50": 48}
+              "obst_only_x65536": (lambda: sc.corridor(B=65536, unique_maps=False, config_id=22), "obst_only params, 65536 corridor "
+                         "scenarios, 256 shared costmaps (throughput-mode check)", False),
+    "soc_work_obst_x65536_A3": (lambda: sc.crowd(B=65536, A=3, config_id=23), "soc_work_obst params, 65536 crowd "
+                                "scenarios with the reference's 3 agents", False),
+    "multistart_256x1024": 256, "crowd_x131072_A50": 48}
 
 
 def flops_per_solve(S, P, A_eff, m, n_jac, n_cost, iters):

@@ -101,26 +101,27 @@ __device__ __forceinline__ double wrap_to_pi(double a) {
 
 __device__ __forceinline__ void social_pair(double dx, double dy, double wx, double wy, PairOut& o) {
   const double kLambda = 2.0, kGamma = 0.35, kNPrime = 3.0, kN = 2.0, kFactor = 2.1;
-  double rho = sqrt(dx * dx + dy * dy);
-  const bool tiny = rho < 1e-6;
+  double d2 = dx * dx + dy * dy;
+  const bool tiny = d2 < 1e-12;  // |d| < 1e-6
   if (tiny) {  // coincident: fixed direction (1e-6, 0), a constant for the derivative
     dx = 1e-6;
     dy = 0.0;
-    rho = sqrt(dx * dx);
+    d2 = dx * dx;
   }
-  const double inv_rho = 1.0 / rho;
-  double ex = dx, ey = dy;
-  if (rho * rho > 0.0) {  // Eigen normalized()
-    ex = dx * inv_rho;
-    ey = dy * inv_rho;
-  }
+  const double inv_rho = rsqrt(d2);
+  const double rho = d2 * inv_rho;
+  const double ex = dx * inv_rho, ey = dy * inv_rho;  // Eigen normalized() (|d|^2 > 0 always holds here)
   const double Ix = kLambda * wx + ex, Iy = kLambda * wy + ey;
-  const double L = sqrt(Ix * Ix + Iy * Iy);
-  const double inv_L = 1.0 / L;
+  const double L2 = Ix * Ix + Iy * Iy;
+  const double inv_L = rsqrt(L2);
+  const double L = L2 * inv_L;
   const double ix = Ix * inv_L, iy = Iy * inv_L;
-  const double theta = wrap_to_pi(atan2(ey, ex) - atan2(iy, ix));
+  // theta = wrapToPi(atan2(e) - atan2(i)): the signed angle from i to e, taken with one atan2 of (cross, dot).
+  // "+ 0.0" turns a -0 cross product into +0 so that exactly (anti)parallel vectors give 0 / +pi like the reference.
+  const double cross = (ey * ix - ex * iy) + 0.0, dot = ex * ix + ey * iy;
+  const double theta = atan2(cross, dot);
   const double Bq = kGamma * L;
-  const double inv_B = 1.0 / Bq;
+  const double inv_B = inv_L * (1.0 / kGamma);
   const double t1 = kNPrime * Bq * theta, t2 = kN * Bq * theta;
   const double base = -rho * inv_B;
   const double E1 = exp(base - t1 * t1);

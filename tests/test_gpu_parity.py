@@ -243,3 +243,25 @@ def test_mixed_batch_with_refill(oracle, make_opt, group):
         assert r["ok"].mean() >= 0.95, (group, r["ok"].mean(), r["du"].max(), r["dc"].max())
     finally:
         opt.set_group(0)
+
+
+def test_exact_head_on_and_degenerate_social_geometry(oracle, make_opt):
+    """Exactly symmetric geometry (agent dead ahead walking straight at the robot, robot heading 0, all y equal):
+    the social force's angle theta is exactly 0 / pi and its sign convention (sgn(0) = -1) must match the
+    reference's two-atan2 formulation; also a padded phantom agent at the origin."""
+    batch = sc.single("soc_work_obst", n_people=2)
+    ag = batch.arrays["agents"]
+    S = batch.n_steps
+    t = np.arange(S + 1) * batch.dt
+    # agent 0: dead ahead on the robot's axis, walking toward it; agent 1: dead ahead walking away
+    ag[0, 0, 0, :], ag[0, 0, 1, :], ag[0, 0, 2, :], ag[0, 0, 4, :] = 3.5 - 0.5 * t, 2.0, np.pi, 0.5
+    ag[0, 1, 0, :], ag[0, 1, 1, :], ag[0, 1, 2, :], ag[0, 1, 4, :] = 3.0 + 0.3 * t, 2.0, 0.0, 0.3
+    batch.arrays["u0"][0, :, 1] = 0.0  # straight seed: the whole rollout stays on y = 2
+    opt = make_opt(batch.params)
+    P = 2 * batch.n_blocks
+    x = batch.arrays["u0"].reshape(1, P).copy()
+    got = opt.eval_batch(batch, x)
+    e = oracle.evaluate(batch, 0, x[0])
+    assert bool(got["ok"][0]) == e["ok"]
+    assert got["cost"][0] == pytest.approx(e["cost"], rel=1e-11)
+    assert np.abs(got["grad"][0] - e["grad"]).max() <= 1e-9 * max(1.0, np.abs(e["grad"]).max())
