@@ -116,10 +116,17 @@ __device__ __forceinline__ void social_pair(double dx, double dy, double wx, dou
   const double inv_L = rsqrt(L2);
   const double L = L2 * inv_L;
   const double ix = Ix * inv_L, iy = Iy * inv_L;
-  // theta = wrapToPi(atan2(e) - atan2(i)): the signed angle from i to e, taken with one atan2 of (cross, dot).
-  // "+ 0.0" turns a -0 cross product into +0 so that exactly (anti)parallel vectors give 0 / +pi like the reference.
-  const double cross = (ey * ix - ex * iy) + 0.0, dot = ex * ix + ey * iy;
-  const double theta = atan2(cross, dot);
+  // theta = wrapToPi(atan2(e) - atan2(i)), the signed angle from i to e. Generic geometry: one atan2 of
+  // (cross, dot) (same value to ~1 ulp, and sgn(theta) = sgn(cross) robustly). Near-degenerate geometry
+  // (|sin theta| < 1e-9: exactly (anti)parallel set-ups such as a person dead ahead): the model is discontinuous
+  // at theta = 0 and +-pi and the reference's own rounding decides the branch, so its formulation is used verbatim.
+  const double cross = ey * ix - ex * iy, dot = ex * ix + ey * iy;
+  double theta;
+  if (fabs(cross) > 1e-9) {
+    theta = atan2(cross, dot);
+  } else {
+    theta = wrap_to_pi(atan2(ey, ex) - atan2(iy, ix));
+  }
   const double Bq = kGamma * L;
   const double inv_B = inv_L * (1.0 / kGamma);
   const double t1 = kNPrime * Bq * theta, t2 = kN * Bq * theta;
