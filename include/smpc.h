@@ -190,6 +190,58 @@ int smpc_eval_batch_device(smpc_handle* h, const smpc_batch* in, const double* x
 /* Host-buffer convenience wrapper of the above (tests). */
 int smpc_eval_batch(smpc_handle* h, const smpc_batch* in, const double* x, smpc_eval_out* out);
 
+/* ---- level-2 entry: mirrors bool Optimizer::optimize(...) (optimizer.hpp:167-170) for ONE robot ------------------
+ * Pre-solve stages run on the host exactly as in the reference (people_to_status src/optimizer.cpp:454-482,
+ * format_to_optimize :484-551 with the handle's previous path / cmds standing in for the TrajectoryMemory singleton
+ * (trajectory_memory.hpp), project_people :554-671 + sfm.hpp, computeObstacle :673-728); the solve and the
+ * post-solve expansion run on the GPU (level-1 path); the handle's memory is updated like :448-449. */
+typedef struct smpc_obstacle_distance { /* obstacle_distance_msgs::msg::ObstacleDistance */
+  uint32_t width;
+  uint32_t height;
+  float resolution;
+  double origin_x;
+  double origin_y;
+  const float* distances;  /* [height*width] (unused by the reference beyond the emptiness check) */
+  const uint32_t* indexes; /* [height*width] index of the nearest obstacle cell */
+} smpc_obstacle_distance;
+
+typedef struct smpc_optimize_io {
+  /* in/out: seed path from the trajectorizer -> optimised path. poses [capacity][3] = x, y, yaw (tf2::getYaw of the
+   * pose quaternion); n_poses is updated. cmds [capacity][2] = linear.x, angular.z; n_cmds is updated. */
+  int capacity;
+  int n_poses;
+  double* poses;
+  int n_cmds;
+  double* cmds;
+  /* in */
+  int n_people;
+  const double* people; /* [n_people][5] position.x, position.y, velocity.x, velocity.y, velocity.z (people_msgs) */
+  double speed_v;       /* speed.linear.x */
+  double speed_w;       /* speed.angular.z */
+  float time_step;
+  const uint8_t* costmap; /* Costmap2D::getCharMap() */
+  int size_x;
+  int size_y;
+  double origin_x;
+  double origin_y;
+  double resolution;
+  smpc_obstacle_distance od;
+  /* out */
+  int n_proj_steps;    /* P = number of poses optimised */
+  double* people_proj; /* [capacity][3][6] AgentsTrajectories (may be NULL) */
+  int optimized;       /* the bool optimize() returns */
+  int termination;
+  int iterations;
+  double cost_initial;
+  double cost_final;
+} smpc_optimize_io;
+
+/* Returns SMPC_OK when the call itself worked (io->optimized holds the reference's return value); the
+ * std::runtime_error cases of computeObstacle (src/optimizer.cpp:676-713) map to SMPC_ERR_ARGUMENT. */
+int smpc_optimize(smpc_handle* h, smpc_optimize_io* io);
+/* Forget the previous path / cmds (a fresh TrajectoryMemory). */
+int smpc_reset_memory(smpc_handle* h);
+
 /* Multi-start selection: per robot arg-min of cost_final over `n_starts`
  * consecutive problems (device pointers). best_index [R] i32 (global problem
  * index, -1 if no usable start), best_cost [R], best_u [R][NB][2]. */

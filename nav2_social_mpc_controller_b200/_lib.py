@@ -59,6 +59,10 @@ def lib():
     L.smpc_launch_count.restype = C.c_longlong
     L.smpc_measure_fp64_peak.argtypes = [C.c_void_p, P(C.c_double)]
     L.smpc_measure_fp64_peak.restype = C.c_int
+    L.smpc_optimize.argtypes = [C.c_void_p, P(abi.SmpcOptimizeIo)]
+    L.smpc_optimize.restype = C.c_int
+    L.smpc_reset_memory.argtypes = [C.c_void_p]
+    L.smpc_reset_memory.restype = C.c_int
     L.smpc_set_group.argtypes = [C.c_void_p, C.c_int]
     L.smpc_set_group.restype = C.c_int
     L.smpc_debug_polymin.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -79,4 +83,5 @@ EXPORTED_SYMBOLS = (
     "smpc_create", "smpc_destroy", "smpc_solve_batch", "smpc_solve_batch_device", "smpc_eval_batch_device",
     "smpc_eval_batch", "smpc_multistart_argmin_device", "smpc_last_kernel_ms", "smpc_launch_count",
     "smpc_measure_fp64_peak", "smpc_debug_polymin", "smpc_set_group",
+    "smpc_optimize", "smpc_reset_memory",
 )

@@ -167,3 +167,46 @@ def make_result_struct(arrays: dict) -> SmpcResult:
     for f in RESULT_FIELDS:
         setattr(r, f, _ptr(arrays.get(f)))
     return r
+
+
+class SmpcObstacleDistance(C.Structure):
+    """struct smpc_obstacle_distance — obstacle_distance_msgs::msg::ObstacleDistance."""
+    _fields_ = [
+        ("width", C.c_uint32),
+        ("height", C.c_uint32),
+        ("resolution", C.c_float),
+        ("origin_x", C.c_double),
+        ("origin_y", C.c_double),
+        ("distances", C.c_void_p),
+        ("indexes", C.c_void_p),
+    ]
+
+
+class SmpcOptimizeIo(C.Structure):
+    """struct smpc_optimize_io — arguments of the level-2 entry mirroring Optimizer::optimize."""
+    _fields_ = [
+        ("capacity", C.c_int),
+        ("n_poses", C.c_int),
+        ("poses", C.c_void_p),
+        ("n_cmds", C.c_int),
+        ("cmds", C.c_void_p),
+        ("n_people", C.c_int),
+        ("people", C.c_void_p),
+        ("speed_v", C.c_double),
+        ("speed_w", C.c_double),
+        ("time_step", C.c_float),
+        ("costmap", C.c_void_p),
+        ("size_x", C.c_int),
+        ("size_y", C.c_int),
+        ("origin_x", C.c_double),
+        ("origin_y", C.c_double),
+        ("resolution", C.c_double),
+        ("od", SmpcObstacleDistance),
+        ("n_proj_steps", C.c_int),
+        ("people_proj", C.c_void_p),
+        ("optimized", C.c_int),
+        ("termination", C.c_int),
+        ("iterations", C.c_int),
+        ("cost_initial", C.c_double),
+        ("cost_final", C.c_double),
+    ]

@@ -264,7 +264,8 @@ struct Layout {
   static constexpr int kDelta = kDiag + P;
   static constexpr int kCand = kDelta + P;
   static constexpr int kCarry = kCand + P;
-  static constexpr int kAa = kCarry + NC;  // agent-angle steering target per step [S]
+  static constexpr int kYaw = kCarry + NC;  // sin, cos of yaw0
+  static constexpr int kAa = kYaw + 2;  // agent-angle steering target per step [S]
   __host__ __device__ static constexpr int total(int S) { return ((kAa + S) | 1); }  // odd stride: no bank conflicts
   __host__ __device__ static constexpr int g(int c) { return 1 + c; }
   __host__ __device__ static constexpr int h(int a, int b) { return 1 + P + a * (a + 1) / 2 + b; }
@@ -290,9 +291,24 @@ __device__ __forceinline__ double wrap_angle(double a) {
 // (SURVEY Appendix D). Must be called by all 32 lanes of the warp (scans use full-mask shuffles of width G);
 // `live` = this group holds a problem.
 // ---------------------------------------------------------------------------------------------------
+// Per-lane constants of the first chunk (steps 0..G-1): block of the lane's step and dt * #{steps before j in
+// block b}. They depend only on (S, bl, dt), i.e. on the batch, and are hoisted out of the whole solve.
+template <int NB>
+struct LaneConst {
+  int bj;
+  double tau[NB];
+};
+
+template <int NB>
+__device__ __forceinline__ void lane_setup(int j, int bl, double dt, LaneConst<NB>& lc) {
+  lc.bj = min(j / bl, NB - 1);
+  SMPC_UNROLL for (int b = 0; b < NB; ++b) lc.tau[b] = dt * (double)steps_in_block_before<NB>(j, b, bl);
+}
+
 template <int NB, int G>
 __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatch& bt, const Prob& pb, bool live,
-                                             double* ws, const double* xs, int lane, double* out) {
+                                             const LaneConst<NB>& lc0, double* ws, const double* xs, int lane,
+                                             double* out) {
   using L = Layout<NB>;
   constexpr int P = L::P;
   const int gl = lane & (G - 1);
@@ -311,15 +327,16 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
   SMPC_UNROLL for (int e = 0; e < L::NE; ++e) acc[e] = 0.0;
   unsigned flags = 0;
 
-  // heading before the group's first step: sin / cos of yaw0, then carried from chunk to chunk
-  double s0, c0;
-  sincos(pb.yaw0, &s0, &c0);
+  // heading before the group's first step: sin / cos of yaw0 (stored at problem set-up), then carried chunk to chunk
+  const double s0 = ws[L::kYaw], c0 = ws[L::kYaw + 1];
 
 #pragma unroll 1
   for (int base = 0; base < S; base += G) {
     const int j = base + gl;
     const bool act = live && (j < S);
-    const int bj = min(j / bl, NB - 1);
+    LaneConst<NB> lc = lc0;
+    if (base != 0) lane_setup<NB>(j, bl, dt, lc);
+    const int bj = lc.bj;
     double vj = x[0], wj = x[1];
     double Th = pb.yaw0;  // heading AFTER step j = yaw0 + sum_b w_b dt #{steps <= j in block b}
     double tau[NB];       // d theta_j / d w_b (heading before step j)
@@ -328,9 +345,10 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
         vj = x[2 * b];
         wj = x[2 * b + 1];
       }
-      tau[b] = dt * (double)steps_in_block_before<NB>(j, b, bl);
-      Th += x[2 * b + 1] * (dt * (double)steps_in_block_before<NB>(j + 1, b, bl));
+      tau[b] = lc.tau[b];
+      Th += x[2 * b + 1] * lc.tau[b];
     }
+    Th += wj * dt;
     // one sincos per step: lane j evaluates the heading after its step; the heading before it is the
     // previous lane's (the previous chunk's last lane / yaw0 for the group's first lane)
     double sT, cT;
@@ -948,6 +966,12 @@ template <int NB, int G>
 __device__ __forceinline__ void agent_angle_setup(const DevBatch& bt, const Prob& pb, int lane, double* ws) {
   using L = Layout<NB>;
   const int gl = lane & (G - 1);
+  if (gl == 0) {
+    double s0, c0;
+    sincos(pb.yaw0, &s0, &c0);
+    ws[L::kYaw] = s0;
+    ws[L::kYaw + 1] = c0;
+  }
   for (int j = gl; j < bt.S; j += G) {
     double tgt = NAN;
     if (pb.has_people && bt.A > 0 && pb.agents != nullptr) tgt = agent_angle_target(bt, pb, j + 1);
@@ -1038,6 +1062,8 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
   double* cur = ws + L::kBuf0;    // normal equations at x
   double* trial = ws + L::kBuf1;  // normal equations at the trial point
 
+  LaneConst<NB> lc0;
+  lane_setup<NB>(gl, prm.bl, bt.dt, lc0);
   Prob pb;
   pb.x0 = pb.y0 = pb.yaw0 = pb.goal_yaw = pb.fin_x = pb.fin_y = pb.org_x = pb.org_y = 0.0;
   pb.px = pb.py = pb.agents = nullptr;
@@ -1089,7 +1115,7 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
     }
     if (__all_sync(kFullMask, exhausted)) break;
 
-    const unsigned fl = evaluate<NB, G>(prm, bt, pb, live, ws, cand, lane, trial);
+    const unsigned fl = evaluate<NB, G>(prm, bt, pb, live, lc0, ws, cand, lane, trial);
     if (!live) continue;
     ++n_eval;
     const double t_cost = trial[0];

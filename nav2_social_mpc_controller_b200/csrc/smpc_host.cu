@@ -18,6 +18,7 @@
 
 #include "../../include/smpc.h"
 #include "smpc_device.cuh"
+#include "smpc_host_state.h"
 #include "smpc_internal.h"
 
 namespace {
@@ -83,7 +84,12 @@ struct smpc_handle {
   std::mutex mu;
   // staging for the host-buffer entry points
   DeviceBuffer in_buf, out_buf;
+  smpc_memory memory;  // previous path / cmds of the level-2 entry
 };
+
+const smpc_params* smpc_handle_params(smpc_handle* h) { return &h->params; }
+smpc_memory* smpc_handle_memory(smpc_handle* h) { return &h->memory; }
+int smpc_host_fail(int code, const std::string& msg) { return fail(code, msg); }
 
 namespace {
 

@@ -36,6 +36,8 @@ __global__ void __launch_bounds__(kThreads) smpc_eval_kernel(DevParams prm, DevB
   double* ws = smem + (size_t)group_in_cta * L::total(bt.S);
   const int groups_per_cta = kThreads / G;
   const int n_groups = gridDim.x * groups_per_cta;
+  LaneConst<NB> lc0;
+  lane_setup<NB>(gl, prm.bl, bt.dt, lc0);
   for (int base = blockIdx.x * groups_per_cta; base < bt.B; base += n_groups) {
     const int b = base + group_in_cta;
     const bool live = b < bt.B;
@@ -50,7 +52,7 @@ __global__ void __launch_bounds__(kThreads) smpc_eval_kernel(DevParams prm, DevB
       for (int c = gl; c < P; c += G) ws[L::kCand + c] = __ldg(xin + (size_t)b * P + c);
     }
     __syncwarp(gmask);
-    const unsigned fl = evaluate<NB, G>(prm, bt, pb, live, ws, ws + L::kCand, lane, ws + L::kBuf0);
+    const unsigned fl = evaluate<NB, G>(prm, bt, pb, live, lc0, ws, ws + L::kCand, lane, ws + L::kBuf0);
     if (live) {
       if (gl == 0) {
         if (eo.cost) eo.cost[b] = ws[L::kBuf0];

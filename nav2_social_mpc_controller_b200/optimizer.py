@@ -113,6 +113,50 @@ class Optimizer:
         _lib.check(_lib.lib().smpc_solve_batch_device(self._h, C.byref(batch_struct), C.byref(rs),
                                                       C.c_void_p(stream) if stream else None))
 
+    # ---- level-2 entry: bool Optimizer::optimize(path, people_proj, costmap, obstacles, cmds, people, speed, dt) ----
+    def optimize(self, path: np.ndarray, cmds: np.ndarray, people: np.ndarray, speed, time_step: float,
+                 costmap: np.ndarray, costmap_origin, costmap_resolution: float, od: dict):
+        """Mirror of the reference call (include/nav2_social_mpc_controller/optimizer.hpp:167-170).
+        path [n][3] (x, y, yaw) and cmds [m][2] are the trajectorizer's seed and come back optimised (in-out like
+        the reference); people [k][5] = position.x/y, velocity.x/y/z; speed = (linear.x, angular.z); od = dict(width,
+        height, resolution, origin_x, origin_y, distances f32[], indexes u32[]).
+        Returns (ok, path, cmds, people_proj[P][3][6], info). ok == False <=> the reference returns false."""
+        self._need()
+        path = np.ascontiguousarray(path, dtype=np.float64).reshape(-1, 3)
+        cmds = np.ascontiguousarray(cmds, dtype=np.float64).reshape(-1, 2)
+        people = np.ascontiguousarray(people, dtype=np.float64).reshape(-1, 5)
+        costmap = np.ascontiguousarray(costmap, dtype=np.uint8)
+        cap = max(path.shape[0], cmds.shape[0]) + 2
+        poses_buf = np.zeros((cap, 3))
+        poses_buf[: path.shape[0]] = path
+        cmds_buf = np.zeros((cap, 2))
+        cmds_buf[: cmds.shape[0]] = cmds
+        proj = np.zeros((cap, 3, 6))
+        dist = np.ascontiguousarray(od["distances"], dtype=np.float32)
+        idx = np.ascontiguousarray(od["indexes"], dtype=np.uint32)
+        io = abi.SmpcOptimizeIo()
+        io.capacity, io.n_poses, io.n_cmds, io.n_people = cap, path.shape[0], cmds.shape[0], people.shape[0]
+        io.poses, io.cmds, io.people = poses_buf.ctypes.data, cmds_buf.ctypes.data, people.ctypes.data
+        io.speed_v, io.speed_w, io.time_step = float(speed[0]), float(speed[1]), float(time_step)
+        io.costmap, io.size_x, io.size_y = costmap.ctypes.data, costmap.shape[1], costmap.shape[0]
+        io.origin_x, io.origin_y, io.resolution = float(costmap_origin[0]), float(costmap_origin[1]), float(
+            costmap_resolution)
+        io.od.width, io.od.height, io.od.resolution = int(od["width"]), int(od["height"]), float(od["resolution"])
+        io.od.origin_x, io.od.origin_y = float(od["origin_x"]), float(od["origin_y"])
+        io.od.distances = dist.ctypes.data if dist.size else None
+        io.od.indexes = idx.ctypes.data if idx.size else None
+        io.people_proj = proj.ctypes.data
+        _lib.check(_lib.lib().smpc_optimize(self._h, C.byref(io)))
+        info = dict(termination=io.termination, iterations=io.iterations, cost_initial=io.cost_initial,
+                    cost_final=io.cost_final)
+        return (bool(io.optimized), poses_buf[: io.n_poses].copy(), cmds_buf[: io.n_cmds].copy(),
+                proj[: io.n_proj_steps].copy(), info)
+
+    def reset_memory(self) -> None:
+        """Forget the previous path / cmds (fresh TrajectoryMemory)."""
+        self._need()
+        _lib.check(_lib.lib().smpc_reset_memory(self._h))
+
     def eval_batch(self, batch, x: np.ndarray) -> dict:
         """cost, J^T r, J^T J at block values x [B][NB][2] (host buffers)."""
         self._need()

@@ -1,0 +1,122 @@
+"""GPU tests of the level-2 entry smpc_optimize (mirror of bool Optimizer::optimize, reference
+optimizer.hpp:167-170) against tests/presolve_ref.py (pre-solve stages) + the CPU oracle (solve, post-solve)."""
+import math
+
+import numpy as np
+import pytest
+
+from nav2_social_mpc_controller_b200 import scenarios as sc
+from tests import presolve_ref as ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _scene(param_set="soc_work_obst", n_people=2, seed=0):
+    rng = np.random.default_rng(seed)
+    p = sc.make_params(param_set)
+    pose = np.array([[2.0, 2.0 + rng.uniform(-0.2, 0.2), rng.uniform(-0.3, 0.3)]])
+    gpath = sc._straight_path(1, pose[:, 0], np.array([2.0]))
+    poses, cmds = sc.pure_pursuit_seed(gpath, pose, p)
+    people = []
+    for _ in range(n_people):
+        r, b = rng.uniform(0.9, 1.8), rng.uniform(-0.7, 0.7)
+        px, py = pose[0, 0] + r * math.cos(b), pose[0, 1] + r * math.sin(b)
+        h = math.atan2(pose[0, 1] - py, pose[0, 0] - px) + rng.uniform(-0.4, 0.4)
+        v = rng.uniform(0.2, 0.9)
+        people.append([px, py, v * math.cos(h), v * math.sin(h), 0.0])
+    costmap = sc.wall_costmap(80, 80, 0.05, walls_y=(0.6, 3.4))
+    # obstacle-distance grid: nearest wall cell of each cell (walls at rows 12 and 68)
+    W = H = 80
+    rows = np.arange(H)[:, None] * np.ones((1, W), dtype=int)
+    cols = np.ones((H, 1), dtype=int) * np.arange(W)[None, :]
+    near = np.where(np.abs(rows - 12) <= np.abs(rows - 68), 12, 68)
+    od = dict(width=W, height=H, resolution=0.05, origin_x=0.0, origin_y=0.0,
+              distances=(np.abs(rows - near) * 0.05).astype(np.float32).ravel(),
+              indexes=(near * W + cols).astype(np.uint32).ravel())
+    return p, poses[0], cmds[0], np.array(people).reshape(-1, 5), (0.3, 0.05), costmap, od
+
+
+@pytest.fixture()
+def opt_for():
+    from nav2_social_mpc_controller_b200.optimizer import Optimizer
+    made = []
+
+    def _mk(params):
+        o = Optimizer(0)
+        o.initialize(params)
+        made.append(o)
+        return o
+    yield _mk
+    for o in made:
+        o.close()
+
+
+def _reference_tick(oracle, p, poses, cmds, prev, people, speed, costmap, od):
+    init = ref.people_to_status(people)
+    prev_poses, prev_cmds = prev if prev is not None else (poses, cmds)
+    robot, blended = ref.format_to_optimize(poses, cmds, prev_poses, prev_cmds, speed, p.current_path_w,
+                                            p.current_cmds_w, p.max_time, p.time_step)
+    proj = ref.project_people(init, robot, od, p.max_time, p.time_step)
+    batch = ref.build_level1_batch(p, robot, proj, len(people) != 0, costmap, (0.0, 0.0), 0.05, p.time_step)
+    out = oracle.solve_batch(batch)
+    return robot, proj, batch, out
+
+
+@pytest.mark.parametrize("param_set,n_people", [("soc_work_obst", 2), ("readme", 3), ("params_yaml", 1),
+                                                ("obst_only", 0), ("soc_work_obst", 5)])
+def test_optimize_matches_reference_pipeline(oracle, opt_for, param_set, n_people):
+    p, poses, cmds, people, speed, costmap, od = _scene(param_set, n_people, seed=n_people)
+    opt = opt_for(p)
+    ok, path, new_cmds, proj, info = opt.optimize(poses, cmds, people, speed, p.time_step, costmap, (0.0, 0.0), 0.05,
+                                                  od)
+    robot, proj_ref, batch, out = _reference_tick(oracle, p, poses, cmds, None, people, speed, costmap, od)
+    assert proj.shape == (len(robot), 3, 6)
+    assert np.allclose(proj, np.array(proj_ref), rtol=1e-12, atol=1e-12)  # SFM projection, host C++ vs numpy
+    assert ok == bool(out["usable"][0])
+    assert info["termination"] == out["termination"][0] and info["iterations"] == out["iterations"][0]
+    assert info["cost_final"] == pytest.approx(out["cost_final"][0], rel=1e-8)
+    assert np.abs(new_cmds - out["cmds"][0]).max() <= 1e-6
+    assert np.abs(path[:, :2] - out["path"][0][:, :2]).max() <= 1e-6
+    assert np.abs(np.cos(path[:, 2] - out["path"][0][:, 2]) - 1).max() <= 1e-10
+    assert new_cmds.shape[0] == batch.n_steps + 1 and path.shape[0] == batch.n_steps + 1
+
+
+def test_warm_start_memory_blends_previous_solution(oracle, opt_for):
+    """Second tick: previous path / cmds (the first tick's OUTPUT, shifted by one step — SURVEY Q12) are blended
+    with current_cmds_weight 0.5; reset_memory() restores first-call behaviour."""
+    p, poses, cmds, people, speed, costmap, od = _scene("soc_work_obst", 2, seed=5)
+    opt = opt_for(p)
+    ok1, path1, cmds1, _, _ = opt.optimize(poses, cmds, people, speed, p.time_step, costmap, (0.0, 0.0), 0.05, od)
+    assert ok1
+    ok2, path2, cmds2, proj2, info2 = opt.optimize(poses, cmds, people, speed, p.time_step, costmap, (0.0, 0.0), 0.05,
+                                                   od)
+    robot, proj_ref, batch, out = _reference_tick(oracle, p, poses, cmds, (path1.tolist(), cmds1.tolist()), people,
+                                                  speed, costmap, od)
+    # u0 of block 1 is the 0.5/0.5 blend of the seed cmd and the previous optimised cmd (reference :538-547)
+    assert batch.arrays["u0"][0, 1, 0] == pytest.approx(0.5 * cmds[0][0] + 0.5 * cmds1[0][0], rel=1e-14)
+    assert ok2 == bool(out["usable"][0])
+    assert np.abs(cmds2 - out["cmds"][0]).max() <= 1e-6
+    assert info2["cost_final"] == pytest.approx(out["cost_final"][0], rel=1e-8)
+    opt.reset_memory()
+    ok3, path3, cmds3, _, _ = opt.optimize(poses, cmds, people, speed, p.time_step, costmap, (0.0, 0.0), 0.05, od)
+    assert np.array_equal(cmds3, cmds1) and np.array_equal(path3, path1)
+
+
+def test_optimize_failure_modes(opt_for):
+    from nav2_social_mpc_controller_b200 import _lib
+    p, poses, cmds, people, speed, costmap, od = _scene("soc_work_obst", 2, seed=7)
+    opt = opt_for(p)
+    # path with fewer than 2 poses -> false (reference :158-162)
+    ok, *_ = opt.optimize(poses[:1], cmds[:1], people, speed, p.time_step, costmap, (0.0, 0.0), 0.05, od)
+    assert not ok
+    # 100x100 obstacle grid "is NOT valid": every person is dropped -> all projected agents invalid -> Ceres
+    # FAILURE on the NaN proxemics Jacobian -> optimize returns false
+    od100 = dict(od, width=100, height=100, distances=np.zeros(10000, np.float32), indexes=np.zeros(10000, np.uint32))
+    ok, path, new_cmds, proj, info = opt.optimize(poses, cmds, people, speed, p.time_step, costmap, (0.0, 0.0), 0.05,
+                                                  od100)
+    assert not ok and info["termination"] == 6
+    assert np.all(proj[1:, :, 3] == -1.0)
+    # empty obstacle grid -> std::runtime_error in the reference -> call error here
+    bad = dict(od, distances=np.zeros(0, np.float32), indexes=np.zeros(0, np.uint32))
+    with pytest.raises(_lib.SmpcError):
+        opt.optimize(poses, cmds, people, speed, p.time_step, costmap, (0.0, 0.0), 0.05, bad)
