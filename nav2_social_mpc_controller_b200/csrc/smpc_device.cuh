@@ -1113,7 +1113,9 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
         trial = ws + L::kBuf1;
       }
     }
-    if (__all_sync(kFullMask, exhausted)) break;
+    // CTA barrier per evaluation: the warps of a CTA walk the large unrolled evaluation code together and share its
+    // instruction-cache lines (measured +15..40 %); it also ends the loop once every group of the CTA is out of work
+    if (__syncthreads_and(exhausted)) break;
 
     const unsigned fl = evaluate<NB, G>(prm, bt, pb, live, lc0, ws, cand, lane, trial);
     if (!live) continue;

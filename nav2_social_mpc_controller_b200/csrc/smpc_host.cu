@@ -80,6 +80,7 @@ struct smpc_handle {
   bool timed = false;
   int* queue = nullptr;
   long long launches = 0;
+  int forced_warps = 0;  // 0 = pick warps-per-CTA from the batch size; SMPC_WARPS env overrides (4 or 16)
   int forced_group = 0;  // 0 = pick lanes-per-problem from the batch size; SMPC_GROUP env / smpc_set_group override
   std::mutex mu;
   // staging for the host-buffer entry points
@@ -393,6 +394,7 @@ int smpc_create(const smpc_params* p, int device, smpc_handle** out) {
     return cuda_fail(e, "smpc_create resources");
   }
   if (const char* env = std::getenv("SMPC_GROUP")) h->forced_group = std::atoi(env);
+  if (const char* env = std::getenv("SMPC_WARPS")) h->forced_warps = std::atoi(env);
   *out = h;
   return SMPC_OK;
 }
@@ -434,7 +436,7 @@ static int solve_device_locked(smpc_handle* h, const smpc_batch* in, smpc_result
   SMPC_CUDA(cudaSetDevice(h->device));
   SMPC_CUDA(cudaMemsetAsync(h->queue, 0, sizeof(int), stream));
   SMPC_CUDA(cudaEventRecord(h->ev0, stream));
-  SMPC_CUDA(smpc::launch_solve(prm, bt, rs, h->queue, h->n_sm, h->forced_group, stream));
+  SMPC_CUDA(smpc::launch_solve(prm, bt, rs, h->queue, h->n_sm, h->forced_group, h->forced_warps, stream));
   SMPC_CUDA(cudaEventRecord(h->ev1, stream));
   h->timed = true;
   h->launches += 1;

@@ -10,7 +10,7 @@ struct DevResult;
 struct DevEvalOut;
 
 cudaError_t launch_solve(const DevParams& prm, const DevBatch& bt, const DevResult& rs, int* queue, int n_sm,
-                         int forced_group, cudaStream_t stream);
+                         int forced_group, int forced_warps, cudaStream_t stream);
 cudaError_t launch_eval(const DevParams& prm, const DevBatch& bt, const double* x, const DevEvalOut& eo, int n_sm,
                         int forced_group, cudaStream_t stream);
 cudaError_t launch_argmin(int n_robots, int n_starts, int n_blocks, const double* cost_final, const uint8_t* usable,

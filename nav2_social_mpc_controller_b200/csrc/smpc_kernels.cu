@@ -1,5 +1,5 @@
 // smpc_kernels.cu — sm_100a kernels of libsmpc.so and their launchers.
-//   smpc_solve_kernel<NB>    persistent warps pull problems from an atomic queue and run the whole bounded
+//   smpc_solve_kernel<NB,G,W> (smpc_kernels_nb.inc) persistent groups pull problems from an atomic queue and run the whole bounded
 //                            TR-LM solve (replaces ceres::Solve, reference src/optimizer.cpp:381) plus the
 //                            post-solve expansion of reference src/optimizer.cpp:390-446.
 //   smpc_eval_kernel<NB>     one evaluation (cost, J^T r, J^T J) per problem: the parity / first-slice entry.
@@ -9,63 +9,14 @@
 
 namespace smpc {
 
-constexpr int kWarpsPerCta = 4;
+#ifndef SMPC_WARPS_PER_CTA
+#define SMPC_WARPS_PER_CTA 4
+#endif
+constexpr int kWarpsPerCta = SMPC_WARPS_PER_CTA;
 constexpr int kThreads = kWarpsPerCta * 32;
 #ifndef SMPC_MIN_CTAS
-#define SMPC_MIN_CTAS 4
+#define SMPC_MIN_CTAS (16 / SMPC_WARPS_PER_CTA)
 #endif
-
-template <int NB, int G>
-__global__ void __launch_bounds__(kThreads, SMPC_MIN_CTAS) smpc_solve_kernel(DevParams prm, DevBatch bt, DevResult rs, int* queue) {
-  extern __shared__ double smem[];
-  const int lane = threadIdx.x & 31;
-  const int group_in_cta = threadIdx.x / G;
-  double* ws = smem + (size_t)group_in_cta * Layout<NB>::total(bt.S);
-  solve_loop<NB, G>(prm, bt, rs, queue, ws, lane);
-}
-
-template <int NB, int G>
-__global__ void __launch_bounds__(kThreads) smpc_eval_kernel(DevParams prm, DevBatch bt, const double* xin, DevEvalOut eo) {
-  using L = Layout<NB>;
-  constexpr int P = 2 * NB;
-  extern __shared__ double smem[];
-  const int lane = threadIdx.x & 31;
-  const int gl = lane & (G - 1);
-  const unsigned gmask = Group<G>::mask(lane);
-  const int group_in_cta = threadIdx.x / G;
-  double* ws = smem + (size_t)group_in_cta * L::total(bt.S);
-  const int groups_per_cta = kThreads / G;
-  const int n_groups = gridDim.x * groups_per_cta;
-  LaneConst<NB> lc0;
-  lane_setup<NB>(gl, prm.bl, bt.dt, lc0);
-  for (int base = blockIdx.x * groups_per_cta; base < bt.B; base += n_groups) {
-    const int b = base + group_in_cta;
-    const bool live = b < bt.B;
-    Prob pb;
-    pb.x0 = pb.y0 = pb.yaw0 = pb.goal_yaw = pb.fin_x = pb.fin_y = pb.org_x = pb.org_y = 0.0;
-    pb.px = pb.py = pb.agents = nullptr;
-    pb.map = nullptr;
-    pb.has_people = false;
-    if (live) {
-      load_problem(bt, b, pb);
-      agent_angle_setup<NB, G>(bt, pb, lane, ws);
-      for (int c = gl; c < P; c += G) ws[L::kCand + c] = __ldg(xin + (size_t)b * P + c);
-    }
-    __syncwarp(gmask);
-    const unsigned fl = evaluate<NB, G>(prm, bt, pb, live, lc0, ws, ws + L::kCand, lane, ws + L::kBuf0);
-    if (live) {
-      if (gl == 0) {
-        if (eo.cost) eo.cost[b] = ws[L::kBuf0];
-        if (eo.ok) eo.ok[b] = (fl == 0) ? 1 : 0;
-      }
-      if (eo.grad)
-        for (int c = gl; c < P; c += G) eo.grad[(size_t)b * P + c] = ws[L::kBuf0 + 1 + c];
-      if (eo.hess)
-        for (int e = gl; e < L::NH; e += G) eo.hess[(size_t)b * L::NH + e] = ws[L::kBuf0 + 1 + P + e];
-    }
-    __syncwarp(gmask);
-  }
-}
 
 // Line-search polynomial minimiser exposed for unit tests: rows of (lo, hi, f0, g0, t1, f1, g1, t2, f2, g2);
 // t2 <= 0 selects the two-sample (cubic) case.
@@ -137,93 +88,35 @@ __global__ void smpc_argmin_kernel(int n_starts, int n_blocks, const double* __r
 // -------------------------------------------------------------------------------------------------------
 // launchers
 // -------------------------------------------------------------------------------------------------------
-// Lanes per problem: the throughput mapping (G = 4) once the batch alone fills the GPU with warps, wider groups
-// for smaller batches so that every SM sub-partition still has several warps, G = 32 for single-digit batches
-// (lowest latency per solve).
-static int pick_group(int B, int n_sm, int forced) {
-  if (forced == 4 || forced == 8 || forced == 16 || forced == 32) return forced;
-  // G = 4 needs several problems per resident group (4 CTAs x 32 groups per SM) for the queue refill to balance the
-  // very uneven iteration counts; measured on B200: 65536 problems -> G = 4 wins by 1.2-1.6x, 16384 -> G = 32 wins.
-  const long long resident_groups_g4 = (long long)n_sm * 4 * (kThreads / 4);
-  return (B >= 3 * resident_groups_g4) ? 4 : 32;
-}
-
-template <int NB, int G>
-static cudaError_t launch_solve_ng(const DevParams& prm, const DevBatch& bt, const DevResult& rs, int* queue, int n_sm,
-                                   cudaStream_t stream) {
-  const size_t smem = sizeof(double) * (kThreads / G) * Layout<NB>::total(bt.S);
-  cudaError_t e = cudaFuncSetAttribute(smpc_solve_kernel<NB, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  int ctas_per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, smpc_solve_kernel<NB, G>, kThreads, smem);
-  if (e != cudaSuccess) return e;
-  if (ctas_per_sm < 1) return cudaErrorLaunchOutOfResources;
-  // persistent grid: a multiple of the SM count, never more groups than problems
-  const int groups_per_cta = kThreads / G;
-  long long want_ctas = ((long long)bt.B + groups_per_cta - 1) / groups_per_cta;
-  long long grid = (long long)n_sm * ctas_per_sm;
-  if (want_ctas < grid) grid = want_ctas;
-  if (grid < 1) grid = 1;
-  smpc_solve_kernel<NB, G><<<(unsigned)grid, kThreads, smem, stream>>>(prm, bt, rs, queue);
-  return cudaGetLastError();
-}
-
-template <int NB>
-static cudaError_t launch_solve_nb(const DevParams& prm, const DevBatch& bt, const DevResult& rs, int* queue, int n_sm,
-                                   int forced_group, cudaStream_t stream) {
-  switch (pick_group(bt.B, n_sm, forced_group)) {
-    case 4: return launch_solve_ng<NB, 4>(prm, bt, rs, queue, n_sm, stream);
-    case 8: return launch_solve_ng<NB, 8>(prm, bt, rs, queue, n_sm, stream);
-    case 16: return launch_solve_ng<NB, 16>(prm, bt, rs, queue, n_sm, stream);
-    default: return launch_solve_ng<NB, 32>(prm, bt, rs, queue, n_sm, stream);
-  }
-}
-
-template <int NB, int G>
-static cudaError_t launch_eval_ng(const DevParams& prm, const DevBatch& bt, const double* x, const DevEvalOut& eo, int n_sm,
-                                  cudaStream_t stream) {
-  const size_t smem = sizeof(double) * (kThreads / G) * Layout<NB>::total(bt.S);
-  cudaError_t e = cudaFuncSetAttribute(smpc_eval_kernel<NB, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  const int groups_per_cta = kThreads / G;
-  long long want_ctas = ((long long)bt.B + groups_per_cta - 1) / groups_per_cta;
-  long long grid = (long long)n_sm * 4;
-  if (want_ctas < grid) grid = want_ctas;
-  if (grid < 1) grid = 1;
-  smpc_eval_kernel<NB, G><<<(unsigned)grid, kThreads, smem, stream>>>(prm, bt, x, eo);
-  return cudaGetLastError();
-}
-
-template <int NB>
-static cudaError_t launch_eval_nb(const DevParams& prm, const DevBatch& bt, const double* x, const DevEvalOut& eo, int n_sm,
-                                  int forced_group, cudaStream_t stream) {
-  switch (pick_group(bt.B, n_sm, forced_group)) {
-    case 4: return launch_eval_ng<NB, 4>(prm, bt, x, eo, n_sm, stream);
-    case 8: return launch_eval_ng<NB, 8>(prm, bt, x, eo, n_sm, stream);
-    case 16: return launch_eval_ng<NB, 16>(prm, bt, x, eo, n_sm, stream);
-    default: return launch_eval_ng<NB, 32>(prm, bt, x, eo, n_sm, stream);
-  }
-}
-
-#define SMPC_DISPATCH_NB(FN, ...)                  \
-  switch (prm.nb) {                                \
-    case 1: return FN<1>(__VA_ARGS__);             \
-    case 2: return FN<2>(__VA_ARGS__);             \
-    case 3: return FN<3>(__VA_ARGS__);             \
-    case 4: return FN<4>(__VA_ARGS__);             \
-    case 5: return FN<5>(__VA_ARGS__);             \
-    case 6: return FN<6>(__VA_ARGS__);             \
-    default: return cudaErrorInvalidValue;         \
-  }
+#define SMPC_DECL_NB(k)                                                                                              \
+  cudaError_t launch_solve_nb##k(const DevParams&, const DevBatch&, const DevResult&, int*, int, int, int, cudaStream_t); \
+  cudaError_t launch_eval_nb##k(const DevParams&, const DevBatch&, const double*, const DevEvalOut&, int, int, cudaStream_t);
+SMPC_DECL_NB(1) SMPC_DECL_NB(2) SMPC_DECL_NB(3) SMPC_DECL_NB(4) SMPC_DECL_NB(5) SMPC_DECL_NB(6)
 
 cudaError_t launch_solve(const DevParams& prm, const DevBatch& bt, const DevResult& rs, int* queue, int n_sm,
-                         int forced_group, cudaStream_t stream) {
-  SMPC_DISPATCH_NB(launch_solve_nb, prm, bt, rs, queue, n_sm, forced_group, stream)
+                         int forced_group, int forced_warps, cudaStream_t stream) {
+  switch (prm.nb) {
+    case 1: return launch_solve_nb1(prm, bt, rs, queue, n_sm, forced_group, forced_warps, stream);
+    case 2: return launch_solve_nb2(prm, bt, rs, queue, n_sm, forced_group, forced_warps, stream);
+    case 3: return launch_solve_nb3(prm, bt, rs, queue, n_sm, forced_group, forced_warps, stream);
+    case 4: return launch_solve_nb4(prm, bt, rs, queue, n_sm, forced_group, forced_warps, stream);
+    case 5: return launch_solve_nb5(prm, bt, rs, queue, n_sm, forced_group, forced_warps, stream);
+    case 6: return launch_solve_nb6(prm, bt, rs, queue, n_sm, forced_group, forced_warps, stream);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 cudaError_t launch_eval(const DevParams& prm, const DevBatch& bt, const double* x, const DevEvalOut& eo, int n_sm,
                         int forced_group, cudaStream_t stream) {
-  SMPC_DISPATCH_NB(launch_eval_nb, prm, bt, x, eo, n_sm, forced_group, stream)
+  switch (prm.nb) {
+    case 1: return launch_eval_nb1(prm, bt, x, eo, n_sm, forced_group, stream);
+    case 2: return launch_eval_nb2(prm, bt, x, eo, n_sm, forced_group, stream);
+    case 3: return launch_eval_nb3(prm, bt, x, eo, n_sm, forced_group, stream);
+    case 4: return launch_eval_nb4(prm, bt, x, eo, n_sm, forced_group, stream);
+    case 5: return launch_eval_nb5(prm, bt, x, eo, n_sm, forced_group, stream);
+    case 6: return launch_eval_nb6(prm, bt, x, eo, n_sm, forced_group, stream);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 cudaError_t launch_argmin(int n_robots, int n_starts, int n_blocks, const double* cost_final, const uint8_t* usable,
