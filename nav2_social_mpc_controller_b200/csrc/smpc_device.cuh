@@ -90,6 +90,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 struct PairOut {
   double fx, fy;
   double dfx[4], dfy[4];
+  bool degenerate;  // theta came from the reference's two-atan2 branch (the pair is then not odd in (d, w))
 };
 
 __device__ __forceinline__ double wrap_to_pi(double a) {
@@ -122,7 +123,8 @@ __device__ __forceinline__ void social_pair(double dx, double dy, double wx, dou
   // at theta = 0 and +-pi and the reference's own rounding decides the branch, so its formulation is used verbatim.
   const double cross = ey * ix - ex * iy, dot = ex * ix + ey * iy;
   double theta;
-  if (fabs(cross) > 1e-9) {
+  o.degenerate = tiny || !(fabs(cross) > 1e-9);  // the coincident-position fix-up is not odd in d either
+  if (!o.degenerate) {
     theta = atan2(cross, dot);
   } else {
     theta = wrap_to_pi(atan2(ey, ex) - atan2(iy, ix));
@@ -448,25 +450,30 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
             double sa, ca;
             sincos(ayaw, &sa, &ca);
             const double avx = alv * ca, avy = alv * sa;
-            // role 0: agent k (also a padded one) <- robot (d and w change sign);
-            // role 1: robot <- agent k (valid agents only). One inlined call site keeps the code small.
-#pragma unroll 1
-            for (int role = 0; role < (valid ? 2 : 1); ++role) {
-              const double sg = role ? 1.0 : -1.0;
-              PairOut po;
-              social_pair(sg * ddx, sg * ddy, sg * (rvx - avx), sg * (rvy - avy), po);
-              if (role) {
-                Frx += po.fx;
-                Fry += po.fy;
-                SMPC_UNROLL for (int c = 0; c < 4; ++c) {
-                  JFx[c] += po.dfx[c];
-                  JFy[c] += po.dfy[c];
-                }
-              } else {
-                wp += po.fx * po.fx + po.fy * po.fy;
-                SMPC_UNROLL for (int c = 0; c < 4; ++c) G4[c] -= 2.0 * (po.fx * po.dfx[c] + po.fy * po.dfy[c]);
+            // F(robot <- agent k) = pair(d, w) with d = robot - agent, w = v_robot - v_agent, and
+            // F(agent k <- robot) = pair(-d, -w). The pair function is odd, pair(-d, -w) = -pair(d, w) (e, I and
+            // their unit vectors flip, theta / B / |d| do not), so ONE evaluation serves both terms of the
+            // residual; only the near-degenerate branch (reference rounding decides theta = +-pi / 0) is evaluated
+            // per role. Padded agents only have the agent <- robot term.
+            PairOut po;
+            social_pair(ddx, ddy, rvx - avx, rvy - avy, po);
+            if (valid) {
+              Frx += po.fx;
+              Fry += po.fy;
+              SMPC_UNROLL for (int c = 0; c < 4; ++c) {
+                JFx[c] += po.dfx[c];
+                JFy[c] += po.dfy[c];
               }
             }
+            if (po.degenerate) {
+              social_pair(-ddx, -ddy, avx - rvx, avy - rvy, po);  // d(-d)/dX = -1: the gradient changes sign
+              SMPC_UNROLL for (int c = 0; c < 4; ++c) {
+                po.dfx[c] = -po.dfx[c];
+                po.dfy[c] = -po.dfy[c];
+              }
+            }
+            wp += po.fx * po.fx + po.fy * po.fy;
+            SMPC_UNROLL for (int c = 0; c < 4; ++c) G4[c] += 2.0 * (po.fx * po.dfx[c] + po.fy * po.dfy[c]);
           }
         }
         if (do_social) {
