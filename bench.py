@@ -50,20 +50,23 @@ WORKLOADS = {
                                 "scenarios with the reference's 3 agents", False),
     "multistart_256x1024": (lambda: sc.multistart(256, 1024), "BASELINE configs[3]: 1024 perturbed starts x 256 robots, "
                             "A=3, per-robot arg-min", False),
-    "crowd_x131072_A50": (lambda: sc.crowd(B=131072, A=50, config_id=5), "BASELINE configs[4] slice: 131072 problems, "
-                          "50 agents (per-GPU shard of the 10^6 sweep)", False),
+    "crowd_x16384_A50": (lambda: sc.crowd(B=16384, A=50, config_id=5), "BASELINE configs[4] slice: 16384 problems, "
+                         "50 agents, S=28, P=6 (a 1.1 GB slice of one GPU's shard of the 10^6 sweep)", False),
 }
 CPU_SAMPLE = {"obst_only_x4096": 768, "soc_work_obst_x65536_A20": 96, "soc_work_obst_x16384_A3": 256,
               "obst_only_x65536": (lambda: sc.corridor(B=65536, unique_maps=False, config_id=22), "obst_only params, 65536 corridor "
                          "scenarios, 256 shared costmaps (throughput-mode check)", False),
     "soc_work_obst_x65536_A3": (lambda: sc.crowd(B=65536, A=3, config_id=23), "soc_work_obst params, 65536 crowd "
                                 "scenarios with the reference's 3 agents", False),
-    "multistart_256x1024": 256, "crowd_x131072_A50": 48}
+    "multistart_256x1024": 256, "crowd_x16384_A50": 48, "obst_only_x65536": 768,
+              "soc_work_obst_x65536_A3": 256}
 
 
 def flops_per_solve(S, P, A_eff, m, n_jac, n_cost, iters):
-    """SURVEY §8d algorithmic FLOPs: F_solve = n_J F_jac + n_c F_cost + K F_lin."""
-    f_jac = S * (224 + 29 * P + 810 * A_eff) + 2 * m * (P * (P + 1) / 2 + P)
+    """SURVEY §8d algorithmic FLOPs: F_solve = n_J F_jac + n_c F_cost + K F_lin. The per-agent term is 410 instead of
+    SURVEY's a-priori 810: the social pair function is odd, so the minimal algorithm needs ONE pair interaction
+    (~400 FLOPs with its 2x4 Jacobian) per agent and step, not two."""
+    f_jac = S * (224 + 29 * P + 410 * A_eff) + 2 * m * (P * (P + 1) / 2 + P)
     f_cost = S * (120 + 170 * A_eff)
     f_lin = P ** 3 / 3 + 2 * P ** 2 + 4 * P
     return n_jac * f_jac + n_cost * f_cost + iters * f_lin

@@ -92,6 +92,8 @@ __global__ void smpc_argmin_kernel(int n_starts, int n_blocks, const double* __r
   cudaError_t launch_solve_nb##k(const DevParams&, const DevBatch&, const DevResult&, int*, int, int, int, cudaStream_t); \
   cudaError_t launch_eval_nb##k(const DevParams&, const DevBatch&, const double*, const DevEvalOut&, int, int, cudaStream_t);
 SMPC_DECL_NB(1) SMPC_DECL_NB(2) SMPC_DECL_NB(3) SMPC_DECL_NB(4) SMPC_DECL_NB(5) SMPC_DECL_NB(6)
+SMPC_DECL_NB(7) SMPC_DECL_NB(8) SMPC_DECL_NB(9) SMPC_DECL_NB(10) SMPC_DECL_NB(11) SMPC_DECL_NB(12)
+SMPC_DECL_NB(13) SMPC_DECL_NB(14) SMPC_DECL_NB(15) SMPC_DECL_NB(16) SMPC_DECL_NB(17) SMPC_DECL_NB(18)
 
 cudaError_t launch_solve(const DevParams& prm, const DevBatch& bt, const DevResult& rs, int* queue, int n_sm,
                          int forced_group, int forced_warps, cudaStream_t stream) {
@@ -102,6 +104,18 @@ cudaError_t launch_solve(const DevParams& prm, const DevBatch& bt, const DevResu
     case 4: return launch_solve_nb4(prm, bt, rs, queue, n_sm, forced_group, forced_warps, stream);
     case 5: return launch_solve_nb5(prm, bt, rs, queue, n_sm, forced_group, forced_warps, stream);
     case 6: return launch_solve_nb6(prm, bt, rs, queue, n_sm, forced_group, forced_warps, stream);
+    case 7: return launch_solve_nb7(prm, bt, rs, queue, n_sm, forced_group, forced_warps, stream);
+    case 8: return launch_solve_nb8(prm, bt, rs, queue, n_sm, forced_group, forced_warps, stream);
+    case 9: return launch_solve_nb9(prm, bt, rs, queue, n_sm, forced_group, forced_warps, stream);
+    case 10: return launch_solve_nb10(prm, bt, rs, queue, n_sm, forced_group, forced_warps, stream);
+    case 11: return launch_solve_nb11(prm, bt, rs, queue, n_sm, forced_group, forced_warps, stream);
+    case 12: return launch_solve_nb12(prm, bt, rs, queue, n_sm, forced_group, forced_warps, stream);
+    case 13: return launch_solve_nb13(prm, bt, rs, queue, n_sm, forced_group, forced_warps, stream);
+    case 14: return launch_solve_nb14(prm, bt, rs, queue, n_sm, forced_group, forced_warps, stream);
+    case 15: return launch_solve_nb15(prm, bt, rs, queue, n_sm, forced_group, forced_warps, stream);
+    case 16: return launch_solve_nb16(prm, bt, rs, queue, n_sm, forced_group, forced_warps, stream);
+    case 17: return launch_solve_nb17(prm, bt, rs, queue, n_sm, forced_group, forced_warps, stream);
+    case 18: return launch_solve_nb18(prm, bt, rs, queue, n_sm, forced_group, forced_warps, stream);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -115,6 +129,18 @@ cudaError_t launch_eval(const DevParams& prm, const DevBatch& bt, const double* 
     case 4: return launch_eval_nb4(prm, bt, x, eo, n_sm, forced_group, stream);
     case 5: return launch_eval_nb5(prm, bt, x, eo, n_sm, forced_group, stream);
     case 6: return launch_eval_nb6(prm, bt, x, eo, n_sm, forced_group, stream);
+    case 7: return launch_eval_nb7(prm, bt, x, eo, n_sm, forced_group, stream);
+    case 8: return launch_eval_nb8(prm, bt, x, eo, n_sm, forced_group, stream);
+    case 9: return launch_eval_nb9(prm, bt, x, eo, n_sm, forced_group, stream);
+    case 10: return launch_eval_nb10(prm, bt, x, eo, n_sm, forced_group, stream);
+    case 11: return launch_eval_nb11(prm, bt, x, eo, n_sm, forced_group, stream);
+    case 12: return launch_eval_nb12(prm, bt, x, eo, n_sm, forced_group, stream);
+    case 13: return launch_eval_nb13(prm, bt, x, eo, n_sm, forced_group, stream);
+    case 14: return launch_eval_nb14(prm, bt, x, eo, n_sm, forced_group, stream);
+    case 15: return launch_eval_nb15(prm, bt, x, eo, n_sm, forced_group, stream);
+    case 16: return launch_eval_nb16(prm, bt, x, eo, n_sm, forced_group, stream);
+    case 17: return launch_eval_nb17(prm, bt, x, eo, n_sm, forced_group, stream);
+    case 18: return launch_eval_nb18(prm, bt, x, eo, n_sm, forced_group, stream);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -128,7 +154,7 @@ cudaError_t launch_argmin(int n_robots, int n_starts, int n_blocks, const double
   return cudaGetLastError();
 }
 
-int max_supported_blocks() { return 6; }
+int max_supported_blocks() { return 18; }
 
 cudaError_t launch_polymin(int n, const double* in, double* out, cudaStream_t stream) {
   smpc_polymin_kernel<<<(n + 127) / 128, 128, 0, stream>>>(n, in, out);

@@ -265,3 +265,25 @@ def test_exact_head_on_and_degenerate_social_geometry(oracle, make_opt):
     assert bool(got["ok"][0]) == e["ok"]
     assert got["cost"][0] == pytest.approx(e["cost"], rel=1e-11)
     assert np.abs(got["grad"][0] - e["grad"]).max() <= 1e-9 * max(1.0, np.abs(e["grad"]).max())
+
+
+@pytest.mark.parametrize("ch,bl,nb", [(18, 1, 18), (18, 2, 9), (12, 1, 12), (14, 2, 7)])
+def test_many_parameter_blocks_up_to_the_36_parameter_class(oracle, make_opt, ch, bl, nb):
+    """SURVEY §8 size table, last row: parameter_block_length 1 with control_horizon 18 gives 18 blocks = 36
+    parameters (the '36x36-class' normal equations); 7..18 blocks run on the 32-lane mapping."""
+    from nav2_social_mpc_controller_b200.optimizer import hess_to_dense
+    batch = sc.crowd(B=6, A=3, config_id=31, control_horizon=ch, parameter_block_length=bl)
+    assert batch.n_blocks == nb
+    opt = make_opt(batch.params)
+    P = 2 * nb
+    x = batch.arrays["u0"].reshape(6, P) + 0.01
+    got = opt.eval_batch(batch, x)
+    H = hess_to_dense(got["hess"], P)
+    for b in range(2):
+        e = oracle.evaluate(batch, b, x[b])
+        assert got["cost"][b] == pytest.approx(e["cost"], rel=1e-11)
+        H_ref = e["jac"].T @ e["jac"]
+        assert np.abs(H[b] - H_ref).max() <= 1e-9 * np.abs(H_ref).max()
+        assert np.abs(got["grad"][b] - e["grad"]).max() <= 1e-9 * np.abs(e["grad"]).max()
+    r = _compare_solves(oracle, opt, batch)
+    assert r["ok"].mean() >= 0.8, (r["du"], r["dc"], r["got"]["termination"], r["ref"]["termination"])
