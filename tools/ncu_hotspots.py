@@ -39,8 +39,14 @@ for op, n in ops.most_common(18):
     print(f"{op:10s} {100*n/tot:5.1f}% inst  {100*sm[op]/tots:5.1f}% samples")
 with tempfile.TemporaryDirectory() as td:
     subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=td, capture_output=True)
-    sass = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(td, "smpc_kernels.sm_100a.cubin")],
-                          capture_output=True, text=True).stdout.split("\n")
+    sass = []
+    for cub in sorted(os.listdir(td)):
+        if not cub.endswith(".cubin"):
+            continue
+        txt = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(td, cub)], capture_output=True, text=True).stdout
+        if kern in txt:
+            sass = txt.split("\n")
+            break
 start = [i for i, l in enumerate(sass) if l.startswith("\t.section\t.text.") and kern in l][0]
 end = [i for i, l in enumerate(sass) if i > start and l.startswith("\t.section")][0]
 cur, seq = None, {}
@@ -59,7 +65,7 @@ for addr, n, s, _ in data:
     agg[key] += n
     aggs[key] += s
 src = {}
-for fn in ("smpc_device.cuh", "smpc_kernels.cu"):
+for fn in ("smpc_device.cuh", "smpc_kernels.cu", "smpc_kernels_nb.inc"):
     src[fn] = open(os.path.join(root, "nav2_social_mpc_controller_b200", "csrc", fn)).read().split("\n")
 print("--- source lines")
 for (fn, ln), n in agg.most_common(top):
