@@ -79,37 +79,59 @@ def n_residuals(batch):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed regions (B200_PROFILING.md recipe): one long-running
+    `nvidia-smi -lms 50` process, every line time-stamped; summary() keeps the samples inside the marked windows."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
         self.samples = []
-        self.stop_flag = threading.Event()
+        self.windows = []
+        self.proc = None
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                parts = [s.strip() for s in out.stdout.strip().split(",")]
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                parts = [x.strip() for x in line.strip().split(",")]
                 if len(parts) >= 7:
-                    self.samples.append(parts)
-            except Exception:
-                pass
-            self.stop_flag.wait(0.1)
+                    self.samples.append((time.perf_counter(), parts))
+        except Exception:
+            pass
+
+    def mark(self, t0, t1):
+        self.windows.append((t0, t1))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
 
     def summary(self):
-        if not self.samples:
+        inside = [p for (t, p) in self.samples if any(a <= t <= b for a, b in self.windows)]
+        used = inside if inside else [p for _, p in self.samples]
+        if not used:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        sm = sorted(float(x[0]) for x in used if x[0].replace(".", "").isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]),
-                "reasons": reasons, "samples": len(self.samples)}
+        reasons = [n for i, n in enumerate(names) if any(x[3 + i].lower().startswith("active") for x in used)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(used[0][1]), "reasons": reasons,
+                "samples_in_timed_regions": len(inside), "samples_total": len(self.samples)}
+
+
+def load_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the solve kernel, per launch, from the committed
+    `ncu --set full` capture of this workload (profiles/r01_traffic.json); None when no capture exists."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get(workload)
+    return None
 
 
 def load_peaks():
@@ -171,7 +193,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="obst_only_x4096", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -237,9 +259,11 @@ def main():
         dist.barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    time.sleep(0.15)
     launches0 = opt.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     torch.cuda.synchronize()
+    t_region0 = time.perf_counter()
     with torch.cuda.stream(stream):
         for s in range(args.steps):
             flush.fill_(s & 0xFF)  # L2 flush between timed iterations (outside the event pair)
@@ -247,6 +271,7 @@ def main():
             step_device()
             ev[s][1].record(stream)
     torch.cuda.synchronize()
+    sampler.mark(t_region0, time.perf_counter())
     launches = opt.launch_count() - launches0
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(step_ms))
@@ -263,6 +288,7 @@ def main():
     if world > 1:
         dist.barrier()
     e2e_t = []
+    t_region0 = time.perf_counter()
     for s in range(args.steps):
         flush.fill_(s & 0xFF)
         torch.cuda.synchronize()
@@ -270,7 +296,9 @@ def main():
         opt.solve_batch(hbatch, out=host_out)
         e2e_t.append(time.perf_counter() - t0)
     e2e_total = float(sum(e2e_t))
-    sampler.stop_flag.set()
+    sampler.mark(t_region0, time.perf_counter())
+    time.sleep(0.06)
+    sampler.stop()
     sampler.join(timeout=2)
     h2d = int(sum(v.nbytes for v in host_np.values() if v is not None))
     d2h = int(sum(v.nbytes for v in host_out.values()))
@@ -316,7 +344,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved_tflops / fp64_peak if fp64_peak > 0 else None, "traffic": None,
+                         "frac": achieved_tflops / fp64_peak if fp64_peak > 0 else None,
+                         "traffic": load_traffic(args.workload),
                          "kernel": f"smpc_solve_kernel<{nb}>", "kernel_ms": k_ms,
                          "peak_source": "DFMA microbenchmark measured in this run (smpc_measure_fp64_peak); "
                                         "MEASURED_PEAKS.json has no FP64 entry",

@@ -267,7 +267,9 @@ struct Layout {
   static constexpr int kCand = kDelta + P;
   static constexpr int kCarry = kCand + P;
   static constexpr int kYaw = kCarry + NC;  // sin, cos of yaw0
-  static constexpr int kAa = kYaw + 2;  // agent-angle steering target per step [S]
+  static constexpr int kState = kYaw + 2;    // LmState (solver scalars parked here across the evaluation)
+  static constexpr int kProb = kState + 20;  // Prob (group-uniform problem view)
+  static constexpr int kAa = kProb + 13;  // agent-angle steering target per step [S]
   __host__ __device__ static constexpr int total(int S) { return ((kAa + S) | 1); }  // odd stride: no bank conflicts
   __host__ __device__ static constexpr int g(int c) { return 1 + c; }
   __host__ __device__ static constexpr int h(int a, int b) { return 1 + P + a * (a + 1) / 2 + b; }
@@ -1052,6 +1054,19 @@ __device__ __forceinline__ void expand_outputs(const DevParams& prm, const DevBa
 // ---------------------------------------------------------------------------------------------------
 enum Phase { kFetch = 0, kInit = 1, kLineSearch = 2, kFullStep = 3 };
 
+// Solver scalars of one group. They live in shared memory across the evaluation (which needs every register
+// for the FP64 math) and are loaded into registers only for the short phase logic after it.
+struct LmState {
+  double x_cost, x_norm, gmax, radius, decrease_factor, minimum_cost, it_cost, cost_initial, cost_final,
+      model_cost_change, g0, dmax, t, prev_x, prev_value, prev_gradient;
+  int iteration, n_invalid, n_eval, ls_iters, term, phase, b, flags;
+};
+static_assert(sizeof(LmState) == 20 * sizeof(double), "Layout::kState reserves 20 doubles");
+static_assert(sizeof(Prob) <= 13 * sizeof(double), "Layout::kProb reserves 13 doubles");
+enum StateFlags {
+  kReuseDiagonal = 1, kItSuccessful = 2, kAnySuccess = 4, kPrevOk = 8, kLive = 16, kExhausted = 32, kSwapped = 64
+};
+
 template <int NB, int G>
 __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch& bt, const DevResult& rs, int* queue,
                                            double* ws, int lane) {
@@ -1066,75 +1081,78 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
   double* diag = ws + L::kDiag;
   double* delta = ws + L::kDelta;
   double* cand = ws + L::kCand;
-  double* cur = ws + L::kBuf0;    // normal equations at x
-  double* trial = ws + L::kBuf1;  // normal equations at the trial point
+  LmState* gs = reinterpret_cast<LmState*>(ws + L::kState);
+  Prob* pbs = reinterpret_cast<Prob*>(ws + L::kProb);
 
   LaneConst<NB> lc0;
   lane_setup<NB>(gl, prm.bl, bt.dt, lc0);
-  Prob pb;
-  pb.x0 = pb.y0 = pb.yaw0 = pb.goal_yaw = pb.fin_x = pb.fin_y = pb.org_x = pb.org_y = 0.0;
-  pb.px = pb.py = pb.agents = nullptr;
-  pb.map = nullptr;
-  pb.has_people = false;
-  int b = -1;
-  bool live = false, exhausted = false;
-
-  int phase = kFetch;
-  int term = kNoConvergence;
-  int iteration = 0, n_invalid = 0, n_eval = 0, ls_iters = 0;
-  double x_cost = 0.0, x_norm = 0.0, gmax = 0.0, radius = 1e4, decrease_factor = 2.0, minimum_cost = DBL_MAX;
-  double it_cost = 0.0, cost_initial = 0.0, cost_final = 0.0, model_cost_change = 0.0, g0 = 0.0, dmax = 0.0, t = 1.0;
-  bool reuse_diagonal = false, it_successful = true, any_success = false;
-  LsSample prev{0.0, 0.0, 0.0, false};
+  if (gl == 0) {
+    gs->phase = kFetch;
+    gs->flags = 0;
+    gs->b = -1;
+  }
+  __syncwarp(gmask);
 
   for (;;) {
-    if (phase == kFetch && !exhausted) {
+    if (gs->phase == kFetch && !(gs->flags & kExhausted)) {
       int nb_ = 0;
       if (gl == 0) nb_ = atomicAdd(queue, 1);
       nb_ = __shfl_sync(gmask, nb_, 0, G);
+      __syncwarp(gmask);
       if (nb_ >= bt.B) {
-        exhausted = true;
-        live = false;
+        if (gl == 0) gs->flags = kExhausted;
       } else {
-        b = nb_;
-        live = true;
-        load_problem(bt, b, pb);
+        if (gl == 0) load_problem(bt, nb_, *pbs);
         __syncwarp(gmask);
-        agent_angle_setup<NB, G>(bt, pb, lane, ws);
+        agent_angle_setup<NB, G>(bt, *pbs, lane, ws);
         // IterationZero: project the start point onto the box
         for (int c = gl; c < P; c += G) {
-          const double v = __ldg(bt.u0 + (size_t)b * P + c);
+          const double v = __ldg(bt.u0 + (size_t)nb_ * P + c);
           xs[c] = v;
           best[c] = v;
           cand[c] = project_param(v, c, nbd);
         }
-        __syncwarp(gmask);
-        phase = kInit;
-        term = kNoConvergence;
-        iteration = 0; n_invalid = 0; n_eval = 0; ls_iters = 0;
-        x_cost = 0.0; x_norm = 0.0; gmax = 0.0; radius = 1e4; decrease_factor = 2.0; minimum_cost = DBL_MAX;
-        it_cost = 0.0; cost_initial = 0.0; cost_final = 0.0; model_cost_change = 0.0; g0 = 0.0; dmax = 0.0; t = 1.0;
-        reuse_diagonal = false; it_successful = true; any_success = false;
-        prev.ok = false;
-        cur = ws + L::kBuf0;
-        trial = ws + L::kBuf1;
+        if (gl == 0) {
+          LmState z;
+          z.x_cost = z.x_norm = z.gmax = 0.0;
+          z.radius = 1e4;
+          z.decrease_factor = 2.0;
+          z.minimum_cost = DBL_MAX;
+          z.it_cost = z.cost_initial = z.cost_final = z.model_cost_change = z.g0 = z.dmax = 0.0;
+          z.t = 1.0;
+          z.prev_x = z.prev_value = z.prev_gradient = 0.0;
+          z.iteration = z.n_invalid = z.n_eval = z.ls_iters = 0;
+          z.term = kNoConvergence;
+          z.phase = kInit;
+          z.b = nb_;
+          z.flags = kLive | kItSuccessful;
+          *gs = z;
+        }
       }
+      __syncwarp(gmask);
     }
     // CTA barrier per evaluation: the warps of a CTA walk the large unrolled evaluation code together and share its
     // instruction-cache lines (measured +15..40 %); it also ends the loop once every group of the CTA is out of work
-    if (__syncthreads_and(exhausted)) break;
+    if (__syncthreads_and((gs->flags & kExhausted) != 0)) break;
 
-    const unsigned fl = evaluate<NB, G>(prm, bt, pb, live, lc0, ws, cand, lane, trial);
+    const bool live = (gs->flags & kLive) != 0;
+    double* cur = ws + ((gs->flags & kSwapped) ? L::kBuf1 : L::kBuf0);    // normal equations at x
+    double* trial = ws + ((gs->flags & kSwapped) ? L::kBuf0 : L::kBuf1);  // normal equations at the trial point
+    const unsigned fl = evaluate<NB, G>(prm, bt, *pbs, live, lc0, ws, cand, lane, trial);
     if (!live) continue;
-    ++n_eval;
-    const double t_cost = trial[0];
-    bool take_step = false;  // proceed to accept/reject with `cand`
-    bool finished = false;   // the solve of this problem has terminated
 
-    if (phase == kInit) {
-      cost_initial = cost_final = t_cost;
+    // ---- phase logic on register copies of the group state -------------------------------------------------
+    LmState st = *gs;
+    ++st.n_eval;
+    const double t_cost = trial[0];
+    bool take_step = false;   // proceed to accept/reject with `cand`
+    bool finished = false;    // the solve of this problem has terminated
+    bool next_sample = false; // another line-search sample has been set up in `cand`
+
+    if (st.phase == kInit) {
+      st.cost_initial = st.cost_final = t_cost;
       if (fl) {
-        term = kFailEvaluation;
+        st.term = kFailEvaluation;
         finished = true;
       } else {
         // x <- projected seed; cur <- trial; Jacobi scaling from the column norms (= sqrt of diag(J^T J))
@@ -1143,51 +1161,54 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
           scale[c] = 1.0 / (1.0 + sqrt(trial[L::h(0, 0) + c * (c + 1) / 2 + c]));
         }
         __syncwarp(gmask);
+        st.flags ^= kSwapped;
         { double* tmp = cur; cur = trial; trial = tmp; }
-        x_cost = t_cost;
-        it_cost = x_cost;
-        it_successful = true;
+        st.x_cost = t_cost;
+        st.it_cost = t_cost;
+        st.flags |= kItSuccessful;
       }
-    } else if (phase == kLineSearch) {
+    } else if (st.phase == kLineSearch) {
       // Armijo sufficient decrease at step t along delta (projected)
       const bool sample_ok = (fl == 0);
       double gd = 0.0;
       SMPC_UNROLL for (int c = 0; c < P; ++c) gd += delta[c] * trial[L::g(c)];
-      if (sample_ok && !(t_cost > x_cost + 1e-4 * g0 * t)) {
+      if (sample_ok && !(t_cost > st.x_cost + 1e-4 * st.g0 * st.t)) {
         take_step = true;  // success: delta <- t * delta, candidate = this trial point
       } else {
-        ++ls_iters;
-        bool ls_failed = ls_iters >= 20;
-        double t_new = t;
+        ++st.ls_iters;
+        bool ls_failed = st.ls_iters >= 20;
+        double t_new = st.t;
         if (!ls_failed) {
-          const double lo = 1e-3 * t, hi = 0.6 * t;
+          const double lo = 1e-3 * st.t, hi = 0.6 * st.t;
           if (!sample_ok) {
-            t_new = fmin(fmax(t * 0.5, lo), hi);
-          } else if (prev.ok) {
-            t_new = quintic_interp_min(x_cost, g0, t, t_cost, gd, prev.x, prev.value, prev.gradient, lo, hi);
+            t_new = fmin(fmax(st.t * 0.5, lo), hi);
+          } else if (st.flags & kPrevOk) {
+            t_new = quintic_interp_min(st.x_cost, st.g0, st.t, t_cost, gd, st.prev_x, st.prev_value, st.prev_gradient,
+                                       lo, hi);
           } else {
-            t_new = cubic_interp_min(x_cost, g0, t, t_cost, gd, lo, hi);
+            t_new = cubic_interp_min(st.x_cost, st.g0, st.t, t_cost, gd, lo, hi);
           }
-          if (t_new * dmax < 1e-9) ls_failed = true;
+          if (t_new * st.dmax < 1e-9) ls_failed = true;
         }
         if (!ls_failed) {
-          prev = LsSample{t, t_cost, gd, sample_ok};
-          t = t_new;
+          st.prev_x = st.t;
+          st.prev_value = t_cost;
+          st.prev_gradient = gd;
+          st.flags = sample_ok ? (st.flags | kPrevOk) : (st.flags & ~kPrevOk);
+          st.t = t_new;
           __syncwarp(gmask);
-          for (int c = gl; c < P; c += G) cand[c] = project_param(xs[c] + t * delta[c], c, nbd);
-          __syncwarp(gmask);
-          continue;  // evaluate the next line-search sample
-        }
-        // line search failed: the un-shortened TR step is the candidate (delta unchanged)
-        if (t != 1.0) {
-          t = 1.0;
+          for (int c = gl; c < P; c += G) cand[c] = project_param(xs[c] + t_new * delta[c], c, nbd);
+          next_sample = true;  // evaluate the next line-search sample
+        } else if (st.t != 1.0) {
+          // line search failed: the un-shortened TR step is the candidate (delta unchanged)
+          st.t = 1.0;
           __syncwarp(gmask);
           for (int c = gl; c < P; c += G) cand[c] = project_param(xs[c] + delta[c], c, nbd);
-          __syncwarp(gmask);
-          phase = kFullStep;
-          continue;
+          st.phase = kFullStep;
+          next_sample = true;
+        } else {
+          take_step = true;  // t is still 1: this trial IS Plus(x, delta)
         }
-        take_step = true;  // t is still 1: this trial IS Plus(x, delta)
       }
     } else {  // kFullStep: evaluation of Plus(x, delta) after a failed line search
       take_step = true;
@@ -1195,91 +1216,91 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
 
     if (take_step) {
       const double cand_cost = (fl & kResidualBad) ? DBL_MAX : t_cost;
-      const bool tol_armed = (prm.ceres_compat < 210) || any_success;
+      const bool tol_armed = (prm.ceres_compat < 210) || (st.flags & kAnySuccess);
       double step_norm = 0.0;
       SMPC_UNROLL for (int c = 0; c < P; ++c) {
         const double dd = xs[c] - cand[c];
         step_norm += dd * dd;
       }
       step_norm = sqrt(step_norm);
-      const double cost_change = x_cost - cand_cost;
-      if (tol_armed && step_norm <= prm.param_tol * (x_norm + prm.param_tol)) {
-        --iteration;
-        term = kConvParameter;
+      const double cost_change = st.x_cost - cand_cost;
+      if (tol_armed && step_norm <= prm.param_tol * (st.x_norm + prm.param_tol)) {
+        --st.iteration;
+        st.term = kConvParameter;
         finished = true;
-      } else if (tol_armed && fabs(cost_change) <= prm.fn_tol * x_cost) {
-        --iteration;
-        term = kConvFunction;
+      } else if (tol_armed && fabs(cost_change) <= prm.fn_tol * st.x_cost) {
+        --st.iteration;
+        st.term = kConvFunction;
         finished = true;
       } else {
-        const double rho = (cand_cost >= DBL_MAX) ? -DBL_MAX : cost_change / model_cost_change;
+        const double rho = (cand_cost >= DBL_MAX) ? -DBL_MAX : cost_change / st.model_cost_change;
         if (rho > 1e-3) {  // HandleSuccessfulStep
           if (fl & kJacobianBad) {
-            --iteration;
-            term = kFailEvaluation;
+            --st.iteration;
+            st.term = kFailEvaluation;
             finished = true;
           } else {
             __syncwarp(gmask);
             for (int c = gl; c < P; c += G) xs[c] = cand[c];
             __syncwarp(gmask);
+            st.flags ^= kSwapped;
             { double* tmp = cur; cur = trial; trial = tmp; }
-            x_cost = cand_cost;
-            any_success = true;
-            it_successful = true;
-            it_cost = x_cost;
+            st.x_cost = cand_cost;
+            st.flags |= kAnySuccess | kItSuccessful;
+            st.flags &= ~kReuseDiagonal;
+            st.it_cost = cand_cost;
             const double qq = 2.0 * rho - 1.0;
-            radius = fmin(1e16, radius / fmax(1.0 / 3.0, 1.0 - qq * qq * qq));
-            decrease_factor = 2.0;
-            reuse_diagonal = false;
+            st.radius = fmin(1e16, st.radius / fmax(1.0 / 3.0, 1.0 - qq * qq * qq));
+            st.decrease_factor = 2.0;
           }
         } else {
-          it_successful = false;
-          it_cost = cand_cost;
-          radius = radius / decrease_factor;
-          decrease_factor *= 2.0;
-          reuse_diagonal = true;
+          st.flags &= ~kItSuccessful;
+          st.flags |= kReuseDiagonal;
+          st.it_cost = cand_cost;
+          st.radius = st.radius / st.decrease_factor;
+          st.decrease_factor *= 2.0;
         }
       }
     }
 
     // ---- a new outer iteration starts here (after iteration zero or after accept / reject) ----
-    if (!finished) {
-      if (it_successful) {  // x changed: refresh |x| and the projected-gradient max norm
+    if (!finished && !next_sample) {
+      if (st.flags & kItSuccessful) {  // x changed: refresh |x| and the projected-gradient max norm
         double xn = 0.0, gm = 0.0;
         SMPC_UNROLL for (int c = 0; c < P; ++c) {
           const double xv = xs[c];
           xn += xv * xv;
           gm = fmax(gm, fabs(xv - project_param(xv - cur[L::g(c)], c, nbd)));
         }
-        x_norm = sqrt(xn);
-        gmax = gm;
+        st.x_norm = sqrt(xn);
+        st.gmax = gm;
       }
       for (;;) {
         // FinalizeIterationAndCheckIfMinimizerCanContinue
-        if (it_successful && x_cost < minimum_cost) {
-          minimum_cost = x_cost;
+        if ((st.flags & kItSuccessful) && st.x_cost < st.minimum_cost) {
+          st.minimum_cost = st.x_cost;
           __syncwarp(gmask);
           for (int c = gl; c < P; c += G) best[c] = xs[c];
           __syncwarp(gmask);
         }
-        cost_final = fmin(cost_final, it_cost);
-        if (iteration >= prm.max_iterations) { term = kNoConvergence; finished = true; break; }
-        if (it_successful && gmax <= prm.gradient_tol) { term = kConvGradient; finished = true; break; }
-        if (radius <= 1e-32) { term = kConvRadius; finished = true; break; }
-        ++iteration;
+        st.cost_final = fmin(st.cost_final, st.it_cost);
+        if (st.iteration >= prm.max_iterations) { st.term = kNoConvergence; finished = true; break; }
+        if ((st.flags & kItSuccessful) && st.gmax <= prm.gradient_tol) { st.term = kConvGradient; finished = true; break; }
+        if (st.radius <= 1e-32) { st.term = kConvRadius; finished = true; break; }
+        ++st.iteration;
 
         // LevenbergMarquardtStrategy::ComputeStep on the column-scaled normal equations
         __syncwarp(gmask);
-        if (!reuse_diagonal) {
+        if (!(st.flags & kReuseDiagonal)) {
           for (int c = gl; c < P; c += G) {
             const double scv = scale[c];
             diag[c] = fmin(fmax(scv * scv * cur[L::h(0, 0) + c * (c + 1) / 2 + c], 1e-6), 1e32);
           }
         }
         __syncwarp(gmask);
-        reuse_diagonal = true;
+        st.flags |= kReuseDiagonal;
         double sc[P], Lc[L::NH], step[P];
-        const double inv_radius = 1.0 / radius;
+        const double inv_radius = 1.0 / st.radius;
         SMPC_UNROLL for (int c = 0; c < P; ++c) sc[c] = scale[c];
         SMPC_UNROLL for (int a = 0; a < P; ++a) {
           SMPC_UNROLL for (int bq = 0; bq <= a; ++bq) Lc[a * (a + 1) / 2 + bq] = sc[a] * sc[bq] * cur[L::h(a, bq)];
@@ -1293,20 +1314,20 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
           const double inv_d = rsqrt(d);
           Lc[jc * (jc + 1) / 2 + jc] = inv_d;  // store 1/L_jj
           SMPC_UNROLL for (int i = jc + 1; i < P; ++i) {
-            double s = Lc[i * (i + 1) / 2 + jc];
-            SMPC_UNROLL for (int k = 0; k < jc; ++k) s -= Lc[i * (i + 1) / 2 + k] * Lc[jc * (jc + 1) / 2 + k];
-            Lc[i * (i + 1) / 2 + jc] = s * inv_d;
+            double sacc = Lc[i * (i + 1) / 2 + jc];
+            SMPC_UNROLL for (int k = 0; k < jc; ++k) sacc -= Lc[i * (i + 1) / 2 + k] * Lc[jc * (jc + 1) / 2 + k];
+            Lc[i * (i + 1) / 2 + jc] = sacc * inv_d;
           }
         }
         SMPC_UNROLL for (int i = 0; i < P; ++i) {  // forward substitution
-          double s = sc[i] * cur[L::g(i)];
-          SMPC_UNROLL for (int k = 0; k < i; ++k) s -= Lc[i * (i + 1) / 2 + k] * step[k];
-          step[i] = s * Lc[i * (i + 1) / 2 + i];
+          double sacc = sc[i] * cur[L::g(i)];
+          SMPC_UNROLL for (int k = 0; k < i; ++k) sacc -= Lc[i * (i + 1) / 2 + k] * step[k];
+          step[i] = sacc * Lc[i * (i + 1) / 2 + i];
         }
         SMPC_UNROLL for (int i = P - 1; i >= 0; --i) {  // back substitution
-          double s = step[i];
-          SMPC_UNROLL for (int k = i + 1; k < P; ++k) s -= Lc[k * (k + 1) / 2 + i] * step[k];
-          step[i] = s * Lc[i * (i + 1) / 2 + i];
+          double sacc = step[i];
+          SMPC_UNROLL for (int k = i + 1; k < P; ++k) sacc -= Lc[k * (k + 1) / 2 + i] * step[k];
+          step[i] = sacc * Lc[i * (i + 1) / 2 + i];
         }
         SMPC_UNROLL for (int c = 0; c < P; ++c) {
           step_ok = step_ok && isfinite(step[c]);
@@ -1321,18 +1342,19 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
           SMPC_UNROLL for (int bq = 0; bq < a; ++bq) rowv += cur[L::h(a, bq)] * (sc[bq] * step[bq]);
           quad += sa * (2.0 * rowv + cur[L::h(a, a)] * sa);
         }
-        model_cost_change = -lin - 0.5 * quad;
-        const bool valid = step_ok && (model_cost_change > 0.0);
+        st.model_cost_change = -lin - 0.5 * quad;
+        const bool valid = step_ok && (st.model_cost_change > 0.0);
         if (valid) {
-          n_invalid = 0;
-          g0 = 0.0;
-          dmax = 0.0;
+          st.n_invalid = 0;
+          double g0 = 0.0, dmax = 0.0;
           SMPC_UNROLL for (int c = 0; c < P; ++c) {
             const double dl = step[c] * sc[c];
             g0 += cur[L::g(c)] * dl;
             dmax = fmax(dmax, fabs(dl));
             step[c] = dl;
           }
+          st.g0 = g0;
+          st.dmax = dmax;
           __syncwarp(gmask);
           if (gl == 0) {
             SMPC_UNROLL for (int c = 0; c < P; ++c) {
@@ -1340,32 +1362,32 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
               cand[c] = project_param(xs[c] + step[c], c, nbd);
             }
           }
-          __syncwarp(gmask);
           break;
         }
         // HandleInvalidStep
-        if (++n_invalid >= 5) {
-          --iteration;
-          term = kFailInvalidSteps;
+        if (++st.n_invalid >= 5) {
+          --st.iteration;
+          st.term = kFailInvalidSteps;
           finished = true;
           break;
         }
-        radius /= decrease_factor;
-        decrease_factor *= 2.0;
-        it_successful = false;
-        it_cost = x_cost;
+        st.radius /= st.decrease_factor;
+        st.decrease_factor *= 2.0;
+        st.flags &= ~kItSuccessful;
+        st.it_cost = st.x_cost;
       }
       if (!finished) {
-        phase = kLineSearch;
-        t = 1.0;
-        ls_iters = 0;
-        prev.ok = false;
+        st.phase = kLineSearch;
+        st.t = 1.0;
+        st.ls_iters = 0;
+        st.flags &= ~kPrevOk;
       }
     }
 
     if (finished) {
       // results. Solution = best accepted iterate when usable (Solver::Summary::IsSolutionUsable), else the seed.
-      const bool usable = term <= kNoConvergence;
+      const bool usable = st.term <= kNoConvergence;
+      const int b = st.b;
       __syncwarp(gmask);
       double x[P];
       SMPC_UNROLL for (int c = 0; c < P; ++c) x[c] = usable ? best[c] : __ldg(bt.u0 + (size_t)b * P + c);
@@ -1373,21 +1395,24 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
         if (rs.u) {
           SMPC_UNROLL for (int c = 0; c < P; ++c) rs.u[(size_t)b * P + c] = x[c];
         }
-        if (rs.cost_initial) rs.cost_initial[b] = cost_initial;
-        if (rs.cost_final) rs.cost_final[b] = cost_final;
-        if (rs.iterations) rs.iterations[b] = iteration;
-        if (rs.termination) rs.termination[b] = term;
+        if (rs.cost_initial) rs.cost_initial[b] = st.cost_initial;
+        if (rs.cost_final) rs.cost_final[b] = st.cost_final;
+        if (rs.iterations) rs.iterations[b] = st.iteration;
+        if (rs.termination) rs.termination[b] = st.term;
         if (rs.usable) rs.usable[b] = usable ? 1 : 0;
         if (rs.n_evals) {
-          rs.n_evals[2 * b] = n_eval;
+          rs.n_evals[2 * b] = st.n_eval;
           rs.n_evals[2 * b + 1] = 0;
         }
       }
-      if (rs.cmds || rs.path) expand_outputs<NB, G>(prm, bt, rs, pb, b, x, lane);
-      __syncwarp(gmask);
-      phase = kFetch;
-      live = false;
+      if (rs.cmds || rs.path) expand_outputs<NB, G>(prm, bt, rs, *pbs, b, x, lane);
+      st.phase = kFetch;
+      st.flags &= ~kLive;
     }
+    // park the scalars for the next evaluation
+    __syncwarp(gmask);
+    if (gl == 0) *gs = st;
+    __syncwarp(gmask);
   }
 }
 
