@@ -1054,8 +1054,8 @@ __device__ __forceinline__ void expand_outputs(const DevParams& prm, const DevBa
 // ---------------------------------------------------------------------------------------------------
 enum Phase { kFetch = 0, kInit = 1, kLineSearch = 2, kFullStep = 3 };
 
-// Solver scalars of one group. They live in shared memory across the evaluation (which needs every register
-// for the FP64 math) and are loaded into registers only for the short phase logic after it.
+// Solver scalars of one group, resident in shared memory: the evaluation needs every register for the FP64
+// math, and the phase logic after it reads / updates them in place.
 struct LmState {
   double x_cost, x_norm, gmax, radius, decrease_factor, minimum_cost, it_cost, cost_initial, cost_final,
       model_cost_change, g0, dmax, t, prev_x, prev_value, prev_gradient;
@@ -1136,13 +1136,15 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
     if (__syncthreads_and((gs->flags & kExhausted) != 0)) break;
 
     const bool live = (gs->flags & kLive) != 0;
-    double* cur = ws + ((gs->flags & kSwapped) ? L::kBuf1 : L::kBuf0);    // normal equations at x
-    double* trial = ws + ((gs->flags & kSwapped) ? L::kBuf0 : L::kBuf1);  // normal equations at the trial point
-    const unsigned fl = evaluate<NB, G>(prm, bt, *pbs, live, lc0, ws, cand, lane, trial);
+    const unsigned fl = evaluate<NB, G>(prm, bt, *pbs, live, lc0, ws, cand, lane,
+                                        ws + ((gs->flags & kSwapped) ? L::kBuf0 : L::kBuf1));
     if (!live) continue;
 
-    // ---- phase logic on register copies of the group state -------------------------------------------------
-    LmState st = *gs;
+    // ---- phase logic, directly on the group's shared-memory state. The lanes of a group are converged here and
+    //      take the same (group-uniform) branches, so they all store identical values. ---------------------------
+    LmState& st = *gs;
+    double* cur = ws + ((st.flags & kSwapped) ? L::kBuf1 : L::kBuf0);    // normal equations at x
+    double* trial = ws + ((st.flags & kSwapped) ? L::kBuf0 : L::kBuf1);  // normal equations at the trial point
     ++st.n_eval;
     const double t_cost = trial[0];
     bool take_step = false;   // proceed to accept/reject with `cand`
@@ -1409,9 +1411,6 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
       st.phase = kFetch;
       st.flags &= ~kLive;
     }
-    // park the scalars for the next evaluation
-    __syncwarp(gmask);
-    if (gl == 0) *gs = st;
     __syncwarp(gmask);
   }
 }
