@@ -1075,14 +1075,15 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
   const int gl = lane & (G - 1);
   const unsigned gmask = Group<G>::mask(lane);
   const int nbd = prm.n_bounded;
-  double* xs = ws + L::kX;
-  double* best = ws + L::kBest;
-  double* scale = ws + L::kScale;
-  double* diag = ws + L::kDiag;
-  double* delta = ws + L::kDelta;
-  double* cand = ws + L::kCand;
-  LmState* gs = reinterpret_cast<LmState*>(ws + L::kState);
-  Prob* pbs = reinterpret_cast<Prob*>(ws + L::kProb);
+  // every piece of group state is addressed as ws + constant so that only `ws` stays live across the evaluation
+#define xs (ws + L::kX)
+#define best (ws + L::kBest)
+#define scale (ws + L::kScale)
+#define diag (ws + L::kDiag)
+#define delta (ws + L::kDelta)
+#define cand (ws + L::kCand)
+#define gs (reinterpret_cast<LmState*>(ws + L::kState))
+#define pbs (reinterpret_cast<Prob*>(ws + L::kProb))
 
   LaneConst<NB> lc0;
   lane_setup<NB>(gl, prm.bl, bt.dt, lc0);
@@ -1414,5 +1415,14 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
     __syncwarp(gmask);
   }
 }
+
+#undef xs
+#undef best
+#undef scale
+#undef diag
+#undef delta
+#undef cand
+#undef gs
+#undef pbs
 
 }  // namespace smpc
