@@ -53,13 +53,11 @@ WORKLOADS = {
     "crowd_x16384_A50": (lambda: sc.crowd(B=16384, A=50, config_id=5), "BASELINE configs[4] slice: 16384 problems, "
                          "50 agents, S=28, P=6 (a 1.1 GB slice of one GPU's shard of the 10^6 sweep)", False),
 }
-CPU_SAMPLE = {"obst_only_x4096": 768, "soc_work_obst_x65536_A20": 96, "soc_work_obst_x16384_A3": 256,
-              "obst_only_x65536": (lambda: sc.corridor(B=65536, unique_maps=False, config_id=22), "obst_only params, 65536 corridor "
-                         "scenarios, 256 shared costmaps (throughput-mode check)", False),
-    "soc_work_obst_x65536_A3": (lambda: sc.crowd(B=65536, A=3, config_id=23), "soc_work_obst params, 65536 crowd "
-                                "scenarios with the reference's 3 agents", False),
-    "multistart_256x1024": 256, "crowd_x16384_A50": 48, "obst_only_x65536": 768,
-              "soc_work_obst_x65536_A3": 256}
+# bounded CPU samples: roughly 10-30 s of single-core oracle work each (a solve costs ~7 ms without people,
+# ~15 ms at A = 3, ~30 ms at A = 20, ~75 ms at A = 50)
+CPU_SAMPLE = {"obst_only_x4096": 3072, "obst_only_x65536": 3072, "soc_work_obst_x16384_A3": 1536,
+              "soc_work_obst_x65536_A3": 1536, "multistart_256x1024": 1536, "soc_work_obst_x65536_A20": 512,
+              "crowd_x16384_A50": 256}
 
 
 def flops_per_solve(S, P, A_eff, m, n_jac, n_cost, iters):
