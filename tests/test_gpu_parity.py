@@ -287,3 +287,74 @@ def test_many_parameter_blocks_up_to_the_36_parameter_class(oracle, make_opt, ch
         assert np.abs(got["grad"][b] - e["grad"]).max() <= 1e-9 * np.abs(e["grad"]).max()
     r = _compare_solves(oracle, opt, batch)
     assert r["ok"].mean() >= 0.8, (r["du"], r["dc"], r["got"]["termination"], r["ref"]["termination"])
+
+
+def _tiny_horizon_batch(S, B=24, seed=3, **overrides):
+    """Crowd scenarios cut to S optimised steps (edge sizes: a path of 2 or 3 poses)."""
+    full = sc.crowd(B=B, A=3, config_id=40 + seed, **overrides)
+    arr = dict(full.arrays)
+    arr["path_xy"] = np.ascontiguousarray(full.arrays["path_xy"][:, :, : S + 1])
+    arr["agents"] = np.ascontiguousarray(full.arrays["agents"][:, :, :, : S + 1])
+    nb = sc.abi.problem_dims(full.params.control_horizon, full.params.parameter_block_length, S)[2]
+    arr["u0"] = np.ascontiguousarray(full.arrays["u0"][:, :nb])
+    import dataclasses
+    return dataclasses.replace(full, n_steps=S, arrays=arr)
+
+
+@pytest.mark.parametrize("S", [1, 2, 3, 7, 31, 32, 33])
+def test_edge_horizons(oracle, make_opt, S):
+    """Shortest path the reference accepts (2 poses -> S = 1), horizons around the 32-lane chunk boundary."""
+    if S <= 28:
+        batch = _tiny_horizon_batch(S)
+    else:  # longer than the shipped yamls: params.yaml-like set with a longer max_time
+        batch = _tiny_horizon_batch(S, B=12, param_set="params_yaml", max_time=2.0) if S <= 38 else None
+    opt = make_opt(batch.params)
+    r = _compare_solves(oracle, opt, batch)
+    assert r["ok"].mean() >= 0.9, (S, r["ok"].mean(), r["du"].max(), r["dc"].max())
+    assert (r["got"]["usable"] == r["ref"]["usable"]).all()
+
+
+@pytest.mark.parametrize("overrides", [
+    dict(ceres_compat=220),
+    dict(control_horizon=5, parameter_block_length=5),           # reference defaults: one block, P = 2
+    dict(control_horizon=4, parameter_block_length=3),           # ch % bl != 0: last block unbounded (Q2)
+    dict(socialwork_w=0.0, proxemics_w=0.0, agent_angle_w=0.0),  # zero-weight people critics stay in the problem (Q13)
+    dict(velocity_feasibility_w=0.0, goal_align_w=0.0, obstacle_w=0.0, angle_w=0.0),
+    dict(max_iterations=3),
+    dict(fn_tol=1e-12, param_tol=1e-14, gradient_tol=1e-14, max_iterations=100),
+])
+def test_parameter_variants(oracle, make_opt, overrides):
+    batch = sc.crowd(B=48, A=3, config_id=50, n_valid=2, **overrides)
+    opt = make_opt(batch.params)
+    r = _compare_solves(oracle, opt, batch)
+    assert r["ok"].mean() >= 0.9, (overrides, r["ok"].mean(), r["du"].max(), r["dc"].max())
+    assert r["same_term"].mean() >= 0.9
+
+
+def test_randomised_eval_parity_many_agent_counts(oracle, make_opt):
+    """cost / J^T r / J^T J against the oracle's jets for A in 1..7 with random validity patterns and slow / stopped
+    agents (the agent-angle 0.05 m/s gate, padded phantoms at the origin)."""
+    from nav2_social_mpc_controller_b200.optimizer import hess_to_dense
+    rng = np.random.default_rng(9)
+    for A in (1, 2, 4, 7):
+        batch = sc.crowd(B=8, A=A, config_id=60 + A)
+        ag = batch.arrays["agents"]
+        invalid = rng.random((8, A)) < 0.3
+        ag[invalid] = 0.0
+        ag[invalid, 3, :] = -1.0
+        slow = rng.random((8, A)) < 0.3
+        ag[slow, 4, :] *= 0.02
+        opt = make_opt(batch.params)
+        P = 2 * batch.n_blocks
+        x = batch.arrays["u0"].reshape(8, P) + rng.normal(0, 0.05, (8, P))
+        got = opt.eval_batch(batch, x)
+        H = hess_to_dense(got["hess"], P)
+        for b in range(8):
+            e = oracle.evaluate(batch, b, x[b])
+            assert bool(got["ok"][b]) == e["ok"], (A, b)
+            if not e["ok"]:
+                continue
+            assert got["cost"][b] == pytest.approx(e["cost"], rel=1e-11)
+            H_ref = e["jac"].T @ e["jac"]
+            assert np.abs(H[b] - H_ref).max() <= 1e-9 * max(1.0, np.abs(H_ref).max())
+            assert np.abs(got["grad"][b] - e["grad"]).max() <= 1e-9 * max(1.0, np.abs(e["grad"]).max())
