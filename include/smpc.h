@@ -242,6 +242,35 @@ int smpc_optimize(smpc_handle* h, smpc_optimize_io* io);
 /* Forget the previous path / cmds (a fresh TrajectoryMemory). */
 int smpc_reset_memory(smpc_handle* h);
 
+/* ---- batched pre-solve stage on the GPU: project_people (src/optimizer.cpp:554-671 + sfm.hpp) -----------------
+ * One warp per problem, lanes over agents, sequential over the horizon. Generalised from the reference's 3 people to
+ * A columns. Inputs (device pointers): robot [B][S+1][6] = the robot AgentTrajectory of format_to_optimize
+ * (x, y, yaw, t, lv, av), people_init [B][A][6] = people_to_status output (t == -1: padded), the obstacle-distance
+ * grids od_indexes [M][height*width] (od_index [B] selects one, NULL: grid b % M). Output agents [B][A][6][S+1] in the
+ * level-1 layout (valid people compacted to the front from step 1 on, like the reference), status [B]: 0 ok,
+ * 1 = a person left the obstacle grid (the reference throws std::runtime_error there; its agents are marked invalid). */
+typedef struct smpc_project_args {
+  int n_problems;
+  int n_steps;  /* S: robot has S+1 states */
+  int n_agents; /* A <= 63 */
+  int n_grids;  /* M */
+  uint32_t od_width;
+  uint32_t od_height;
+  float od_resolution;
+  float max_time;
+  float time_step;
+  const double* od_origin; /* [M][2] */
+  const uint32_t* od_indexes;
+  const int32_t* od_index; /* may be NULL */
+  const double* robot;
+  const double* people_init;
+  double* agents;
+  int32_t* status; /* may be NULL */
+} smpc_project_args;
+int smpc_project_people_batch_device(smpc_handle* h, const smpc_project_args* a, void* stream);
+/* Host-buffer wrapper (tests): same struct with host pointers. */
+int smpc_project_people_batch(smpc_handle* h, const smpc_project_args* a);
+
 /* Multi-start selection: per robot arg-min of cost_final over `n_starts`
  * consecutive problems (device pointers). best_index [R] i32 (global problem
  * index, -1 if no usable start), best_cost [R], best_u [R][NB][2]. */

@@ -63,6 +63,10 @@ def lib():
     L.smpc_optimize.restype = C.c_int
     L.smpc_reset_memory.argtypes = [C.c_void_p]
     L.smpc_reset_memory.restype = C.c_int
+    L.smpc_project_people_batch.argtypes = [C.c_void_p, P(abi.SmpcProjectArgs)]
+    L.smpc_project_people_batch.restype = C.c_int
+    L.smpc_project_people_batch_device.argtypes = [C.c_void_p, P(abi.SmpcProjectArgs), C.c_void_p]
+    L.smpc_project_people_batch_device.restype = C.c_int
     L.smpc_set_group.argtypes = [C.c_void_p, C.c_int]
     L.smpc_set_group.restype = C.c_int
     L.smpc_debug_polymin.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -83,5 +87,5 @@ EXPORTED_SYMBOLS = (
     "smpc_create", "smpc_destroy", "smpc_solve_batch", "smpc_solve_batch_device", "smpc_eval_batch_device",
     "smpc_eval_batch", "smpc_multistart_argmin_device", "smpc_last_kernel_ms", "smpc_launch_count",
     "smpc_measure_fp64_peak", "smpc_debug_polymin", "smpc_set_group",
-    "smpc_optimize", "smpc_reset_memory",
+    "smpc_optimize", "smpc_reset_memory", "smpc_project_people_batch", "smpc_project_people_batch_device",
 )

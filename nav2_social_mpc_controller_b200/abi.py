@@ -210,3 +210,25 @@ class SmpcOptimizeIo(C.Structure):
         ("cost_initial", C.c_double),
         ("cost_final", C.c_double),
     ]
+
+
+class SmpcProjectArgs(C.Structure):
+    """struct smpc_project_args — batched project_people (SFM crowd projection)."""
+    _fields_ = [
+        ("n_problems", C.c_int),
+        ("n_steps", C.c_int),
+        ("n_agents", C.c_int),
+        ("n_grids", C.c_int),
+        ("od_width", C.c_uint32),
+        ("od_height", C.c_uint32),
+        ("od_resolution", C.c_float),
+        ("max_time", C.c_float),
+        ("time_step", C.c_float),
+        ("od_origin", C.c_void_p),
+        ("od_indexes", C.c_void_p),
+        ("od_index", C.c_void_p),
+        ("robot", C.c_void_p),
+        ("people_init", C.c_void_p),
+        ("agents", C.c_void_p),
+        ("status", C.c_void_p),
+    ]

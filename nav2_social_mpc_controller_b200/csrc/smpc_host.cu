@@ -91,6 +91,8 @@ struct smpc_handle {
 const smpc_params* smpc_handle_params(smpc_handle* h) { return &h->params; }
 smpc_memory* smpc_handle_memory(smpc_handle* h) { return &h->memory; }
 int smpc_host_fail(int code, const std::string& msg) { return fail(code, msg); }
+cudaStream_t smpc_handle_stream(smpc_handle* h) { return h->stream; }
+void smpc_handle_count_launch(smpc_handle* h) { h->launches += 1; }
 
 namespace {
 

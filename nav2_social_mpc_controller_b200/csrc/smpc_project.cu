@@ -1,0 +1,336 @@
+// smpc_project.cu — batched GPU version of Optimizer::project_people (reference src/optimizer.cpp:554-671) with the
+// lightsfm social force model it calls (include/nav2_social_mpc_controller/sfm.hpp:188-323, 462-560) and
+// computeObstacle (:673-728). One warp per problem: lanes own people, the horizon is walked sequentially, the agent
+// states of the current step live in shared memory. Same arithmetic as the host version in smpc_optimize.cu.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/smpc.h"
+#include "smpc_host_state.h"
+
+namespace {
+
+constexpr int kMaxAgents = 64;  // people + robot
+constexpr int kWarps = 4;
+
+struct AgentSmem {  // structure of arrays, one slot per agent of the current step
+  double px[kMaxAgents], py[kMaxAgents], vx[kMaxAgents], vy[kMaxAgents];
+  double nx[kMaxAgents], ny[kMaxAgents], nvx[kMaxAgents], nvy[kMaxAgents];  // next-step staging
+};
+
+__device__ __forceinline__ double wrap_pi(double a) {
+  while (a <= -M_PI) a += 2 * M_PI;
+  while (a > M_PI) a -= 2 * M_PI;
+  return a;
+}
+
+// computeObstacle: the vector the reference stores in obstacles1 (agent - nearest obstacle cell)
+__device__ __forceinline__ bool nearest_obstacle(const smpc_project_args& a, const uint32_t* idx, double ox, double oy,
+                                                 double x, double y, double* out_x, double* out_y) {
+  const unsigned int xc = (unsigned int)floor((x - ox) / a.od_resolution);
+  const unsigned int yc = (unsigned int)floor((y - oy) / a.od_resolution);
+  if (xc >= a.od_width || yc >= a.od_height) return false;
+  const unsigned int ob = idx[xc + yc * a.od_width];
+  if (ob >= a.od_width * a.od_height) return false;
+  const unsigned int cy = ob / a.od_width, cx = ob % a.od_width;
+  const float fx = cx * a.od_resolution + ox;  // float-rounded like the reference (:719-720)
+  const float fy = cy * a.od_resolution + oy;
+  *out_x = x - (double)fx;
+  *out_y = y - (double)fy;
+  return true;
+}
+
+__global__ void __launch_bounds__(kWarps * 32) smpc_project_kernel(smpc_project_args a) {
+  __shared__ AgentSmem sm[kWarps];
+  AgentSmem& s = sm[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  const int S = a.n_steps, A = a.n_agents, stride = S + 1;
+  const double dt = (double)a.time_step;
+  const double kDesired = 2.0, kObstacle = 20.0, kSigma = 0.2, kSocial = 2.1, kLambda = 2.0, kGamma = 0.35, kN = 2.0,
+               kNPrime = 3.0, kRelax = 0.5;
+
+  for (int b = warp; b < a.n_problems; b += n_warps) {
+    const double* robot = a.robot + (size_t)b * stride * 6;
+    const double* init = a.people_init + (size_t)b * A * 6;
+    double* out = a.agents + (size_t)b * A * 6 * stride;
+    const int gi = a.od_index ? a.od_index[b] : (b % a.n_grids);
+    const uint32_t* idx = a.od_indexes + (size_t)gi * a.od_width * a.od_height;
+    const double ox = a.od_origin[2 * gi], oy = a.od_origin[2 * gi + 1];
+    const bool grid_ok = !(a.od_width == 100 && a.od_height == 100);  // "grid is NOT valid" (:598-603)
+    int err = 0;
+
+    // step 0 = the raw (uncompacted) initial people; invalid everything else for now
+    for (int e = lane; e < A * 6; e += 32) {
+      const int k = e / 6, c = e % 6;
+      out[((size_t)k * 6 + c) * stride] = init[e];
+    }
+    // compaction of the valid people: slot of agent k = number of valid agents before it
+    // per-lane agent state (lane owns compacted slots lane, lane + 32)
+    double yaw[2], lv[2], av[2], gx[2], gy[2], obx[2], oby[2], vdes[2];
+    bool has_goal[2], mine[2];
+    int n = 0;
+    {
+      int slot_of[2] = {-1, -1};
+      // sequential prefix over agents in chunks of 32
+      for (int base = 0; base < A; base += 32) {
+        const int k = base + lane;
+        const bool valid = (k < A) && grid_ok && !(init[k * 6 + 3] == -1.0);
+        const unsigned m = __ballot_sync(0xffffffffu, valid);
+        const int my_slot = n + __popc(m & ((1u << lane) - 1u));
+        if (valid) {
+          // hand the agent to the lane that owns its compacted slot through shared memory
+          s.px[my_slot] = init[k * 6 + 0];
+          s.py[my_slot] = init[k * 6 + 1];
+          s.nx[my_slot] = init[k * 6 + 2];   // yaw
+          s.ny[my_slot] = init[k * 6 + 4];   // lv
+          s.nvx[my_slot] = init[k * 6 + 5];  // av
+        }
+        n += __popc(m);
+      }
+      __syncwarp();
+      for (int q = 0; q < 2; ++q) {
+        const int slot = lane + 32 * q;
+        mine[q] = slot < n;
+        slot_of[q] = slot;
+        yaw[q] = lv[q] = av[q] = gx[q] = gy[q] = obx[q] = oby[q] = 0.0;
+        vdes[q] = 0.5;
+        has_goal[q] = false;
+        if (mine[q]) {
+          yaw[q] = s.nx[slot];
+          lv[q] = s.ny[slot];
+          av[q] = s.nvx[slot];
+        }
+      }
+      __syncwarp();
+      for (int q = 0; q < 2; ++q) {
+        if (!mine[q]) continue;
+        const int slot = slot_of[q];
+        double sy, cy;
+        sincos(yaw[q], &sy, &cy);
+        s.vx[slot] = lv[q] * cy;
+        s.vy[slot] = lv[q] * sy;
+        gx[q] = s.px[slot] + (double)a.max_time * s.vx[slot];
+        gy[q] = s.py[slot] + (double)a.max_time * s.vy[slot];
+        has_goal[q] = true;
+        if (!nearest_obstacle(a, idx, ox, oy, s.px[slot], s.py[slot], &obx[q], &oby[q])) err = 1;
+      }
+      __syncwarp();
+    }
+    if (__any_sync(0xffffffffu, err != 0)) {
+      // the reference throws here; mark every projected agent invalid and report
+      for (int e = lane; e < A * S; e += 32) {
+        const int k = e / S, i = e % S + 1;
+        for (int c = 0; c < 6; ++c) out[((size_t)k * 6 + c) * stride + i] = (c == 3) ? -1.0 : 0.0;
+      }
+      if (lane == 0 && a.status) a.status[b] = 1;
+      continue;
+    }
+
+    const double goal_rx = robot[(size_t)S * 6 + 0], goal_ry = robot[(size_t)S * 6 + 1];
+    for (int i = 0; i < S; ++i) {
+      // robot appended as agent n (its own force / update are discarded by the reference)
+      if (lane == 0) {
+        const double ryaw = robot[(size_t)i * 6 + 2], rlv = robot[(size_t)i * 6 + 4];
+        double sy, cy;
+        sincos(ryaw, &sy, &cy);
+        s.px[n] = robot[(size_t)i * 6 + 0];
+        s.py[n] = robot[(size_t)i * 6 + 1];
+        s.vx[n] = rlv * cy;
+        s.vy[n] = rlv * sy;
+      }
+      __syncwarp();
+      for (int q = 0; q < 2; ++q) {
+        const int slot = lane + 32 * q;
+        if (!mine[q]) continue;
+        const double px = s.px[slot], py = s.py[slot], vx = s.vx[slot], vy = s.vy[slot];
+        // desired force (sfm.hpp:188-204)
+        double fx, fy;
+        {
+          const double dx = gx[q] - px, dy = gy[q] - py;
+          const double dn = sqrt(dx * dx + dy * dy);
+          if (has_goal[q] && dn > 0.25) {
+            const double z = dx * dx + dy * dy;
+            double ex = dx, ey = dy;
+            if (z > 0.0) {
+              const double sq = sqrt(z);
+              ex = dx / sq;
+              ey = dy / sq;
+            }
+            fx = kDesired * (ex * vdes[q] - vx) / kRelax;
+            fy = kDesired * (ey * vdes[q] - vy) / kRelax;
+          } else {
+            fx = -vx / kRelax;
+            fy = -vy / kRelax;
+          }
+        }
+        // obstacle force (sfm.hpp:206-221): obstacles1 holds ONE entry
+        {
+          const double mx = px - obx[q], my = py - oby[q];
+          const double mn = sqrt(mx * mx + my * my);
+          const double distance = mn - 0.5;
+          const double z = mx * mx + my * my;
+          double ex = mx, ey = my;
+          if (z > 0.0) {
+            const double sq = sqrt(z);
+            ex = mx / sq;
+            ey = my / sq;
+          }
+          const double k = kObstacle * exp(-distance / kSigma);
+          fx += (k * ex) / 1.0;
+          fy += (k * ey) / 1.0;
+        }
+        // social force from every other agent incl. the robot (sfm.hpp:239-281)
+        double sfx = 0.0, sfy = 0.0;
+        for (int k = 0; k <= n; ++k) {
+          if (k == slot) continue;
+          const double dx = s.px[k] - px, dy = s.py[k] - py;
+          const double z = dx * dx + dy * dy;
+          const double dn = sqrt(z);
+          double ex = dx, ey = dy;
+          if (z > 0.0) {
+            ex = dx / dn;
+            ey = dy / dn;
+          }
+          const double wx = vx - s.vx[k], wy = vy - s.vy[k];
+          const double Ix = kLambda * wx + ex, Iy = kLambda * wy + ey;
+          const double il = sqrt(Ix * Ix + Iy * Iy);
+          const double ix = Ix / il, iy = Iy / il;
+          const double a1 = wrap_pi(atan2(iy, ix));
+          const double a2 = wrap_pi(atan2(ey, ex));
+          const double th = wrap_pi(a2 - a1);
+          const double B = kGamma * il;
+          const double fv = -exp(-dn / B - (kNPrime * B * th) * (kNPrime * B * th));
+          double sgn = -1.0;
+          if (th == 0) sgn = 0; else if (th > 0) sgn = 1;
+          const double fa = -sgn * exp(-dn / B - (kN * B * th) * (kN * B * th));
+          sfx += kSocial * (fv * ix + fa * (-iy));
+          sfy += kSocial * (fv * iy + fa * ix);
+        }
+        fx += sfx;
+        fy += sfy;
+        // updatePosition (sfm.hpp:512-545)
+        double nvx = vx + fx * dt, nvy = vy + fy * dt;
+        const double vn = sqrt(nvx * nvx + nvy * nvy);
+        if (vn > vdes[q]) {
+          const double z = nvx * nvx + nvy * nvy;
+          if (z > 0.0) {
+            const double sq = sqrt(z);
+            nvx = nvx / sq;
+            nvy = nvy / sq;
+          }
+          nvx *= vdes[q];
+          nvy *= vdes[q];
+        }
+        const double y0 = yaw[q];
+        yaw[q] = wrap_pi(atan2(nvy, nvx));
+        av[q] = wrap_pi(yaw[q] - y0) / dt;
+        const double npx = px + nvx * dt, npy = py + nvy * dt;
+        lv[q] = sqrt(nvx * nvx + nvy * nvy);
+        if (has_goal[q]) {
+          const double dx = gx[q] - npx, dy = gy[q] - npy;
+          if (sqrt(dx * dx + dy * dy) <= 0.25) has_goal[q] = false;
+        }
+        s.nx[slot] = npx;
+        s.ny[slot] = npy;
+        s.nvx[slot] = nvx;
+        s.nvy[slot] = nvy;
+      }
+      __syncwarp();
+      for (int q = 0; q < 2; ++q) {
+        const int slot = lane + 32 * q;
+        if (!mine[q]) continue;
+        s.px[slot] = s.nx[slot];
+        s.py[slot] = s.ny[slot];
+        s.vx[slot] = s.nvx[slot];
+        s.vy[slot] = s.nvy[slot];
+        if (!nearest_obstacle(a, idx, ox, oy, s.px[slot], s.py[slot], &obx[q], &oby[q])) err = 1;
+        double* o = out + (size_t)slot * 6 * stride + (i + 1);
+        o[0] = s.px[slot];
+        o[stride] = s.py[slot];
+        o[2 * stride] = yaw[q];
+        o[3 * stride] = (double)((float)(i + 1) * a.time_step);
+        o[4 * stride] = lv[q];
+        o[5 * stride] = av[q];
+      }
+      // padded (invalid) columns of this step
+      for (int k = n + lane; k < A; k += 32) {
+        double* o = out + (size_t)k * 6 * stride + (i + 1);
+        o[0] = 0.0; o[stride] = 0.0; o[2 * stride] = 0.0; o[3 * stride] = -1.0; o[4 * stride] = 0.0; o[5 * stride] = 0.0;
+      }
+      __syncwarp();
+    }
+    const bool any_err = __any_sync(0xffffffffu, err != 0);
+    if (lane == 0 && a.status) a.status[b] = any_err ? 1 : 0;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int smpc_project_people_batch_device(smpc_handle* h, const smpc_project_args* a, void* stream) {
+  if (!h || !a) return smpc_host_fail(SMPC_ERR_ARGUMENT, "NULL argument");
+  if (a->n_problems < 0 || a->n_steps < 1 || a->n_agents < 1 || a->n_agents > kMaxAgents - 1)
+    return smpc_host_fail(SMPC_ERR_ARGUMENT, "project_people: need n_steps >= 1 and 1 <= n_agents <= 63");
+  if (!a->robot || !a->people_init || !a->agents || !a->od_indexes || !a->od_origin || a->n_grids < 1)
+    return smpc_host_fail(SMPC_ERR_ARGUMENT, "project_people: missing buffer");
+  if (a->od_width == 0 || a->od_height == 0) return smpc_host_fail(SMPC_ERR_ARGUMENT, "ObstacleDistance grid has invalid size");
+  if (!(a->od_resolution > 0.0f)) return smpc_host_fail(SMPC_ERR_ARGUMENT, "ObstacleDistance grid has invalid resolution");
+  if (a->n_problems == 0) return SMPC_OK;
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : smpc_handle_stream(h);
+  const int ctas = (a->n_problems + kWarps - 1) / kWarps;
+  const int grid = ctas < 148 * 8 ? ctas : 148 * 8;
+  smpc_project_kernel<<<grid, kWarps * 32, 0, st>>>(*a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return smpc_host_fail(SMPC_ERR_CUDA, std::string("project kernel: ") + cudaGetErrorString(e));
+  smpc_handle_count_launch(h);
+  return SMPC_OK;
+}
+
+int smpc_project_people_batch(smpc_handle* h, const smpc_project_args* a) {
+  if (!h || !a) return smpc_host_fail(SMPC_ERR_ARGUMENT, "NULL argument");
+  if (a->n_problems <= 0) return SMPC_OK;
+  const size_t B = a->n_problems, S1 = (size_t)a->n_steps + 1, A = a->n_agents, M = a->n_grids;
+  const size_t cells = (size_t)a->od_width * a->od_height;
+  smpc_project_args d = *a;
+  std::vector<void*> to_free;
+  auto up = [&](const void* host, size_t bytes) -> void* {
+    if (!host) return nullptr;
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+    to_free.push_back(p);
+    cudaMemcpy(p, host, bytes, cudaMemcpyHostToDevice);
+    return p;
+  };
+  d.od_origin = (const double*)up(a->od_origin, M * 2 * 8);
+  d.od_indexes = (const uint32_t*)up(a->od_indexes, M * cells * 4);
+  d.od_index = (const int32_t*)up(a->od_index, B * 4);
+  d.robot = (const double*)up(a->robot, B * S1 * 6 * 8);
+  d.people_init = (const double*)up(a->people_init, B * A * 6 * 8);
+  void* dout = nullptr;
+  void* dstat = nullptr;
+  cudaMalloc(&dout, B * A * 6 * S1 * 8);
+  cudaMalloc(&dstat, B * 4);
+  to_free.push_back(dout);
+  to_free.push_back(dstat);
+  d.agents = (double*)dout;
+  d.status = (int32_t*)dstat;
+  int rc = smpc_project_people_batch_device(h, &d, nullptr);
+  if (rc == SMPC_OK) {
+    cudaStreamSynchronize(smpc_handle_stream(h));
+    cudaMemcpy(a->agents, dout, B * A * 6 * S1 * 8, cudaMemcpyDeviceToHost);
+    if (a->status) cudaMemcpy(a->status, dstat, B * 4, cudaMemcpyDeviceToHost);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) rc = smpc_host_fail(SMPC_ERR_CUDA, std::string("project_people: ") + cudaGetErrorString(e));
+  }
+  for (void* p : to_free) cudaFree(p);
+  return rc;
+}
+
+}  // extern "C"

@@ -152,6 +152,32 @@ class Optimizer:
         return (bool(io.optimized), poses_buf[: io.n_poses].copy(), cmds_buf[: io.n_cmds].copy(),
                 proj[: io.n_proj_steps].copy(), info)
 
+    def project_people_batch(self, robot: np.ndarray, people_init: np.ndarray, od: dict, max_time: float,
+                             time_step: float, od_index: np.ndarray | None = None):
+        """Batched GPU project_people (reference src/optimizer.cpp:554-671): robot [B][S+1][6], people_init [B][A][6]
+        (t == -1: padded), od = dict(width, height, resolution, origins [M][2], indexes u32 [M][h*w]).
+        Returns (agents [B][A][6][S+1] in the level-1 layout, status [B])."""
+        self._need()
+        robot = np.ascontiguousarray(robot, dtype=np.float64)
+        people_init = np.ascontiguousarray(people_init, dtype=np.float64)
+        B, S1, _ = robot.shape
+        A = people_init.shape[1]
+        origins = np.ascontiguousarray(od["origins"], dtype=np.float64).reshape(-1, 2)
+        idx = np.ascontiguousarray(od["indexes"], dtype=np.uint32).reshape(origins.shape[0], -1)
+        out = np.zeros((B, A, 6, S1))
+        status = np.zeros(B, dtype=np.int32)
+        a = abi.SmpcProjectArgs()
+        a.n_problems, a.n_steps, a.n_agents, a.n_grids = B, S1 - 1, A, origins.shape[0]
+        a.od_width, a.od_height, a.od_resolution = int(od["width"]), int(od["height"]), float(od["resolution"])
+        a.max_time, a.time_step = float(max_time), float(time_step)
+        a.od_origin, a.od_indexes = origins.ctypes.data, idx.ctypes.data
+        oi = None if od_index is None else np.ascontiguousarray(od_index, dtype=np.int32)
+        a.od_index = None if oi is None else oi.ctypes.data
+        a.robot, a.people_init, a.agents, a.status = (robot.ctypes.data, people_init.ctypes.data, out.ctypes.data,
+                                                      status.ctypes.data)
+        _lib.check(_lib.lib().smpc_project_people_batch(self._h, C.byref(a)))
+        return out, status
+
     def reset_memory(self) -> None:
         """Forget the previous path / cmds (fresh TrajectoryMemory)."""
         self._need()

@@ -120,3 +120,69 @@ def test_optimize_failure_modes(opt_for):
     bad = dict(od, distances=np.zeros(0, np.float32), indexes=np.zeros(0, np.uint32))
     with pytest.raises(_lib.SmpcError):
         opt.optimize(poses, cmds, people, speed, p.time_step, costmap, (0.0, 0.0), 0.05, bad)
+
+
+def _od_grid(W=80, H=80, res=0.05):
+    rows = np.arange(H)[:, None] * np.ones((1, W), dtype=int)
+    cols = np.ones((H, 1), dtype=int) * np.arange(W)[None, :]
+    near = np.where(np.abs(rows - 12) <= np.abs(rows - 68), 12, 68)
+    return dict(width=W, height=H, resolution=res, origin_x=0.0, origin_y=0.0,
+                distances=(np.abs(rows - near) * res).astype(np.float32).ravel(),
+                indexes=(near * W + cols).astype(np.uint32).ravel())
+
+
+@pytest.mark.parametrize("A,n_valid", [(3, 3), (3, 1), (7, 5), (20, 20)])
+def test_batched_gpu_project_people_matches_reference(opt_for, A, n_valid):
+    """GPU project_people (one warp per problem) vs the numpy restatement of reference src/optimizer.cpp:554-671 +
+    sfm.hpp, including compaction of the valid people, goals reached on the way and padded columns."""
+    rng = np.random.default_rng(A * 10 + n_valid)
+    p = sc.make_params("soc_work_obst")
+    opt = opt_for(p)
+    B = 12
+    od = _od_grid()
+    robots, inits, want = [], [], []
+    for b in range(B):
+        pose = np.array([[1.0 + rng.uniform(0, 0.5), 2.0 + rng.uniform(-0.3, 0.3), rng.uniform(-0.3, 0.3)]])
+        gpath = sc._straight_path(1, pose[:, 0], np.array([2.0]))
+        poses, cmds = sc.pure_pursuit_seed(gpath, pose, p)
+        robot, _ = ref.format_to_optimize(poses[0].tolist(), cmds[0].tolist(), poses[0].tolist(), cmds[0].tolist(),
+                                          (0.3, 0.0), p.current_path_w, p.current_cmds_w, p.max_time, p.time_step)
+        people = []
+        for k in range(n_valid):
+            px, py = rng.uniform(0.8, 3.2), rng.uniform(1.0, 3.0)
+            h, v = rng.uniform(-np.pi, np.pi), rng.uniform(0.0, 0.9) if k % 3 else 0.08  # slow walkers reach their goal
+            people.append([px, py, h, 0.0, v, 0.0])
+        while len(people) < A:
+            people.append([0.0, 0.0, 0.0, -1.0, 0.0, 0.0])
+        perm = rng.permutation(A) if b % 2 else np.arange(A)  # invalid columns anywhere, not only at the end
+        people = [people[i] for i in perm]
+        robots.append(robot)
+        inits.append(people)
+        want.append(np.transpose(np.array(ref.project_people(people, robot, od, p.max_time, p.time_step)), (1, 2, 0)))
+    od_b = dict(width=80, height=80, resolution=0.05, origins=[[0.0, 0.0]], indexes=od["indexes"])
+    got, status = opt.project_people_batch(np.array(robots), np.array(inits), od_b, p.max_time, p.time_step)
+    assert np.all(status == 0)
+    want = np.array(want)
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= 1e-10, np.abs(got - want).max()
+
+
+def test_gpu_project_people_grid_quirks(opt_for):
+    """100x100 grids drop every person; leaving the grid is reported in status (the reference throws)."""
+    p = sc.make_params("soc_work_obst")
+    opt = opt_for(p)
+    S = 28
+    robot = np.zeros((2, S + 1, 6))
+    robot[:, :, 0] = 1.0 + 0.03 * np.arange(S + 1)
+    robot[:, :, 1] = 2.0
+    robot[:, :, 4] = 0.6
+    init = np.array([[[2.5, 2.0, np.pi, 0.0, 0.5, 0.0], [0, 0, 0, -1.0, 0, 0], [0, 0, 0, -1.0, 0, 0]]] * 2)
+    od100 = dict(width=100, height=100, resolution=0.05, origins=[[0.0, 0.0]], indexes=np.zeros(10000, np.uint32))
+    got, status = opt.project_people_batch(robot, init, od100, p.max_time, p.time_step)
+    assert np.all(status == 0) and np.all(got[:, :, 3, 1:] == -1.0) and np.all(got[:, 0, 3, 0] == 0.0)
+    init[1, 0, 0] = 3.97  # walks out of the 4 m grid within the horizon
+    init[1, 0, 2] = 0.0
+    od = _od_grid()
+    got, status = opt.project_people_batch(robot, init, dict(width=80, height=80, resolution=0.05, origins=[[0.0, 0.0]],
+                                                             indexes=od["indexes"]), p.max_time, p.time_step)
+    assert status[0] == 0 and status[1] == 1
