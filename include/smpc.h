@@ -271,6 +271,44 @@ int smpc_project_people_batch_device(smpc_handle* h, const smpc_project_args* a,
 /* Host-buffer wrapper (tests): same struct with host pointers. */
 int smpc_project_people_batch(smpc_handle* h, const smpc_project_args* a);
 
+/* ---- batched pre-solve stage on the GPU: format_to_optimize + unpacking (src/optimizer.cpp:484-551, :197-237) ----
+ * One thread per (problem, pose). poses [B][n_poses][3] (x, y, yaw = tf2::getYaw), cmds [B][n_poses-1][2], speed [B][2];
+ * prev_poses / prev_cmds: the previous tick's OUTPUT with n_prev_poses / n_prev_cmds entries per robot (NULL or 0 on
+ * the first tick: previous = current, :177-181). The caller has already applied the max_time cut (:492-497).
+ * Outputs: robot [B][n_poses][6] (input of project_people) and the level-1 arrays pose0 [B][3], u0 [B][NB][2],
+ * path_xy [B][2][n_poses], goal_yaw [B]. All device pointers. */
+typedef struct smpc_format_args {
+  int n_problems;
+  int n_poses;
+  int n_prev_poses;
+  int n_prev_cmds;
+  int n_blocks;
+  float time_step;
+  float current_path_w;
+  float current_cmds_w;
+  const double* poses;
+  const double* cmds;
+  const double* speed;
+  const double* prev_poses;
+  const double* prev_cmds;
+  double* robot;
+  double* pose0;
+  double* u0;
+  double* path_xy;
+  double* goal_yaw;
+} smpc_format_args;
+int smpc_format_batch_device(smpc_handle* h, const smpc_format_args* a, void* stream);
+
+/* people_to_status (src/optimizer.cpp:454-482) for a fleet: people_raw [B][A][5] = position.x/y, velocity.x/y/z,
+ * n_people [B] (entries >= n_people[b] are padding; more than A people are truncated by the caller like :476-479).
+ * Outputs people_init [B][A][6] and has_people [B] (u8). Device pointers. */
+int smpc_people_to_status_device(smpc_handle* h, int n_problems, int n_agents, const double* people_raw,
+                                 const int32_t* n_people, double* people_init, uint8_t* has_people, void* stream);
+/* TrajectoryMemory update of a fleet tick (src/optimizer.cpp:448-449): where usable[b], prev_poses[b] <- path[b] and
+ * prev_cmds[b] <- cmds[b] (n entries of 3 / 2 doubles each); other robots keep their memory. Device pointers. */
+int smpc_memory_update_device(smpc_handle* h, int n_problems, int n, const uint8_t* usable, const double* path,
+                              const double* cmds, double* prev_poses, double* prev_cmds, void* stream);
+
 /* Multi-start selection: per robot arg-min of cost_final over `n_starts`
  * consecutive problems (device pointers). best_index [R] i32 (global problem
  * index, -1 if no usable start), best_cost [R], best_u [R][NB][2]. */

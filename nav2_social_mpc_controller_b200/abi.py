@@ -232,3 +232,27 @@ class SmpcProjectArgs(C.Structure):
         ("agents", C.c_void_p),
         ("status", C.c_void_p),
     ]
+
+
+class SmpcFormatArgs(C.Structure):
+    """struct smpc_format_args — batched format_to_optimize + unpacking."""
+    _fields_ = [
+        ("n_problems", C.c_int),
+        ("n_poses", C.c_int),
+        ("n_prev_poses", C.c_int),
+        ("n_prev_cmds", C.c_int),
+        ("n_blocks", C.c_int),
+        ("time_step", C.c_float),
+        ("current_path_w", C.c_float),
+        ("current_cmds_w", C.c_float),
+        ("poses", C.c_void_p),
+        ("cmds", C.c_void_p),
+        ("speed", C.c_void_p),
+        ("prev_poses", C.c_void_p),
+        ("prev_cmds", C.c_void_p),
+        ("robot", C.c_void_p),
+        ("pose0", C.c_void_p),
+        ("u0", C.c_void_p),
+        ("path_xy", C.c_void_p),
+        ("goal_yaw", C.c_void_p),
+    ]

@@ -270,9 +270,134 @@ __global__ void __launch_bounds__(kWarps * 32) smpc_project_kernel(smpc_project_
   }
 }
 
+// format_to_optimize (reference src/optimizer.cpp:484-551) + unpacking (:197-237), one thread per (problem, pose)
+__global__ void smpc_format_kernel(smpc_format_args a) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int P = a.n_poses;
+  if (t >= (long long)a.n_problems * P) return;
+  const int b = (int)(t / P), i = (int)(t % P);
+  const double* cp = a.poses + ((size_t)b * P + i) * 3;
+  const bool have_prev = a.prev_poses != nullptr && a.n_prev_poses > 0;
+  // first tick: previous = current (TrajectoryMemory seeding, :177-181) -> blending happens against itself
+  const int n_prev_poses = have_prev ? a.n_prev_poses : P;
+  const double wp = a.current_path_w, wc = a.current_cmds_w;
+  double x = cp[0], y = cp[1], yaw = cp[2];
+  if (i < n_prev_poses) {
+    const double* pp = have_prev ? a.prev_poses + ((size_t)b * a.n_prev_poses + i) * 3 : cp;
+    x = wp * cp[0] + (1.0 - wp) * pp[0];
+    y = wp * cp[1] + (1.0 - wp) * pp[1];
+    const double sm = wp * cp[2] + (1.0 - wp) * pp[2];
+    double sh, ch;
+    sincos(sm * 0.5, &sh, &ch);
+    yaw = atan2(2.0 * (ch * sh), ch * ch - sh * sh);  // setRPY -> getYaw (:517-525)
+  }
+  double lv, av;
+  if (i == 0) {
+    lv = a.speed[2 * b];
+    av = a.speed[2 * b + 1];
+  } else {
+    const double* cc = a.cmds + ((size_t)b * (P - 1) + (i - 1)) * 2;
+    const bool have_pc = a.prev_cmds != nullptr && (i - 1) < a.n_prev_cmds;  // SURVEY Q11 guard
+    const double* pc = have_pc ? a.prev_cmds + ((size_t)b * a.n_prev_cmds + (i - 1)) * 2 : cc;
+    lv = wc * cc[0] + (1.0 - wc) * pc[0];
+    av = wc * cc[1] + (1.0 - wc) * pc[1];
+  }
+  double* r = a.robot + ((size_t)b * P + i) * 6;
+  r[0] = x; r[1] = y; r[2] = yaw; r[3] = (double)((float)i * a.time_step); r[4] = lv; r[5] = av;
+  a.path_xy[(size_t)b * 2 * P + i] = x;
+  a.path_xy[(size_t)b * 2 * P + P + i] = y;
+  if (i < a.n_blocks) {
+    a.u0[((size_t)b * a.n_blocks + i) * 2] = lv;  // block b starts at the seed velocity of time index b (Q1)
+    a.u0[((size_t)b * a.n_blocks + i) * 2 + 1] = av;
+  }
+  if (i == 0) {
+    double sh, ch;
+    sincos(yaw * 0.5, &sh, &ch);
+    a.pose0[3 * b] = x;
+    a.pose0[3 * b + 1] = y;
+    a.pose0[3 * b + 2] = atan2(2.0 * (ch * sh), ch * ch - sh * sh);  // evolving_poses[0]: setRPY (:224-226) + getYaw
+  }
+  if (i == P - 1) a.goal_yaw[b] = yaw;
+}
+
+__global__ void smpc_people_status_kernel(int B, int A, const double* __restrict__ raw, const int32_t* __restrict__ n_people,
+                                          double* __restrict__ init, uint8_t* __restrict__ has_people) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)B * A) return;
+  const int b = (int)(t / A), k = (int)(t % A);
+  const int n = n_people[b];
+  double* o = init + (size_t)t * 6;
+  if (k < n) {
+    const double* p = raw + (size_t)t * 5;
+    o[0] = p[0]; o[1] = p[1]; o[2] = atan2(p[3], p[2]); o[3] = 0.0; o[4] = sqrt(p[2] * p[2] + p[3] * p[3]); o[5] = p[4];
+  } else {  // invalid agent: time = -1 (:468-474)
+    o[0] = 0.0; o[1] = 0.0; o[2] = 0.0; o[3] = -1.0; o[4] = 0.0; o[5] = 0.0;
+  }
+  if (k == 0 && has_people) has_people[b] = n != 0;
+}
+
+__global__ void smpc_memory_update_kernel(int B, int n, const uint8_t* __restrict__ usable, const double* __restrict__ path,
+                                          const double* __restrict__ cmds, double* __restrict__ prev_poses,
+                                          double* __restrict__ prev_cmds) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)B * n) return;
+  const int b = (int)(t / n);
+  if (!usable[b]) return;
+  for (int c = 0; c < 3; ++c) prev_poses[t * 3 + c] = path[t * 3 + c];
+  for (int c = 0; c < 2; ++c) prev_cmds[t * 2 + c] = cmds[t * 2 + c];
+}
+
 }  // namespace
 
 extern "C" {
+
+int smpc_people_to_status_device(smpc_handle* h, int n_problems, int n_agents, const double* people_raw,
+                                 const int32_t* n_people, double* people_init, uint8_t* has_people, void* stream) {
+  if (!h || n_problems < 0 || n_agents < 1 || !people_raw || !n_people || !people_init)
+    return smpc_host_fail(SMPC_ERR_ARGUMENT, "people_to_status: bad arguments");
+  if (n_problems == 0) return SMPC_OK;
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : smpc_handle_stream(h);
+  const long long n = (long long)n_problems * n_agents;
+  smpc_people_status_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n_problems, n_agents, people_raw, n_people, people_init,
+                                                                       has_people);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return smpc_host_fail(SMPC_ERR_CUDA, std::string("people_status kernel: ") + cudaGetErrorString(e));
+  smpc_handle_count_launch(h);
+  return SMPC_OK;
+}
+
+int smpc_memory_update_device(smpc_handle* h, int n_problems, int n, const uint8_t* usable, const double* path,
+                              const double* cmds, double* prev_poses, double* prev_cmds, void* stream) {
+  if (!h || n_problems < 0 || n < 1 || !usable || !path || !cmds || !prev_poses || !prev_cmds)
+    return smpc_host_fail(SMPC_ERR_ARGUMENT, "memory_update: bad arguments");
+  if (n_problems == 0) return SMPC_OK;
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : smpc_handle_stream(h);
+  const long long total = (long long)n_problems * n;
+  smpc_memory_update_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(n_problems, n, usable, path, cmds, prev_poses,
+                                                                           prev_cmds);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return smpc_host_fail(SMPC_ERR_CUDA, std::string("memory_update kernel: ") + cudaGetErrorString(e));
+  smpc_handle_count_launch(h);
+  return SMPC_OK;
+}
+
+
+int smpc_format_batch_device(smpc_handle* h, const smpc_format_args* a, void* stream) {
+  if (!h || !a) return smpc_host_fail(SMPC_ERR_ARGUMENT, "NULL argument");
+  if (a->n_problems < 0 || a->n_poses < 2 || a->n_blocks < 1 || a->n_blocks > a->n_poses - 1)
+    return smpc_host_fail(SMPC_ERR_ARGUMENT, "format: need n_poses >= 2 and 1 <= n_blocks <= n_poses - 1");
+  if (!a->poses || !a->cmds || !a->speed || !a->robot || !a->pose0 || !a->u0 || !a->path_xy || !a->goal_yaw)
+    return smpc_host_fail(SMPC_ERR_ARGUMENT, "format: missing buffer");
+  if (a->n_problems == 0) return SMPC_OK;
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : smpc_handle_stream(h);
+  const long long n = (long long)a->n_problems * a->n_poses;
+  smpc_format_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(*a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return smpc_host_fail(SMPC_ERR_CUDA, std::string("format kernel: ") + cudaGetErrorString(e));
+  smpc_handle_count_launch(h);
+  return SMPC_OK;
+}
+
 
 int smpc_project_people_batch_device(smpc_handle* h, const smpc_project_args* a, void* stream) {
   if (!h || !a) return smpc_host_fail(SMPC_ERR_ARGUMENT, "NULL argument");

@@ -186,3 +186,52 @@ def test_gpu_project_people_grid_quirks(opt_for):
     got, status = opt.project_people_batch(robot, init, dict(width=80, height=80, resolution=0.05, origins=[[0.0, 0.0]],
                                                              indexes=od["indexes"]), p.max_time, p.time_step)
     assert status[0] == 0 and status[1] == 1
+
+
+def test_fleet_tick_matches_per_robot_optimize(opt_for):
+    """FleetOptimizer (every stage a kernel, B robots per call) vs the single-robot level-2 entry, two ticks so that
+    the per-robot warm-start memory (previous path / cmds) is exercised."""
+    from nav2_social_mpc_controller_b200.fleet import FleetOptimizer
+    from nav2_social_mpc_controller_b200.optimizer import Optimizer
+    B, A = 6, 3
+    scenes = [_scene("soc_work_obst", n_people=(b % 3) + 1, seed=20 + b) for b in range(B)]
+    p = scenes[0][0]
+    od = scenes[0][6]
+    costmap = scenes[0][5]
+    n_in = scenes[0][1].shape[0]
+    poses = np.stack([s[1] for s in scenes])
+    cmds = np.stack([s[2] for s in scenes])
+    speed = np.array([[0.3, 0.05]] * B)
+    people_raw = np.zeros((B, A, 5))
+    n_people = np.zeros(B, dtype=np.int32)
+    for b, s in enumerate(scenes):
+        k = min(A, s[3].shape[0])
+        people_raw[b, :k] = s[3][:k]
+        n_people[b] = k
+    fleet = FleetOptimizer(p, n_robots=B, n_agents=A)
+    singles = []
+    for b in range(B):
+        o = Optimizer(0)
+        o.initialize(p)
+        singles.append(o)
+    try:
+        od_b = dict(width=od["width"], height=od["height"], resolution=od["resolution"], origins=[[0.0, 0.0]],
+                    indexes=od["indexes"])
+        for tick in range(2):
+            got = fleet.optimize_batch(poses, cmds, people_raw, n_people, speed, costmap[None], np.zeros((1, 2)), 0.05,
+                                       od_b)
+            assert np.all(got["project_status"] == 0)
+            for b in range(B):
+                ok, path, new_cmds, proj, info = singles[b].optimize(poses[b], cmds[b], scenes[b][3][:A], speed[b],
+                                                                      p.time_step, costmap, (0.0, 0.0), 0.05, od)
+                assert bool(got["optimized"][b]) == ok
+                assert np.abs(got["people_proj"][b] - np.transpose(proj, (1, 2, 0))).max() <= 1e-9
+                assert got["termination"][b] == info["termination"]
+                assert np.abs(got["cmds"][b] - new_cmds).max() <= 1e-6, (tick, b)
+                assert np.abs(got["path"][b][:, :2] - path[:, :2]).max() <= 1e-6
+                assert got["cost_final"][b] == pytest.approx(info["cost_final"], rel=1e-8)
+    finally:
+        fleet.close()
+        for o in singles:
+            o.close()
+    assert n_in >= 2
