@@ -299,6 +299,31 @@ typedef struct smpc_format_args {
 } smpc_format_args;
 int smpc_format_batch_device(smpc_handle* h, const smpc_format_args* a, void* stream);
 
+/* ---- batched seed generation on the GPU: PathTrajectorizer::trajectorize (src/path_trajectorizer.cpp:120-288) ----
+ * One thread per robot: pure-pursuit look-ahead on its global path, diff-drive (curvature law, rotate in place beyond
+ * 90 deg) or omnidirectional branch (:190-194), forward-Euler simulation with the DOUBLE time_step, early
+ * stop within 0.2 m of the goal. global_path [B][n_path][2] (path_index NULL) or [Mp][n_path][2] selected by
+ * path_index [B]; pose [B][3]. Outputs poses [B][max_steps+1][3] (pose 0 = the robot pose, yaw round-tripped like
+ * setRPY/getYaw), cmds [B][max_steps][3] = linear.x, linear.y, angular.z, n_steps [B] = steps actually produced
+ * (entries beyond it are left untouched). Returns the reference's `false` (path with < 2 poses) as SMPC_ERR_ARGUMENT. */
+typedef struct smpc_trajectorize_args {
+  int n_problems;
+  int n_path;
+  int max_steps;
+  int omnidirectional;
+  double desired_linear_vel;
+  double lookahead_dist;
+  double max_angular_vel;
+  double time_step;
+  const double* global_path;
+  const int32_t* path_index; /* may be NULL */
+  const double* pose;
+  double* poses;
+  double* cmds;
+  int32_t* n_steps;
+} smpc_trajectorize_args;
+int smpc_trajectorize_batch_device(smpc_handle* h, const smpc_trajectorize_args* a, void* stream);
+
 /* people_to_status (src/optimizer.cpp:454-482) for a fleet: people_raw [B][A][5] = position.x/y, velocity.x/y/z,
  * n_people [B] (entries >= n_people[b] are padding; more than A people are truncated by the caller like :476-479).
  * Outputs people_init [B][A][6] and has_people [B] (u8). Device pointers. */

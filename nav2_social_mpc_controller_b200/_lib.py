@@ -75,6 +75,8 @@ def lib():
     L.smpc_memory_update_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_void_p, C.c_void_p]
     L.smpc_memory_update_device.restype = C.c_int
+    L.smpc_trajectorize_batch_device.argtypes = [C.c_void_p, P(abi.SmpcTrajectorizeArgs), C.c_void_p]
+    L.smpc_trajectorize_batch_device.restype = C.c_int
     L.smpc_set_group.argtypes = [C.c_void_p, C.c_int]
     L.smpc_set_group.restype = C.c_int
     L.smpc_debug_polymin.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -97,4 +99,5 @@ EXPORTED_SYMBOLS = (
     "smpc_measure_fp64_peak", "smpc_debug_polymin", "smpc_set_group",
     "smpc_optimize", "smpc_reset_memory", "smpc_project_people_batch", "smpc_project_people_batch_device",
     "smpc_format_batch_device", "smpc_people_to_status_device", "smpc_memory_update_device",
+    "smpc_trajectorize_batch_device",
 )

@@ -256,3 +256,23 @@ class SmpcFormatArgs(C.Structure):
         ("path_xy", C.c_void_p),
         ("goal_yaw", C.c_void_p),
     ]
+
+
+class SmpcTrajectorizeArgs(C.Structure):
+    """struct smpc_trajectorize_args — batched PathTrajectorizer::trajectorize."""
+    _fields_ = [
+        ("n_problems", C.c_int),
+        ("n_path", C.c_int),
+        ("max_steps", C.c_int),
+        ("omnidirectional", C.c_int),
+        ("desired_linear_vel", C.c_double),
+        ("lookahead_dist", C.c_double),
+        ("max_angular_vel", C.c_double),
+        ("time_step", C.c_double),
+        ("global_path", C.c_void_p),
+        ("path_index", C.c_void_p),
+        ("pose", C.c_void_p),
+        ("poses", C.c_void_p),
+        ("cmds", C.c_void_p),
+        ("n_steps", C.c_void_p),
+    ]

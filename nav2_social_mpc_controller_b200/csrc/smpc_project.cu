@@ -320,6 +320,77 @@ __global__ void smpc_format_kernel(smpc_format_args a) {
   if (i == P - 1) a.goal_yaw[b] = yaw;
 }
 
+// PathTrajectorizer::trajectorize, reference src/path_trajectorizer.cpp:120-288; one thread per robot
+__global__ void smpc_trajectorize_kernel(smpc_trajectorize_args a) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.n_problems) return;
+  const int N = a.n_path;
+  const double* path = a.global_path + (size_t)(a.path_index ? a.path_index[b] : b) * N * 2;
+  double rx = a.pose[3 * b], ry = a.pose[3 * b + 1];
+  double rth;
+  {
+    double sh, ch;
+    sincos(a.pose[3 * b + 2] * 0.5, &sh, &ch);
+    rth = atan2(2.0 * (ch * sh), ch * ch - sh * sh);  // tf2::getYaw(robot_pose.pose.orientation)
+  }
+  double* poses = a.poses + (size_t)b * (a.max_steps + 1) * 3;
+  double* cmds = a.cmds + (size_t)b * a.max_steps * 3;
+  poses[0] = rx; poses[1] = ry; poses[2] = rth;
+  const double gx = path[2 * (N - 1)], gy = path[2 * (N - 1) + 1];
+  double goal_dist = 1000.0;
+  int steps = 0;
+  while (goal_dist > 0.2 && steps < a.max_steps) {
+    // look-ahead point: scanning from the END, the first pose within lookahead_dist, else the nearest one
+    double min_dist = 100.0;
+    int wp = -1;
+    for (int i = N - 1; i >= 0; --i) {
+      const double dx = rx - path[2 * i], dy = ry - path[2 * i + 1];
+      const double d = sqrt(dx * dx + dy * dy);
+      if (d <= a.lookahead_dist) { wp = i; break; }
+      if (d < min_dist) { min_dist = d; wp = i; }
+    }
+    if (wp < 0) wp = N - 1;  // every pose farther than 100 m: the reference would index -1 (UB); take the goal
+    const double wpx = path[2 * wp], wpy = path[2 * wp + 1];
+    double st, ct;
+    sincos(rth, &st, &ct);
+    const double dx = (wpx - rx) * ct + (wpy - ry) * st;
+    const double dy = -(wpx - rx) * st + (wpy - ry) * ct;
+    const double dtheta = atan2(dy, dx);
+    double vx = 0.0, vy = 0.0, wz = 0.0;
+    if (a.omnidirectional) {
+      vx = a.desired_linear_vel * cos(dtheta);
+      vy = a.desired_linear_vel * sin(dtheta);
+    } else {
+      const double d2 = dx * dx + dy * dy;
+      double curvature = 0.0;
+      if (d2 > 0.001) curvature = 2.0 * dy / d2;
+      vx = a.desired_linear_vel;
+      if (fabs(dtheta) > M_PI / 2.0) {
+        vx = 0.0;
+        wz = a.max_angular_vel * (dtheta > 0 ? 1.0 : -1.0);
+      } else {
+        wz = vx * curvature;
+      }
+    }
+    // computeNewX/Y/ThetaPosition (path_trajectorizer.hpp:106-133)
+    rx = rx + (vx * ct + vy * cos(M_PI_2 + rth)) * a.time_step;
+    ry = ry + (vx * st + vy * sin(M_PI_2 + rth)) * a.time_step;
+    rth = rth + wz * a.time_step;
+    double sh, ch;
+    sincos(rth * 0.5, &sh, &ch);
+    poses[3 * (steps + 1)] = rx;
+    poses[3 * (steps + 1) + 1] = ry;
+    poses[3 * (steps + 1) + 2] = atan2(2.0 * (ch * sh), ch * ch - sh * sh);  // setRPY(0, 0, rtheta) as read back by getYaw
+    cmds[3 * steps] = vx;
+    cmds[3 * steps + 1] = vy;
+    cmds[3 * steps + 2] = wz;
+    const double ex = rx - gx, ey = ry - gy;
+    goal_dist = sqrt(ex * ex + ey * ey);
+    ++steps;
+  }
+  a.n_steps[b] = steps;
+}
+
 __global__ void smpc_people_status_kernel(int B, int A, const double* __restrict__ raw, const int32_t* __restrict__ n_people,
                                           double* __restrict__ init, uint8_t* __restrict__ has_people) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -350,6 +421,21 @@ __global__ void smpc_memory_update_kernel(int B, int n, const uint8_t* __restric
 }  // namespace
 
 extern "C" {
+
+int smpc_trajectorize_batch_device(smpc_handle* h, const smpc_trajectorize_args* a, void* stream) {
+  if (!h || !a) return smpc_host_fail(SMPC_ERR_ARGUMENT, "NULL argument");
+  if (a->n_path < 2) return smpc_host_fail(SMPC_ERR_ARGUMENT, "Path has less than 2 poses, cannot trajectorize");
+  if (a->n_problems < 0 || a->max_steps < 1 || !(a->time_step > 0.0) || !a->global_path || !a->pose || !a->poses ||
+      !a->cmds || !a->n_steps)
+    return smpc_host_fail(SMPC_ERR_ARGUMENT, "trajectorize: bad arguments");
+  if (a->n_problems == 0) return SMPC_OK;
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : smpc_handle_stream(h);
+  smpc_trajectorize_kernel<<<(a->n_problems + 127) / 128, 128, 0, st>>>(*a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return smpc_host_fail(SMPC_ERR_CUDA, std::string("trajectorize kernel: ") + cudaGetErrorString(e));
+  smpc_handle_count_launch(h);
+  return SMPC_OK;
+}
 
 int smpc_people_to_status_device(smpc_handle* h, int n_problems, int n_agents, const double* people_raw,
                                  const int32_t* n_people, double* people_init, uint8_t* has_people, void* stream) {

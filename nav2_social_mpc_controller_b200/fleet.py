@@ -34,6 +34,28 @@ class FleetOptimizer:
     def _t(self, a, dtype):
         return self.torch.as_tensor(np.ascontiguousarray(a, dtype=dtype)).to(self.dev)
 
+    def trajectorize_batch(self, global_path, pose):
+        """Batched PathTrajectorizer::trajectorize (reference src/path_trajectorizer.cpp:120-288) on the GPU.
+        global_path [B][N][2], pose [B][3] -> poses [B][max_steps+1][3], cmds [B][max_steps][3], n_steps [B]."""
+        torch, L, h, p = self.torch, _lib.lib(), self.opt._h, self.p
+        gp = np.ascontiguousarray(global_path, dtype=np.float64)
+        B, N, _ = gp.shape
+        max_steps = int(round(float(p.max_time) / round(float(p.time_step), 6)))
+        with torch.cuda.stream(self.stream):
+            d_gp, d_pose = self._t(gp, np.float64), self._t(pose, np.float64)
+            poses = torch.zeros(B, max_steps + 1, 3, dtype=torch.float64, device=self.dev)
+            cmds = torch.zeros(B, max_steps, 3, dtype=torch.float64, device=self.dev)
+            n_steps = torch.zeros(B, dtype=torch.int32, device=self.dev)
+            a = abi.SmpcTrajectorizeArgs()
+            a.n_problems, a.n_path, a.max_steps, a.omnidirectional = B, N, max_steps, int(p.omnidirectional)
+            a.desired_linear_vel, a.lookahead_dist = p.traj_desired_linear_vel, p.lookahead_dist
+            a.max_angular_vel, a.time_step = p.max_angular_vel, round(float(p.time_step), 6)
+            a.global_path, a.path_index, a.pose = d_gp.data_ptr(), None, d_pose.data_ptr()
+            a.poses, a.cmds, a.n_steps = poses.data_ptr(), cmds.data_ptr(), n_steps.data_ptr()
+            _lib.check(L.smpc_trajectorize_batch_device(h, C.byref(a), self.stream.cuda_stream))
+        self.stream.synchronize()
+        return poses.cpu().numpy(), cmds.cpu().numpy(), n_steps.cpu().numpy()
+
     def optimize_batch(self, poses, cmds, people_raw, n_people, speed, costmaps, costmap_origin, costmap_resolution,
                        od: dict, costmap_index=None, od_index=None) -> dict:
         """poses [B][n][3], cmds [B][n-1][2] (trajectorizer seeds, same length for the fleet), people_raw [B][A][5],

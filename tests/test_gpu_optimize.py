@@ -235,3 +235,55 @@ def test_fleet_tick_matches_per_robot_optimize(opt_for):
         for o in singles:
             o.close()
     assert n_in >= 2
+
+
+def test_gpu_trajectorize_matches_numpy_restatement():
+    """Seed generation kernel vs scenarios.pure_pursuit_seed (numpy restatement of reference
+    src/path_trajectorizer.cpp:120-288), diff-drive branch, goals beyond the horizon; plus the early stop near the
+    goal and the omnidirectional branch against a scalar Python restatement."""
+    from nav2_social_mpc_controller_b200.fleet import FleetOptimizer
+    rng = np.random.default_rng(4)
+    B = 64
+    p = sc.make_params("soc_work_obst")
+    pose = np.stack([rng.uniform(0.5, 1.0, B), 2.0 + rng.uniform(-0.4, 0.4, B), rng.uniform(-2.5, 2.5, B)], axis=1)
+    gpath = sc._straight_path(B, np.full(B, 0.6), np.full(B, 2.0))
+    want_poses, want_cmds = sc.pure_pursuit_seed(gpath, pose, p)
+    fleet = FleetOptimizer(p, n_robots=B)
+    try:
+        poses, cmds, n_steps = fleet.trajectorize_batch(gpath, pose)
+        assert np.all(n_steps == want_cmds.shape[1])
+        assert np.abs(poses[:, :, :2] - want_poses[:, :, :2]).max() <= 1e-12
+        assert np.abs(np.cos(poses[:, :, 2] - want_poses[:, :, 2]) - 1).max() <= 1e-12
+        assert np.abs(cmds[:, :, 0] - want_cmds[:, :, 0]).max() <= 1e-12 and np.all(cmds[:, :, 1] == 0.0)
+        assert np.abs(cmds[:, :, 2] - want_cmds[:, :, 1]).max() <= 1e-11
+        # early stop: a goal 0.5 m ahead is reached (<= 0.2 m) after a few steps
+        short = sc._straight_path(B, pose[:, 0], pose[:, 1], length=0.5)
+        pose0 = pose.copy()
+        pose0[:, 2] = 0.0
+        _, _, n_short = fleet.trajectorize_batch(short, pose0)
+        want_n = int(np.ceil((0.5 - 0.2) / (0.6 * 0.05) - 1e-9))
+        assert np.all(n_short == want_n), (n_short[:4], want_n)
+    finally:
+        fleet.close()
+    po = sc.make_params("soc_work_obst", omnidirectional=1)
+    fleet = FleetOptimizer(po, n_robots=4)
+    try:
+        poses, cmds, n_steps = fleet.trajectorize_batch(gpath[:4], pose[:4])
+        for b in range(4):
+            rx, ry, rth = pose[b, 0], pose[b, 1], float(sc.yaw_roundtrip(pose[b, 2]))
+            for s in range(3):
+                d = np.hypot(rx - gpath[b, :, 0], ry - gpath[b, :, 1])
+                within = np.nonzero(d <= po.lookahead_dist)[0]
+                wp = within[-1] if within.size else (len(d) - 1 - int(np.argmin(d[::-1])))
+                dx = (gpath[b, wp, 0] - rx) * math.cos(rth) + (gpath[b, wp, 1] - ry) * math.sin(rth)
+                dy = -(gpath[b, wp, 0] - rx) * math.sin(rth) + (gpath[b, wp, 1] - ry) * math.cos(rth)
+                dth = math.atan2(dy, dx)
+                vx, vy = 0.6 * math.cos(dth), 0.6 * math.sin(dth)
+                assert cmds[b, s, 0] == pytest.approx(vx, abs=1e-12) and cmds[b, s, 1] == pytest.approx(vy, abs=1e-12)
+                assert cmds[b, s, 2] == 0.0
+                rx += (vx * math.cos(rth) + vy * math.cos(math.pi / 2 + rth)) * 0.05
+                ry += (vx * math.sin(rth) + vy * math.sin(math.pi / 2 + rth)) * 0.05
+                assert poses[b, s + 1, 0] == pytest.approx(rx, abs=1e-12)
+                assert poses[b, s + 1, 1] == pytest.approx(ry, abs=1e-12)
+    finally:
+        fleet.close()
