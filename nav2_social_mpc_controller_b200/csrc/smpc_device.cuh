@@ -39,6 +39,8 @@ struct DevBatch {
   const double* path_xy;
   const double* goal_yaw;
   const double* agents;
+  const double* agents_packed;  // [B][A][S+1][4] = x, y, vx, vy (built once per batch by smpc_pack_agents_kernel)
+  const uint8_t* agents_valid;  // [B][A][S+1]   = (t != -1)
   const uint8_t* has_people;
   const uint8_t* costmaps;
   const double* costmap_origin;
@@ -70,6 +72,8 @@ struct Prob {
   const double* px;
   const double* py;
   const double* agents;  // [A][6][S+1]
+  const double* packed;  // [A][S+1][4]
+  const uint8_t* valid;  // [A][S+1]
   const uint8_t* map;
   bool has_people;
 };
@@ -269,7 +273,7 @@ struct Layout {
   static constexpr int kYaw = kCarry + NC;  // sin, cos of yaw0
   static constexpr int kState = kYaw + 2;    // LmState (solver scalars parked here across the evaluation)
   static constexpr int kProb = kState + 20;  // Prob (group-uniform problem view)
-  static constexpr int kAa = kProb + 13;  // agent-angle steering target per step [S]
+  static constexpr int kAa = kProb + 15;  // agent-angle steering target per step [S]
   __host__ __device__ static constexpr int total(int S) { return ((kAa + S) | 1); }  // odd stride: no bank conflicts
   __host__ __device__ static constexpr int g(int c) { return 1 + c; }
   __host__ __device__ static constexpr int h(int a, int b) { return 1 + P + a * (a + 1) / 2 + b; }
@@ -433,11 +437,27 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
         double G4[4] = {0, 0, 0, 0};  // gradient of (wr + wp) wrt (dX, dY, dvx, dvy) of the robot
         double dmin = DBL_MAX, pdx = 0.0, pdy = 0.0;
         const bool do_social = prm.w_social != 0.0;
+        // agent records (x, y, vx, vy) of step j+1, one 32-byte sector each; the next agent's record is fetched
+        // while the current pair interaction is evaluated
+        const double2* rec = reinterpret_cast<const double2*>(pb.packed) + ((size_t)(j + 1)) * 2;
+        const uint8_t* vld = pb.valid + (j + 1);
+        double2 nxt_p = make_double2(0.0, 0.0), nxt_v = make_double2(0.0, 0.0);
+        bool nxt_valid = false;
+        if (bt.A > 0) {
+          nxt_p = __ldg(rec);
+          nxt_v = __ldg(rec + 1);
+          nxt_valid = __ldg(vld) != 0;
+        }
 #pragma unroll 1
         for (int k = 0; k < bt.A; ++k) {
-          const double* a = pb.agents + (size_t)k * 6 * stride + (j + 1);
-          const double ax = __ldg(a), ay = __ldg(a + stride), at = __ldg(a + 3 * stride);
-          const bool valid = !(at == -1.0);
+          const double ax = nxt_p.x, ay = nxt_p.y, avx = nxt_v.x, avy = nxt_v.y;
+          const bool valid = nxt_valid;
+          if (k + 1 < bt.A) {
+            const double2* r2 = rec + (size_t)(k + 1) * stride * 2;
+            nxt_p = __ldg(r2);
+            nxt_v = __ldg(r2 + 1);
+            nxt_valid = __ldg(vld + (size_t)(k + 1) * stride) != 0;
+          }
           const double ddx = X - ax, ddy = Y - ay;
           if (valid) {
             const double d2 = ddx * ddx + ddy * ddy;
@@ -448,10 +468,6 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
             }
           }
           if (do_social) {
-            const double ayaw = __ldg(a + 2 * stride), alv = __ldg(a + 4 * stride);
-            double sa, ca;
-            sincos(ayaw, &sa, &ca);
-            const double avx = alv * ca, avy = alv * sa;
             // F(robot <- agent k) = pair(d, w) with d = robot - agent, w = v_robot - v_agent, and
             // F(agent k <- robot) = pair(-d, -w). The pair function is odd, pair(-d, -w) = -pair(d, w) (e, I and
             // their unit vectors flip, theta / B / |d| do not), so ONE evaluation serves both terms of the
@@ -963,6 +979,8 @@ __device__ __forceinline__ void load_problem(const DevBatch& bt, int b, Prob& pb
   pb.fin_x = __ldg(pb.px + S);
   pb.fin_y = __ldg(pb.py + S);
   pb.agents = (bt.A > 0 && bt.agents) ? bt.agents + (size_t)b * bt.A * 6 * (S + 1) : nullptr;
+  pb.packed = pb.agents ? bt.agents_packed + (size_t)b * bt.A * (S + 1) * 4 : nullptr;
+  pb.valid = pb.agents ? bt.agents_valid + (size_t)b * bt.A * (S + 1) : nullptr;
   pb.has_people = (bt.has_people != nullptr) && (bt.has_people[b] != 0);
   const int mi = bt.costmap_index ? __ldg(bt.costmap_index + b) : (b % bt.M);
   pb.map = bt.costmaps + (size_t)mi * bt.size_x * bt.size_y;
@@ -1062,7 +1080,7 @@ struct LmState {
   int iteration, n_invalid, n_eval, ls_iters, term, phase, b, flags;
 };
 static_assert(sizeof(LmState) == 20 * sizeof(double), "Layout::kState reserves 20 doubles");
-static_assert(sizeof(Prob) <= 13 * sizeof(double), "Layout::kProb reserves 13 doubles");
+static_assert(sizeof(Prob) <= 15 * sizeof(double), "Layout::kProb reserves 15 doubles");
 enum StateFlags {
   kReuseDiagonal = 1, kItSuccessful = 2, kAnySuccess = 4, kPrevOk = 8, kLive = 16, kExhausted = 32, kSwapped = 64
 };

@@ -85,6 +85,7 @@ struct smpc_handle {
   std::mutex mu;
   // staging for the host-buffer entry points
   DeviceBuffer in_buf, out_buf;
+  DeviceBuffer pack_buf;  // agent records (x, y, vx, vy) + validity bytes of the current batch
   smpc_memory memory;  // previous path / cmds of the level-2 entry
 };
 
@@ -166,6 +167,9 @@ void to_dev_batch(const smpc_batch& in, smpc::DevBatch* d) {
   d->costmap_index = in.costmap_index;
 }
 
+// Build the packed agent records of a batch in the handle's scratch buffer (one small kernel per batch).
+int pack_agents(smpc_handle* h, smpc::DevBatch* bt, cudaStream_t stream);
+
 void to_dev_result(const smpc_result& out, smpc::DevResult* d) {
   d->u = out.u;
   d->cmds = out.cmds;
@@ -179,6 +183,22 @@ void to_dev_result(const smpc_result& out, smpc::DevResult* d) {
 }
 
 size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+int pack_agents(smpc_handle* h, smpc::DevBatch* bt, cudaStream_t stream) {
+  bt->agents_packed = nullptr;
+  bt->agents_valid = nullptr;
+  if (bt->A <= 0 || bt->agents == nullptr) return SMPC_OK;
+  const size_t rows = static_cast<size_t>(bt->B) * bt->A, S1 = static_cast<size_t>(bt->S) + 1;
+  const size_t rec_bytes = align256(rows * S1 * 4 * sizeof(double));
+  SMPC_CUDA(h->pack_buf.reserve(rec_bytes + rows * S1));
+  double* packed = static_cast<double*>(h->pack_buf.ptr);
+  uint8_t* valid = static_cast<uint8_t*>(h->pack_buf.ptr) + rec_bytes;
+  SMPC_CUDA(smpc::launch_pack_agents(static_cast<long long>(rows), static_cast<int>(S1), bt->agents, packed, valid, stream));
+  h->launches += 1;
+  bt->agents_packed = packed;
+  bt->agents_valid = valid;
+  return SMPC_OK;
+}
 
 struct Carver {  // carve aligned sub-buffers out of one device allocation
   char* base;
@@ -416,6 +436,7 @@ void smpc_destroy(smpc_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   h->in_buf.release();
   h->out_buf.release();
+  h->pack_buf.release();
   if (h->queue) cudaFree(h->queue);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -436,6 +457,8 @@ static int solve_device_locked(smpc_handle* h, const smpc_batch* in, smpc_result
   smpc::DevResult rs;
   to_dev_result(*out, &rs);
   SMPC_CUDA(cudaSetDevice(h->device));
+  rc = pack_agents(h, &bt, stream);
+  if (rc != SMPC_OK) return rc;
   SMPC_CUDA(cudaMemsetAsync(h->queue, 0, sizeof(int), stream));
   SMPC_CUDA(cudaEventRecord(h->ev0, stream));
   SMPC_CUDA(smpc::launch_solve(prm, bt, rs, h->queue, h->n_sm, h->forced_group, h->forced_warps, stream));
@@ -532,6 +555,8 @@ int smpc_eval_batch_device(smpc_handle* h, const smpc_batch* in, const double* x
   smpc::DevEvalOut eo{out->cost, out->grad, out->hess, out->ok};
   SMPC_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+  rc = pack_agents(h, &bt, st);
+  if (rc != SMPC_OK) return rc;
   SMPC_CUDA(smpc::launch_eval(prm, bt, x, eo, h->n_sm, h->forced_group, st));
   h->launches += 1;
   return SMPC_OK;

@@ -16,6 +16,8 @@ cudaError_t launch_eval(const DevParams& prm, const DevBatch& bt, const double* 
 cudaError_t launch_argmin(int n_robots, int n_starts, int n_blocks, const double* cost_final, const uint8_t* usable,
                           const double* u, int32_t* best_index, double* best_cost, double* best_u, cudaStream_t stream);
 int max_supported_blocks();
+cudaError_t launch_pack_agents(long long n_rows, int S1, const double* agents, double* packed, uint8_t* valid,
+                               cudaStream_t stream);
 cudaError_t launch_polymin(int n, const double* in, double* out, cudaStream_t stream);
 cudaError_t launch_dfma_peak(double* sink, int n_sm, int iters, cudaStream_t stream);
 }  // namespace smpc

@@ -18,6 +18,34 @@ constexpr int kThreads = kWarpsPerCta * 32;
 #define SMPC_MIN_CTAS (16 / SMPC_WARPS_PER_CTA)
 #endif
 
+// Agent records for the evaluation: (x, y, v cos yaw, v sin yaw) per agent and step, one 32-byte sector each, plus
+// a validity byte. Built once per batch so that the solve never calls sincos on agent headings (61 evaluations per
+// problem on average) and reads every agent with one coalesced sector instead of five strided rows.
+__global__ void smpc_pack_agents_kernel(long long n_rows, int S1, const double* __restrict__ agents,
+                                        double* __restrict__ packed, uint8_t* __restrict__ valid) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (problem * A + agent) * S1 + step
+  if (t >= n_rows * S1) return;
+  const long long row = t / S1;
+  const int step = (int)(t % S1);
+  const double* a = agents + row * 6 * S1 + step;
+  const double yaw = a[2 * (size_t)S1], lv = a[4 * (size_t)S1];
+  double sy, cy;
+  sincos(yaw, &sy, &cy);
+  double* o = packed + t * 4;
+  o[0] = a[0];
+  o[1] = a[S1];
+  o[2] = lv * cy;
+  o[3] = lv * sy;
+  valid[t] = !(a[3 * (size_t)S1] == -1.0);
+}
+
+cudaError_t launch_pack_agents(long long n_rows, int S1, const double* agents, double* packed, uint8_t* valid,
+                               cudaStream_t stream) {
+  const long long n = n_rows * S1;
+  smpc_pack_agents_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n_rows, S1, agents, packed, valid);
+  return cudaGetLastError();
+}
+
 // Line-search polynomial minimiser exposed for unit tests: rows of (lo, hi, f0, g0, t1, f1, g1, t2, f2, g2);
 // t2 <= 0 selects the two-sample (cubic) case.
 __global__ void smpc_polymin_kernel(int n, const double* __restrict__ in, double* __restrict__ out) {
