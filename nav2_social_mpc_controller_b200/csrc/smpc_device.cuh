@@ -255,6 +255,8 @@ __device__ __forceinline__ double agent_angle_target(const DevBatch& bt, const P
 
 // Per-group shared-memory state. Buffers hold [cost, g[P], H[NH]] (H row-major lower triangle,
 // H[a(a+1)/2 + b], a >= b) of the current iterate and of the trial point; the LM vectors follow.
+constexpr int kRedStride = 33;  // odd stride of the per-warp reduction scratch: conflict-free rows and columns
+
 template <int NB>
 struct Layout {
   static constexpr int P = 2 * NB;
@@ -275,6 +277,7 @@ struct Layout {
   static constexpr int kProb = kState + 20;  // Prob (group-uniform problem view)
   static constexpr int kAa = kProb + 15;  // agent-angle steering target per step [S]
   __host__ __device__ static constexpr int total(int S) { return ((kAa + S) | 1); }  // odd stride: no bank conflicts
+  static constexpr int kRedDoubles = NE * kRedStride;  // per-WARP scratch behind the per-group regions
   __host__ __device__ static constexpr int g(int c) { return 1 + c; }
   __host__ __device__ static constexpr int h(int a, int b) { return 1 + P + a * (a + 1) / 2 + b; }
 };
@@ -315,8 +318,8 @@ __device__ __forceinline__ void lane_setup(int j, int bl, double dt, LaneConst<N
 
 template <int NB, int G>
 __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatch& bt, const Prob& pb, bool live,
-                                             const LaneConst<NB>& lc0, double* ws, const double* xs, int lane,
-                                             double* out) {
+                                             const LaneConst<NB>& lc0, double* ws, double* red, const double* xs,
+                                             int lane, double* out) {
   using L = Layout<NB>;
   constexpr int P = L::P;
   const int gl = lane & (G - 1);
@@ -331,8 +334,9 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
   double x[P];
   SMPC_UNROLL for (int c = 0; c < P; ++c) x[c] = xs[c];
 
-  double acc[L::NE];  // [cost, g, H] partial sums of this lane
-  SMPC_UNROLL for (int e = 0; e < L::NE; ++e) acc[e] = 0.0;
+  // [cost, g, H] partial sums of this lane: column `lane` of the warp's shared scratch red[NE][33] (keeping them in
+  // registers costs 2 NE registers through the whole evaluation and a shuffle reduction at the end)
+  SMPC_UNROLL for (int e = 0; e < L::NE; ++e) red[e * kRedStride + lane] = 0.0;
   unsigned flags = 0;
 
   // heading before the group's first step: sin / cos of yaw0 (stored at problem set-up), then carried chunk to chunk
@@ -578,7 +582,7 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
 
       // --- lane block -> parameter space, one column at a time (T = M D[:,a] is never stored).
       //     Column of v_b: (dX, dY, 0, [b == bj]); of w_b: (dX, dY, dTheta, 0). ------------------------------
-      acc[0] += cost;
+      red[(0) * kRedStride + lane] += cost;
       SMPC_UNROLL for (int ba = 0; ba < NB; ++ba) {
         const double la = (ba == bj) ? 1.0 : 0.0;
         const double twa = tau[ba] + ((ba == bj) ? dt : 0.0);  // d Theta_j / d w_ba (heading after step j)
@@ -588,13 +592,13 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
           const double t1 = mXY * xv + mYY * yv + mYL * la;
           const double t2 = mXT * xv + mYT * yv + mTL * la;
           const double t3 = mXL * xv + mYL * yv + mLL * la;
-          acc[L::g(2 * ba)] += qX * xv + qY * yv + qL * la;
+          red[(L::g(2 * ba)) * kRedStride + lane] += qX * xv + qY * yv + qL * la;
           SMPC_UNROLL for (int bb = 0; bb <= ba; ++bb) {
             const double lb = (bb == bj) ? 1.0 : 0.0;
-            acc[L::h(2 * ba, 2 * bb)] += sd[4 * bb + 0] * t0 + sd[4 * bb + 1] * t1 + lb * t3;
+            red[(L::h(2 * ba, 2 * bb)) * kRedStride + lane] += sd[4 * bb + 0] * t0 + sd[4 * bb + 1] * t1 + lb * t3;
             if (bb < ba) {
               const double twb = tau[bb] + ((bb == bj) ? dt : 0.0);
-              acc[L::h(2 * ba, 2 * bb + 1)] += sd[4 * bb + 2] * t0 + sd[4 * bb + 3] * t1 + twb * t2;
+              red[(L::h(2 * ba, 2 * bb + 1)) * kRedStride + lane] += sd[4 * bb + 2] * t0 + sd[4 * bb + 3] * t1 + twb * t2;
             }
           }
         }
@@ -604,12 +608,12 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
           const double t1 = mXY * xw + mYY * yw + mYT * twa;
           const double t2 = mXT * xw + mYT * yw + mTT * twa;
           const double t3 = mXL * xw + mYL * yw + mTL * twa;
-          acc[L::g(2 * ba + 1)] += qX * xw + qY * yw + qT * twa;
+          red[(L::g(2 * ba + 1)) * kRedStride + lane] += qX * xw + qY * yw + qT * twa;
           SMPC_UNROLL for (int bb = 0; bb <= ba; ++bb) {
             const double lb = (bb == bj) ? 1.0 : 0.0;
             const double twb = tau[bb] + ((bb == bj) ? dt : 0.0);
-            acc[L::h(2 * ba + 1, 2 * bb)] += sd[4 * bb + 0] * t0 + sd[4 * bb + 1] * t1 + lb * t3;
-            acc[L::h(2 * ba + 1, 2 * bb + 1)] += sd[4 * bb + 2] * t0 + sd[4 * bb + 3] * t1 + twb * t2;
+            red[(L::h(2 * ba + 1, 2 * bb)) * kRedStride + lane] += sd[4 * bb + 0] * t0 + sd[4 * bb + 1] * t1 + lb * t3;
+            red[(L::h(2 * ba + 1, 2 * bb + 1)) * kRedStride + lane] += sd[4 * bb + 2] * t0 + sd[4 * bb + 3] * t1 + twb * t2;
           }
         }
       }
@@ -624,50 +628,40 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
         const double dv = x[2 * i] - x[2 * i - 2], dw = x[2 * i + 1] - x[2 * i - 1];
         const double r = prm.w_vf * dv * dv + prm.w_vf * dw * dw;
         const double jv = 2.0 * prm.w_vf * dv, jw = 2.0 * prm.w_vf * dw;
-        acc[0] += 0.5 * r * r;
+        red[(0) * kRedStride + lane] += 0.5 * r * r;
         // row: [2i-2] = -jv, [2i-1] = -jw, [2i] = jv, [2i+1] = jw
         const int p0 = 2 * i - 2, p1 = 2 * i - 1, p2 = 2 * i, p3 = 2 * i + 1;
-        acc[L::g(p0)] -= jv * r; acc[L::g(p1)] -= jw * r; acc[L::g(p2)] += jv * r; acc[L::g(p3)] += jw * r;
-        acc[L::h(p0, p0)] += jv * jv;
-        acc[L::h(p1, p0)] += jw * jv;
-        acc[L::h(p1, p1)] += jw * jw;
-        acc[L::h(p2, p0)] -= jv * jv;
-        acc[L::h(p2, p1)] -= jv * jw;
-        acc[L::h(p2, p2)] += jv * jv;
-        acc[L::h(p3, p0)] -= jw * jv;
-        acc[L::h(p3, p1)] -= jw * jw;
-        acc[L::h(p3, p2)] += jw * jv;
-        acc[L::h(p3, p3)] += jw * jw;
+        red[(L::g(p0)) * kRedStride + lane] -= jv * r; red[(L::g(p1)) * kRedStride + lane] -= jw * r; red[(L::g(p2)) * kRedStride + lane] += jv * r; red[(L::g(p3)) * kRedStride + lane] += jw * r;
+        red[(L::h(p0, p0)) * kRedStride + lane] += jv * jv;
+        red[(L::h(p1, p0)) * kRedStride + lane] += jw * jv;
+        red[(L::h(p1, p1)) * kRedStride + lane] += jw * jw;
+        red[(L::h(p2, p0)) * kRedStride + lane] -= jv * jv;
+        red[(L::h(p2, p1)) * kRedStride + lane] -= jv * jw;
+        red[(L::h(p2, p2)) * kRedStride + lane] += jv * jv;
+        red[(L::h(p3, p0)) * kRedStride + lane] -= jw * jv;
+        red[(L::h(p3, p1)) * kRedStride + lane] -= jw * jw;
+        red[(L::h(p3, p2)) * kRedStride + lane] += jw * jv;
+        red[(L::h(p3, p3)) * kRedStride + lane] += jw * jw;
       }
     }
   }
 
-  // group reduction. Halving exchange: after round r each lane keeps half of its entries summed with its
-  // partner's; after log2(G) rounds lane gl owns the group totals of entries e == gl (mod G) ... in the
-  // bit order of the exchange, and stores them. Entry count is padded with zeros to a multiple of G.
-  constexpr int NEP = ((L::NE + G - 1) / G) * G;
-  double v[NEP];
-  SMPC_UNROLL for (int e = 0; e < NEP; ++e) v[e] = (e < L::NE) ? acc[e] : 0.0;
-  {
-    int n = NEP;
-    SMPC_UNROLL for (int d = G / 2; d >= 1; d >>= 1) {
-      n >>= 1;
-      const bool up = (gl & d) != 0;
-      SMPC_UNROLL for (int k = 0; k < n; ++k) {
-        const double send = up ? v[k] : v[k + n];
-        const double keep = up ? v[k + n] : v[k];
-        v[k] = keep + __shfl_xor_sync(kFullMask, send, d, G);
-      }
-    }
-  }
-  // after the exchange lane gl holds, in v[k], the total of entry (NEP / G) * gl + k
+  // group reduction through shared memory: lane (g, r) of the warp sums, for the entries e = r, r + G, ..., the G
+  // columns of its group and stores the group totals
+  __syncwarp();
   bool bad_res = false, bad_jac = false;
-  constexpr int PER = NEP / G;
-  SMPC_UNROLL for (int k = 0; k < PER; ++k) {
-    const int e = PER * gl + k;
-    if (e < L::NE) {
-      out[e] = v[k];
-      if (!isfinite(v[k])) {
+  {
+    const int col0 = lane & ~(G - 1);
+    for (int e = gl; e < L::NE; e += G) {
+      const double* row = red + e * kRedStride + col0;
+      double t0 = 0.0, t1 = 0.0;
+      SMPC_UNROLL for (int t = 0; t < G; t += 2) {
+        t0 += row[t];
+        t1 += row[t + 1];
+      }
+      const double tot = t0 + t1;
+      out[e] = tot;
+      if (!isfinite(tot)) {
         if (e == 0) bad_res = true; else bad_jac = true;
       }
     }
@@ -1087,7 +1081,7 @@ enum StateFlags {
 
 template <int NB, int G>
 __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch& bt, const DevResult& rs, int* queue,
-                                           double* ws, int lane) {
+                                           double* ws, double* red, int lane) {
   using L = Layout<NB>;
   constexpr int P = L::P;
   const int gl = lane & (G - 1);
@@ -1112,6 +1106,7 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
   }
   __syncwarp(gmask);
 
+  unsigned loop_count = 0;
   for (;;) {
     if (gs->phase == kFetch && !(gs->flags & kExhausted)) {
       int nb_ = 0;
@@ -1152,24 +1147,28 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
     }
     // CTA barrier per evaluation: the warps of a CTA walk the large unrolled evaluation code together and share its
     // instruction-cache lines (measured +15..40 %); it also ends the loop once every group of the CTA is out of work
-    if (__syncthreads_and((gs->flags & kExhausted) != 0)) break;
+#ifndef SMPC_SYNC_EVERY
+#define SMPC_SYNC_EVERY 1
+#endif
+    if ((loop_count++ % SMPC_SYNC_EVERY) == 0) {
+      if (__syncthreads_and((gs->flags & kExhausted) != 0)) break;
+    }
 
     const bool live = (gs->flags & kLive) != 0;
-    const unsigned fl = evaluate<NB, G>(prm, bt, *pbs, live, lc0, ws, cand, lane,
+    const unsigned fl = evaluate<NB, G>(prm, bt, *pbs, live, lc0, ws, red, cand, lane,
                                         ws + ((gs->flags & kSwapped) ? L::kBuf0 : L::kBuf1));
-    if (!live) continue;
-
     // ---- phase logic, directly on the group's shared-memory state. The lanes of a group are converged here and
     //      take the same (group-uniform) branches, so they all store identical values. ---------------------------
     LmState& st = *gs;
     double* cur = ws + ((st.flags & kSwapped) ? L::kBuf1 : L::kBuf0);    // normal equations at x
     double* trial = ws + ((st.flags & kSwapped) ? L::kBuf0 : L::kBuf1);  // normal equations at the trial point
-    ++st.n_eval;
     const double t_cost = trial[0];
     bool take_step = false;   // proceed to accept/reject with `cand`
     bool finished = false;    // the solve of this problem has terminated
     bool next_sample = false; // another line-search sample has been set up in `cand`
 
+    if (live) {  // ===== part A: classify the evaluated point (init / line-search sample / full step), accept or reject
+    ++st.n_eval;
     if (st.phase == kInit) {
       st.cost_initial = st.cost_final = t_cost;
       if (fl) {
@@ -1284,8 +1283,13 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
       }
     }
 
+    }  // ===== end of part A
+#ifdef SMPC_MID_BARRIER
+    __syncthreads();  // part B (the LM step) is another large code region: enter it together as well
+#endif
+
     // ---- a new outer iteration starts here (after iteration zero or after accept / reject) ----
-    if (!finished && !next_sample) {
+    if (live && !finished && !next_sample) {
       if (st.flags & kItSuccessful) {  // x changed: refresh |x| and the projected-gradient max norm
         double xn = 0.0, gm = 0.0;
         SMPC_UNROLL for (int c = 0; c < P; ++c) {
@@ -1405,7 +1409,7 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
       }
     }
 
-    if (finished) {
+    if (live && finished) {
       // results. Solution = best accepted iterate when usable (Solver::Summary::IsSolutionUsable), else the seed.
       const bool usable = st.term <= kNoConvergence;
       const int b = st.b;
