@@ -1,0 +1,60 @@
+#!/usr/bin/env python
+"""Turn `ncu --set full` reports into the committed evidence under profiles/: key metrics + top stalls
+(r01_ncu_summaries.json), DRAM traffic per launch (r01_traffic.json) and source-level hot spots (text).
+Usage: tools/summarize_profiles.py DIR   (DIR holds prof_<workload>.ncu-rep files)"""
+import csv
+import glob
+import io
+import json
+import os
+import subprocess
+import sys
+
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+src = sys.argv[1]
+keys = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread',
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
+        'smsp__thread_inst_executed_per_inst_executed.ratio', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'smsp__sass_thread_inst_executed_op_dfma_pred_on.sum', 'smsp__sass_thread_inst_executed_op_dmul_pred_on.sum',
+        'smsp__sass_thread_inst_executed_op_dadd_pred_on.sum', 'l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum',
+        'l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+        'launch__shared_mem_per_block_dynamic']
+mult = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+spath = os.path.join(root, 'profiles', 'r01_ncu_summaries.json')
+summ = json.load(open(spath)) if os.path.exists(spath) else {}
+summ = {k: v for k, v in summ.items() if not k.startswith('final')}
+traffic = {}
+for rep in sorted(glob.glob(os.path.join(src, 'prof_*.ncu-rep'))):
+    w = os.path.basename(rep)[len('prof_'):-len('.ncu-rep')]
+    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    kname = vals[hdr.index('Kernel Name')]
+    d = {'what': f'final round-1 build, bench.py --workload {w}', 'kernel': kname}
+    for h, u, v in zip(hdr, units, vals):
+        if h in keys:
+            d[h] = f'{v} {u}'.strip()
+    st = [(h, float(v)) for h, v in zip(hdr, vals)
+          if 'smsp__average_warps_issue_stalled' in h and h.endswith('_per_issue_active.ratio')]
+    d['top_stalls_per_issue'] = {h.replace('smsp__average_warps_issue_stalled_', '').replace(
+        '_per_issue_active.ratio', ''): round(v, 3) for h, v in sorted(st, key=lambda t: -t[1])[:6]}
+    summ[f'final_{w}'] = d
+
+    def g(k):
+        return float(vals[hdr.index(k)]) * mult[units[hdr.index(k)]]
+    traffic[w] = {'bytes': g('dram__bytes_read.sum') + g('dram__bytes_write.sum'),
+                  'read_bytes': g('dram__bytes_read.sum'), 'write_bytes': g('dram__bytes_write.sum'),
+                  'unit': 'bytes per launch',
+                  'source': f'ncu --set full capture of `bench.py --workload {w}` (final_{w} in r01_ncu_summaries.json)'}
+    import re
+    m = re.search(r'smpc_solve_kernel<(\d+), (\d+), (\d+)>', kname)
+    mangled = f'smpc_solve_kernelILi{m.group(1)}ELi{m.group(2)}ELi{m.group(3)}E'
+    out = subprocess.run(['python', os.path.join(root, 'tools', 'ncu_hotspots.py'), rep, mangled, '25'],
+                         capture_output=True, text=True).stdout
+    open(os.path.join(root, 'profiles', f'r01_final_{w}_hotspots.txt'), 'w').write(out)
+    print(w, d['gpu__time_duration.sum'], 'issue', d['smsp__issue_active.avg.pct_of_peak_sustained_active'], 'fp64',
+          d['sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active'], d['top_stalls_per_issue'],
+          'dram MB r/w', traffic[w]['read_bytes'] / 1e6, traffic[w]['write_bytes'] / 1e6)
+json.dump(summ, open(spath, 'w'), indent=1)
+json.dump(traffic, open(os.path.join(root, 'profiles', 'r01_traffic.json'), 'w'), indent=1)
