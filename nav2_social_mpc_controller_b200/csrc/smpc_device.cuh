@@ -316,7 +316,7 @@ __device__ __forceinline__ void lane_setup(int j, int bl, double dt, LaneConst<N
   SMPC_UNROLL for (int b = 0; b < NB; ++b) lc.tau[b] = dt * (double)steps_in_block_before<NB>(j, b, bl);
 }
 
-template <int NB, int G>
+template <int NB, int G, bool PPL>
 __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatch& bt, const Prob& pb, bool live,
                                              const LaneConst<NB>& lc0, double* ws, double* red, const double* xs,
                                              int lane, double* out) {
@@ -422,7 +422,7 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
       double qX = 0, qY = 0, qT = 0, qL = 0;
       double cost = 0.0;
 
-      if (pb.has_people) {
+      if (PPL && pb.has_people) {  // PPL == false: the people critics are compiled out (people-free batch)
         // --- AgentAngle (k=0): w * wrap(Theta - target)^2 ------------------------------------------
         const double tgt = aa[j];
         if (tgt == tgt) {
@@ -843,7 +843,7 @@ __device__ __forceinline__ int quartic_real_parts(const double (&c)[5], double x
 }
 
 // Minimiser on [lo, hi] of the cubic through (0, f0, g0), (t, f1, g1).
-__device__ __forceinline__ double cubic_interp_min(double f0, double g0, double t, double f1, double g1, double lo,
+static __device__ __noinline__ double cubic_interp_min(double f0, double g0, double t, double f1, double g1, double lo,
                                                    double hi) {
   const double A = f1 - f0 - g0 * t, Bv = g1 - g0;
   const double inv_t = 1.0 / t;
@@ -887,7 +887,7 @@ __device__ __forceinline__ double cubic_interp_min(double f0, double g0, double 
 }
 
 // Minimiser on [lo, hi] of the quintic through (0, f0, g0), (t1, f1, g1), (t2, f2, g2), 0 < t1 < t2.
-__device__ __forceinline__ double quintic_interp_min(double f0, double g0, double t1, double f1, double g1, double t2,
+static __device__ __noinline__ double quintic_interp_min(double f0, double g0, double t1, double f1, double g1, double t2,
                                                      double f2, double g2, double lo, double hi) {
   // work in xi = x / t2: nodes 0, tau, 1 (Hermite divided differences), then expand to monomials
   const double tau = t1 / t2;
@@ -983,7 +983,7 @@ __device__ __forceinline__ void load_problem(const DevBatch& bt, int b, Prob& pb
 }
 
 // Agent-angle steering targets of every step -> group shared memory (once per problem).
-template <int NB, int G>
+template <int NB, int G, bool PPL>
 __device__ __forceinline__ void agent_angle_setup(const DevBatch& bt, const Prob& pb, int lane, double* ws) {
   using L = Layout<NB>;
   const int gl = lane & (G - 1);
@@ -993,10 +993,12 @@ __device__ __forceinline__ void agent_angle_setup(const DevBatch& bt, const Prob
     ws[L::kYaw] = s0;
     ws[L::kYaw + 1] = c0;
   }
-  for (int j = gl; j < bt.S; j += G) {
-    double tgt = NAN;
-    if (pb.has_people && bt.A > 0 && pb.agents != nullptr) tgt = agent_angle_target(bt, pb, j + 1);
-    ws[L::kAa + j] = tgt;
+  if (PPL) {
+    for (int j = gl; j < bt.S; j += G) {
+      double tgt = NAN;
+      if (pb.has_people && bt.A > 0 && pb.agents != nullptr) tgt = agent_angle_target(bt, pb, j + 1);
+      ws[L::kAa + j] = tgt;
+    }
   }
 }
 
@@ -1079,7 +1081,7 @@ enum StateFlags {
   kReuseDiagonal = 1, kItSuccessful = 2, kAnySuccess = 4, kPrevOk = 8, kLive = 16, kExhausted = 32, kSwapped = 64
 };
 
-template <int NB, int G>
+template <int NB, int G, bool PPL>
 __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch& bt, const DevResult& rs, int* queue,
                                            double* ws, double* red, int lane) {
   using L = Layout<NB>;
@@ -1118,7 +1120,7 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
       } else {
         if (gl == 0) load_problem(bt, nb_, *pbs);
         __syncwarp(gmask);
-        agent_angle_setup<NB, G>(bt, *pbs, lane, ws);
+        agent_angle_setup<NB, G, PPL>(bt, *pbs, lane, ws);
         // IterationZero: project the start point onto the box
         for (int c = gl; c < P; c += G) {
           const double v = __ldg(bt.u0 + (size_t)nb_ * P + c);
@@ -1155,7 +1157,7 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
     }
 
     const bool live = (gs->flags & kLive) != 0;
-    const unsigned fl = evaluate<NB, G>(prm, bt, *pbs, live, lc0, ws, red, cand, lane,
+    const unsigned fl = evaluate<NB, G, PPL>(prm, bt, *pbs, live, lc0, ws, red, cand, lane,
                                         ws + ((gs->flags & kSwapped) ? L::kBuf0 : L::kBuf1));
     // ---- phase logic, directly on the group's shared-memory state. The lanes of a group are converged here and
     //      take the same (group-uniform) branches, so they all store identical values. ---------------------------

@@ -40,6 +40,8 @@ int cuda_fail(cudaError_t e, const char* what) {
     if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
   } while (0)
 
+constexpr int kMaxChunks = 8;  // chunks of the host-buffer pipeline (one queue counter each)
+
 struct DeviceBuffer {
   void* ptr = nullptr;
   size_t cap = 0;
@@ -76,11 +78,13 @@ struct smpc_handle {
   int device = 0;
   int n_sm = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t stream2 = nullptr;  // second lane of the chunked host-buffer pipeline (smpc_solve_batch)
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_shared = nullptr;
   bool timed = false;
   int* queue = nullptr;
   long long launches = 0;
-  int forced_warps = 0;  // 0 = pick warps-per-CTA from the batch size; SMPC_WARPS env overrides (4 or 16)
+  int forced_warps = 0;  // 0 = pick warps-per-CTA from the batch size; SMPC_WARPS env overrides (4 / 16 with people, 4 / 12 without)
+  int forced_chunks = 0; // 0 = pick the chunk count of the host-buffer pipeline from the batch; SMPC_CHUNKS env overrides (1..8)
   int forced_group = 0;  // 0 = pick lanes-per-problem from the batch size; SMPC_GROUP env / smpc_set_group override
   std::mutex mu;
   // staging for the host-buffer entry points
@@ -184,20 +188,27 @@ void to_dev_result(const smpc_result& out, smpc::DevResult* d) {
 
 size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 
-int pack_agents(smpc_handle* h, smpc::DevBatch* bt, cudaStream_t stream) {
+// `total_problems` sizes the scratch buffer (>= bt->B); `first` = index of this batch's first problem inside it, so
+// that the chunks of one host-buffer call pack into disjoint slices.
+int pack_agents_at(smpc_handle* h, smpc::DevBatch* bt, size_t total_problems, size_t first, cudaStream_t stream) {
   bt->agents_packed = nullptr;
   bt->agents_valid = nullptr;
   if (bt->A <= 0 || bt->agents == nullptr) return SMPC_OK;
-  const size_t rows = static_cast<size_t>(bt->B) * bt->A, S1 = static_cast<size_t>(bt->S) + 1;
-  const size_t rec_bytes = align256(rows * S1 * 4 * sizeof(double));
-  SMPC_CUDA(h->pack_buf.reserve(rec_bytes + rows * S1));
-  double* packed = static_cast<double*>(h->pack_buf.ptr);
-  uint8_t* valid = static_cast<uint8_t*>(h->pack_buf.ptr) + rec_bytes;
+  const size_t S1 = static_cast<size_t>(bt->S) + 1;
+  const size_t all_rows = total_problems * bt->A, rows = static_cast<size_t>(bt->B) * bt->A;
+  const size_t rec_bytes = align256(all_rows * S1 * 4 * sizeof(double));
+  SMPC_CUDA(h->pack_buf.reserve(rec_bytes + all_rows * S1));
+  double* packed = static_cast<double*>(h->pack_buf.ptr) + first * bt->A * S1 * 4;
+  uint8_t* valid = static_cast<uint8_t*>(h->pack_buf.ptr) + rec_bytes + first * bt->A * S1;
   SMPC_CUDA(smpc::launch_pack_agents(static_cast<long long>(rows), static_cast<int>(S1), bt->agents, packed, valid, stream));
   h->launches += 1;
   bt->agents_packed = packed;
   bt->agents_valid = valid;
   return SMPC_OK;
+}
+
+int pack_agents(smpc_handle* h, smpc::DevBatch* bt, cudaStream_t stream) {
+  return pack_agents_at(h, bt, static_cast<size_t>(bt->B), 0, stream);
 }
 
 struct Carver {  // carve aligned sub-buffers out of one device allocation
@@ -409,14 +420,17 @@ int smpc_create(const smpc_params* p, int device, smpc_handle** out) {
   h->device = device;
   h->n_sm = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
-      cudaMalloc(&h->queue, sizeof(int)) != cudaSuccess) {
+      cudaEventCreateWithFlags(&h->ev_shared, cudaEventDisableTiming) != cudaSuccess ||
+      cudaMalloc(&h->queue, kMaxChunks * sizeof(int)) != cudaSuccess) {
     e = cudaGetLastError();
     smpc_destroy(h);
     return cuda_fail(e, "smpc_create resources");
   }
   if (const char* env = std::getenv("SMPC_GROUP")) h->forced_group = std::atoi(env);
   if (const char* env = std::getenv("SMPC_WARPS")) h->forced_warps = std::atoi(env);
+  if (const char* env = std::getenv("SMPC_CHUNKS")) h->forced_chunks = std::atoi(env);
   *out = h;
   return SMPC_OK;
 }
@@ -434,14 +448,39 @@ void smpc_destroy(smpc_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->stream2) cudaStreamSynchronize(h->stream2);
   h->in_buf.release();
   h->out_buf.release();
   h->pack_buf.release();
   if (h->queue) cudaFree(h->queue);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->ev_shared) cudaEventDestroy(h->ev_shared);
+  if (h->stream2) cudaStreamDestroy(h->stream2);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
+}
+
+// One solve launch of `in` (device pointers) on `stream`. `queue` = this launch's work-queue counter; the packed agent
+// records go to slice [first, first + B) of a scratch buffer sized for `total_problems`.
+static int launch_solve_on(smpc_handle* h, const smpc_batch* in, smpc_result* out, int* queue, size_t total_problems,
+                           size_t first, bool timed, cudaStream_t stream) {
+  smpc::DevParams prm;
+  int rc = make_dev_params(h->params, in->n_steps, &prm);
+  if (rc != SMPC_OK) return rc;
+  smpc::DevBatch bt;
+  to_dev_batch(*in, &bt);
+  smpc::DevResult rs;
+  to_dev_result(*out, &rs);
+  rc = pack_agents_at(h, &bt, total_problems, first, stream);
+  if (rc != SMPC_OK) return rc;
+  SMPC_CUDA(cudaMemsetAsync(queue, 0, sizeof(int), stream));
+  if (timed) SMPC_CUDA(cudaEventRecord(h->ev0, stream));
+  SMPC_CUDA(smpc::launch_solve(prm, bt, rs, queue, h->n_sm, h->forced_group, h->forced_warps, stream));
+  if (timed) SMPC_CUDA(cudaEventRecord(h->ev1, stream));
+  h->timed = timed;
+  h->launches += 1;
+  return SMPC_OK;
 }
 
 static int solve_device_locked(smpc_handle* h, const smpc_batch* in, smpc_result* out, cudaStream_t stream) {
@@ -449,23 +488,8 @@ static int solve_device_locked(smpc_handle* h, const smpc_batch* in, smpc_result
   if (rc != SMPC_OK) return rc;
   if (!out) return fail(SMPC_ERR_ARGUMENT, "result is NULL");
   if (in->n_problems == 0) return SMPC_OK;
-  smpc::DevParams prm;
-  rc = make_dev_params(h->params, in->n_steps, &prm);
-  if (rc != SMPC_OK) return rc;
-  smpc::DevBatch bt;
-  to_dev_batch(*in, &bt);
-  smpc::DevResult rs;
-  to_dev_result(*out, &rs);
   SMPC_CUDA(cudaSetDevice(h->device));
-  rc = pack_agents(h, &bt, stream);
-  if (rc != SMPC_OK) return rc;
-  SMPC_CUDA(cudaMemsetAsync(h->queue, 0, sizeof(int), stream));
-  SMPC_CUDA(cudaEventRecord(h->ev0, stream));
-  SMPC_CUDA(smpc::launch_solve(prm, bt, rs, h->queue, h->n_sm, h->forced_group, h->forced_warps, stream));
-  SMPC_CUDA(cudaEventRecord(h->ev1, stream));
-  h->timed = true;
-  h->launches += 1;
-  return SMPC_OK;
+  return launch_solve_on(h, in, out, h->queue, static_cast<size_t>(in->n_problems), 0, true, stream);
 }
 
 int smpc_solve_batch_device(smpc_handle* h, const smpc_batch* in, smpc_result* out, void* stream) {
@@ -474,6 +498,10 @@ int smpc_solve_batch_device(smpc_handle* h, const smpc_batch* in, smpc_result* o
   return solve_device_locked(h, in, out, stream ? static_cast<cudaStream_t>(stream) : h->stream);
 }
 
+// Host buffers in, host buffers out. The batch is cut into up to kMaxChunks chunks of consecutive problems that
+// alternate between two streams: chunk k+1's host-to-device copies run while chunk k solves, and chunk k's results
+// travel back while chunk k+1 solves (problems are independent, so a chunk is a complete batch of its own). Copies
+// overlap only when the caller's buffers are page-locked; pageable buffers work, serialised by the driver.
 int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out) {
   if (!h) return fail(SMPC_ERR_ARGUMENT, "handle is NULL");
   std::lock_guard<std::mutex> lk(h->mu);
@@ -487,56 +515,128 @@ int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out) {
   SMPC_CUDA(cudaSetDevice(h->device));
   const size_t B = in->n_problems, S1 = static_cast<size_t>(in->n_steps) + 1, A = in->agents ? in->n_agents : 0;
   const size_t M = in->n_costmaps, P = 2 * static_cast<size_t>(nb);
-  const size_t map_bytes = M * in->size_x * in->size_y;
-  struct Item { const void* host; size_t bytes; void** dev; };
-  smpc_batch din = *in;
-  std::vector<Item> items = {
-      {in->pose0, B * 3 * 8, (void**)&din.pose0},
-      {in->u0, B * P * 8, (void**)&din.u0},
-      {in->path_xy, B * 2 * S1 * 8, (void**)&din.path_xy},
-      {in->goal_yaw, B * 8, (void**)&din.goal_yaw},
-      {A ? in->agents : nullptr, B * A * 6 * S1 * 8, (void**)&din.agents},
-      {in->has_people, B, (void**)&din.has_people},
-      {in->costmaps, map_bytes, (void**)&din.costmaps},
-      {in->costmap_origin, M * 2 * 8, (void**)&din.costmap_origin},
-      {in->costmap_index, B * 4, (void**)&din.costmap_index},
+  const size_t map_cells = static_cast<size_t>(in->size_x) * in->size_y;
+
+  // ---- chunking. Costmaps follow their problems when map b belongs to problem b (no index, M == B); otherwise the
+  //      M maps are shared: they go up once, ahead of the first chunk, and every chunk start must keep b % M intact.
+  const bool maps_per_problem = (in->costmap_index == nullptr) && (M == B);
+  // Chunking pays where the copies are a large share of the call: batches with people (28 kB per problem at 20
+  // agents; measured +22 % end to end at A = 20, +14 % at A = 50, +3 % at A = 3). People-free batches are one chunk:
+  // their copies are small next to the solve and smaller launches balance worse (measured -2..-13 %).
+  // A chunk must not push the launch heuristics of smpc_kernels_nb.inc into another kernel variant than the whole
+  // batch would get: 16-warp CTAs need >= 2 warps per warp slot, i.e. >= 2 * 16 * n_sm problems per launch.
+  const size_t w16_min = 2 * 16 * static_cast<size_t>(h->n_sm);
+  size_t n_chunks = 1;
+  if (A > 0 && in->has_people) n_chunks = std::min<size_t>(kMaxChunks, B / (w16_min + 128));
+  if (h->forced_chunks >= 1) n_chunks = std::min<size_t>(h->forced_chunks, kMaxChunks);
+  n_chunks = std::max<size_t>(1, std::min(n_chunks, B));
+  size_t chunk = B;
+  for (; n_chunks > 1; --n_chunks) {
+    chunk = ((B + n_chunks - 1) / n_chunks + 255) & ~static_cast<size_t>(255);
+    const size_t used = (B + chunk - 1) / chunk;  // chunks actually needed at this (rounded-up) size
+    const size_t last = B - (used - 1) * chunk;
+    const bool modulo_ok = maps_per_problem || in->costmap_index != nullptr || (chunk % M) == 0;  // b % M must not shift
+    const bool size_ok = h->forced_chunks >= 1 || last >= w16_min;
+    if (modulo_ok && size_ok) {
+      n_chunks = used;
+      break;
+    }
+  }
+  if (n_chunks <= 1) {
+    n_chunks = 1;
+    chunk = B;
+  }
+
+  // ---- device staging: every array whole, same layout as the host's, so a chunk is a pointer offset
+  struct Item { const void* host; size_t per_problem; size_t shared_bytes; char* dev; };
+  enum { kPose, kU0, kPath, kGoal, kAgents, kHas, kIndex, kMaps, kOrigin, kItems };
+  Item items[kItems] = {
+      {in->pose0, 3 * 8, 0, nullptr},
+      {in->u0, P * 8, 0, nullptr},
+      {in->path_xy, 2 * S1 * 8, 0, nullptr},
+      {in->goal_yaw, 8, 0, nullptr},
+      {A ? in->agents : nullptr, A * 6 * S1 * 8, 0, nullptr},
+      {in->has_people, 1, 0, nullptr},
+      {in->costmap_index, 4, 0, nullptr},
+      {in->costmaps, maps_per_problem ? map_cells : 0, maps_per_problem ? 0 : M * map_cells, nullptr},
+      {in->costmap_origin, maps_per_problem ? 16 : 0, maps_per_problem ? 0 : M * 16, nullptr},
   };
   size_t total = 0;
-  for (auto& it : items) total += it.host ? align256(it.bytes) : 0;
+  for (auto& it : items)
+    if (it.host) total += align256(it.per_problem * B + it.shared_bytes);
   SMPC_CUDA(h->in_buf.reserve(total));
   Carver cin(h->in_buf.ptr);
-  for (auto& it : items) {
-    if (!it.host) {
-      *it.dev = nullptr;
-      continue;
-    }
-    void* d = cin.take(it.bytes);
-    SMPC_CUDA(cudaMemcpyAsync(d, it.host, it.bytes, cudaMemcpyHostToDevice, h->stream));
-    *it.dev = d;
-  }
-  struct OItem { void* host; size_t bytes; void** dev; };
-  smpc_result dout = *out;
-  std::vector<OItem> oitems = {
-      {out->u, B * P * 8, (void**)&dout.u},
-      {out->cmds, B * S1 * 2 * 8, (void**)&dout.cmds},
-      {out->path, B * S1 * 3 * 8, (void**)&dout.path},
-      {out->cost_initial, B * 8, (void**)&dout.cost_initial},
-      {out->cost_final, B * 8, (void**)&dout.cost_final},
-      {out->iterations, B * 4, (void**)&dout.iterations},
-      {out->termination, B * 4, (void**)&dout.termination},
-      {out->usable, B, (void**)&dout.usable},
-      {out->n_evals, B * 2 * 4, (void**)&dout.n_evals},
+  for (auto& it : items)
+    if (it.host) it.dev = static_cast<char*>(cin.take(it.per_problem * B + it.shared_bytes));
+
+  struct OItem { void* host; size_t per_problem; char* dev; };
+  enum { kOU, kOCmds, kOPath, kOCi, kOCf, kOIt, kOTerm, kOUsable, kOEvals, kOItems };
+  OItem oitems[kOItems] = {
+      {out->u, P * 8, nullptr},        {out->cmds, S1 * 2 * 8, nullptr}, {out->path, S1 * 3 * 8, nullptr},
+      {out->cost_initial, 8, nullptr}, {out->cost_final, 8, nullptr},    {out->iterations, 4, nullptr},
+      {out->termination, 4, nullptr},  {out->usable, 1, nullptr},        {out->n_evals, 2 * 4, nullptr},
   };
   size_t ototal = 0;
-  for (auto& it : oitems) ototal += it.host ? align256(it.bytes) : 0;
+  for (auto& it : oitems)
+    if (it.host) ototal += align256(it.per_problem * B);
   SMPC_CUDA(h->out_buf.reserve(ototal));
   Carver cout_(h->out_buf.ptr);
-  for (auto& it : oitems) *it.dev = it.host ? cout_.take(it.bytes) : nullptr;
-  rc = solve_device_locked(h, &din, &dout, h->stream);
-  if (rc != SMPC_OK) return rc;
   for (auto& it : oitems)
-    if (it.host) SMPC_CUDA(cudaMemcpyAsync(it.host, *it.dev, it.bytes, cudaMemcpyDeviceToHost, h->stream));
-  SMPC_CUDA(cudaStreamSynchronize(h->stream));
+    if (it.host) it.dev = static_cast<char*>(cout_.take(it.per_problem * B));
+
+  // ---- shared arrays first (stream 1), the second stream waits for them
+  cudaStream_t lanes[2] = {h->stream, h->stream2};
+  bool any_shared = false;
+  for (auto& it : items)
+    if (it.host && it.shared_bytes) {
+      SMPC_CUDA(cudaMemcpyAsync(it.dev, it.host, it.shared_bytes, cudaMemcpyHostToDevice, lanes[0]));
+      any_shared = true;
+    }
+  if (any_shared && n_chunks > 1) {
+    SMPC_CUDA(cudaEventRecord(h->ev_shared, lanes[0]));
+    SMPC_CUDA(cudaStreamWaitEvent(lanes[1], h->ev_shared, 0));
+  }
+
+  for (size_t c = 0; c < n_chunks; ++c) {
+    const size_t c0 = c * chunk, n = std::min(chunk, B - c0);
+    cudaStream_t st = lanes[c & 1];
+    for (auto& it : items)
+      if (it.host && it.per_problem)
+        SMPC_CUDA(cudaMemcpyAsync(it.dev + it.per_problem * c0, static_cast<const char*>(it.host) + it.per_problem * c0,
+                                  it.per_problem * n, cudaMemcpyHostToDevice, st));
+    auto at = [&](int k) -> const void* { return items[k].dev ? items[k].dev + items[k].per_problem * c0 : nullptr; };
+    smpc_batch din = *in;
+    din.n_problems = static_cast<int>(n);
+    din.pose0 = static_cast<const double*>(at(kPose));
+    din.u0 = static_cast<const double*>(at(kU0));
+    din.path_xy = static_cast<const double*>(at(kPath));
+    din.goal_yaw = static_cast<const double*>(at(kGoal));
+    din.agents = static_cast<const double*>(at(kAgents));
+    din.has_people = static_cast<const uint8_t*>(at(kHas));
+    din.costmap_index = static_cast<const int32_t*>(at(kIndex));
+    din.costmaps = static_cast<const uint8_t*>(at(kMaps));
+    din.costmap_origin = static_cast<const double*>(at(kOrigin));
+    if (maps_per_problem) din.n_costmaps = static_cast<int>(n);
+    auto oat = [&](int k) -> void* { return oitems[k].dev ? oitems[k].dev + oitems[k].per_problem * c0 : nullptr; };
+    smpc_result dout;
+    dout.u = static_cast<double*>(oat(kOU));
+    dout.cmds = static_cast<double*>(oat(kOCmds));
+    dout.path = static_cast<double*>(oat(kOPath));
+    dout.cost_initial = static_cast<double*>(oat(kOCi));
+    dout.cost_final = static_cast<double*>(oat(kOCf));
+    dout.iterations = static_cast<int32_t*>(oat(kOIt));
+    dout.termination = static_cast<int32_t*>(oat(kOTerm));
+    dout.usable = static_cast<uint8_t*>(oat(kOUsable));
+    dout.n_evals = static_cast<int32_t*>(oat(kOEvals));
+    rc = launch_solve_on(h, &din, &dout, h->queue + c, B, c0, /*timed=*/n_chunks == 1, st);
+    if (rc != SMPC_OK) return rc;
+    for (auto& it : oitems)
+      if (it.host)
+        SMPC_CUDA(cudaMemcpyAsync(static_cast<char*>(it.host) + it.per_problem * c0, it.dev + it.per_problem * c0,
+                                  it.per_problem * n, cudaMemcpyDeviceToHost, st));
+  }
+  SMPC_CUDA(cudaStreamSynchronize(lanes[0]));
+  if (n_chunks > 1) SMPC_CUDA(cudaStreamSynchronize(lanes[1]));
   return SMPC_OK;
 }
 

@@ -358,3 +358,61 @@ def test_randomised_eval_parity_many_agent_counts(oracle, make_opt):
             H_ref = e["jac"].T @ e["jac"]
             assert np.abs(H[b] - H_ref).max() <= 1e-9 * max(1.0, np.abs(H_ref).max())
             assert np.abs(got["grad"][b] - e["grad"]).max() <= 1e-9 * max(1.0, np.abs(e["grad"]).max())
+
+
+@pytest.mark.parametrize("kind", ["maps_per_problem", "shared_maps_modulo", "shared_maps_indexed", "people"])
+def test_chunked_host_pipeline_is_bit_identical(kind, monkeypatch):
+    """smpc_solve_batch cuts a host batch into chunks that alternate between two streams (copies of chunk k+1 under
+    the solve of chunk k). Problems are independent, so every output must be bit-identical to the one-chunk call —
+    also for a ragged last chunk, shared costmaps addressed by b % M, and an explicit costmap_index."""
+    from nav2_social_mpc_controller_b200.optimizer import Optimizer
+    if kind == "maps_per_problem":
+        batch = sc.corridor(B=1300)
+    elif kind == "shared_maps_modulo":
+        batch = sc.corridor(B=1300, unique_maps=False, config_id=22)
+    elif kind == "shared_maps_indexed":
+        batch = sc.corridor(B=1300, unique_maps=False, config_id=22)
+        rng = np.random.default_rng(3)
+        batch.arrays["costmap_index"] = rng.integers(0, batch.n_costmaps, size=1300).astype(np.int32)
+    else:
+        batch = sc.crowd(B=700, A=3, config_id=6)
+    outs = []
+    for chunks in ("1", "3", "5"):
+        monkeypatch.setenv("SMPC_CHUNKS", chunks)
+        opt = Optimizer(0)
+        opt.initialize(batch.params)
+        opt.set_group(32)  # the lanes-per-problem heuristic looks at the launch size; pin it so summation order is fixed
+        try:
+            outs.append(opt.solve_batch(batch, want=("u", "cmds", "path", "cost_initial", "cost_final", "iterations",
+                                                     "termination", "usable", "n_evals")))
+        finally:
+            opt.close()
+    for o in outs[1:]:
+        for k, v in outs[0].items():
+            assert np.array_equal(v, o[k]), f"{kind}: output {k} differs between chunk counts"
+    assert outs[0]["usable"].mean() > 0.9
+
+
+def test_people_free_cta_shapes_are_bit_identical(monkeypatch):
+    """People-free batches run either one 12-warp CTA per SM or 4-warp CTAs (small batches); both must return the
+    same bits (same lanes per problem, same summation order). With people the two CTA shapes are separate
+    compilations of a much larger evaluation and agree only to round-off (checked against the oracle instead)."""
+    from nav2_social_mpc_controller_b200.optimizer import Optimizer
+    batch = sc.corridor(B=2048)
+    outs = []
+    for warps in ("4", "12"):
+        monkeypatch.setenv("SMPC_WARPS", warps)
+        for group in (32, 4):
+            opt = Optimizer(0)
+            opt.initialize(batch.params)
+            opt.set_group(group)
+            try:
+                outs.append((group, opt.solve_batch(batch)))
+            finally:
+                opt.close()
+    by_group = {}
+    for group, o in outs:
+        by_group.setdefault(group, []).append(o)
+    for group, (a, b) in by_group.items():
+        for k in a:
+            assert np.array_equal(a[k], b[k]), f"G={group}: output {k} differs between 4-warp and 12-warp CTAs"

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
-"""Turn `ncu --set full` reports into the committed evidence under profiles/: key metrics + top stalls
+"""Turn `ncu --set full` captures into the committed evidence under profiles/: key metrics + top stalls
 (r01_ncu_summaries.json), DRAM traffic per launch (r01_traffic.json) and source-level hot spots (text).
-Usage: tools/summarize_profiles.py DIR   (DIR holds prof_<workload>.ncu-rep files)"""
+Usage: tools/summarize_profiles.py DIR   (DIR holds raw_<workload>.csv raw pages exported on the GPU box by
+tools/ncu_capture.sh and, for the workloads whose report travelled back, prof_<workload>.ncu-rep)"""
 import csv
 import glob
 import io
@@ -25,9 +26,10 @@ spath = os.path.join(root, 'profiles', 'r01_ncu_summaries.json')
 summ = json.load(open(spath)) if os.path.exists(spath) else {}
 summ = {k: v for k, v in summ.items() if not k.startswith('final')}
 traffic = {}
-for rep in sorted(glob.glob(os.path.join(src, 'prof_*.ncu-rep'))):
-    w = os.path.basename(rep)[len('prof_'):-len('.ncu-rep')]
-    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+for rawf in sorted(glob.glob(os.path.join(src, 'raw_*.csv'))):
+    w = os.path.basename(rawf)[len('raw_'):-len('.csv')]
+    rep = os.path.join(src, f'prof_{w}.ncu-rep')
+    raw = open(rawf).read()
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, vals = rows[0], rows[1], rows[2]
     kname = vals[hdr.index('Kernel Name')]
@@ -48,11 +50,12 @@ for rep in sorted(glob.glob(os.path.join(src, 'prof_*.ncu-rep'))):
                   'unit': 'bytes per launch',
                   'source': f'ncu --set full capture of `bench.py --workload {w}` (final_{w} in r01_ncu_summaries.json)'}
     import re
-    m = re.search(r'smpc_solve_kernel<(\d+), (\d+), (\d+)>', kname)
+    m = re.search(r'smpc_solve_kernel<(\d+), (\d+), (\d+)', kname)
     mangled = f'smpc_solve_kernelILi{m.group(1)}ELi{m.group(2)}ELi{m.group(3)}E'
-    out = subprocess.run(['python', os.path.join(root, 'tools', 'ncu_hotspots.py'), rep, mangled, '25'],
-                         capture_output=True, text=True).stdout
-    open(os.path.join(root, 'profiles', f'r01_final_{w}_hotspots.txt'), 'w').write(out)
+    if os.path.exists(rep):
+        out = subprocess.run(['python', os.path.join(root, 'tools', 'ncu_hotspots.py'), rep, mangled, '25'],
+                             capture_output=True, text=True).stdout
+        open(os.path.join(root, 'profiles', f'r01_final_{w}_hotspots.txt'), 'w').write(out)
     print(w, d['gpu__time_duration.sum'], 'issue', d['smsp__issue_active.avg.pct_of_peak_sustained_active'], 'fp64',
           d['sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active'], d['top_stalls_per_issue'],
           'dram MB r/w', traffic[w]['read_bytes'] / 1e6, traffic[w]['write_bytes'] / 1e6)
