@@ -53,11 +53,19 @@ WORKLOADS = {
     "crowd_x16384_A50": (lambda: sc.crowd(B=16384, A=50, config_id=5), "BASELINE configs[4] slice: 16384 problems, "
                          "50 agents, S=28, P=6 (a 1.1 GB slice of one GPU's shard of the 10^6 sweep)", False),
 }
+# Workloads whose device batch is larger than the generated one: the unique scenarios are tiled on the device up to
+# this many problems IN TOTAL over all ranks (strong scaling: each rank takes total / world). 10^6 problems at A = 50
+# are 70 GB of agent trajectories: resident in one B200's HBM, never materialised on the host.
+TILED_TOTAL = {"crowd_x1M_A50": 1_000_000}
+WORKLOADS["crowd_x1M_A50"] = (lambda: sc.crowd(B=16384, A=50, config_id=5), "BASELINE configs[4] (unicycle): 10^6 "
+                              "problems, 50 agents, S=28, P=6 = 16384 unique crowd scenarios tiled on the device "
+                              "(70 GB of agent trajectories resident in HBM); e2e and CPU arms use the unique 16384",
+                              False)
 # bounded CPU samples: roughly 10-30 s of single-core oracle work each (a solve costs ~7 ms without people,
 # ~15 ms at A = 3, ~30 ms at A = 20, ~75 ms at A = 50)
 CPU_SAMPLE = {"obst_only_x4096": 3072, "obst_only_x65536": 3072, "soc_work_obst_x16384_A3": 1536,
               "soc_work_obst_x65536_A3": 1536, "multistart_256x1024": 1536, "soc_work_obst_x65536_A20": 512,
-              "crowd_x16384_A50": 256}
+              "crowd_x16384_A50": 256, "crowd_x1M_A50": 256}
 
 
 def flops_per_solve(S, P, A_eff, m, n_jac, n_cost, iters):
@@ -228,6 +236,10 @@ def main():
             if v is not None and k not in ("costmaps", "costmap_origin"):
                 batch.arrays[k] = np.ascontiguousarray(v[perm])
     B, S, A = batch.n_problems, batch.n_steps, batch.n_agents
+    B_unique = B
+    tiled = args.workload in TILED_TOTAL
+    if tiled:
+        B = TILED_TOTAL[args.workload] // world
     ch, bl, nb, nbd = batch.dims
     P = 2 * nb
 
@@ -237,11 +249,25 @@ def main():
     # ---- device-resident arm ------------------------------------------------------------------------
     host_pinned = {k: (torch.from_numpy(v).pin_memory() if v is not None else None) for k, v in batch.arrays.items()}
     dev_arrays = {k: (t.to(dev, non_blocking=True) if t is not None else None) for k, t in host_pinned.items()}
+    if tiled:  # problem b of the device batch = unique scenario (rank offset + b) % B_unique; costmap = b % M as before
+        assert batch.arrays.get("costmap_index") is not None or B_unique % batch.n_costmaps == 0
+        off = (rank * B) % B_unique
+        for k, t in list(dev_arrays.items()):
+            if t is None or k in ("costmaps", "costmap_origin"):
+                continue
+            big = torch.empty((B,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+            rolled = torch.roll(t, shifts=-off, dims=0) if off else t
+            for lo in range(0, B, B_unique):
+                n = min(B_unique, B - lo)
+                big[lo:lo + n] = rolled[:n]
+            dev_arrays[k] = big
+            del rolled
     shapes = abi.result_shapes(B, S, nb)
     want = ("u", "cmds", "cost_initial", "cost_final", "iterations", "termination", "usable", "n_evals")
     tdt = {np.float64: torch.float64, np.int32: torch.int32, np.uint8: torch.uint8}
     dev_out = {k: torch.zeros(shapes[k][0], dtype=tdt[shapes[k][1]], device=dev) for k in want}
-    dstruct = batch.struct(dev_arrays)
+    dstruct = abi.make_batch_struct(dev_arrays, B, S, A, batch.n_costmaps, batch.size_x, batch.size_y,
+                                    batch.resolution, batch.dt)
     stream = torch.cuda.Stream(device=dev)  # non-default stream: the kernel and the events share it
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
     torch.cuda.synchronize()
@@ -277,9 +303,10 @@ def main():
 
     # ---- end-to-end arm: host-buffer C-ABI call, pinned host memory, H2D + kernel + D2H every step ---------
     host_np = {k: (t.numpy() if t is not None else None) for k, t in host_pinned.items()}
-    host_out_t = {k: torch.zeros(shapes[k][0], dtype=tdt[shapes[k][1]]).pin_memory() for k in want}
+    hshapes = abi.result_shapes(B_unique, S, nb)
+    host_out_t = {k: torch.zeros(hshapes[k][0], dtype=tdt[hshapes[k][1]]).pin_memory() for k in want}
     host_out = {k: t.numpy() for k, t in host_out_t.items()}
-    hbatch = sc.Batch(params=batch.params, n_problems=B, n_steps=S, n_agents=A, n_costmaps=batch.n_costmaps,
+    hbatch = sc.Batch(params=batch.params, n_problems=B_unique, n_steps=S, n_agents=A, n_costmaps=batch.n_costmaps,
                       size_x=batch.size_x, size_y=batch.size_y, resolution=batch.resolution, dt=batch.dt, arrays=host_np)
     for _ in range(args.warmup):
         opt.solve_batch(hbatch, out=host_out)
@@ -302,8 +329,10 @@ def main():
     d2h = int(sum(v.nbytes for v in host_out.values()))
 
     # parity spot check of the timed run against the e2e run (same inputs -> identical results)
-    dev_u = dev_out["u"].cpu().numpy()
-    if not np.array_equal(dev_u, host_out["u"]):
+    dev_u = dev_out["u"][:B_unique].cpu().numpy()
+    if tiled and (rank * B) % B_unique:
+        dev_u = None  # this rank's device batch starts at another unique scenario
+    if dev_u is not None and not np.array_equal(dev_u, host_out["u"]):
         raise SystemExit("device-resident and host-buffer solves disagree")
 
     # ---- reduce over ranks (max time), whole-job value ---------------------------------------------------
@@ -312,7 +341,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, e2e_total = float(t[0]), float(t[1])
     value = world * B * args.steps / (total_ms * 1e-3)
-    e2e_value = world * B * args.steps / e2e_total
+    e2e_value = world * B_unique * args.steps / e2e_total
 
     line = None
     if rank == 0:
@@ -331,9 +360,11 @@ def main():
             alg_bytes += batch.n_costmaps * batch.size_x * batch.size_y
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if tiled else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "description": desc, "problems_per_gpu": B, "n_steps": S,
+                       "e2e_problems_per_gpu": B_unique,
                        "n_params": P, "n_agents": A, "l2": "flushed between timed steps (256 MiB write)",
                        "timing": "CUDA events per step on the launching stream, max over ranks"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -29,6 +29,7 @@ struct DevParams {
   double param_tol, fn_tol, gradient_tol;
   int max_iterations, ceres_compat;
   int ch, bl, nb, n_bounded;
+  int sync_every;  // evaluations between two CTA barriers of the solve loop (1)
 };
 
 struct DevBatch {
@@ -1149,12 +1150,12 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
     }
     // CTA barrier per evaluation: the warps of a CTA walk the large unrolled evaluation code together and share its
     // instruction-cache lines (measured +15..40 %); it also ends the loop once every group of the CTA is out of work
-#ifndef SMPC_SYNC_EVERY
-#define SMPC_SYNC_EVERY 1
-#endif
-    if ((loop_count++ % SMPC_SYNC_EVERY) == 0) {
+    // (prm.sync_every = evaluations between two barriers; 1 unless overridden for experiments)
+    if (loop_count == 0) {
       if (__syncthreads_and((gs->flags & kExhausted) != 0)) break;
+      loop_count = prm.sync_every;
     }
+    --loop_count;
 
     const bool live = (gs->flags & kLive) != 0;
     const unsigned fl = evaluate<NB, G, PPL>(prm, bt, *pbs, live, lc0, ws, red, cand, lane,

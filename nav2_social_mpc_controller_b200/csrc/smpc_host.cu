@@ -135,6 +135,8 @@ int make_dev_params(const smpc_params& p, int S, smpc::DevParams* d) {
   d->gradient_tol = p.gradient_tol;
   d->max_iterations = p.max_iterations;
   d->ceres_compat = p.ceres_compat ? p.ceres_compat : 200;
+  d->sync_every = 1;
+  if (const char* env = std::getenv("SMPC_SYNC_EVERY")) d->sync_every = std::max(1, std::atoi(env));
   return SMPC_OK;
 }
 
