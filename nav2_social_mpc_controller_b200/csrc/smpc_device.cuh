@@ -46,6 +46,9 @@ struct DevBatch {
   const uint8_t* costmaps;
   const double* costmap_origin;
   const int32_t* costmap_index;
+  // Host-buffer pipeline only (else NULL): arrival[0] = number of leading problems whose costmap has landed in device
+  // memory (written by the copy stream after each map chunk), arrival[1] = set by the kernel if it gave up waiting.
+  unsigned* arrival;
 };
 
 struct DevResult {
@@ -962,6 +965,29 @@ enum Termination {
   kFailEvaluation = 6
 };
 
+// Host-buffer pipeline: the per-problem costmaps stream in on a second stream WHILE the solve kernel runs. Problems are
+// handed out in index order, so a group only has to wait until the arrival counter has passed its problem. The copy
+// engine needs no SM, so the wait cannot deadlock; it still gives up after 2 s and reports through arrival[1].
+__device__ __forceinline__ void wait_for_costmap(unsigned* arrival, int b) {
+  unsigned long long t0 = 0;
+  for (;;) {
+    unsigned seen;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(arrival) : "memory");
+    if (seen > (unsigned)b) return;
+    unsigned gave_up;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(gave_up) : "l"(arrival + 1) : "memory");
+    if (gave_up) return;  // another group already timed out: the call fails, do not wait again
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    if (t0 == 0) t0 = now;
+    if (now - t0 > 2000000000ull) {
+      atomicExch(arrival + 1, 1u);
+      return;
+    }
+    __nanosleep(200);
+  }
+}
+
 // Load the group-uniform problem view.
 __device__ __forceinline__ void load_problem(const DevBatch& bt, int b, Prob& pb) {
   const int S = bt.S;
@@ -1119,7 +1145,10 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
       if (nb_ >= bt.B) {
         if (gl == 0) gs->flags = kExhausted;
       } else {
-        if (gl == 0) load_problem(bt, nb_, *pbs);
+        if (gl == 0) {
+          if (bt.arrival != nullptr) wait_for_costmap(bt.arrival, nb_);
+          load_problem(bt, nb_, *pbs);
+        }
         __syncwarp(gmask);
         agent_angle_setup<NB, G, PPL>(bt, *pbs, lane, ws);
         // IterationZero: project the start point onto the box

@@ -41,6 +41,7 @@ int cuda_fail(cudaError_t e, const char* what) {
   } while (0)
 
 constexpr int kMaxChunks = 8;  // chunks of the host-buffer pipeline (one queue counter each)
+constexpr int kMapChunks = 16; // pieces the per-problem costmaps are streamed in under a running solve
 
 struct DeviceBuffer {
   void* ptr = nullptr;
@@ -84,6 +85,9 @@ struct smpc_handle {
   int* queue = nullptr;
   long long launches = 0;
   int forced_warps = 0;  // 0 = pick warps-per-CTA from the batch size; SMPC_WARPS env overrides (4 / 16 with people, 4 / 12 without)
+  int stream_maps = 1;   // 1 = stream per-problem costmaps under the solve (pinned host buffers only); SMPC_STREAM_MAPS=0 disables
+  unsigned* arrival = nullptr;       // device: {problems whose costmap has arrived, kernel gave up waiting}
+  unsigned* arrival_host = nullptr;  // pinned: the values the copy stream writes to arrival[0], one per map chunk
   int forced_chunks = 0; // 0 = pick the chunk count of the host-buffer pipeline from the batch; SMPC_CHUNKS env overrides (1..8)
   int forced_group = 0;  // 0 = pick lanes-per-problem from the batch size; SMPC_GROUP env / smpc_set_group override
   std::mutex mu;
@@ -171,6 +175,7 @@ void to_dev_batch(const smpc_batch& in, smpc::DevBatch* d) {
   d->costmaps = in.costmaps;
   d->costmap_origin = in.costmap_origin;
   d->costmap_index = in.costmap_index;
+  d->arrival = nullptr;
 }
 
 // Build the packed agent records of a batch in the handle's scratch buffer (one small kernel per batch).
@@ -425,7 +430,9 @@ int smpc_create(const smpc_params* p, int device, smpc_handle** out) {
       cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_shared, cudaEventDisableTiming) != cudaSuccess ||
-      cudaMalloc(&h->queue, kMaxChunks * sizeof(int)) != cudaSuccess) {
+      cudaMalloc(&h->queue, kMaxChunks * sizeof(int)) != cudaSuccess ||
+      cudaMalloc(&h->arrival, 2 * sizeof(unsigned)) != cudaSuccess ||
+      cudaHostAlloc(&h->arrival_host, (kMapChunks + 2) * sizeof(unsigned), cudaHostAllocDefault) != cudaSuccess) {
     e = cudaGetLastError();
     smpc_destroy(h);
     return cuda_fail(e, "smpc_create resources");
@@ -433,6 +440,7 @@ int smpc_create(const smpc_params* p, int device, smpc_handle** out) {
   if (const char* env = std::getenv("SMPC_GROUP")) h->forced_group = std::atoi(env);
   if (const char* env = std::getenv("SMPC_WARPS")) h->forced_warps = std::atoi(env);
   if (const char* env = std::getenv("SMPC_CHUNKS")) h->forced_chunks = std::atoi(env);
+  if (const char* env = std::getenv("SMPC_STREAM_MAPS")) h->stream_maps = std::atoi(env);
   *out = h;
   return SMPC_OK;
 }
@@ -455,6 +463,8 @@ void smpc_destroy(smpc_handle* h) {
   h->out_buf.release();
   h->pack_buf.release();
   if (h->queue) cudaFree(h->queue);
+  if (h->arrival) cudaFree(h->arrival);
+  if (h->arrival_host) cudaFreeHost(h->arrival_host);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->ev_shared) cudaEventDestroy(h->ev_shared);
@@ -466,12 +476,13 @@ void smpc_destroy(smpc_handle* h) {
 // One solve launch of `in` (device pointers) on `stream`. `queue` = this launch's work-queue counter; the packed agent
 // records go to slice [first, first + B) of a scratch buffer sized for `total_problems`.
 static int launch_solve_on(smpc_handle* h, const smpc_batch* in, smpc_result* out, int* queue, size_t total_problems,
-                           size_t first, bool timed, cudaStream_t stream) {
+                           size_t first, bool timed, cudaStream_t stream, unsigned* arrival = nullptr) {
   smpc::DevParams prm;
   int rc = make_dev_params(h->params, in->n_steps, &prm);
   if (rc != SMPC_OK) return rc;
   smpc::DevBatch bt;
   to_dev_batch(*in, &bt);
+  bt.arrival = arrival;
   smpc::DevResult rs;
   to_dev_result(*out, &rs);
   rc = pack_agents_at(h, &bt, total_problems, first, stream);
@@ -521,7 +532,11 @@ int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out) {
 
   // ---- chunking. Costmaps follow their problems when map b belongs to problem b (no index, M == B); otherwise the
   //      M maps are shared: they go up once, ahead of the first chunk, and every chunk start must keep b % M intact.
-  const bool maps_per_problem = (in->costmap_index == nullptr) && (M == B);
+  // an explicit identity index (map b for problem b) is the same thing as no index with M == B
+  bool identity_index = (in->costmap_index != nullptr) && (M == B);
+  for (size_t b = 0; identity_index && b < B; ++b) identity_index = in->costmap_index[b] == static_cast<int32_t>(b);
+  const int32_t* host_index = identity_index ? nullptr : in->costmap_index;
+  const bool maps_per_problem = (host_index == nullptr) && (M == B);
   // Chunking pays where the copies are a large share of the call: batches with people (28 kB per problem at 20
   // agents; measured +22 % end to end at A = 20, +14 % at A = 50, +3 % at A = 3). People-free batches are one chunk:
   // their copies are small next to the solve and smaller launches balance worse (measured -2..-13 %).
@@ -537,7 +552,7 @@ int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out) {
     chunk = ((B + n_chunks - 1) / n_chunks + 255) & ~static_cast<size_t>(255);
     const size_t used = (B + chunk - 1) / chunk;  // chunks actually needed at this (rounded-up) size
     const size_t last = B - (used - 1) * chunk;
-    const bool modulo_ok = maps_per_problem || in->costmap_index != nullptr || (chunk % M) == 0;  // b % M must not shift
+    const bool modulo_ok = maps_per_problem || host_index != nullptr || (chunk % M) == 0;  // b % M must not shift
     const bool size_ok = h->forced_chunks >= 1 || last >= w16_min;
     if (modulo_ok && size_ok) {
       n_chunks = used;
@@ -559,7 +574,7 @@ int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out) {
       {in->goal_yaw, 8, 0, nullptr},
       {A ? in->agents : nullptr, A * 6 * S1 * 8, 0, nullptr},
       {in->has_people, 1, 0, nullptr},
-      {in->costmap_index, 4, 0, nullptr},
+      {host_index, 4, 0, nullptr},
       {in->costmaps, maps_per_problem ? map_cells : 0, maps_per_problem ? 0 : M * map_cells, nullptr},
       {in->costmap_origin, maps_per_problem ? 16 : 0, maps_per_problem ? 0 : M * 16, nullptr},
   };
@@ -586,6 +601,19 @@ int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out) {
   for (auto& it : oitems)
     if (it.host) it.dev = static_cast<char*>(cout_.take(it.per_problem * B));
 
+  // ---- people-free batch with one costmap per problem: the maps are 90 % of the input bytes. They stream in on the
+  //      second stream WHILE the solve runs: problems are handed out in index order and a group waits until the
+  //      arrival counter has passed its problem (wait_for_costmap). Only with page-locked host maps (the copies must
+  //      be truly asynchronous) and no other kernel of this call in flight (nothing may need an SM while groups wait).
+  bool stream_maps = false;
+  if (h->stream_maps && n_chunks == 1 && maps_per_problem && !(A > 0 && in->has_people) && B >= 1024) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, in->costmaps) == cudaSuccess && attr.type == cudaMemoryTypeHost)
+      stream_maps = true;
+    else
+      (void)cudaGetLastError();
+  }
+
   // ---- shared arrays first (stream 1), the second stream waits for them
   cudaStream_t lanes[2] = {h->stream, h->stream2};
   bool any_shared = false;
@@ -602,10 +630,17 @@ int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out) {
   for (size_t c = 0; c < n_chunks; ++c) {
     const size_t c0 = c * chunk, n = std::min(chunk, B - c0);
     cudaStream_t st = lanes[c & 1];
-    for (auto& it : items)
-      if (it.host && it.per_problem)
+    for (int k = 0; k < kItems; ++k) {
+      const Item& it = items[k];
+      if (it.host && it.per_problem && !(stream_maps && k == kMaps))
         SMPC_CUDA(cudaMemcpyAsync(it.dev + it.per_problem * c0, static_cast<const char*>(it.host) + it.per_problem * c0,
                                   it.per_problem * n, cudaMemcpyHostToDevice, st));
+    }
+    if (stream_maps) {  // reset the arrival words before anything of this call can read or write them
+      SMPC_CUDA(cudaMemsetAsync(h->arrival, 0, 2 * sizeof(unsigned), st));
+      SMPC_CUDA(cudaEventRecord(h->ev_shared, st));
+      SMPC_CUDA(cudaStreamWaitEvent(lanes[1], h->ev_shared, 0));
+    }
     auto at = [&](int k) -> const void* { return items[k].dev ? items[k].dev + items[k].per_problem * c0 : nullptr; };
     smpc_batch din = *in;
     din.n_problems = static_cast<int>(n);
@@ -630,15 +665,33 @@ int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out) {
     dout.termination = static_cast<int32_t*>(oat(kOTerm));
     dout.usable = static_cast<uint8_t*>(oat(kOUsable));
     dout.n_evals = static_cast<int32_t*>(oat(kOEvals));
-    rc = launch_solve_on(h, &din, &dout, h->queue + c, B, c0, /*timed=*/n_chunks == 1, st);
+    rc = launch_solve_on(h, &din, &dout, h->queue + c, B, c0, /*timed=*/n_chunks == 1, st,
+                         stream_maps ? h->arrival : nullptr);
     if (rc != SMPC_OK) return rc;
+    if (stream_maps) {  // the kernel is in flight: feed it the maps, piece by piece, each followed by its arrival count
+      const Item& mp = items[kMaps];
+      const size_t piece = ((B + kMapChunks - 1) / kMapChunks + 63) & ~static_cast<size_t>(63);
+      int k = 0;
+      for (size_t p0 = 0; p0 < B; p0 += piece, ++k) {
+        const size_t pn = std::min(piece, B - p0);
+        SMPC_CUDA(cudaMemcpyAsync(mp.dev + mp.per_problem * p0, static_cast<const char*>(mp.host) + mp.per_problem * p0,
+                                  mp.per_problem * pn, cudaMemcpyHostToDevice, lanes[1]));
+        h->arrival_host[k] = static_cast<unsigned>(p0 + pn);
+        SMPC_CUDA(cudaMemcpyAsync(h->arrival, h->arrival_host + k, sizeof(unsigned), cudaMemcpyHostToDevice, lanes[1]));
+      }
+    }
     for (auto& it : oitems)
       if (it.host)
         SMPC_CUDA(cudaMemcpyAsync(static_cast<char*>(it.host) + it.per_problem * c0, it.dev + it.per_problem * c0,
                                   it.per_problem * n, cudaMemcpyDeviceToHost, st));
   }
+  if (stream_maps)
+    SMPC_CUDA(cudaMemcpyAsync(h->arrival_host + kMapChunks, h->arrival, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost,
+                              lanes[0]));
   SMPC_CUDA(cudaStreamSynchronize(lanes[0]));
-  if (n_chunks > 1) SMPC_CUDA(cudaStreamSynchronize(lanes[1]));
+  if (n_chunks > 1 || stream_maps) SMPC_CUDA(cudaStreamSynchronize(lanes[1]));
+  if (stream_maps && h->arrival_host[kMapChunks + 1] != 0)
+    return fail(SMPC_ERR_CUDA, "costmap stream stalled: the solve kernel waited 2 s for host-to-device copies");
   return SMPC_OK;
 }
 

@@ -416,3 +416,36 @@ def test_people_free_cta_shapes_are_bit_identical(monkeypatch):
     for group, (a, b) in by_group.items():
         for k in a:
             assert np.array_equal(a[k], b[k]), f"G={group}: output {k} differs between 4-warp and 12-warp CTAs"
+
+
+def test_streamed_costmaps_are_bit_identical(monkeypatch):
+    """People-free batches with one costmap per problem and PAGE-LOCKED host buffers: smpc_solve_batch launches the
+    solve first and streams the maps in on a second stream while it runs (groups wait for the arrival counter to pass
+    their problem). Must give the bits of the classic copy-then-solve order, for both lane mappings, a ragged size,
+    and repeated calls on one handle (the arrival words are reset per call)."""
+    import torch
+    from nav2_social_mpc_controller_b200.optimizer import Optimizer
+    batch = sc.corridor(B=3000)
+    pinned = {k: (torch.from_numpy(v).pin_memory() if v is not None else None) for k, v in batch.arrays.items()}
+    pbatch = sc.Batch(params=batch.params, n_problems=batch.n_problems, n_steps=batch.n_steps, n_agents=batch.n_agents,
+                      n_costmaps=batch.n_costmaps, size_x=batch.size_x, size_y=batch.size_y,
+                      resolution=batch.resolution, dt=batch.dt,
+                      arrays={k: (t.numpy() if t is not None else None) for k, t in pinned.items()})
+    results = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("SMPC_STREAM_MAPS", mode)
+        opt = Optimizer(0)
+        opt.initialize(batch.params)
+        try:
+            for group in (32, 4):
+                opt.set_group(group)
+                for rep in range(2):
+                    results[(mode, group, rep)] = opt.solve_batch(pbatch)
+        finally:
+            opt.close()
+    for group in (32, 4):
+        ref = results[("0", group, 0)]
+        for key in (("0", group, 1), ("1", group, 0), ("1", group, 1)):
+            for k, v in ref.items():
+                assert np.array_equal(v, results[key][k]), f"{key}: output {k} differs from the copy-then-solve call"
+    assert ref["usable"].mean() > 0.9
