@@ -29,7 +29,6 @@ struct DevParams {
   double param_tol, fn_tol, gradient_tol;
   int max_iterations, ceres_compat;
   int ch, bl, nb, n_bounded;
-  int sync_every;  // evaluations between two CTA barriers of the solve loop (1)
 };
 
 struct DevBatch {
@@ -49,6 +48,14 @@ struct DevBatch {
   // Host-buffer pipeline only (else NULL): arrival[0] = number of leading problems whose costmap has landed in device
   // memory (written by the copy stream after each map chunk), arrival[1] = set by the kernel if it gave up waiting.
   unsigned* arrival;
+  // Time slicing of the solve queue (NULL = off; smpc_host.cu enables it for batches of a few waves, where the tail of
+  // late-started long solves dominates): a group that has spent `park_quantum` evaluations on a problem while fresh
+  // problems are still waiting parks it — saves its shared-memory state to park_state[b], publishes b in park_ring —
+  // and starts a fresh one; parked problems are resumed, to completion, once the main queue has drained.
+  double* park_state;  // [B][Layout::total(S)]
+  int* park_ring;      // [B] problem ids in parking order, -1 = not published yet
+  int* park_counters;  // [0] = published slots reserved (tail), [1] = slots claimed by resumers (head)
+  int park_quantum;
 };
 
 struct DevResult {
@@ -285,6 +292,15 @@ struct Layout {
   __host__ __device__ static constexpr int g(int c) { return 1 + c; }
   __host__ __device__ static constexpr int h(int a, int b) { return 1 + P + a * (a + 1) / 2 + b; }
 };
+
+// Layout<NB>::total(S) for a run-time NB (the host sizes the parking area of the time-sliced queue with it).
+__host__ __device__ constexpr int layout_total(int nb, int S) {
+  const int P = 2 * nb, NE = 1 + P + P * (P + 1) / 2, NC = 4 + 4 * nb;
+  return ((2 * NE + 6 * P + NC + 2 + 20 + 15 + S) | 1);
+}
+static_assert(layout_total(3, 28) == Layout<3>::total(28) && layout_total(5, 38) == Layout<5>::total(38) &&
+                  layout_total(18, 18) == Layout<18>::total(18),
+              "layout_total must mirror Layout<NB>::total");
 
 template <int G>
 struct Group {
@@ -1095,6 +1111,24 @@ __device__ __forceinline__ void expand_outputs(const DevParams& prm, const DevBa
 // ---------------------------------------------------------------------------------------------------
 enum Phase { kFetch = 0, kInit = 1, kLineSearch = 2, kFullStep = 3 };
 
+// Claim the next parked problem (lane 0 of a group that has seen the main queue empty). Parks in flight are counted
+// in park_counters[2] (raised BEFORE the parker tries to fetch its fresh problem, lowered after it has published or
+// failed to fetch), so "main queue empty and nothing in flight" means the published count can no longer change: from
+// then on a plain atomicAdd hands out the slots (no compare-and-swap storm when thousands of groups go idle at once)
+// and a ticket beyond the final count means the queue is closed for good.
+// Returns the problem id, -1 = parks still in flight (ask again next iteration), -2 = closed and empty.
+__device__ __forceinline__ int park_pop(const DevBatch& bt) {
+  volatile int* cnt = bt.park_counters;
+  if (cnt[2] != 0) return -1;
+  __threadfence();
+  const int tail = cnt[0];
+  const int h = atomicAdd(bt.park_counters + 1, 1);
+  if (h >= tail) return -2;
+  const int id = atomicAdd(bt.park_ring + h, 0);
+  __threadfence();
+  return id;
+}
+
 // Solver scalars of one group, resident in shared memory: the evaluation needs every register for the FP64
 // math, and the phase logic after it reads / updates them in place.
 struct LmState {
@@ -1105,7 +1139,9 @@ struct LmState {
 static_assert(sizeof(LmState) == 20 * sizeof(double), "Layout::kState reserves 20 doubles");
 static_assert(sizeof(Prob) <= 15 * sizeof(double), "Layout::kProb reserves 15 doubles");
 enum StateFlags {
-  kReuseDiagonal = 1, kItSuccessful = 2, kAnySuccess = 4, kPrevOk = 8, kLive = 16, kExhausted = 32, kSwapped = 64
+  kReuseDiagonal = 1, kItSuccessful = 2, kAnySuccess = 4, kPrevOk = 8, kLive = 16, kExhausted = 32, kSwapped = 64,
+  kDrained = 128,  // this group has seen the main queue empty
+  kClosed = 256    // ... and the parked queue closed and empty: nothing will ever come again
 };
 
 template <int NB, int G, bool PPL>
@@ -1137,16 +1173,57 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
 
   unsigned loop_count = 0;
   for (;;) {
-    if (gs->phase == kFetch && !(gs->flags & kExhausted)) {
-      int nb_ = 0;
-      if (gl == 0) nb_ = atomicAdd(queue, 1);
+    // ---- work acquisition. An idle group takes the next fresh problem, else (time slicing) the next parked one. A
+    //      group whose live problem reaches a quantum boundary while fresh problems are still waiting parks it and
+    //      takes a fresh one: long solves no longer start late behind short ones (the tail of a few-wave batch).
+    const int fl0 = gs->flags;
+    const bool slicing = !PPL && bt.park_state != nullptr;  // people kernels: compiled out (register budget)
+    const bool idle = gs->phase == kFetch;
+    const bool at_quantum = slicing && !idle && (fl0 & kLive) && !(fl0 & kDrained) && gs->n_eval > 0 &&
+                            (gs->n_eval % bt.park_quantum) == 0;
+    if ((idle && !(fl0 & kClosed) && (slicing || !(fl0 & kExhausted))) || at_quantum) {
+      int nb_ = bt.B, resume = -2;
+      if (gl == 0) {
+        if (at_quantum) {  // announce the park before trying to fetch (see park_pop)
+          atomicAdd(bt.park_counters + 2, 1);
+          __threadfence();
+        }
+        if (!(fl0 & kDrained)) nb_ = atomicAdd(queue, 1);
+        if (at_quantum && nb_ >= bt.B) atomicSub(bt.park_counters + 2, 1);
+        if (nb_ >= bt.B && idle && slicing) {
+          __threadfence();
+          resume = park_pop(bt);
+        }
+      }
       nb_ = __shfl_sync(gmask, nb_, 0, G);
+      resume = __shfl_sync(gmask, resume, 0, G);
       __syncwarp(gmask);
-      if (nb_ >= bt.B) {
-        if (gl == 0) gs->flags = kExhausted;
+      const int stride = L::total(bt.S);
+      if (nb_ >= bt.B && resume >= 0) {
+        // resume a parked problem: its whole group state comes back from L2 (never through a stale L1 line)
+        const double* src = bt.park_state + (size_t)resume * stride;
+        for (int i = gl; i < stride; i += G) ws[i] = __ldcg(src + i);
+        __syncwarp(gmask);
+        if (gl == 0) gs->flags |= kDrained;
+      } else if (nb_ >= bt.B) {
+        if (gl == 0)
+          gs->flags = idle ? (kExhausted | kDrained | ((resume == -2) ? kClosed : 0)) : (fl0 | kDrained);
       } else {
+        if (at_quantum) {  // park the live problem: state -> global, then publish its id
+          const int self = gs->b;
+          double* dst = bt.park_state + (size_t)self * stride;
+          for (int i = gl; i < stride; i += G) dst[i] = ws[i];
+          __threadfence();
+          __syncwarp(gmask);
+          if (gl == 0) {
+            atomicExch(bt.park_ring + atomicAdd(bt.park_counters, 1), self);
+            __threadfence();
+            atomicSub(bt.park_counters + 2, 1);
+          }
+          __syncwarp(gmask);
+        }
         if (gl == 0) {
-          if (bt.arrival != nullptr) wait_for_costmap(bt.arrival, nb_);
+          if (!PPL && bt.arrival != nullptr) wait_for_costmap(bt.arrival, nb_);
           load_problem(bt, nb_, *pbs);
         }
         __syncwarp(gmask);
@@ -1179,12 +1256,13 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
     }
     // CTA barrier per evaluation: the warps of a CTA walk the large unrolled evaluation code together and share its
     // instruction-cache lines (measured +15..40 %); it also ends the loop once every group of the CTA is out of work
-    // (prm.sync_every = evaluations between two barriers; 1 unless overridden for experiments)
-    if (loop_count == 0) {
+    // (a barrier every 2nd / 3rd / 4th evaluation measured -8 / -17 / -20 %: SMPC_SYNC_EVERY stays 1)
+#ifndef SMPC_SYNC_EVERY
+#define SMPC_SYNC_EVERY 1
+#endif
+    if ((loop_count++ % SMPC_SYNC_EVERY) == 0) {
       if (__syncthreads_and((gs->flags & kExhausted) != 0)) break;
-      loop_count = prm.sync_every;
     }
-    --loop_count;
 
     const bool live = (gs->flags & kLive) != 0;
     const unsigned fl = evaluate<NB, G, PPL>(prm, bt, *pbs, live, lc0, ws, red, cand, lane,

@@ -85,6 +85,8 @@ struct smpc_handle {
   int* queue = nullptr;
   long long launches = 0;
   int forced_warps = 0;  // 0 = pick warps-per-CTA from the batch size; SMPC_WARPS env overrides (4 / 16 with people, 4 / 12 without)
+  int park_quantum = 32; // evaluations per time slice of the solve queue (0 = off); SMPC_PARK_QUANTUM env overrides
+  DeviceBuffer park_buf; // parked group states + ring + counters of the time-sliced queue
   int stream_maps = 1;   // 1 = stream per-problem costmaps under the solve (pinned host buffers only); SMPC_STREAM_MAPS=0 disables
   unsigned* arrival = nullptr;       // device: {problems whose costmap has arrived, kernel gave up waiting}
   unsigned* arrival_host = nullptr;  // pinned: the values the copy stream writes to arrival[0], one per map chunk
@@ -139,8 +141,6 @@ int make_dev_params(const smpc_params& p, int S, smpc::DevParams* d) {
   d->gradient_tol = p.gradient_tol;
   d->max_iterations = p.max_iterations;
   d->ceres_compat = p.ceres_compat ? p.ceres_compat : 200;
-  d->sync_every = 1;
-  if (const char* env = std::getenv("SMPC_SYNC_EVERY")) d->sync_every = std::max(1, std::atoi(env));
   return SMPC_OK;
 }
 
@@ -176,6 +176,10 @@ void to_dev_batch(const smpc_batch& in, smpc::DevBatch* d) {
   d->costmap_origin = in.costmap_origin;
   d->costmap_index = in.costmap_index;
   d->arrival = nullptr;
+  d->park_state = nullptr;
+  d->park_ring = nullptr;
+  d->park_counters = nullptr;
+  d->park_quantum = 0;
 }
 
 // Build the packed agent records of a batch in the handle's scratch buffer (one small kernel per batch).
@@ -441,6 +445,7 @@ int smpc_create(const smpc_params* p, int device, smpc_handle** out) {
   if (const char* env = std::getenv("SMPC_WARPS")) h->forced_warps = std::atoi(env);
   if (const char* env = std::getenv("SMPC_CHUNKS")) h->forced_chunks = std::atoi(env);
   if (const char* env = std::getenv("SMPC_STREAM_MAPS")) h->stream_maps = std::atoi(env);
+  if (const char* env = std::getenv("SMPC_PARK_QUANTUM")) h->park_quantum = std::max(0, std::atoi(env));
   *out = h;
   return SMPC_OK;
 }
@@ -462,6 +467,7 @@ void smpc_destroy(smpc_handle* h) {
   h->in_buf.release();
   h->out_buf.release();
   h->pack_buf.release();
+  h->park_buf.release();
   if (h->queue) cudaFree(h->queue);
   if (h->arrival) cudaFree(h->arrival);
   if (h->arrival_host) cudaFreeHost(h->arrival_host);
@@ -488,6 +494,23 @@ static int launch_solve_on(smpc_handle* h, const smpc_batch* in, smpc_result* ou
   rc = pack_agents_at(h, &bt, total_problems, first, stream);
   if (rc != SMPC_OK) return rc;
   SMPC_CUDA(cudaMemsetAsync(queue, 0, sizeof(int), stream));
+  // parking area of the time-sliced queue (the launcher drops it again when the batch is not a few waves large). One
+  // area per handle: only the single-launch calls use it (the chunks of the host pipeline run concurrently).
+  const bool people = bt.A > 0 && bt.agents != nullptr && bt.has_people != nullptr;  // = batch_has_people of the launcher
+  if (h->park_quantum > 0 && !people && total_problems == static_cast<size_t>(in->n_problems) &&
+      in->n_problems <= (1 << 18)) {
+    const size_t Bp = static_cast<size_t>(in->n_problems);
+    const size_t state_bytes = align256(Bp * smpc::layout_total(prm.nb, in->n_steps) * sizeof(double));
+    const size_t ring_bytes = align256(Bp * sizeof(int));
+    SMPC_CUDA(h->park_buf.reserve(state_bytes + ring_bytes + 256));
+    char* base = static_cast<char*>(h->park_buf.ptr);
+    bt.park_state = reinterpret_cast<double*>(base);
+    bt.park_ring = reinterpret_cast<int*>(base + state_bytes);
+    bt.park_counters = reinterpret_cast<int*>(base + state_bytes + ring_bytes);
+    bt.park_quantum = h->park_quantum;
+    SMPC_CUDA(cudaMemsetAsync(bt.park_ring, 0xFF, ring_bytes, stream));
+    SMPC_CUDA(cudaMemsetAsync(bt.park_counters, 0, 4 * sizeof(int), stream));
+  }
   if (timed) SMPC_CUDA(cudaEventRecord(h->ev0, stream));
   SMPC_CUDA(smpc::launch_solve(prm, bt, rs, queue, h->n_sm, h->forced_group, h->forced_warps, stream));
   if (timed) SMPC_CUDA(cudaEventRecord(h->ev1, stream));

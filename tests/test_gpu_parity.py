@@ -449,3 +449,30 @@ def test_streamed_costmaps_are_bit_identical(monkeypatch):
             for k, v in ref.items():
                 assert np.array_equal(v, results[key][k]), f"{key}: output {k} differs from the copy-then-solve call"
     assert ref["usable"].mean() > 0.9
+
+
+@pytest.mark.parametrize("kind", ["corridor_g32", "corridor_g4", "crowd_a3"])
+def test_time_sliced_queue_is_bit_identical(kind, monkeypatch):
+    """Batches of a few waves run a time-sliced queue: a group parks a problem after `quantum` evaluations while fresh
+    problems are waiting (its shared-memory state goes to global memory) and parked problems are resumed once the main
+    queue has drained. Parking and resuming move the state bit for bit, so every output must equal the plain FIFO run."""
+    from nav2_social_mpc_controller_b200.optimizer import Optimizer
+    if kind == "crowd_a3":
+        batch, group = sc.crowd(B=6000, A=3, config_id=6), 32
+    else:
+        batch, group = sc.corridor(B=4096 if kind == "corridor_g32" else 30000, unique_maps=False, config_id=22), \
+            (32 if kind == "corridor_g32" else 4)
+    outs = {}
+    for quantum in ("0", "5", "32"):
+        monkeypatch.setenv("SMPC_PARK_QUANTUM", quantum)
+        opt = Optimizer(0)
+        opt.initialize(batch.params)
+        opt.set_group(group)
+        try:
+            outs[quantum] = opt.solve_batch(batch)
+        finally:
+            opt.close()
+    for quantum in ("5", "32"):
+        for k, v in outs["0"].items():
+            assert np.array_equal(v, outs[quantum][k]), f"{kind}: output {k} differs with quantum {quantum}"
+    assert outs["0"]["usable"].mean() > 0.9

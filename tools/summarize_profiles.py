@@ -41,6 +41,22 @@ for rawf in sorted(glob.glob(os.path.join(src, 'raw_*.csv'))):
           if 'smsp__average_warps_issue_stalled' in h and h.endswith('_per_issue_active.ratio')]
     d['top_stalls_per_issue'] = {h.replace('smsp__average_warps_issue_stalled_', '').replace(
         '_per_issue_active.ratio', ''): round(v, 3) for h, v in sorted(st, key=lambda t: -t[1])[:6]}
+    # executed FP64 work per solve (thread-level SASS counters: DFMA = 2 flops) next to the algorithmic model
+    bj = os.path.join(src, f'bench_{w}.json')
+    if os.path.exists(bj):
+        bl = json.loads(open(bj).read().strip().splitlines()[-1])
+        nprob = bl['config']['problems_per_gpu']
+
+        def per_cycle(op):  # thread-level instructions per elapsed SM cycle, summed over all sub-partitions
+            k = f'smsp__sass_thread_inst_executed_op_{op}_pred_on.sum.per_cycle_elapsed'
+            return float(vals[hdr.index(k)]) if k in hdr else 0.0
+        cycles = float(vals[hdr.index('sm__cycles_elapsed.avg')])
+        ex = (2 * per_cycle('dfma') + per_cycle('dmul') + per_cycle('dadd')) * cycles  # DFMA = 2 flops
+        dur = float(vals[hdr.index('gpu__time_duration.sum')])
+        dur_s = dur * {'ns': 1e-9, 'us': 1e-6, 'ms': 1e-3, 's': 1.0}.get(units[hdr.index('gpu__time_duration.sum')], 1e-3)
+        d['executed_fp64_flop_per_solve'] = round(ex / nprob)
+        d['algorithmic_flop_per_solve'] = round(bl['roofline']['algorithmic_flops_per_launch'] / nprob)
+        d['executed_fp64_tflops_under_ncu'] = round(ex / dur_s / 1e12, 2)
     summ[f'final_{w}'] = d
 
     def g(k):
