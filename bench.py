@@ -154,7 +154,7 @@ def cpu_baseline(batch, workload, threads, kind_note=True):
     n = min(CPU_SAMPLE.get(workload, 256), batch.n_problems)
     sub = batch.slice(0, n)
     t0 = time.perf_counter()
-    out = o.solve_batch(sub, n_threads=threads, want=("u", "cost_final", "usable", "iterations"))
+    out = o.solve_batch(sub, n_threads=threads, want=("u", "cost_final", "usable", "iterations", "termination"))
     dt = time.perf_counter() - t0
     return {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"first {n} problems of {workload}, {threads} host threads, {dt:.2f} s wall; "
@@ -410,6 +410,8 @@ def main():
             ok = (~us & (host_out["usable"][:n] == 0)) | (us & (du <= 1e-6) & (dc <= 1e-8))
             line["cpu_baseline"] = cb
             line["parity_vs_oracle"] = {"problems": int(n), "within_1e-6_u_and_1e-8_cost": float(ok.mean()),
+                                        "same_termination": float((host_out["termination"][:n] == ref_out["termination"]).mean()),
+                                        "same_iteration_count": float((host_out["iterations"][:n] == ref_out["iterations"]).mean()),
                                         "max_du": float(du[us].max()) if us.any() else None,
                                         "max_rel_dcost": float(dc[us].max()) if us.any() else None}
         print(json.dumps(line))
