@@ -121,7 +121,8 @@ typedef struct smpc_batch {
   const double* path_xy;
   const double* goal_yaw;
   const double* agents;       /* may be NULL when n_agents == 0 */
-  const uint8_t* has_people;  /* may be NULL: no problem has people */
+  const uint8_t* has_people;  /* may be NULL: no problem has people. Ignored (treated as all zero) when n_agents == 0 or
+                                 agents == NULL: the people critics have no agent columns to act on */
   const uint8_t* costmaps;
   const double* costmap_origin;
   const int32_t* costmap_index; /* may be NULL */
@@ -181,9 +182,14 @@ const char* smpc_last_error(void);
 int smpc_abi_version(void);
 
 /* ---- level-1 solve: replaces ceres::Solve at src/optimizer.cpp:381 ------ */
-/* Host buffers in, host buffers out (H2D, kernels, D2H inside the call). */
+/* Host buffers in, host buffers out (H2D, kernels, D2H inside the call; returns when the results are in `out`). Copies
+ * and solves are pipelined over two streams (batches with people: chunks of problems; people-free batches with one
+ * costmap per problem: the maps stream into the running solve) when the caller's buffers are page-locked; pageable
+ * buffers work too, without the overlap. Results do not depend on it. */
 int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out);
-/* Device buffers in/out; asynchronous on `stream` (a cudaStream_t, NULL = default). */
+/* Device buffers in/out; asynchronous on `stream` (a cudaStream_t, NULL = the handle's own stream). A handle owns ONE set
+ * of work-queue counters and scratch buffers: a new solve may be enqueued only on the stream of the previous one, or
+ * after that one has finished (use one handle per stream to overlap solves). */
 int smpc_solve_batch_device(smpc_handle* h, const smpc_batch* in, smpc_result* out, void* stream);
 /* Evaluate cost, J^T r and J^T J at given block values x [B][NB][2] (device pointers). */
 int smpc_eval_batch_device(smpc_handle* h, const smpc_batch* in, const double* x, smpc_eval_out* out, void* stream);

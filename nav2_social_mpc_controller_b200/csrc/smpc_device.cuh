@@ -756,7 +756,11 @@ static __device__ __noinline__ void quartic_aberth(const double* c, double* re) 
 }
 
 // Real parts of the roots of c[0] + c[1] x + c[2] x^2 + c[3] x^3 + c[4] x^4 (c[4] != 0). Returns 4.
-__device__ __forceinline__ int quartic_real_parts(const double (&c)[5], double xlo, double xhi, double (&re)[4]) {
+// `width` lanes starting at the caller's group base (mask `gmask`) call this together with identical arguments; with
+// width >= 4 the four roots are polished by four lanes at once (lane gl polishes root gl & 3, the same arithmetic as
+// the serial loop, gathered by shuffles); width == 1 = a lone thread (unit-test kernel).
+__device__ __forceinline__ int quartic_real_parts(const double (&c)[5], double xlo, double xhi, double (&re)[4], int gl,
+                                                  unsigned gmask, int width) {
   const double inv = 1.0 / c[4];
   const double a = c[3] * inv, b = c[2] * inv, cc = c[1] * inv, d = c[0] * inv;
   const double a2 = a * a;
@@ -832,8 +836,7 @@ __device__ __forceinline__ int quartic_real_parts(const double (&c)[5], double x
   const double shift = 0.25 * a;
   const double margin = 0.05 * (xhi - xlo) + 1e-3 * fabs(xhi);
   const double co[4] = {a, b, cc, d};
-  SMPC_UNROLL for (int k = 0; k < 4; ++k) {
-    double xr = yr[k] - shift, xi = yi[k];
+  auto polish = [&](double xr, double xi, double& out_re) -> bool {
     const bool near = (xr >= xlo - margin) && (xr <= xhi + margin);
     double res = 0.0;
     const int n_it = near ? 3 : 1;
@@ -855,8 +858,21 @@ __device__ __forceinline__ int quartic_real_parts(const double (&c)[5], double x
     }
     const double ax = fabs(xr) + fabs(xi);
     const double scale = fabs(d) + ax * (fabs(cc) + ax * (fabs(b) + ax * (fabs(a) + ax)));
-    if (!(res <= (near ? 1e-10 : 1e-6) * scale + 1e-300)) ok = false;
-    re[k] = xr;
+    out_re = xr;
+    return res <= (near ? 1e-10 : 1e-6) * scale + 1e-300;
+  };
+  if (width >= 4) {
+    const int k = gl & 3;
+    const double myr = (k == 0) ? yr[0] : (k == 1) ? yr[1] : (k == 2) ? yr[2] : yr[3];
+    const double myi = (k == 0) ? yi[0] : (k == 1) ? yi[1] : (k == 2) ? yi[2] : yi[3];
+    double mine;
+    const bool mine_ok = polish(myr - shift, myi, mine);
+    SMPC_UNROLL for (int kk = 0; kk < 4; ++kk) re[kk] = __shfl_sync(gmask, mine, kk, width);
+    ok = __all_sync(gmask, ok && mine_ok);
+  } else {
+    SMPC_UNROLL for (int k = 0; k < 4; ++k) {
+      if (!polish(yr[k] - shift, yi[k], re[k])) ok = false;
+    }
   }
   if (!ok) quartic_aberth(c, re);
   return 4;
@@ -908,7 +924,8 @@ static __device__ __noinline__ double cubic_interp_min(double f0, double g0, dou
 
 // Minimiser on [lo, hi] of the quintic through (0, f0, g0), (t1, f1, g1), (t2, f2, g2), 0 < t1 < t2.
 static __device__ __noinline__ double quintic_interp_min(double f0, double g0, double t1, double f1, double g1, double t2,
-                                                     double f2, double g2, double lo, double hi) {
+                                                        double f2, double g2, double lo, double hi, int gl, unsigned gmask,
+                                                        int width) {
   // work in xi = x / t2: nodes 0, tau, 1 (Hermite divided differences), then expand to monomials
   const double tau = t1 / t2;
   const double d0 = g0 * t2, d1 = g1 * t2, d2 = g2 * t2;
@@ -937,7 +954,7 @@ static __device__ __noinline__ double quintic_interp_min(double f0, double g0, d
   double roots[4];
   int nr = 0;
   if (dq[4] != 0.0) {
-    nr = quartic_real_parts(dq, xlo, xhi, roots);
+    nr = quartic_real_parts(dq, xlo, xhi, roots, gl, gmask, width);
   } else if (dq[3] != 0.0) {
     // exactly-zero leading coefficient (never seen on real data): x * cubic has the cubic's roots plus 0,
     // and 0 lies outside [xlo, xhi]
@@ -1314,7 +1331,7 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
             t_new = fmin(fmax(st.t * 0.5, lo), hi);
           } else if (st.flags & kPrevOk) {
             t_new = quintic_interp_min(st.x_cost, st.g0, st.t, t_cost, gd, st.prev_x, st.prev_value, st.prev_gradient,
-                                       lo, hi);
+                                       lo, hi, gl, gmask, G);
           } else {
             t_new = cubic_interp_min(st.x_cost, st.g0, st.t, t_cost, gd, lo, hi);
           }

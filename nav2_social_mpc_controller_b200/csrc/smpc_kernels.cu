@@ -52,7 +52,7 @@ __global__ void smpc_polymin_kernel(int n, const double* __restrict__ in, double
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double* r = in + (size_t)i * 10;
-  out[i] = (r[7] > 0.0) ? quintic_interp_min(r[2], r[3], r[4], r[5], r[6], r[7], r[8], r[9], r[0], r[1])
+  out[i] = (r[7] > 0.0) ? quintic_interp_min(r[2], r[3], r[4], r[5], r[6], r[7], r[8], r[9], r[0], r[1], 0, 0u, 1)
                         : cubic_interp_min(r[2], r[3], r[4], r[5], r[6], r[0], r[1]);
 }
 
