@@ -41,7 +41,7 @@ int cuda_fail(cudaError_t e, const char* what) {
   } while (0)
 
 constexpr int kMaxChunks = 8;  // chunks of the host-buffer pipeline (one queue counter each)
-constexpr int kMapChunks = 16; // pieces the per-problem costmaps are streamed in under a running solve
+constexpr int kMapChunks = 8;  // pieces the per-problem costmaps are streamed in under a running solve
 
 struct DeviceBuffer {
   void* ptr = nullptr;
@@ -688,10 +688,11 @@ int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out) {
     dout.termination = static_cast<int32_t*>(oat(kOTerm));
     dout.usable = static_cast<uint8_t*>(oat(kOUsable));
     dout.n_evals = static_cast<int32_t*>(oat(kOEvals));
-    rc = launch_solve_on(h, &din, &dout, h->queue + c, B, c0, /*timed=*/n_chunks == 1, st,
-                         stream_maps ? h->arrival : nullptr);
-    if (rc != SMPC_OK) return rc;
-    if (stream_maps) {  // the kernel is in flight: feed it the maps, piece by piece, each followed by its arrival count
+    if (stream_maps) {
+      // Feed the solve its maps, piece by piece, each followed by its arrival count. Everything is enqueued BEFORE
+      // the kernel launch: the copies then make progress whether or not the launch call returns early (profilers,
+      // compute-sanitizer and CUDA_LAUNCH_BLOCKING=1 make launches synchronous — pieces enqueued after the launch
+      // would never arrive and the solve would wait for its timeout).
       const Item& mp = items[kMaps];
       const size_t piece = ((B + kMapChunks - 1) / kMapChunks + 63) & ~static_cast<size_t>(63);
       int k = 0;
@@ -703,6 +704,9 @@ int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out) {
         SMPC_CUDA(cudaMemcpyAsync(h->arrival, h->arrival_host + k, sizeof(unsigned), cudaMemcpyHostToDevice, lanes[1]));
       }
     }
+    rc = launch_solve_on(h, &din, &dout, h->queue + c, B, c0, /*timed=*/n_chunks == 1, st,
+                         stream_maps ? h->arrival : nullptr);
+    if (rc != SMPC_OK) return rc;
     for (auto& it : oitems)
       if (it.host)
         SMPC_CUDA(cudaMemcpyAsync(static_cast<char*>(it.host) + it.per_problem * c0, it.dev + it.per_problem * c0,
