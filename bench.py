@@ -251,17 +251,17 @@ def main():
     dev_arrays = {k: (t.to(dev, non_blocking=True) if t is not None else None) for k, t in host_pinned.items()}
     if tiled:  # problem b of the device batch = unique scenario (rank offset + b) % B_unique; costmap = b % M as before
         assert batch.arrays.get("costmap_index") is not None or B_unique % batch.n_costmaps == 0
-        off = (rank * B) % B_unique
+        from nav2_social_mpc_controller_b200.sharding import tiled_source_index
+        src = torch.from_numpy(tiled_source_index(TILED_TOTAL[args.workload], B_unique, world, rank)).to(dev)
         for k, t in list(dev_arrays.items()):
             if t is None or k in ("costmaps", "costmap_origin"):
                 continue
             big = torch.empty((B,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
-            rolled = torch.roll(t, shifts=-off, dims=0) if off else t
-            for lo in range(0, B, B_unique):
+            for lo in range(0, B, B_unique):  # gather piecewise: index_select on the whole batch would double the 70 GB
                 n = min(B_unique, B - lo)
-                big[lo:lo + n] = rolled[:n]
+                torch.index_select(t, 0, src[lo:lo + n], out=big[lo:lo + n])
             dev_arrays[k] = big
-            del rolled
+        del src
     shapes = abi.result_shapes(B, S, nb)
     want = ("u", "cmds", "cost_initial", "cost_final", "iterations", "termination", "usable", "n_evals")
     tdt = {np.float64: torch.float64, np.int32: torch.int32, np.uint8: torch.uint8}

@@ -17,6 +17,15 @@ def shard_bounds(n_problems: int, world: int, rank: int, granule: int = 1):
     return lo_u * granule, hi_u * granule
 
 
+def tiled_source_index(total: int, unique: int, world: int, rank: int) -> np.ndarray:
+    """Strong-scaling batches that are larger than their set of generated scenarios (bench.py `crowd_x1M_A50`: 10^6
+    problems from 16384 unique ones): problem g of the global batch is unique scenario g % unique, and rank r owns the
+    contiguous range [r * (total // world), (r + 1) * (total // world)). Returns the unique-scenario index of every
+    problem of `rank`, in order."""
+    per_rank = total // world
+    return (rank * per_rank + np.arange(per_rank, dtype=np.int64)) % unique
+
+
 def gather_results(local: dict, dst: int = 0):
     """Concatenate the per-rank result dicts on `dst` in rank order (torch.distributed must be initialised;
     works with gloo on CPU and nccl on GPU since results are host numpy arrays gathered as objects)."""

@@ -64,3 +64,15 @@ def test_two_rank_sharded_solve_matches_single_process(oracle):
     ref = oracle.solve_batch(batch, want=("u", "cost_final", "usable", "termination"))
     for k in ref:
         assert np.array_equal(np.array(got[k]), ref[k]), k
+
+
+def test_tiled_strong_scaling_partition():
+    """bench.py `crowd_x1M_A50`: 10^6 problems tiled from 16384 unique scenarios, total / world per rank."""
+    from nav2_social_mpc_controller_b200.sharding import tiled_source_index
+    total, unique = 1_000_000, 16384
+    for world in (1, 2, 4, 8):
+        parts = [tiled_source_index(total, unique, world, r) for r in range(world)]
+        assert all(len(p) == total // world for p in parts)
+        whole = np.concatenate(parts)
+        assert np.array_equal(whole, np.arange(total) % unique)          # global problem g = scenario g % unique
+        assert parts[0][0] == 0 and whole.max() == unique - 1
