@@ -14,6 +14,17 @@
 
 namespace smpc_oracle {
 
+// Optional operation counting (make -C oracle liboracle_count.so, -DSMPC_ORACLE_COUNT_OPS): every Jet operator adds
+// its FLOPs — SURVEY §8d convention: add / sub / mul / div / sqrt = 1, each sin / cos / exp / atan2 = 1, negation and
+// comparisons free — to a thread-local counter. It measures what the REFERENCE-SHAPED algorithm executes (per-residual
+// Jet<4> passes, every functor re-rolling-out steps 0..i) next to the minimal single-rollout model of bench.py.
+#ifdef SMPC_ORACLE_COUNT_OPS
+extern thread_local unsigned long long g_jet_flops;
+#define SMPC_OPS(n) (g_jet_flops += static_cast<unsigned long long>(n))
+#else
+#define SMPC_OPS(n) ((void)0)
+#endif
+
 template <int N>
 struct Jet {
   double a;
@@ -45,6 +56,7 @@ inline Jet<N> operator-(const Jet<N>& f) {
 }
 template <int N>
 inline Jet<N> operator+(const Jet<N>& f, const Jet<N>& g) {
+  SMPC_OPS(1 + N);
   Jet<N> r;
   r.a = f.a + g.a;
   SMPC_JET_LOOP r.v[i] = f.v[i] + g.v[i];
@@ -52,18 +64,21 @@ inline Jet<N> operator+(const Jet<N>& f, const Jet<N>& g) {
 }
 template <int N>
 inline Jet<N> operator+(const Jet<N>& f, double s) {
+  SMPC_OPS(1);
   Jet<N> r = f;
   r.a = f.a + s;
   return r;
 }
 template <int N>
 inline Jet<N> operator+(double s, const Jet<N>& f) {
+  SMPC_OPS(1);
   Jet<N> r = f;
   r.a = f.a + s;
   return r;
 }
 template <int N>
 inline Jet<N> operator-(const Jet<N>& f, const Jet<N>& g) {
+  SMPC_OPS(1 + N);
   Jet<N> r;
   r.a = f.a - g.a;
   SMPC_JET_LOOP r.v[i] = f.v[i] - g.v[i];
@@ -71,12 +86,14 @@ inline Jet<N> operator-(const Jet<N>& f, const Jet<N>& g) {
 }
 template <int N>
 inline Jet<N> operator-(const Jet<N>& f, double s) {
+  SMPC_OPS(1);
   Jet<N> r = f;
   r.a = f.a - s;
   return r;
 }
 template <int N>
 inline Jet<N> operator-(double s, const Jet<N>& f) {
+  SMPC_OPS(1);
   Jet<N> r;
   r.a = s - f.a;
   SMPC_JET_LOOP r.v[i] = -f.v[i];
@@ -84,6 +101,7 @@ inline Jet<N> operator-(double s, const Jet<N>& f) {
 }
 template <int N>
 inline Jet<N> operator*(const Jet<N>& f, const Jet<N>& g) {
+  SMPC_OPS(1 + 3 * N);
   Jet<N> r;
   r.a = f.a * g.a;
   SMPC_JET_LOOP r.v[i] = f.a * g.v[i] + f.v[i] * g.a;
@@ -91,6 +109,7 @@ inline Jet<N> operator*(const Jet<N>& f, const Jet<N>& g) {
 }
 template <int N>
 inline Jet<N> operator*(const Jet<N>& f, double s) {
+  SMPC_OPS(1 + N);
   Jet<N> r;
   r.a = f.a * s;
   SMPC_JET_LOOP r.v[i] = f.v[i] * s;
@@ -98,6 +117,7 @@ inline Jet<N> operator*(const Jet<N>& f, double s) {
 }
 template <int N>
 inline Jet<N> operator*(double s, const Jet<N>& f) {
+  SMPC_OPS(1 + N);
   Jet<N> r;
   r.a = f.a * s;
   SMPC_JET_LOOP r.v[i] = f.v[i] * s;
@@ -105,6 +125,7 @@ inline Jet<N> operator*(double s, const Jet<N>& f) {
 }
 template <int N>
 inline Jet<N> operator/(const Jet<N>& f, const Jet<N>& g) {
+  SMPC_OPS(2 + 3 * N);
   const double g_inv = 1.0 / g.a;
   const double q = f.a * g_inv;
   Jet<N> r;
@@ -114,6 +135,7 @@ inline Jet<N> operator/(const Jet<N>& f, const Jet<N>& g) {
 }
 template <int N>
 inline Jet<N> operator/(double s, const Jet<N>& g) {
+  SMPC_OPS(3 + N);
   const double m = -s / (g.a * g.a);
   Jet<N> r;
   r.a = s / g.a;
@@ -122,6 +144,7 @@ inline Jet<N> operator/(double s, const Jet<N>& g) {
 }
 template <int N>
 inline Jet<N> operator/(const Jet<N>& f, double s) {
+  SMPC_OPS(2 + N);
   const double s_inv = 1.0 / s;
   Jet<N> r;
   r.a = f.a * s_inv;
@@ -140,11 +163,13 @@ inline Jet<N>& operator-=(Jet<N>& f, const Jet<N>& g) {
 }
 template <int N>
 inline Jet<N>& operator+=(Jet<N>& f, double s) {
+  SMPC_OPS(1);
   f.a += s;
   return f;
 }
 template <int N>
 inline Jet<N>& operator-=(Jet<N>& f, double s) {
+  SMPC_OPS(1);
   f.a -= s;
   return f;
 }
@@ -172,6 +197,7 @@ SMPC_JET_CMP(!=)
 
 template <int N>
 inline Jet<N> sqrt(const Jet<N>& f) {
+  SMPC_OPS(3 + N);
   const double t = std::sqrt(f.a);
   const double k = 1.0 / (2.0 * t);
   Jet<N> r;
@@ -181,6 +207,7 @@ inline Jet<N> sqrt(const Jet<N>& f) {
 }
 template <int N>
 inline Jet<N> exp(const Jet<N>& f) {
+  SMPC_OPS(1 + N);
   const double t = std::exp(f.a);
   Jet<N> r;
   r.a = t;
@@ -189,6 +216,7 @@ inline Jet<N> exp(const Jet<N>& f) {
 }
 template <int N>
 inline Jet<N> sin(const Jet<N>& f) {
+  SMPC_OPS(2 + N);
   const double c = std::cos(f.a);
   Jet<N> r;
   r.a = std::sin(f.a);
@@ -197,6 +225,7 @@ inline Jet<N> sin(const Jet<N>& f) {
 }
 template <int N>
 inline Jet<N> cos(const Jet<N>& f) {
+  SMPC_OPS(2 + N);
   const double s = -std::sin(f.a);
   Jet<N> r;
   r.a = std::cos(f.a);
@@ -205,6 +234,7 @@ inline Jet<N> cos(const Jet<N>& f) {
 }
 template <int N>
 inline Jet<N> atan2(const Jet<N>& g, const Jet<N>& f) {
+  SMPC_OPS(5 + 3 * N);
   const double t = 1.0 / (f.a * f.a + g.a * g.a);
   Jet<N> r;
   r.a = std::atan2(g.a, f.a);

@@ -12,6 +12,12 @@
 #include "../include/smpc.h"
 #include "solver.hpp"
 
+#ifdef SMPC_ORACLE_COUNT_OPS
+namespace smpc_oracle {
+thread_local unsigned long long g_jet_flops = 0;
+}
+#endif
+
 using namespace smpc_oracle;
 
 namespace {
@@ -143,6 +149,25 @@ int smpc_oracle_evaluate(const smpc_params* p, const smpc_batch* in, int b, cons
   const bool ok = evaluate(v, blocks, x, &c, residuals, grad, jac, nullptr);
   if (cost) *cost = c;
   return ok ? 1 : 0;
+}
+
+// FLOPs of the Jet arithmetic of ONE differentiated evaluation (cost + Jacobian) of problem b at x, as the
+// reference-shaped evaluator executes it; -1 unless built with -DSMPC_ORACLE_COUNT_OPS (liboracle_count.so).
+long long smpc_oracle_count_jet_flops(const smpc_params* p, const smpc_batch* in, int b, const double* x) {
+#ifdef SMPC_ORACLE_COUNT_OPS
+  ProblemView v;
+  if (!make_view(p, in, b, &v)) return -1;
+  const std::vector<ResidualBlock> blocks = assemble(v);
+  const int P = 2 * v.nb;
+  std::vector<double> res(blocks.size()), grad(P), jac(blocks.size() * static_cast<size_t>(P));
+  double c = 0.0;
+  smpc_oracle::g_jet_flops = 0;
+  evaluate(v, blocks, x, &c, res.data(), grad.data(), jac.data(), nullptr);
+  return static_cast<long long>(smpc_oracle::g_jet_flops);
+#else
+  (void)p; (void)in; (void)b; (void)x;
+  return -1;
+#endif
 }
 
 // Residual kinds / steps in assembly order (for tests): kinds[m], steps[m].
