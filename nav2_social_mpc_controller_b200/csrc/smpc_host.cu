@@ -628,13 +628,31 @@ int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out) {
   //      second stream WHILE the solve runs: problems are handed out in index order and a group waits until the
   //      arrival counter has passed its problem (wait_for_costmap). Only with page-locked host maps (the copies must
   //      be truly asynchronous) and no other kernel of this call in flight (nothing may need an SM while groups wait).
-  bool stream_maps = false;
-  if (h->stream_maps && n_chunks == 1 && maps_per_problem && !(A > 0 && in->has_people) && B >= 1024) {
-    cudaPointerAttributes attr;
-    if (cudaPointerGetAttributes(&attr, in->costmaps) == cudaSuccess && attr.type == cudaMemoryTypeHost)
-      stream_maps = true;
-    else
-      (void)cudaGetLastError();
+  // Large batches stream their other per-problem arrays (seed path, pose, start controls: 0.5 kB per problem) the same
+  // way once those are worth more than the extra copy calls (>= 8 MB).
+  bool stream_maps = false;   // streaming mode on (the name is historical: maps were the first thing streamed)
+  bool streamed[kItems] = {false, false, false, false, false, false, false, false, false};
+  if (h->stream_maps && n_chunks == 1 && !(A > 0 && in->has_people) && B >= 1024) {
+    size_t small_bytes = 0;
+    for (int k = 0; k < kItems; ++k)
+      if (k != kMaps && items[k].host && items[k].per_problem) small_bytes += items[k].per_problem * B;
+    const bool stream_small = small_bytes >= (8u << 20);
+    bool all_pinned = true;
+    for (int k = 0; k < kItems; ++k) {
+      if (!(items[k].host && items[k].per_problem)) continue;
+      if (!((k == kMaps && maps_per_problem) || (k != kMaps && stream_small))) continue;
+      cudaPointerAttributes attr;
+      if (cudaPointerGetAttributes(&attr, items[k].host) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
+        streamed[k] = true;
+      } else {
+        (void)cudaGetLastError();
+        all_pinned = false;
+      }
+    }
+    for (int k = 0; k < kItems; ++k) {
+      if (!all_pinned) streamed[k] = false;
+      stream_maps = stream_maps || streamed[k];
+    }
   }
 
   // ---- shared arrays first (stream 1), the second stream waits for them
@@ -655,7 +673,7 @@ int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out) {
     cudaStream_t st = lanes[c & 1];
     for (int k = 0; k < kItems; ++k) {
       const Item& it = items[k];
-      if (it.host && it.per_problem && !(stream_maps && k == kMaps))
+      if (it.host && it.per_problem && !streamed[k])
         SMPC_CUDA(cudaMemcpyAsync(it.dev + it.per_problem * c0, static_cast<const char*>(it.host) + it.per_problem * c0,
                                   it.per_problem * n, cudaMemcpyHostToDevice, st));
     }
@@ -689,17 +707,22 @@ int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out) {
     dout.usable = static_cast<uint8_t*>(oat(kOUsable));
     dout.n_evals = static_cast<int32_t*>(oat(kOEvals));
     if (stream_maps) {
-      // Feed the solve its maps, piece by piece, each followed by its arrival count. Everything is enqueued BEFORE
+      // Feed the solve its streamed inputs, piece by piece, each followed by its arrival count. Everything is enqueued BEFORE
       // the kernel launch: the copies then make progress whether or not the launch call returns early (profilers,
       // compute-sanitizer and CUDA_LAUNCH_BLOCKING=1 make launches synchronous — pieces enqueued after the launch
       // would never arrive and the solve would wait for its timeout).
-      const Item& mp = items[kMaps];
-      const size_t piece = ((B + kMapChunks - 1) / kMapChunks + 63) & ~static_cast<size_t>(63);
+      // pieces end on multiples of 128 problems: no cache line of any per-problem array (down to 1 byte per problem)
+      // holds data of two pieces, so a line read through the read-only path can never be half-arrived
+      const size_t piece = ((B + kMapChunks - 1) / kMapChunks + 127) & ~static_cast<size_t>(127);
       int k = 0;
       for (size_t p0 = 0; p0 < B; p0 += piece, ++k) {
         const size_t pn = std::min(piece, B - p0);
-        SMPC_CUDA(cudaMemcpyAsync(mp.dev + mp.per_problem * p0, static_cast<const char*>(mp.host) + mp.per_problem * p0,
-                                  mp.per_problem * pn, cudaMemcpyHostToDevice, lanes[1]));
+        for (int i = 0; i < kItems; ++i) {
+          if (!streamed[i]) continue;
+          const Item& it = items[i];
+          SMPC_CUDA(cudaMemcpyAsync(it.dev + it.per_problem * p0, static_cast<const char*>(it.host) + it.per_problem * p0,
+                                    it.per_problem * pn, cudaMemcpyHostToDevice, lanes[1]));
+        }
         h->arrival_host[k] = static_cast<unsigned>(p0 + pn);
         SMPC_CUDA(cudaMemcpyAsync(h->arrival, h->arrival_host + k, sizeof(unsigned), cudaMemcpyHostToDevice, lanes[1]));
       }

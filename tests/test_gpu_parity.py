@@ -418,14 +418,16 @@ def test_people_free_cta_shapes_are_bit_identical(monkeypatch):
             assert np.array_equal(a[k], b[k]), f"G={group}: output {k} differs between 4-warp and 12-warp CTAs"
 
 
-def test_streamed_costmaps_are_bit_identical(monkeypatch):
-    """People-free batches with one costmap per problem and PAGE-LOCKED host buffers: smpc_solve_batch launches the
+@pytest.mark.parametrize("kind", ["maps_per_problem", "large_shared_maps"])
+def test_streamed_costmaps_are_bit_identical(kind, monkeypatch):
+    """(large_shared_maps: >= 8 MB of other per-problem arrays stream in the same way.)
+    People-free batches with one costmap per problem and PAGE-LOCKED host buffers: smpc_solve_batch launches the
     solve first and streams the maps in on a second stream while it runs (groups wait for the arrival counter to pass
     their problem). Must give the bits of the classic copy-then-solve order, for both lane mappings, a ragged size,
     and repeated calls on one handle (the arrival words are reset per call)."""
     import torch
     from nav2_social_mpc_controller_b200.optimizer import Optimizer
-    batch = sc.corridor(B=3000)
+    batch = sc.corridor(B=3000) if kind == "maps_per_problem" else sc.corridor(B=20000, unique_maps=False, config_id=22)
     pinned = {k: (torch.from_numpy(v).pin_memory() if v is not None else None) for k, v in batch.arrays.items()}
     pbatch = sc.Batch(params=batch.params, n_problems=batch.n_problems, n_steps=batch.n_steps, n_agents=batch.n_agents,
                       n_costmaps=batch.n_costmaps, size_x=batch.size_x, size_y=batch.size_y,
