@@ -183,8 +183,8 @@ int smpc_abi_version(void);
 
 /* ---- level-1 solve: replaces ceres::Solve at src/optimizer.cpp:381 ------ */
 /* Host buffers in, host buffers out (H2D, kernels, D2H inside the call; returns when the results are in `out`). Copies
- * and solves are pipelined over two streams (batches with people: chunks of problems; people-free batches with one
- * costmap per problem: the maps stream into the running solve) when the caller's buffers are page-locked; pageable
+ * and solves are pipelined over two streams (batches with people: chunks of problems; people-free batches: per-problem
+ * costmaps / large per-problem arrays stream into the running solve) when the caller's buffers are page-locked; pageable
  * buffers work too, without the overlap. Results do not depend on it. */
 int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out);
 /* Device buffers in/out; asynchronous on `stream` (a cudaStream_t, NULL = the handle's own stream). A handle owns ONE set
