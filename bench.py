@@ -374,7 +374,8 @@ def main():
             "clocks": sampler.summary(),
             "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved_tflops / fp64_peak if fp64_peak > 0 else None,
-                         "traffic": load_traffic(args.workload),
+                         "traffic": (load_traffic(args.workload) or {}).get("bytes"),
+                         "traffic_detail": load_traffic(args.workload),
                          "kernel": f"smpc_solve_kernel<{nb}>", "kernel_ms": k_ms,
                          "peak_source": "DFMA microbenchmark measured in this run (smpc_measure_fp64_peak); "
                                         "MEASURED_PEAKS.json has no FP64 entry",
