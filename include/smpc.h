@@ -361,6 +361,13 @@ long long smpc_launch_count(smpc_handle* h);
 /* Measured FP64 FMA throughput of this GPU (TFLOP/s, DFMA-saturating microbenchmark, best of 5): the roofline
  * denominator of the solve kernel ("of measured"; MEASURED_PEAKS.json carries no FP64 figure). */
 int smpc_measure_fp64_peak(smpc_handle* h, double* tflops);
+/* Diagnostics for unit tests (no GPU needed): the chunk plan smpc_solve_batch would use for a host batch of
+ * `n_problems` on a GPU with `n_sm` SMs. has_people = agent columns and a has_people array are given;
+ * maps_per_problem = one costmap per problem (no index, or an identity index); has_index = a non-identity
+ * costmap_index; forced_chunks = the SMPC_CHUNKS override (0 = heuristic). Outputs: number of chunks and problems
+ * per chunk (the last chunk holds the remainder). */
+int smpc_debug_plan_chunks(int n_sm, int n_problems, int has_people, int n_costmaps, int maps_per_problem, int has_index,
+                           int forced_chunks, int* n_chunks, int* chunk);
 /* Diagnostics for unit tests: run the line-search interpolating-polynomial minimiser (Ceres polynomial.cc
  * restatement) on n host rows of (lo, hi, f0, g0, t1, f1, g1, t2, f2, g2); t2 <= 0 selects the 2-sample case. */
 int smpc_debug_polymin(smpc_handle* h, int n, const double* rows, double* out);

@@ -96,7 +96,7 @@ EXPORTED_SYMBOLS = (
     "smpc_abi_version", "smpc_last_error", "smpc_params_default", "smpc_params_from_yaml", "smpc_problem_dims",
     "smpc_create", "smpc_destroy", "smpc_solve_batch", "smpc_solve_batch_device", "smpc_eval_batch_device",
     "smpc_eval_batch", "smpc_multistart_argmin_device", "smpc_last_kernel_ms", "smpc_launch_count",
-    "smpc_measure_fp64_peak", "smpc_debug_polymin", "smpc_set_group",
+    "smpc_measure_fp64_peak", "smpc_debug_polymin", "smpc_debug_plan_chunks", "smpc_set_group",
     "smpc_optimize", "smpc_reset_memory", "smpc_project_people_batch", "smpc_project_people_batch_device",
     "smpc_format_batch_device", "smpc_people_to_status_device", "smpc_memory_update_device",
     "smpc_trajectorize_batch_device",

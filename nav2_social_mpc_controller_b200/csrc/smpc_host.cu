@@ -534,6 +534,52 @@ int smpc_solve_batch_device(smpc_handle* h, const smpc_batch* in, smpc_result* o
   return solve_device_locked(h, in, out, stream ? static_cast<cudaStream_t>(stream) : h->stream);
 }
 
+// Chunk plan of the host-buffer pipeline (pure: no CUDA call, exported for the CPU test suite as
+// smpc_debug_plan_chunks). Chunking pays where the copies are a large share of the call: batches with people (28 kB
+// per problem at 20 agents; measured +22 % end to end at A = 20, +14 % at A = 50, +3 % at A = 3). People-free batches
+// are one chunk: their copies are small next to the solve and smaller launches balance worse (measured -2..-13 %);
+// they stream their inputs into the one launch instead. A chunk must not push the launch heuristics of
+// smpc_kernels_nb.inc into another kernel variant than the whole batch would get: 16-warp CTAs need >= 2 warps per warp
+// slot, i.e. >= 2 * 16 * n_sm problems per launch — also for the ragged last chunk. Shared costmaps addressed by
+// b % M need chunk starts that are multiples of M.
+static void plan_chunks(int n_sm, size_t B, bool people, size_t M, bool maps_per_problem, bool has_index, int forced_chunks,
+                        size_t* n_chunks_out, size_t* chunk_out) {
+  const size_t w16_min = 2 * 16 * static_cast<size_t>(n_sm);
+  size_t n_chunks = 1;
+  if (people) n_chunks = std::min<size_t>(kMaxChunks, B / (w16_min + 128));
+  if (forced_chunks >= 1) n_chunks = std::min<size_t>(forced_chunks, kMaxChunks);
+  n_chunks = std::max<size_t>(1, std::min(n_chunks, B));
+  size_t chunk = B;
+  for (; n_chunks > 1; --n_chunks) {
+    chunk = ((B + n_chunks - 1) / n_chunks + 255) & ~static_cast<size_t>(255);
+    const size_t used = (B + chunk - 1) / chunk;  // chunks actually needed at this (rounded-up) size
+    const size_t last = B - (used - 1) * chunk;
+    const bool modulo_ok = maps_per_problem || has_index || (chunk % M) == 0;  // b % M must not shift
+    const bool size_ok = forced_chunks >= 1 || last >= w16_min;
+    if (modulo_ok && size_ok) {
+      n_chunks = used;
+      break;
+    }
+  }
+  if (n_chunks <= 1) {
+    n_chunks = 1;
+    chunk = B;
+  }
+  *n_chunks_out = n_chunks;
+  *chunk_out = chunk;
+}
+
+int smpc_debug_plan_chunks(int n_sm, int n_problems, int has_people, int n_costmaps, int maps_per_problem, int has_index,
+                           int forced_chunks, int* n_chunks, int* chunk) {
+  if (n_sm < 1 || n_problems < 1 || n_costmaps < 1 || !n_chunks || !chunk) return fail(SMPC_ERR_ARGUMENT, "bad plan arguments");
+  size_t n = 1, c = static_cast<size_t>(n_problems);
+  plan_chunks(n_sm, static_cast<size_t>(n_problems), has_people != 0, static_cast<size_t>(n_costmaps), maps_per_problem != 0,
+              has_index != 0, forced_chunks, &n, &c);
+  *n_chunks = static_cast<int>(n);
+  *chunk = static_cast<int>(c);
+  return SMPC_OK;
+}
+
 // Host buffers in, host buffers out. The batch is cut into up to kMaxChunks chunks of consecutive problems that
 // alternate between two streams: chunk k+1's host-to-device copies run while chunk k solves, and chunk k's results
 // travel back while chunk k+1 solves (problems are independent, so a chunk is a complete batch of its own). Copies
@@ -560,32 +606,9 @@ int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out) {
   for (size_t b = 0; identity_index && b < B; ++b) identity_index = in->costmap_index[b] == static_cast<int32_t>(b);
   const int32_t* host_index = identity_index ? nullptr : in->costmap_index;
   const bool maps_per_problem = (host_index == nullptr) && (M == B);
-  // Chunking pays where the copies are a large share of the call: batches with people (28 kB per problem at 20
-  // agents; measured +22 % end to end at A = 20, +14 % at A = 50, +3 % at A = 3). People-free batches are one chunk:
-  // their copies are small next to the solve and smaller launches balance worse (measured -2..-13 %).
-  // A chunk must not push the launch heuristics of smpc_kernels_nb.inc into another kernel variant than the whole
-  // batch would get: 16-warp CTAs need >= 2 warps per warp slot, i.e. >= 2 * 16 * n_sm problems per launch.
-  const size_t w16_min = 2 * 16 * static_cast<size_t>(h->n_sm);
-  size_t n_chunks = 1;
-  if (A > 0 && in->has_people) n_chunks = std::min<size_t>(kMaxChunks, B / (w16_min + 128));
-  if (h->forced_chunks >= 1) n_chunks = std::min<size_t>(h->forced_chunks, kMaxChunks);
-  n_chunks = std::max<size_t>(1, std::min(n_chunks, B));
-  size_t chunk = B;
-  for (; n_chunks > 1; --n_chunks) {
-    chunk = ((B + n_chunks - 1) / n_chunks + 255) & ~static_cast<size_t>(255);
-    const size_t used = (B + chunk - 1) / chunk;  // chunks actually needed at this (rounded-up) size
-    const size_t last = B - (used - 1) * chunk;
-    const bool modulo_ok = maps_per_problem || host_index != nullptr || (chunk % M) == 0;  // b % M must not shift
-    const bool size_ok = h->forced_chunks >= 1 || last >= w16_min;
-    if (modulo_ok && size_ok) {
-      n_chunks = used;
-      break;
-    }
-  }
-  if (n_chunks <= 1) {
-    n_chunks = 1;
-    chunk = B;
-  }
+  size_t n_chunks = 1, chunk = B;
+  plan_chunks(h->n_sm, B, A > 0 && in->has_people, M, maps_per_problem, host_index != nullptr, h->forced_chunks, &n_chunks,
+              &chunk);
 
   // ---- device staging: every array whole, same layout as the host's, so a chunk is a pointer offset
   struct Item { const void* host; size_t per_problem; size_t shared_bytes; char* dev; };

@@ -133,3 +133,36 @@ def test_scenario_generators_are_deterministic_and_well_formed():
     assert m.n_problems == 32
     assert np.array_equal(m.arrays["u0"][0], sc.crowd(B=4, A=3, config_id=4, n_maps=4).arrays["u0"][0])
     assert np.all(m.arrays["u0"][..., 0] >= 0) and np.all(m.arrays["u0"][..., 0] <= 0.6)
+
+
+def test_host_pipeline_chunk_plan():
+    """Chunk plan of smpc_solve_batch (pure host logic, no GPU): people-free batches are one launch; batches with people
+    are cut into <= 8 chunks of multiples of 256 problems, none smaller than the 16-warp threshold (2 * 16 * n_sm), and
+    chunk starts keep b % M intact for shared costmaps without an index."""
+    import ctypes as C
+    from nav2_social_mpc_controller_b200 import _lib
+    L = _lib.lib()
+    L.smpc_debug_plan_chunks.restype = C.c_int
+    L.smpc_debug_plan_chunks.argtypes = [C.c_int] * 7 + [C.POINTER(C.c_int)] * 2
+
+    def plan(B, people, M, per_problem=0, index=0, forced=0, n_sm=148):
+        n, c = C.c_int(), C.c_int()
+        assert L.smpc_debug_plan_chunks(n_sm, B, people, M, per_problem, index, forced, C.byref(n), C.byref(c)) == 0
+        return n.value, c.value
+
+    assert plan(4096, 0, 4096, per_problem=1) == (1, 4096)          # BASELINE configs[1]: streamed, not chunked
+    assert plan(65536, 0, 256) == (1, 65536)
+    w16 = 2 * 16 * 148
+    for B, M in [(65536, 256), (16384, 256), (262144, 256), (10000, 256), (9471, 1), (9999, 4), (1_000_000, 256)]:
+        n, c = plan(B, 1, M)
+        assert 1 <= n <= 8 and (n - 1) * c < B <= n * c
+        if n > 1:
+            assert c % 256 == 0 and c % M == 0                       # b % M unchanged at every chunk start
+            assert B - (n - 1) * c >= w16 and c >= w16               # no chunk falls below the 16-warp threshold
+    assert plan(65536, 1, 256)[0] == 8 and plan(16384, 1, 256)[0] == 3 and plan(9000, 1, 256)[0] == 1
+    # shared maps without an index whose count does not divide any admissible chunk size: fall back to one launch
+    assert plan(65536, 1, 1000) == (1, 65536)
+    assert plan(65536, 1, 1000, index=1)[0] == 8                     # with an explicit index the maps need no alignment
+    # the SMPC_CHUNKS override ignores the size rule but still honours the modulo rule
+    assert plan(1300, 1, 256, forced=3) == (3, 512)
+    assert L.smpc_debug_plan_chunks(0, 10, 0, 1, 0, 0, 0, None, None) != 0
