@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define SMPC_ABI_VERSION 1
+#define SMPC_ABI_VERSION 2
 #define SMPC_MAX_BLOCKS 18 /* control_horizon 18 with parameter_block_length 1: the "36x36 class" */
 
 /* Return codes of every entry point. Per-problem solver outcomes are NOT call
@@ -101,6 +101,14 @@ typedef struct smpc_params {
    * ceres_compat 200 = Ceres 2.0.0 loop (Ubuntu 22.04 / Humble), 220 = Ceres >= 2.1
    * (parameter / function tolerance only tested after a first successful step). */
   int ceres_compat;
+  /* Deterministic stand-in for Solver::Options::max_solver_time_in_seconds (src/optimizer.cpp:131; Ceres tests it in
+   * FinalizeIterationAndCheckIfMinimizerCanContinue, before the iteration cap): a solve that has spent this many
+   * evaluations stops with NO_CONVERGENCE at its next iteration boundary. 0 = off (the wall clock of the reference is
+   * not reproducible; parity runs keep it off). */
+  int max_evaluations;
+  /* Extension, not reference behaviour: 1 = the solve optimises omnidirectional (vx, vy, w) blocks (the reference's
+   * update_state.hpp:46-61 is unicycle-only; only its trajectorizer has an omni branch). 0 = unicycle (v, w). */
+  int omni_solve;
 } smpc_params;
 
 /* One batch of independent MPC problems, post-projection: exactly the arrays
@@ -109,7 +117,7 @@ typedef struct smpc_params {
  * smpc_solve_batch_device. */
 typedef struct smpc_batch {
   int n_problems; /* B */
-  int n_steps;    /* S = N_v = P_poses - 1, uniform in the batch */
+  int n_steps;    /* S = N_v = P_poses - 1: the longest horizon of the batch (see n_steps_each) and the array stride */
   int n_agents;   /* A: 3 in the reference (src/optimizer.cpp:468-479); any A >= 0 here */
   int n_costmaps; /* M */
   int size_x;
@@ -126,6 +134,13 @@ typedef struct smpc_batch {
   const uint8_t* costmaps;
   const double* costmap_origin;
   const int32_t* costmap_index; /* may be NULL */
+  /* Per-problem horizon S_b <= n_steps ([B] i32, may be NULL: every problem has n_steps steps). The trajectorizer
+   * stops early near the goal (src/path_trajectorizer.cpp:152) and the optimizer sizes the problem from what it got
+   * (src/optimizer.cpp:248-249), so the robots of a fleet have different S, ch, bl and block counts. Array strides stay
+   * those of n_steps (rows are padded); problem b reads steps 0..S_b, uses the first ceil(ch_b/bl_b) blocks of its
+   * u0 / u rows and does not write the rest of its output rows (smpc_solve_batch returns them zero-filled,
+   * smpc_solve_batch_device leaves the caller's memory untouched). */
+  const int32_t* n_steps_each;
 } smpc_batch;
 
 /* Per-problem outputs. Any pointer may be NULL (that output is skipped).
@@ -137,7 +152,8 @@ typedef struct smpc_batch {
  *   iterations   [B]          index of the last recorded TR iteration
  *   termination  [B]          enum smpc_termination
  *   usable       [B]          Summary::IsSolutionUsable(); 0 <=> optimize() would return false
- *   n_evals      [B][2]       {Jacobian evaluations, cost/gradient-only evaluations} spent (roofline numerator)
+ *   n_evals      [B][2]       {evaluations that built J^T J, evaluations that stopped at cost + J^T r (line-search
+ *                             samples that failed the Armijo test)} (roofline numerator)
  */
 typedef struct smpc_result {
   double* u;
@@ -149,15 +165,25 @@ typedef struct smpc_result {
   int32_t* termination;
   uint8_t* usable;
   int32_t* n_evals;
+  /* Optional per-evaluation solver trace (diagnostics: tools/flip_log.py): trace [B][trace_rows][8] =
+   * iteration, phase (1 init / 2 line-search sample / 3 full step), step size t, cost of the differentiated
+   * evaluation, cost of the plain evaluation, aux (rejected sample: Armijo margin; candidate: relative decrease),
+   * code (bit 0 Armijo ok, 1 became the candidate, 2 accepted, 3 terminated, bits 4.. termination), radius.
+   * Rows beyond trace_rows are dropped; unused rows are left untouched. NULL = off. */
+  double* trace;
+  int trace_rows;
 } smpc_result;
 
 /* Normal-equation snapshot of one evaluation (first-slice / test entry):
  *   cost [B], grad [B][P], hess [B][P*(P+1)/2] (row-major lower triangle), P = 2*NB. */
 typedef struct smpc_eval_out {
-  double* cost;
+  double* cost; /* 1/2 sum r^2 as a DIFFERENTIATED evaluation (Jets) of the reference computes it */
   double* grad;
   double* hess;
   uint8_t* ok; /* 0 when a residual or Jacobian entry was non-finite */
+  /* the same sum as a cost-only (double) evaluation computes it; differs from `cost` only under ceres_compat < 210
+   * with people (ProxemicsCost evaluates differently under Ceres 2.0.0 Jets). May be NULL. */
+  double* cost_plain;
 } smpc_eval_out;
 
 typedef struct smpc_handle smpc_handle;

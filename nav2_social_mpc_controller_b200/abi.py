@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import numpy as np
 
-SMPC_ABI_VERSION = 1
+SMPC_ABI_VERSION = 2
 SMPC_MAX_BLOCKS = 18
 
 # enum smpc_termination
@@ -60,6 +60,8 @@ class SmpcParams(C.Structure):
         ("desired_linear_vel", C.c_double),
         ("fov_angle", C.c_double),
         ("ceres_compat", C.c_int),
+        ("max_evaluations", C.c_int),
+        ("omni_solve", C.c_int),
     ]
 
 
@@ -83,6 +85,7 @@ class SmpcBatch(C.Structure):
         ("costmaps", C.c_void_p),
         ("costmap_origin", C.c_void_p),
         ("costmap_index", C.c_void_p),
+        ("n_steps_each", C.c_void_p),
     ]
 
 
@@ -97,6 +100,8 @@ class SmpcResult(C.Structure):
         ("termination", C.c_void_p),
         ("usable", C.c_void_p),
         ("n_evals", C.c_void_p),
+        ("trace", C.c_void_p),
+        ("trace_rows", C.c_int),
     ]
 
 
@@ -106,6 +111,7 @@ class SmpcEvalOut(C.Structure):
         ("grad", C.c_void_p),
         ("hess", C.c_void_p),
         ("ok", C.c_void_p),
+        ("cost_plain", C.c_void_p),
     ]
 
 
@@ -127,10 +133,10 @@ def _ptr(a):
 
 
 BATCH_FIELDS = ("pose0", "u0", "path_xy", "goal_yaw", "agents", "has_people", "costmaps",
-                "costmap_origin", "costmap_index")
+                "costmap_origin", "costmap_index", "n_steps_each")
 BATCH_DTYPES = {"pose0": np.float64, "u0": np.float64, "path_xy": np.float64, "goal_yaw": np.float64,
                 "agents": np.float64, "has_people": np.uint8, "costmaps": np.uint8,
-                "costmap_origin": np.float64, "costmap_index": np.int32}
+                "costmap_origin": np.float64, "costmap_index": np.int32, "n_steps_each": np.int32}
 
 
 def make_batch_struct(arrays: dict, n_problems: int, n_steps: int, n_agents: int, n_costmaps: int,
@@ -166,6 +172,9 @@ def make_result_struct(arrays: dict) -> SmpcResult:
     r = SmpcResult()
     for f in RESULT_FIELDS:
         setattr(r, f, _ptr(arrays.get(f)))
+    tr = arrays.get("trace")
+    r.trace = _ptr(tr)
+    r.trace_rows = int(tr.shape[1]) if tr is not None else 0
     return r
 
 

@@ -6,11 +6,13 @@
 //     re-rolls-out 0..i inside every functor, O(S^2); here it is one O(S) pass per evaluation).
 //   * residuals + ANALYTIC gradients wrt the lane's pose (X, Y, Theta, v_block) for the eight active
 //     critics (reference include/nav2_social_mpc_controller/critics/*.hpp), accumulated per lane as a
-//     4x4 Gauss-Newton block M = sum c c^T and q = sum c r, then H_lane = D^T M D, g_lane = D^T q with
-//     the 4xP sensitivity matrix D; warp-shuffle all-reduce gives J^T J, J^T r, cost.
+//     4x4 Gauss-Newton block M = sum c c^T and q = sum c r, then g_lane = D^T q and — only when the trial point can
+//     become the next iterate — H_lane = D^T M D with the 4xP sensitivity matrix D; a shared-memory column sum
+//     gives cost, J^T r, J^T J of the group.
 //   * the bounded trust-region Levenberg-Marquardt loop of ceres::Solve (reference src/optimizer.cpp:381
-//     with the options of :117-131) runs warp-uniformly: Jacobi scaling, LM diagonal, PxP Cholesky,
-//     projected Armijo line search with cubic / quintic interpolation, tolerance tests, radius update.
+//     with the options of :117-131) is run by the group's FIRST lane on the group's shared-memory state (the other
+//     lanes wait at a __syncwarp): Jacobi scaling, LM diagonal, PxP Cholesky, projected Armijo line search with
+//     cubic / quintic interpolation, tolerance tests, radius update.
 // No CPU fallback exists; this header is the product path.
 #pragma once
 #include <cuda_runtime.h>
@@ -27,8 +29,9 @@ constexpr int kMaxSteps = 64;  // S <= 64 steps (the reference parameter sets gi
 struct DevParams {
   double w_distance, w_social, w_velocity, w_angle, w_agent_angle, w_prox, w_vf, w_obstacle, w_goal;
   double param_tol, fn_tol, gradient_tol;
-  int max_iterations, ceres_compat;
-  int ch, bl, nb, n_bounded;
+  int max_iterations, ceres_compat, max_evaluations;
+  int ch, bl, nb, n_bounded;  // of the batch's longest horizon (nb = template NB of the kernel)
+  int control_horizon, block_length;  // yaml values: per-problem dims are derived from them (src/optimizer.cpp:248-249)
 };
 
 struct DevBatch {
@@ -45,6 +48,7 @@ struct DevBatch {
   const uint8_t* costmaps;
   const double* costmap_origin;
   const int32_t* costmap_index;
+  const int32_t* n_steps_each;  // [B] per-problem horizon S_b <= S, NULL = S for all
   // Host-buffer pipeline only (else NULL): arrival[0] = number of leading problems whose costmap has landed in device
   // memory (written by the copy stream after each map chunk), arrival[1] = set by the kernel if it gave up waiting.
   unsigned* arrival;
@@ -68,16 +72,19 @@ struct DevResult {
   int32_t* termination;
   uint8_t* usable;
   int32_t* n_evals;
+  double* trace;  // [B][trace_rows][8], NULL = off (include/smpc.h)
+  int trace_rows;
 };
 
 struct DevEvalOut {
   double* cost;
+  double* cost_plain;
   double* grad;
   double* hess;
   uint8_t* ok;
 };
 
-// Warp-uniform view of one problem.
+// Group-uniform view of one problem (lives in the group's shared memory).
 struct Prob {
   double x0, y0, yaw0, goal_yaw, fin_x, fin_y, org_x, org_y;
   const double* px;
@@ -86,10 +93,13 @@ struct Prob {
   const double* packed;  // [A][S+1][4]
   const uint8_t* valid;  // [A][S+1]
   const uint8_t* map;
+  // per-problem sizes (src/optimizer.cpp:248-249, :373): S_b steps, ch = min(control_horizon, S_b),
+  // bl = min(block_length, ch), nb = ceil(ch / bl) blocks in use (<= NB of the kernel), nbd = ch / bl bounded blocks
+  int S, ch, bl, nb, nbd;
   bool has_people;
 };
 
-enum EvalFlags : unsigned { kResidualBad = 1u, kJacobianBad = 2u };
+enum EvalFlags : unsigned { kResidualBad = 1u, kJacobianBad = 2u, kNoHessian = 4u };
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -184,6 +194,9 @@ __device__ __forceinline__ void social_pair(double dx, double dy, double wx, dou
 
 // ---------------------------------------------------------------------------------------------------
 // ceres::BiCubicInterpolator<Grid2D<u_char>>: value + d/drow + d/dcol.
+// NC = the map may be read through the non-coherent (read-only) path. People-free batches can stream their costmaps
+// into the RUNNING kernel (host-buffer pipeline, wait_for_costmap); PTX allows ld.global.nc only for data that is
+// read-only for the whole kernel, so those kernels read the maps with coherent ld.global.ca instead.
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void hermite(double p0, double p1, double p2, double p3, double x, double& f, double& dfdx) {
   const double a = 0.5 * (-p0 + 3.0 * p1 - 3.0 * p2 + p3);
@@ -193,8 +206,15 @@ __device__ __forceinline__ void hermite(double p0, double p1, double p2, double 
   dfdx = c + x * (2.0 * b + 3.0 * a * x);
 }
 
-__device__ __forceinline__ void bicubic(const uint8_t* __restrict__ map, int size_x, int size_y, double r, double c,
-                                        double& f, double& dfdr, double& dfdc) {
+template <bool NC, class T>
+__device__ __forceinline__ T ld_in(const T* p) {
+  if (NC) return __ldg(p);
+  return __ldca(p);
+}
+
+template <bool NC>
+__device__ __forceinline__ void bicubic(const uint8_t* map, int size_x, int size_y, double r, double c, double& f,
+                                        double& dfdr, double& dfdc) {
   // clamp the cell index so that a non-finite / huge coordinate cannot overflow the int conversion
   const double rf = floor(fmin(fmax(r, -4.0), (double)size_y + 4.0));
   const double cf = floor(fmin(fmax(c, -4.0), (double)size_x + 4.0));
@@ -208,19 +228,20 @@ __device__ __forceinline__ void bicubic(const uint8_t* __restrict__ map, int siz
   for (int k = 0; k < 4; ++k) {
     const int rr = min(max(row - 1 + k, 0), size_y - 1);
     const uint8_t* line = map + (size_t)rr * size_x;
-    hermite((double)__ldg(line + cc[0]), (double)__ldg(line + cc[1]), (double)__ldg(line + cc[2]),
-            (double)__ldg(line + cc[3]), xc, fr[k], dfr[k]);
+    hermite((double)ld_in<NC>(line + cc[0]), (double)ld_in<NC>(line + cc[1]), (double)ld_in<NC>(line + cc[2]),
+            (double)ld_in<NC>(line + cc[3]), xc, fr[k], dfr[k]);
   }
   double unused;
   hermite(fr[0], fr[1], fr[2], fr[3], xr, f, dfdr);
   hermite(dfr[0], dfr[1], dfr[2], dfr[3], xr, dfdc, unused);
 }
 
-// steps k < j that belong to block beta (blocks hold bl steps, the last one extends to the horizon end)
-template <int NB>
-__device__ __forceinline__ int steps_in_block_before(int j, int beta, int bl) {
+// steps k < j that belong to block beta: blocks hold bl steps, block `last` (= the problem's last block) extends to the
+// horizon end, blocks beyond it do not exist for this problem
+__device__ __forceinline__ int steps_in_block_before(int j, int beta, int bl, int last) {
   const int n = j - beta * bl;
-  if (beta == NB - 1) return max(n, 0);
+  if (beta > last) return 0;
+  if (beta == last) return max(n, 0);
   return min(max(n, 0), bl);
 }
 
@@ -260,19 +281,23 @@ __device__ __forceinline__ double agent_angle_target(const DevBatch& bt, const P
 // Work mapping: a GROUP of G lanes (G = 4, 8, 16 or 32) solves one problem, so a warp holds 32/G problems.
 // Lane gl of the group owns horizon steps gl, gl+G, gl+2G, ... ("chunks" of G consecutive steps are scanned
 // across the group, carries go through shared memory). G = 32 is the latency mapping (one step per lane);
-// small G is the throughput mapping: the warp-uniform part of the solver (LM step, line-search polynomials)
-// and the scan / reduction overheads are then shared by 32/G problems instead of being replicated 32 times.
+// small G is the throughput mapping: the scan / reduction overheads and the group-leader solver logic are then
+// shared by 32/G problems per warp.
 // ---------------------------------------------------------------------------------------------------
 
-// Per-group shared-memory state. Buffers hold [cost, g[P], H[NH]] (H row-major lower triangle,
+// Per-group shared-memory state. Buffers hold [cost_diff, cost_plain, g[P], H[NH]] (H row-major lower triangle,
 // H[a(a+1)/2 + b], a >= b) of the current iterate and of the trial point; the LM vectors follow.
+//   cost_diff  = 1/2 sum r^2 as a DIFFERENTIATED evaluation of the reference computes it (Jets),
+//   cost_plain = the same sum as a cost-only (double) evaluation computes it.
+// They differ only under ceres_compat < 210, where ProxemicsCost evaluates differently under Jets (evaluate()).
 constexpr int kRedStride = 33;  // odd stride of the per-warp reduction scratch: conflict-free rows and columns
 
 template <int NB>
 struct Layout {
   static constexpr int P = 2 * NB;
   static constexpr int NH = P * (P + 1) / 2;
-  static constexpr int NE = 1 + P + NH;
+  static constexpr int NG = 2 + P;       // cost_diff, cost_plain, g[P]: the part every evaluation reduces
+  static constexpr int NE = NG + NH;     // ... plus J^T J
   static constexpr int NC = 4 + 4 * NB;  // scan carries: X, Y, sin, cos of the heading, 4 NB sensitivities
   static constexpr int kBuf0 = 0;
   static constexpr int kBuf1 = NE;
@@ -285,18 +310,18 @@ struct Layout {
   static constexpr int kCarry = kCand + P;
   static constexpr int kYaw = kCarry + NC;  // sin, cos of yaw0
   static constexpr int kState = kYaw + 2;    // LmState (solver scalars parked here across the evaluation)
-  static constexpr int kProb = kState + 20;  // Prob (group-uniform problem view)
-  static constexpr int kAa = kProb + 15;  // agent-angle steering target per step [S]
+  static constexpr int kProb = kState + 22;  // Prob (group-uniform problem view)
+  static constexpr int kAa = kProb + 18;  // agent-angle steering target per step [S]
   __host__ __device__ static constexpr int total(int S) { return ((kAa + S) | 1); }  // odd stride: no bank conflicts
   static constexpr int kRedDoubles = NE * kRedStride;  // per-WARP scratch behind the per-group regions
-  __host__ __device__ static constexpr int g(int c) { return 1 + c; }
-  __host__ __device__ static constexpr int h(int a, int b) { return 1 + P + a * (a + 1) / 2 + b; }
+  __host__ __device__ static constexpr int g(int c) { return 2 + c; }
+  __host__ __device__ static constexpr int h(int a, int b) { return NG + a * (a + 1) / 2 + b; }
 };
 
 // Layout<NB>::total(S) for a run-time NB (the host sizes the parking area of the time-sliced queue with it).
 __host__ __device__ constexpr int layout_total(int nb, int S) {
-  const int P = 2 * nb, NE = 1 + P + P * (P + 1) / 2, NC = 4 + 4 * nb;
-  return ((2 * NE + 6 * P + NC + 2 + 20 + 15 + S) | 1);
+  const int P = 2 * nb, NE = 2 + P + P * (P + 1) / 2, NC = 4 + 4 * nb;
+  return ((2 * NE + 6 * P + NC + 2 + 22 + 18 + S) | 1);
 }
 static_assert(layout_total(3, 28) == Layout<3>::total(28) && layout_total(5, 38) == Layout<5>::total(38) &&
                   layout_total(18, 18) == Layout<18>::total(18),
@@ -316,69 +341,77 @@ __device__ __forceinline__ double wrap_angle(double a) {
   return a - (2.0 * M_PI) * rint(a * (0.5 / M_PI));
 }
 
+// Solver scalars of one group, resident in shared memory and touched ONLY by the group's first lane (between
+// __syncwarp pairs), so that no update depends on the lanes of a group running in lock-step.
+enum Phase { kFetch = 0, kInit = 1, kLineSearch = 2, kFullStep = 3 };
+struct LmState {
+  double x_cost, x_norm, gmax, radius, decrease_factor, minimum_cost, it_cost, cost_initial, cost_final,
+      model_cost_change, g0, dmax, t, prev_x, prev_value, prev_gradient;
+  double se_cost;  // TrustRegionStepEvaluator::current_cost_: iteration-zero cost, then the last accepted CANDIDATE cost
+  int iteration, n_invalid, n_eval, n_light, ls_iters, term, phase, b, flags, pad_;
+};
+static_assert(sizeof(LmState) == 22 * sizeof(double), "Layout::kState reserves 22 doubles");
+static_assert(sizeof(Prob) <= 18 * sizeof(double), "Layout::kProb reserves 18 doubles");
+enum StateFlags {
+  kReuseDiagonal = 1, kItSuccessful = 2, kAnySuccess = 4, kPrevOk = 8, kLive = 16, kExhausted = 32, kSwapped = 64,
+  kDrained = 128,  // this group has seen the main queue empty
+  kClosed = 256,   // ... and the parked queue closed and empty: nothing will ever come again
+  kFinished = 512  // the leader has terminated the solve: all lanes write the results, then the group fetches again
+};
+
 // ---------------------------------------------------------------------------------------------------
-// Full evaluation at block values xs[P] (group shared memory): cost = 1/2 sum r^2, g = J^T r, H = J^T J,
+// Evaluation at block values xs[P] (group shared memory): cost = 1/2 sum r^2, g = J^T r and (when wanted) H = J^T J,
 // written to out[NE] (group shared memory). Residual set and order of reference src/optimizer.cpp:251-371
 // (SURVEY Appendix D). Must be called by all 32 lanes of the warp (scans use full-mask shuffles of width G);
 // `live` = this group holds a problem.
+// `st` (solve kernel) lets the evaluation stop early: a line-search sample that fails the Armijo test is used for
+// its cost and directional derivative only (Ceres evaluates exactly cost + gradient there, line_search.cc), so its
+// J^T J is not built and kNoHessian is returned. st == nullptr: always build J^T J.
 // ---------------------------------------------------------------------------------------------------
-// Per-lane constants of the first chunk (steps 0..G-1): block of the lane's step and dt * #{steps before j in
-// block b}. They depend only on (S, bl, dt), i.e. on the batch, and are hoisted out of the whole solve.
-template <int NB>
-struct LaneConst {
-  int bj;
-  double tau[NB];
-};
-
-template <int NB>
-__device__ __forceinline__ void lane_setup(int j, int bl, double dt, LaneConst<NB>& lc) {
-  lc.bj = min(j / bl, NB - 1);
-  SMPC_UNROLL for (int b = 0; b < NB; ++b) lc.tau[b] = dt * (double)steps_in_block_before<NB>(j, b, bl);
-}
-
 template <int NB, int G, bool PPL>
 __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatch& bt, const Prob& pb, bool live,
-                                             const LaneConst<NB>& lc0, double* ws, double* red, const double* xs,
-                                             int lane, double* out) {
+                                             double* ws, double* red, const double* xs, int lane, double* out,
+                                             const LmState* st) {
   using L = Layout<NB>;
   constexpr int P = L::P;
   const int gl = lane & (G - 1);
   const unsigned gmask = Group<G>::mask(lane);
-  const int S = bt.S, ch = prm.ch, bl = prm.bl;
+  const int Sb = live ? pb.S : 0;
+  // the scans are warp-wide shuffles: every group of the warp walks as many chunks as the longest horizon among them
+  const int Sw = (G == 32) ? Sb : __reduce_max_sync(kFullMask, Sb);
+  const int bl = pb.bl, last_b = pb.nb - 1, ch = pb.ch;
   const double dt = bt.dt;
-  const int stride = S + 1;
+  const int stride = bt.S + 1;
   const double inv_res = 1.0 / bt.resolution;
   double* carry = ws + L::kCarry;
   const double* aa = ws + L::kAa;
-
-  double x[P];
-  SMPC_UNROLL for (int c = 0; c < P; ++c) x[c] = xs[c];
-
-  // [cost, g, H] partial sums of this lane: column `lane` of the warp's shared scratch red[NE][33] (keeping them in
-  // registers costs 2 NE registers through the whole evaluation and a shuffle reduction at the end)
-  SMPC_UNROLL for (int e = 0; e < L::NE; ++e) red[e * kRedStride + lane] = 0.0;
+  const int col0 = lane & ~(G - 1);
   unsigned flags = 0;
+  bool need_h = true;
+  bool bad_res = false, bad_jac = false;
 
   // heading before the group's first step: sin / cos of yaw0 (stored at problem set-up), then carried chunk to chunk
   const double s0 = ws[L::kYaw], c0 = ws[L::kYaw + 1];
 
 #pragma unroll 1
-  for (int base = 0; base < S; base += G) {
+  for (int base = 0; base < Sw; base += G) {
     const int j = base + gl;
-    const bool act = live && (j < S);
-    LaneConst<NB> lc = lc0;
-    if (base != 0) lane_setup<NB>(j, bl, dt, lc);
-    const int bj = lc.bj;
-    double vj = x[0], wj = x[1];
+    const bool act = j < Sb;
+    const bool first = (base == 0);
+    const bool last = (base + G >= Sw);
+    // block of step j (j / bl capped at the problem's last block) and d theta_j / d w_b = dt #{steps < j in block b}
+    int bj = 0;
+    SMPC_UNROLL for (int b = 1; b < NB; ++b) bj += (j >= b * bl && b <= last_b) ? 1 : 0;
+    double vj = xs[0], wj = xs[1];
     double Th = pb.yaw0;  // heading AFTER step j = yaw0 + sum_b w_b dt #{steps <= j in block b}
     double tau[NB];       // d theta_j / d w_b (heading before step j)
     SMPC_UNROLL for (int b = 0; b < NB; ++b) {
       if (b == bj) {
-        vj = x[2 * b];
-        wj = x[2 * b + 1];
+        vj = xs[2 * b];
+        wj = xs[2 * b + 1];
       }
-      tau[b] = lc.tau[b];
-      Th += x[2 * b + 1] * lc.tau[b];
+      tau[b] = dt * (double)steps_in_block_before(j, b, bl, last_b);
+      Th += xs[2 * b + 1] * tau[b];
     }
     Th += wj * dt;
     // one sincos per step: lane j evaluates the heading after its step; the heading before it is the
@@ -388,14 +421,130 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
     double sn = __shfl_up_sync(kFullMask, sT, 1, G);
     double cs = __shfl_up_sync(kFullMask, cT, 1, G);
     if (gl == 0) {
-      sn = (base == 0) ? s0 : carry[2];
-      cs = (base == 0) ? c0 : carry[3];
+      sn = first ? s0 : carry[2];
+      cs = first ? c0 : carry[3];
     }
     const double cdt = act ? cs * dt : 0.0, sdt = act ? sn * dt : 0.0;
     const double aj = vj * cdt, bjv = vj * sdt;
 
-    // scan inputs: positions and the 4*NB sensitivities
+    // ---- positions: two scans -----------------------------------------------------------------------------
     double sx = aj, sy = bjv;
+    SMPC_UNROLL for (int d = 1; d < G; d <<= 1) {
+      const double tx = __shfl_up_sync(kFullMask, sx, d, G);
+      const double ty = __shfl_up_sync(kFullMask, sy, d, G);
+      if (gl >= d) {
+        sx += tx;
+        sy += ty;
+      }
+    }
+    const double X = (first ? pb.x0 : carry[0]) + sx;
+    const double Y = (first ? pb.y0 : carry[1]) + sy;
+
+    // ---- people critics (k = 0, 1, 2), BEFORE the sensitivity scans: the pair loop and the 4 NB scan registers are
+    //      never live together. Each critic leaves its residual and its gradient wrt (X, Y, Theta, lv). ----------
+    double ra = 0.0, caT = 0.0;                                // AgentAngle: residual, d/dTheta
+    double rs = 0.0, sX = 0.0, sY = 0.0, sTh = 0.0, sL = 0.0;  // SocialWork
+    double rp = 0.0, pX = 0.0, pY = 0.0;                       // Proxemics (differentiated evaluation)
+    double cprox_plain = 0.0;                                  // 1/2 r^2 of Proxemics as a cost-only evaluation sees it
+    if (PPL && act && pb.has_people) {  // PPL == false: the people critics are compiled out (people-free batch)
+      // --- AgentAngle (k=0): w * wrap(Theta - target)^2 ------------------------------------------
+      const double tgt = aa[j];
+      if (tgt == tgt) {
+        const double del = wrap_angle(Th - tgt);
+        ra = prm.w_agent_angle * (del * del);
+        caT = 2.0 * prm.w_agent_angle * del;
+      }
+      // --- SocialWork (k=1) and Proxemics (k=2) ----------------------------------------------------
+      const double rvx = vj * cT, rvy = vj * sT;  // robot velocity uses lv = v_{b(i)} and the NEW heading
+      double Frx = 0.0, Fry = 0.0;
+      double JFx[4] = {0, 0, 0, 0}, JFy[4] = {0, 0, 0, 0};
+      double wp = 0.0;
+      double G4[4] = {0, 0, 0, 0};  // gradient of (wr + wp) wrt (dX, dY, dvx, dvy) of the robot
+      double dmin = DBL_MAX, pdx = 0.0, pdy = 0.0;
+      const bool do_social = prm.w_social != 0.0;
+      // agent records (x, y, vx, vy) of step j+1, one 32-byte sector each; the next agent's record is fetched
+      // while the current pair interaction is evaluated
+      const double2* rec = reinterpret_cast<const double2*>(pb.packed) + ((size_t)(j + 1)) * 2;
+      const uint8_t* vld = pb.valid + (j + 1);
+      double2 nxt_p = __ldg(rec);
+      double2 nxt_v = __ldg(rec + 1);
+      bool nxt_valid = __ldg(vld) != 0;
+#pragma unroll 1
+      for (int k = 0; k < bt.A; ++k) {
+        const double ax = nxt_p.x, ay = nxt_p.y, avx = nxt_v.x, avy = nxt_v.y;
+        const bool valid = nxt_valid;
+        if (k + 1 < bt.A) {
+          const double2* r2 = rec + (size_t)(k + 1) * stride * 2;
+          nxt_p = __ldg(r2);
+          nxt_v = __ldg(r2 + 1);
+          nxt_valid = __ldg(vld + (size_t)(k + 1) * stride) != 0;
+        }
+        const double ddx = X - ax, ddy = Y - ay;
+        if (valid) {
+          const double d2 = ddx * ddx + ddy * ddy;
+          if (d2 < dmin) {
+            dmin = d2;
+            pdx = ddx;
+            pdy = ddy;
+          }
+        }
+        if (do_social) {
+          // F(robot <- agent k) = pair(d, w) with d = robot - agent, w = v_robot - v_agent, and
+          // F(agent k <- robot) = pair(-d, -w). The pair function is odd, pair(-d, -w) = -pair(d, w) (e, I and
+          // their unit vectors flip, theta / B / |d| do not), so ONE evaluation serves both terms of the
+          // residual; only the near-degenerate branch (reference rounding decides theta = +-pi / 0) is evaluated
+          // per role. Padded agents only have the agent <- robot term.
+          PairOut po;
+          social_pair(ddx, ddy, rvx - avx, rvy - avy, po);
+          if (valid) {
+            Frx += po.fx;
+            Fry += po.fy;
+            SMPC_UNROLL for (int c = 0; c < 4; ++c) {
+              JFx[c] += po.dfx[c];
+              JFy[c] += po.dfy[c];
+            }
+          }
+          if (po.degenerate) {
+            social_pair(-ddx, -ddy, avx - rvx, avy - rvy, po);  // d(-d)/dX = -1: the gradient changes sign
+            SMPC_UNROLL for (int c = 0; c < 4; ++c) {
+              po.dfx[c] = -po.dfx[c];
+              po.dfy[c] = -po.dfy[c];
+            }
+          }
+          wp += po.fx * po.fx + po.fy * po.fy;
+          SMPC_UNROLL for (int c = 0; c < 4; ++c) G4[c] += 2.0 * (po.fx * po.dfx[c] + po.fy * po.dfy[c]);
+        }
+      }
+      if (do_social) {
+        const double wr = Frx * Frx + Fry * Fry;
+        SMPC_UNROLL for (int c = 0; c < 4; ++c) G4[c] += 2.0 * (Frx * JFx[c] + Fry * JFy[c]);
+        rs = prm.w_social * (wr + wp + 1e-6);
+        sX = prm.w_social * G4[0];
+        sY = prm.w_social * G4[1];
+        sL = prm.w_social * (G4[2] * cT + G4[3] * sT);
+        sTh = prm.w_social * vj * (-G4[2] * sT + G4[3] * cT);
+      }
+      // Proxemics: w * 3 * exp(-dmin / 0.25), proxemics_cost_function.hpp:128-149.
+      //  * Ceres >= 2.1: std::numeric_limits<Jet>::max() is DBL_MAX. With no valid agent the value is 0 but the jet
+      //    derivative is (-inf) * 0 = NaN, i.e. the differentiated evaluation fails.
+      //  * Ceres 2.0.0 (ceres_compat < 210) has no numeric_limits specialisation for Jets: the primary template returns
+      //    Jet() = 0, std::min keeps it, and every DIFFERENTIATED evaluation sees the constant residual 3 w with a zero
+      //    Jacobian row, while cost-only evaluations (candidate cost) see the true minimum distance.
+      const double r_true = (dmin == DBL_MAX) ? 0.0 : prm.w_prox * (3.0 * exp(-dmin / (0.5 * 0.5)));
+      cprox_plain = 0.5 * r_true * r_true;
+      if (prm.ceres_compat < 210) {
+        rp = prm.w_prox * 3.0;
+      } else if (dmin == DBL_MAX) {
+        flags |= kJacobianBad;
+      } else {
+        rp = r_true;
+        const double k = -r_true * (2.0 / (0.5 * 0.5));
+        pX = k * pdx;
+        pY = k * pdy;
+      }
+    }
+
+    // ---- forward sensitivities: 4 NB scans ---------------------------------------------------------------------
     double sd[4 * NB];
     SMPC_UNROLL for (int b = 0; b < NB; ++b) {
       sd[4 * b + 0] = (b == bj) ? cdt : 0.0;  // dX/dv_b
@@ -404,27 +553,15 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
       sd[4 * b + 3] = aj * tau[b];            // dY/dw_b
     }
     SMPC_UNROLL for (int d = 1; d < G; d <<= 1) {
-      const double tx = __shfl_up_sync(kFullMask, sx, d, G);
-      const double ty = __shfl_up_sync(kFullMask, sy, d, G);
-      if (gl >= d) {
-        sx += tx;
-        sy += ty;
-      }
       SMPC_UNROLL for (int e = 0; e < 4 * NB; ++e) {
         const double t = __shfl_up_sync(kFullMask, sd[e], d, G);
         if (gl >= d) sd[e] += t;
       }
     }
-    double X, Y;
-    if (base == 0) {
-      X = pb.x0 + sx;
-      Y = pb.y0 + sy;
-    } else {
-      X = carry[0] + sx;
-      Y = carry[1] + sy;
+    if (!first) {
       SMPC_UNROLL for (int e = 0; e < 4 * NB; ++e) sd[e] += carry[4 + e];
     }
-    if (base + G < S) {  // hand the inclusive totals to the next chunk
+    if (!last) {  // hand the inclusive totals to the next chunk
       __syncwarp(gmask);
       if (gl == G - 1) {
         carry[0] = X;
@@ -436,115 +573,22 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
       __syncwarp(gmask);
     }
 
+    // per-lane Gauss-Newton block wrt (X, Y, Theta, lv): M = sum c c^T (10 entries), q = sum c r
+    double mXX = 0, mXY = 0, mXT = 0, mXL = 0, mYY = 0, mYT = 0, mYL = 0, mTT = 0, mTL = 0, mLL = 0;
+    double qX = 0, qY = 0, qT = 0, qL = 0;
     if (act) {
-      // per-lane Gauss-Newton block wrt (X, Y, Theta, lv): M = sum c c^T (10 entries), q = sum c r
-      double mXX = 0, mXY = 0, mXT = 0, mXL = 0, mYY = 0, mYT = 0, mYL = 0, mTT = 0, mTL = 0, mLL = 0;
-      double qX = 0, qY = 0, qT = 0, qL = 0;
       double cost = 0.0;
-
-      if (PPL && pb.has_people) {  // PPL == false: the people critics are compiled out (people-free batch)
-        // --- AgentAngle (k=0): w * wrap(Theta - target)^2 ------------------------------------------
-        const double tgt = aa[j];
-        if (tgt == tgt) {
-          const double del = wrap_angle(Th - tgt);
-          const double r = prm.w_agent_angle * (del * del);
-          const double cTh = 2.0 * prm.w_agent_angle * del;
-          cost += 0.5 * r * r;
-          mTT += cTh * cTh;
-          qT += cTh * r;
-        }
-        // --- SocialWork (k=1) and Proxemics (k=2) ----------------------------------------------------
-        const double rvx = vj * cT, rvy = vj * sT;  // robot velocity uses lv = v_{b(i)} and the NEW heading
-        double Frx = 0.0, Fry = 0.0;
-        double JFx[4] = {0, 0, 0, 0}, JFy[4] = {0, 0, 0, 0};
-        double wp = 0.0;
-        double G4[4] = {0, 0, 0, 0};  // gradient of (wr + wp) wrt (dX, dY, dvx, dvy) of the robot
-        double dmin = DBL_MAX, pdx = 0.0, pdy = 0.0;
-        const bool do_social = prm.w_social != 0.0;
-        // agent records (x, y, vx, vy) of step j+1, one 32-byte sector each; the next agent's record is fetched
-        // while the current pair interaction is evaluated
-        const double2* rec = reinterpret_cast<const double2*>(pb.packed) + ((size_t)(j + 1)) * 2;
-        const uint8_t* vld = pb.valid + (j + 1);
-        double2 nxt_p = make_double2(0.0, 0.0), nxt_v = make_double2(0.0, 0.0);
-        bool nxt_valid = false;
-        if (bt.A > 0) {
-          nxt_p = __ldg(rec);
-          nxt_v = __ldg(rec + 1);
-          nxt_valid = __ldg(vld) != 0;
-        }
-#pragma unroll 1
-        for (int k = 0; k < bt.A; ++k) {
-          const double ax = nxt_p.x, ay = nxt_p.y, avx = nxt_v.x, avy = nxt_v.y;
-          const bool valid = nxt_valid;
-          if (k + 1 < bt.A) {
-            const double2* r2 = rec + (size_t)(k + 1) * stride * 2;
-            nxt_p = __ldg(r2);
-            nxt_v = __ldg(r2 + 1);
-            nxt_valid = __ldg(vld + (size_t)(k + 1) * stride) != 0;
-          }
-          const double ddx = X - ax, ddy = Y - ay;
-          if (valid) {
-            const double d2 = ddx * ddx + ddy * ddy;
-            if (d2 < dmin) {
-              dmin = d2;
-              pdx = ddx;
-              pdy = ddy;
-            }
-          }
-          if (do_social) {
-            // F(robot <- agent k) = pair(d, w) with d = robot - agent, w = v_robot - v_agent, and
-            // F(agent k <- robot) = pair(-d, -w). The pair function is odd, pair(-d, -w) = -pair(d, w) (e, I and
-            // their unit vectors flip, theta / B / |d| do not), so ONE evaluation serves both terms of the
-            // residual; only the near-degenerate branch (reference rounding decides theta = +-pi / 0) is evaluated
-            // per role. Padded agents only have the agent <- robot term.
-            PairOut po;
-            social_pair(ddx, ddy, rvx - avx, rvy - avy, po);
-            if (valid) {
-              Frx += po.fx;
-              Fry += po.fy;
-              SMPC_UNROLL for (int c = 0; c < 4; ++c) {
-                JFx[c] += po.dfx[c];
-                JFy[c] += po.dfy[c];
-              }
-            }
-            if (po.degenerate) {
-              social_pair(-ddx, -ddy, avx - rvx, avy - rvy, po);  // d(-d)/dX = -1: the gradient changes sign
-              SMPC_UNROLL for (int c = 0; c < 4; ++c) {
-                po.dfx[c] = -po.dfx[c];
-                po.dfy[c] = -po.dfy[c];
-              }
-            }
-            wp += po.fx * po.fx + po.fy * po.fy;
-            SMPC_UNROLL for (int c = 0; c < 4; ++c) G4[c] += 2.0 * (po.fx * po.dfx[c] + po.fy * po.dfy[c]);
-          }
-        }
-        if (do_social) {
-          const double wr = Frx * Frx + Fry * Fry;
-          SMPC_UNROLL for (int c = 0; c < 4; ++c) G4[c] += 2.0 * (Frx * JFx[c] + Fry * JFy[c]);
-          const double r = prm.w_social * (wr + wp + 1e-6);
-          const double cX = prm.w_social * G4[0], cY = prm.w_social * G4[1];
-          const double cL = prm.w_social * (G4[2] * cT + G4[3] * sT);
-          const double cTh = prm.w_social * vj * (-G4[2] * sT + G4[3] * cT);
-          cost += 0.5 * r * r;
-          mXX += cX * cX; mXY += cX * cY; mXT += cX * cTh; mXL += cX * cL;
-          mYY += cY * cY; mYT += cY * cTh; mYL += cY * cL;
-          mTT += cTh * cTh; mTL += cTh * cL; mLL += cL * cL;
-          qX += cX * r; qY += cY * r; qT += cTh * r; qL += cL * r;
-        }
-        {
-          // Proxemics: w * 3 * exp(-dmin/0.25); with no valid agent the value is 0 but the jet derivative is
-          // (-inf)*0 = NaN in Ceres, i.e. the differentiated evaluation fails.
-          if (dmin == DBL_MAX) {
-            flags |= kJacobianBad;
-          } else {
-            const double r = prm.w_prox * (3.0 * exp(-dmin / (0.5 * 0.5)));
-            const double k = -r * (2.0 / (0.5 * 0.5));
-            const double cX = k * pdx, cY = k * pdy;
-            cost += 0.5 * r * r;
-            mXX += cX * cX; mXY += cX * cY; mYY += cY * cY;
-            qX += cX * r; qY += cY * r;
-          }
-        }
+      if (PPL) {  // fold the people critics in (all zero for a problem without people)
+        cost += 0.5 * ra * ra;
+        mTT += caT * caT;
+        qT += caT * ra;
+        cost += 0.5 * rs * rs;
+        mXX += sX * sX; mXY += sX * sY; mXT += sX * sTh; mXL += sX * sL;
+        mYY += sY * sY; mYT += sY * sTh; mYL += sY * sL;
+        mTT += sTh * sTh; mTL += sTh * sL; mLL += sL * sL;
+        qX += sX * rs; qY += sY * rs; qT += sTh * rs; qL += sL * rs;
+        mXX += pX * pX; mXY += pX * pY; mYY += pY * pY;
+        qX += pX * rp; qY += pY * rp;
       }
       // --- Velocity (k=3): w (0.6 - v_b)^2 for i < ch ---------------------------------------------------
       if (j < ch) {
@@ -576,7 +620,7 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
         qX += cX * r; qY += cY * r;
       }
       {
-        const double ex = X - __ldg(pb.px + j + 1), ey = Y - __ldg(pb.px + stride + j + 1);
+        const double ex = X - ld_in<PPL>(pb.px + j + 1), ey = Y - ld_in<PPL>(pb.px + stride + j + 1);
         const double q2 = ex * ex + ey * ey;
         const double r = prm.w_angle * q2 * q2;
         const double k = 4.0 * prm.w_angle * q2;
@@ -590,7 +634,7 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
         const double fxw = X + 0.25 * cT, fyw = Y + 0.25 * sT;
         const double gx = (fxw - pb.org_x) * inv_res, gy = (fyw - pb.org_y) * inv_res;
         double f, dfdr, dfdc;
-        bicubic(pb.map, bt.size_x, bt.size_y, gy, gx, f, dfdr, dfdc);
+        bicubic<PPL>(pb.map, bt.size_x, bt.size_y, gy, gx, f, dfdr, dfdc);
         const double r = prm.w_obstacle * f;
         const double kx = prm.w_obstacle * dfdc * inv_res, ky = prm.w_obstacle * dfdr * inv_res;
         const double cTh = 0.25 * (-kx * sT + ky * cT);
@@ -600,79 +644,145 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
         qX += kx * r; qY += ky * r; qT += cTh * r;
       }
 
-      // --- lane block -> parameter space, one column at a time (T = M D[:,a] is never stored).
-      //     Column of v_b: (dX, dY, 0, [b == bj]); of w_b: (dX, dY, dTheta, 0). ------------------------------
-      red[(0) * kRedStride + lane] += cost;
-      SMPC_UNROLL for (int ba = 0; ba < NB; ++ba) {
-        const double la = (ba == bj) ? 1.0 : 0.0;
-        const double twa = tau[ba] + ((ba == bj) ? dt : 0.0);  // d Theta_j / d w_ba (heading after step j)
-        {  // column a = 2 ba (v_ba)
-          const double xv = sd[4 * ba + 0], yv = sd[4 * ba + 1];
-          const double t0 = mXX * xv + mXY * yv + mXL * la;
-          const double t1 = mXY * xv + mYY * yv + mYL * la;
-          const double t2 = mXT * xv + mYT * yv + mTL * la;
-          const double t3 = mXL * xv + mYL * yv + mLL * la;
-          red[(L::g(2 * ba)) * kRedStride + lane] += qX * xv + qY * yv + qL * la;
-          SMPC_UNROLL for (int bb = 0; bb <= ba; ++bb) {
-            const double lb = (bb == bj) ? 1.0 : 0.0;
-            red[(L::h(2 * ba, 2 * bb)) * kRedStride + lane] += sd[4 * bb + 0] * t0 + sd[4 * bb + 1] * t1 + lb * t3;
-            if (bb < ba) {
+      // --- cost and g = D^T q into column `lane` of the warp's scratch red[NE][33]. First chunk: plain stores (no
+      //     zero fill, no read-modify-write); later chunks accumulate. Column of v_b: (dX, dY, 0, [b == bj]);
+      //     of w_b: (dX, dY, dTheta, 0). ---------------------------------------------------------------------
+      {
+        const double c_diff = cost + 0.5 * rp * rp, c_plain = cost + cprox_plain;
+        double* r0 = red + lane;
+        r0[0 * kRedStride] = (first ? 0.0 : r0[0 * kRedStride]) + c_diff;
+        r0[1 * kRedStride] = (first ? 0.0 : r0[1 * kRedStride]) + c_plain;
+        SMPC_UNROLL for (int ba = 0; ba < NB; ++ba) {
+          const double la = (ba == bj) ? 1.0 : 0.0;
+          const double twa = tau[ba] + ((ba == bj) ? dt : 0.0);  // d Theta_j / d w_ba (heading after step j)
+          double* gv = r0 + L::g(2 * ba) * kRedStride;
+          double* gw = r0 + L::g(2 * ba + 1) * kRedStride;
+          *gv = (first ? 0.0 : *gv) + (qX * sd[4 * ba + 0] + qY * sd[4 * ba + 1] + qL * la);
+          *gw = (first ? 0.0 : *gw) + (qX * sd[4 * ba + 2] + qY * sd[4 * ba + 3] + qT * twa);
+        }
+      }
+    } else if (first) {  // a lane without a step in the first chunk still owns a column of the column sums
+      SMPC_UNROLL for (int e = 0; e < L::NG; ++e) red[e * kRedStride + lane] = 0.0;
+    }
+
+    if (last) {
+      // --- VelocityFeasibility (k=8), cost and gradient part: w ((v_i - v_{i-1})^2 + (w_i - w_{i-1})^2),
+      //     0 < i < ch/bl, on blocks i, i-1. Parameter-space residuals: the group's first lane adds them. -------
+      if (gl == 0 && live) {
+        SMPC_UNROLL for (int i = 1; i < NB; ++i) {
+          if (i < pb.nbd) {
+            const double dv = xs[2 * i] - xs[2 * i - 2], dw = xs[2 * i + 1] - xs[2 * i - 1];
+            const double r = prm.w_vf * dv * dv + prm.w_vf * dw * dw;
+            const double jv = 2.0 * prm.w_vf * dv, jw = 2.0 * prm.w_vf * dw;
+            red[0 * kRedStride + lane] += 0.5 * r * r;
+            red[1 * kRedStride + lane] += 0.5 * r * r;
+            red[L::g(2 * i - 2) * kRedStride + lane] -= jv * r;
+            red[L::g(2 * i - 1) * kRedStride + lane] -= jw * r;
+            red[L::g(2 * i) * kRedStride + lane] += jv * r;
+            red[L::g(2 * i + 1) * kRedStride + lane] += jw * r;
+          }
+        }
+      }
+      // --- group column sums of [cost_diff, cost_plain, g]: lane r of the group sums entries r, r + G, ... -----
+      __syncwarp();
+      for (int e = gl; e < L::NG; e += G) {
+        const double* row = red + e * kRedStride + col0;
+        double t0 = 0.0, t1 = 0.0;
+        SMPC_UNROLL for (int t = 0; t < G; t += 2) {
+          t0 += row[t];
+          t1 += row[t + 1];
+        }
+        const double tot = t0 + t1;
+        out[e] = tot;
+        if (!isfinite(tot)) {
+          if (e < 2) bad_res = true; else bad_jac = true;
+        }
+      }
+      if (__any_sync(gmask, bad_res)) flags |= kResidualBad;
+      if (__any_sync(gmask, bad_jac)) flags |= kJacobianBad;
+      flags = __reduce_or_sync(gmask, flags);
+      __syncwarp(gmask);
+      // --- does this point need J^T J? Not if it is a line-search sample that fails the sufficient-decrease test
+      //     (group-uniform: every lane reads the same shared-memory words) ---------------------------------------
+      if (st != nullptr && live && st->phase == kLineSearch) {
+        const bool armijo_ok = (flags == 0) && !(out[0] > st->x_cost + 1e-4 * st->g0 * st->t);
+        need_h = armijo_ok;
+      }
+    }
+
+    // --- lane block -> J^T J, one column at a time (T = M D[:,a] is never stored) ---------------------------------
+    if (need_h) {
+      if (act) {
+        double* r0 = red + lane;
+        auto acc = [&](int e, double v) {
+          double* p = r0 + e * kRedStride;
+          *p = (first ? 0.0 : *p) + v;
+        };
+        SMPC_UNROLL for (int ba = 0; ba < NB; ++ba) {
+          const double la = (ba == bj) ? 1.0 : 0.0;
+          const double twa = tau[ba] + ((ba == bj) ? dt : 0.0);
+          {  // column a = 2 ba (v_ba)
+            const double xv = sd[4 * ba + 0], yv = sd[4 * ba + 1];
+            const double t0 = mXX * xv + mXY * yv + mXL * la;
+            const double t1 = mXY * xv + mYY * yv + mYL * la;
+            const double t2 = mXT * xv + mYT * yv + mTL * la;
+            const double t3 = mXL * xv + mYL * yv + mLL * la;
+            SMPC_UNROLL for (int bb = 0; bb <= ba; ++bb) {
+              const double lb = (bb == bj) ? 1.0 : 0.0;
+              acc(L::h(2 * ba, 2 * bb), sd[4 * bb + 0] * t0 + sd[4 * bb + 1] * t1 + lb * t3);
+              if (bb < ba) {
+                const double twb = tau[bb] + ((bb == bj) ? dt : 0.0);
+                acc(L::h(2 * ba, 2 * bb + 1), sd[4 * bb + 2] * t0 + sd[4 * bb + 3] * t1 + twb * t2);
+              }
+            }
+          }
+          {  // column a = 2 ba + 1 (w_ba)
+            const double xw = sd[4 * ba + 2], yw = sd[4 * ba + 3];
+            const double t0 = mXX * xw + mXY * yw + mXT * twa;
+            const double t1 = mXY * xw + mYY * yw + mYT * twa;
+            const double t2 = mXT * xw + mYT * yw + mTT * twa;
+            const double t3 = mXL * xw + mYL * yw + mTL * twa;
+            SMPC_UNROLL for (int bb = 0; bb <= ba; ++bb) {
+              const double lb = (bb == bj) ? 1.0 : 0.0;
               const double twb = tau[bb] + ((bb == bj) ? dt : 0.0);
-              red[(L::h(2 * ba, 2 * bb + 1)) * kRedStride + lane] += sd[4 * bb + 2] * t0 + sd[4 * bb + 3] * t1 + twb * t2;
+              acc(L::h(2 * ba + 1, 2 * bb), sd[4 * bb + 0] * t0 + sd[4 * bb + 1] * t1 + lb * t3);
+              acc(L::h(2 * ba + 1, 2 * bb + 1), sd[4 * bb + 2] * t0 + sd[4 * bb + 3] * t1 + twb * t2);
             }
           }
         }
-        {  // column a = 2 ba + 1 (w_ba)
-          const double xw = sd[4 * ba + 2], yw = sd[4 * ba + 3];
-          const double t0 = mXX * xw + mXY * yw + mXT * twa;
-          const double t1 = mXY * xw + mYY * yw + mYT * twa;
-          const double t2 = mXT * xw + mYT * yw + mTT * twa;
-          const double t3 = mXL * xw + mYL * yw + mTL * twa;
-          red[(L::g(2 * ba + 1)) * kRedStride + lane] += qX * xw + qY * yw + qT * twa;
-          SMPC_UNROLL for (int bb = 0; bb <= ba; ++bb) {
-            const double lb = (bb == bj) ? 1.0 : 0.0;
-            const double twb = tau[bb] + ((bb == bj) ? dt : 0.0);
-            red[(L::h(2 * ba + 1, 2 * bb)) * kRedStride + lane] += sd[4 * bb + 0] * t0 + sd[4 * bb + 1] * t1 + lb * t3;
-            red[(L::h(2 * ba + 1, 2 * bb + 1)) * kRedStride + lane] += sd[4 * bb + 2] * t0 + sd[4 * bb + 3] * t1 + twb * t2;
-          }
+      } else if (first) {
+        SMPC_UNROLL for (int e = L::NG; e < L::NE; ++e) red[e * kRedStride + lane] = 0.0;
+      }
+    }
+  }
+
+  if (need_h) {
+    // VelocityFeasibility, J^T J part. Row: [2i-2] = -jv, [2i-1] = -jw, [2i] = jv, [2i+1] = jw
+    if (gl == 0 && live) {
+      SMPC_UNROLL for (int i = 1; i < NB; ++i) {
+        if (i < pb.nbd) {
+          const double dv = xs[2 * i] - xs[2 * i - 2], dw = xs[2 * i + 1] - xs[2 * i - 1];
+          const double jv = 2.0 * prm.w_vf * dv, jw = 2.0 * prm.w_vf * dw;
+          const int p0 = 2 * i - 2, p1 = 2 * i - 1, p2 = 2 * i, p3 = 2 * i + 1;
+          red[(L::h(p0, p0)) * kRedStride + lane] += jv * jv;
+          red[(L::h(p1, p0)) * kRedStride + lane] += jw * jv;
+          red[(L::h(p1, p1)) * kRedStride + lane] += jw * jw;
+          red[(L::h(p2, p0)) * kRedStride + lane] -= jv * jv;
+          red[(L::h(p2, p1)) * kRedStride + lane] -= jv * jw;
+          red[(L::h(p2, p2)) * kRedStride + lane] += jv * jv;
+          red[(L::h(p3, p0)) * kRedStride + lane] -= jw * jv;
+          red[(L::h(p3, p1)) * kRedStride + lane] -= jw * jw;
+          red[(L::h(p3, p2)) * kRedStride + lane] += jw * jv;
+          red[(L::h(p3, p3)) * kRedStride + lane] += jw * jw;
         }
       }
     }
   }
-
-  // --- VelocityFeasibility (k=8): w ((v_i - v_{i-1})^2 + (w_i - w_{i-1})^2), 0 < i < ch/bl, on blocks i, i-1.
-  //     Parameter-space residuals: the group's first lane adds them to its partial sums before the reduction.
-  if (gl == 0 && live) {
-    SMPC_UNROLL for (int i = 1; i < NB; ++i) {
-      if (i < prm.n_bounded) {
-        const double dv = x[2 * i] - x[2 * i - 2], dw = x[2 * i + 1] - x[2 * i - 1];
-        const double r = prm.w_vf * dv * dv + prm.w_vf * dw * dw;
-        const double jv = 2.0 * prm.w_vf * dv, jw = 2.0 * prm.w_vf * dw;
-        red[(0) * kRedStride + lane] += 0.5 * r * r;
-        // row: [2i-2] = -jv, [2i-1] = -jw, [2i] = jv, [2i+1] = jw
-        const int p0 = 2 * i - 2, p1 = 2 * i - 1, p2 = 2 * i, p3 = 2 * i + 1;
-        red[(L::g(p0)) * kRedStride + lane] -= jv * r; red[(L::g(p1)) * kRedStride + lane] -= jw * r; red[(L::g(p2)) * kRedStride + lane] += jv * r; red[(L::g(p3)) * kRedStride + lane] += jw * r;
-        red[(L::h(p0, p0)) * kRedStride + lane] += jv * jv;
-        red[(L::h(p1, p0)) * kRedStride + lane] += jw * jv;
-        red[(L::h(p1, p1)) * kRedStride + lane] += jw * jw;
-        red[(L::h(p2, p0)) * kRedStride + lane] -= jv * jv;
-        red[(L::h(p2, p1)) * kRedStride + lane] -= jv * jw;
-        red[(L::h(p2, p2)) * kRedStride + lane] += jv * jv;
-        red[(L::h(p3, p0)) * kRedStride + lane] -= jw * jv;
-        red[(L::h(p3, p1)) * kRedStride + lane] -= jw * jw;
-        red[(L::h(p3, p2)) * kRedStride + lane] += jw * jv;
-        red[(L::h(p3, p3)) * kRedStride + lane] += jw * jw;
-      }
-    }
-  }
-
-  // group reduction through shared memory: lane (g, r) of the warp sums, for the entries e = r, r + G, ..., the G
-  // columns of its group and stores the group totals
+  // (full-warp barrier: groups that skip J^T J still take part; their rows are simply not summed)
   __syncwarp();
-  bool bad_res = false, bad_jac = false;
-  {
-    const int col0 = lane & ~(G - 1);
-    for (int e = gl; e < L::NE; e += G) {
+  if (need_h) {
+    bool bad_h = false;
+    for (int e = L::NG + gl; e < L::NE; e += G) {
       const double* row = red + e * kRedStride + col0;
       double t0 = 0.0, t1 = 0.0;
       SMPC_UNROLL for (int t = 0; t < G; t += 2) {
@@ -681,15 +791,13 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
       }
       const double tot = t0 + t1;
       out[e] = tot;
-      if (!isfinite(tot)) {
-        if (e == 0) bad_res = true; else bad_jac = true;
-      }
+      if (!isfinite(tot)) bad_h = true;
     }
+    if (__any_sync(gmask, bad_h)) flags |= kJacobianBad;
+  } else {
+    flags |= kNoHessian;
   }
-  if (__any_sync(gmask, bad_res)) flags |= kResidualBad;
-  if (__any_sync(gmask, bad_jac)) flags |= kJacobianBad;
-  flags = __reduce_or_sync(gmask, flags);
-  __syncwarp(gmask);
+  __syncwarp();
   return flags;
 }
 
@@ -1021,25 +1129,32 @@ __device__ __forceinline__ void wait_for_costmap(unsigned* arrival, int b) {
   }
 }
 
-// Load the group-uniform problem view.
-__device__ __forceinline__ void load_problem(const DevBatch& bt, int b, Prob& pb) {
-  const int S = bt.S;
-  pb.x0 = __ldg(bt.pose0 + 3 * (size_t)b);
-  pb.y0 = __ldg(bt.pose0 + 3 * (size_t)b + 1);
-  pb.yaw0 = __ldg(bt.pose0 + 3 * (size_t)b + 2);
-  pb.goal_yaw = __ldg(bt.goal_yaw + b);
-  pb.px = bt.path_xy + (size_t)b * 2 * (S + 1);
-  pb.py = pb.px + (S + 1);
-  pb.fin_x = __ldg(pb.px + S);
-  pb.fin_y = __ldg(pb.py + S);
-  pb.agents = (bt.A > 0 && bt.agents) ? bt.agents + (size_t)b * bt.A * 6 * (S + 1) : nullptr;
-  pb.packed = pb.agents ? bt.agents_packed + (size_t)b * bt.A * (S + 1) * 4 : nullptr;
-  pb.valid = pb.agents ? bt.agents_valid + (size_t)b * bt.A * (S + 1) : nullptr;
+// Load the group-uniform problem view. NC = the inputs are read-only for the whole kernel (see bicubic).
+template <bool NC>
+__device__ __forceinline__ void load_problem(const DevParams& prm, const DevBatch& bt, int b, Prob& pb) {
+  const int S1 = bt.S + 1;
+  const int Sb = bt.n_steps_each ? min(max(__ldg(bt.n_steps_each + b), 1), bt.S) : bt.S;
+  pb.S = Sb;
+  pb.ch = min(prm.control_horizon, Sb);   // src/optimizer.cpp:248
+  pb.bl = min(prm.block_length, pb.ch);   // src/optimizer.cpp:249
+  pb.nb = (pb.ch + pb.bl - 1) / pb.bl;
+  pb.nbd = pb.ch / pb.bl;
+  pb.x0 = ld_in<NC>(bt.pose0 + 3 * (size_t)b);
+  pb.y0 = ld_in<NC>(bt.pose0 + 3 * (size_t)b + 1);
+  pb.yaw0 = ld_in<NC>(bt.pose0 + 3 * (size_t)b + 2);
+  pb.goal_yaw = ld_in<NC>(bt.goal_yaw + b);
+  pb.px = bt.path_xy + (size_t)b * 2 * S1;
+  pb.py = pb.px + S1;
+  pb.fin_x = ld_in<NC>(pb.px + Sb);
+  pb.fin_y = ld_in<NC>(pb.py + Sb);
+  pb.agents = (bt.A > 0 && bt.agents) ? bt.agents + (size_t)b * bt.A * 6 * S1 : nullptr;
+  pb.packed = pb.agents ? bt.agents_packed + (size_t)b * bt.A * S1 * 4 : nullptr;
+  pb.valid = pb.agents ? bt.agents_valid + (size_t)b * bt.A * S1 : nullptr;
   pb.has_people = (bt.has_people != nullptr) && (bt.has_people[b] != 0);
-  const int mi = bt.costmap_index ? __ldg(bt.costmap_index + b) : (b % bt.M);
+  const int mi = bt.costmap_index ? ld_in<NC>(bt.costmap_index + b) : (b % bt.M);
   pb.map = bt.costmaps + (size_t)mi * bt.size_x * bt.size_y;
-  pb.org_x = __ldg(bt.costmap_origin + 2 * mi);
-  pb.org_y = __ldg(bt.costmap_origin + 2 * mi + 1);
+  pb.org_x = ld_in<NC>(bt.costmap_origin + 2 * mi);
+  pb.org_y = ld_in<NC>(bt.costmap_origin + 2 * mi + 1);
 }
 
 // Agent-angle steering targets of every step -> group shared memory (once per problem).
@@ -1054,7 +1169,7 @@ __device__ __forceinline__ void agent_angle_setup(const DevBatch& bt, const Prob
     ws[L::kYaw + 1] = c0;
   }
   if (PPL) {
-    for (int j = gl; j < bt.S; j += G) {
+    for (int j = gl; j < pb.S; j += G) {
       double tgt = NAN;
       if (pb.has_people && bt.A > 0 && pb.agents != nullptr) tgt = agent_angle_target(bt, pb, j + 1);
       ws[L::kAa + j] = tgt;
@@ -1062,14 +1177,14 @@ __device__ __forceinline__ void agent_angle_setup(const DevBatch& bt, const Prob
   }
 }
 
-// Post-solve expansion (reference src/optimizer.cpp:390-446): cmds[S+1] hold block min(i/bl, NB-1) for i < ch
+// Post-solve expansion (reference src/optimizer.cpp:390-446): cmds[S+1] hold block min(i/bl, nb-1) for i < ch
 // and the last block afterwards; the path is the Euler rollout of those cmds from pose0 (pose0 excluded).
 template <int NB, int G>
-__device__ __forceinline__ void expand_outputs(const DevParams& prm, const DevBatch& bt, const DevResult& rs,
-                                               const Prob& pb, int b, const double (&x)[2 * NB], int lane) {
+__device__ __forceinline__ void expand_outputs(const DevBatch& bt, const DevResult& rs, const Prob& pb, int b,
+                                               const double (&x)[2 * NB], int lane) {
   const int gl = lane & (G - 1);
   const unsigned gmask = Group<G>::mask(lane);
-  const int S = bt.S;
+  const int S = pb.S, S1 = bt.S + 1, last_b = pb.nb - 1;
   double s0, c0;
   sincos(pb.yaw0 * 0.5, &s0, &c0);
   const double yaw_rt = atan2(2.0 * (c0 * s0), c0 * c0 - s0 * s0);  // evolving_poses[0] went through setRPY/getYaw
@@ -1077,7 +1192,7 @@ __device__ __forceinline__ void expand_outputs(const DevParams& prm, const DevBa
   for (int base = 0; base <= S; base += G) {
     const int i = base + gl;
     const bool act = i <= S;
-    const int bi = (i < prm.ch) ? min(i / prm.bl, NB - 1) : NB - 1;
+    const int bi = (i < pb.ch) ? min(i / pb.bl, last_b) : last_b;
     double v = x[0], w = x[1];
     double th = yaw_rt, th_next = yaw_rt;
     SMPC_UNROLL for (int bb = 0; bb < NB; ++bb) {
@@ -1085,12 +1200,12 @@ __device__ __forceinline__ void expand_outputs(const DevParams& prm, const DevBa
         v = x[2 * bb];
         w = x[2 * bb + 1];
       }
-      th += x[2 * bb + 1] * (bt.dt * (double)steps_in_block_before<NB>(i, bb, prm.bl));
-      th_next += x[2 * bb + 1] * (bt.dt * (double)steps_in_block_before<NB>(i + 1, bb, prm.bl));
+      th += x[2 * bb + 1] * (bt.dt * (double)steps_in_block_before(i, bb, pb.bl, last_b));
+      th_next += x[2 * bb + 1] * (bt.dt * (double)steps_in_block_before(i + 1, bb, pb.bl, last_b));
     }
     if (act && rs.cmds) {
-      rs.cmds[((size_t)b * (S + 1) + i) * 2] = v;
-      rs.cmds[((size_t)b * (S + 1) + i) * 2 + 1] = w;
+      rs.cmds[((size_t)b * S1 + i) * 2] = v;
+      rs.cmds[((size_t)b * S1 + i) * 2 + 1] = w;
     }
     if (rs.path) {
       double sn, cs;
@@ -1109,7 +1224,7 @@ __device__ __forceinline__ void expand_outputs(const DevParams& prm, const DevBa
       if (act) {
         double sh, chh;
         sincos(th_next * 0.5, &sh, &chh);
-        double* o = rs.path + ((size_t)b * (S + 1) + i) * 3;
+        double* o = rs.path + ((size_t)b * S1 + i) * 3;
         o[0] = X;
         o[1] = Y;
         o[2] = atan2(2.0 * (chh * sh), chh * chh - sh * sh);  // tf2 setRPY -> getYaw
@@ -1121,12 +1236,12 @@ __device__ __forceinline__ void expand_outputs(const DevParams& prm, const DevBa
 // ---------------------------------------------------------------------------------------------------
 // ceres::Solve restated as a per-group state machine around ONE evaluation site.
 // Every trial point (iteration zero, each line-search sample, the un-shortened step after a failed line search)
-// gets a full evaluation, so an accepted point needs no second pass: its cost is the candidate cost and its
-// J^T J / J^T r are the next iterate's. Groups of a warp run different problems in different phases; they meet
-// at the evaluation (warp-convergent) and diverge only in the short scalar phase logic. A group that finishes
-// its problem writes the results and pulls the next problem from the atomic queue.
+// is evaluated once: an accepted point needs no second pass — its plain cost is the candidate cost, its
+// differentiated cost the next iterate's cost and its J^T J / J^T r the next iterate's normal equations. Groups of a
+// warp run different problems in different phases; they meet at the evaluation (warp-convergent) and diverge only in
+// the scalar phase logic, which the group's first lane runs alone. A group that finishes its problem writes the
+// results and pulls the next problem from the atomic queue.
 // ---------------------------------------------------------------------------------------------------
-enum Phase { kFetch = 0, kInit = 1, kLineSearch = 2, kFullStep = 3 };
 
 // Claim the next parked problem (lane 0 of a group that has seen the main queue empty). Parks in flight are counted
 // in park_counters[2] (raised BEFORE the parker tries to fetch its fresh problem, lowered after it has published or
@@ -1146,20 +1261,14 @@ __device__ __forceinline__ int park_pop(const DevBatch& bt) {
   return id;
 }
 
-// Solver scalars of one group, resident in shared memory: the evaluation needs every register for the FP64
-// math, and the phase logic after it reads / updates them in place.
-struct LmState {
-  double x_cost, x_norm, gmax, radius, decrease_factor, minimum_cost, it_cost, cost_initial, cost_final,
-      model_cost_change, g0, dmax, t, prev_x, prev_value, prev_gradient;
-  int iteration, n_invalid, n_eval, ls_iters, term, phase, b, flags;
-};
-static_assert(sizeof(LmState) == 20 * sizeof(double), "Layout::kState reserves 20 doubles");
-static_assert(sizeof(Prob) <= 15 * sizeof(double), "Layout::kProb reserves 15 doubles");
-enum StateFlags {
-  kReuseDiagonal = 1, kItSuccessful = 2, kAnySuccess = 4, kPrevOk = 8, kLive = 16, kExhausted = 32, kSwapped = 64,
-  kDrained = 128,  // this group has seen the main queue empty
-  kClosed = 256    // ... and the parked queue closed and empty: nothing will ever come again
-};
+// One trace row (include/smpc.h smpc_result.trace), written by the group leader when tracing is on.
+__device__ __forceinline__ void trace_row(const DevResult& rs, int b, int row, double iteration, double phase, double t,
+                                          double cost_diff, double cost_plain, double aux, double code, double radius) {
+  if (rs.trace == nullptr || row < 0 || row >= rs.trace_rows) return;
+  double* o = rs.trace + ((size_t)b * rs.trace_rows + row) * 8;
+  o[0] = iteration; o[1] = phase; o[2] = t; o[3] = cost_diff;
+  o[4] = cost_plain; o[5] = aux; o[6] = code; o[7] = radius;
+}
 
 template <int NB, int G, bool PPL>
 __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch& bt, const DevResult& rs, int* queue,
@@ -1168,7 +1277,6 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
   constexpr int P = L::P;
   const int gl = lane & (G - 1);
   const unsigned gmask = Group<G>::mask(lane);
-  const int nbd = prm.n_bounded;
   // every piece of group state is addressed as ws + constant so that only `ws` stays live across the evaluation
 #define xs (ws + L::kX)
 #define best (ws + L::kBest)
@@ -1179,12 +1287,11 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
 #define gs (reinterpret_cast<LmState*>(ws + L::kState))
 #define pbs (reinterpret_cast<Prob*>(ws + L::kProb))
 
-  LaneConst<NB> lc0;
-  lane_setup<NB>(gl, prm.bl, bt.dt, lc0);
   if (gl == 0) {
     gs->phase = kFetch;
     gs->flags = 0;
     gs->b = -1;
+    gs->n_eval = 0;
   }
   __syncwarp(gmask);
 
@@ -1198,6 +1305,7 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
     const bool idle = gs->phase == kFetch;
     const bool at_quantum = slicing && !idle && (fl0 & kLive) && !(fl0 & kDrained) && gs->n_eval > 0 &&
                             (gs->n_eval % bt.park_quantum) == 0;
+    __syncwarp(gmask);  // every lane has read the state words the leader rewrites below
     if ((idle && !(fl0 & kClosed) && (slicing || !(fl0 & kExhausted))) || at_quantum) {
       int nb_ = bt.B, resume = -2;
       if (gl == 0) {
@@ -1241,18 +1349,21 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
         }
         if (gl == 0) {
           if (!PPL && bt.arrival != nullptr) wait_for_costmap(bt.arrival, nb_);
-          load_problem(bt, nb_, *pbs);
+          load_problem<PPL>(prm, bt, nb_, *pbs);
         }
         __syncwarp(gmask);
         agent_angle_setup<NB, G, PPL>(bt, *pbs, lane, ws);
-        // IterationZero: project the start point onto the box
-        for (int c = gl; c < P; c += G) {
-          const double v = __ldg(bt.u0 + (size_t)nb_ * P + c);
-          xs[c] = v;
-          best[c] = v;
-          cand[c] = project_param(v, c, nbd);
-        }
         if (gl == 0) {
+          // IterationZero: project the start point onto the box. Blocks the problem does not use (shorter horizon than
+          // the batch's) stay exactly zero: no residual touches them, so their rows of J^T J and J^T r are zero, the LM
+          // diagonal keeps their pivot positive and their step is exactly zero.
+          const int Pb = 2 * pbs->nb, nbd = pbs->nbd;
+          for (int c = 0; c < P; ++c) {
+            const double v = (c < Pb) ? ld_in<PPL>(bt.u0 + (size_t)nb_ * P + c) : 0.0;
+            xs[c] = v;
+            best[c] = v;
+            cand[c] = project_param(v, c, nbd);
+          }
           LmState z;
           z.x_cost = z.x_norm = z.gmax = 0.0;
           z.radius = 1e4;
@@ -1261,11 +1372,13 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
           z.it_cost = z.cost_initial = z.cost_final = z.model_cost_change = z.g0 = z.dmax = 0.0;
           z.t = 1.0;
           z.prev_x = z.prev_value = z.prev_gradient = 0.0;
-          z.iteration = z.n_invalid = z.n_eval = z.ls_iters = 0;
+          z.se_cost = 0.0;
+          z.iteration = z.n_invalid = z.n_eval = z.n_light = z.ls_iters = 0;
           z.term = kNoConvergence;
           z.phase = kInit;
           z.b = nb_;
           z.flags = kLive | kItSuccessful;
+          z.pad_ = 0;
           *gs = z;
         }
       }
@@ -1282,270 +1395,277 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
     }
 
     const bool live = (gs->flags & kLive) != 0;
-    const unsigned fl = evaluate<NB, G, PPL>(prm, bt, *pbs, live, lc0, ws, red, cand, lane,
-                                        ws + ((gs->flags & kSwapped) ? L::kBuf0 : L::kBuf1));
-    // ---- phase logic, directly on the group's shared-memory state. The lanes of a group are converged here and
-    //      take the same (group-uniform) branches, so they all store identical values. ---------------------------
-    LmState& st = *gs;
-    double* cur = ws + ((st.flags & kSwapped) ? L::kBuf1 : L::kBuf0);    // normal equations at x
-    double* trial = ws + ((st.flags & kSwapped) ? L::kBuf0 : L::kBuf1);  // normal equations at the trial point
-    const double t_cost = trial[0];
-    bool take_step = false;   // proceed to accept/reject with `cand`
-    bool finished = false;    // the solve of this problem has terminated
-    bool next_sample = false; // another line-search sample has been set up in `cand`
+    const unsigned fl = evaluate<NB, G, PPL>(prm, bt, *pbs, live, ws, red, cand, lane,
+                                             ws + ((gs->flags & kSwapped) ? L::kBuf0 : L::kBuf1), gs);
 
-    if (live) {  // ===== part A: classify the evaluated point (init / line-search sample / full step), accept or reject
-    ++st.n_eval;
-    if (st.phase == kInit) {
-      st.cost_initial = st.cost_final = t_cost;
-      if (fl) {
-        st.term = kFailEvaluation;
-        finished = true;
-      } else {
-        // x <- projected seed; cur <- trial; Jacobi scaling from the column norms (= sqrt of diag(J^T J))
-        for (int c = gl; c < P; c += G) {
-          xs[c] = cand[c];
-          scale[c] = 1.0 / (1.0 + sqrt(trial[L::h(0, 0) + c * (c + 1) / 2 + c]));
-        }
-        __syncwarp(gmask);
-        st.flags ^= kSwapped;
-        { double* tmp = cur; cur = trial; trial = tmp; }
-        st.x_cost = t_cost;
-        st.it_cost = t_cost;
-        st.flags |= kItSuccessful;
-      }
-    } else if (st.phase == kLineSearch) {
-      // Armijo sufficient decrease at step t along delta (projected)
-      const bool sample_ok = (fl == 0);
-      double gd = 0.0;
-      SMPC_UNROLL for (int c = 0; c < P; ++c) gd += delta[c] * trial[L::g(c)];
-      if (sample_ok && !(t_cost > st.x_cost + 1e-4 * st.g0 * st.t)) {
-        take_step = true;  // success: delta <- t * delta, candidate = this trial point
-      } else {
-        ++st.ls_iters;
-        bool ls_failed = st.ls_iters >= 20;
-        double t_new = st.t;
-        if (!ls_failed) {
-          const double lo = 1e-3 * st.t, hi = 0.6 * st.t;
-          if (!sample_ok) {
-            t_new = fmin(fmax(st.t * 0.5, lo), hi);
-          } else if (st.flags & kPrevOk) {
-            t_new = quintic_interp_min(st.x_cost, st.g0, st.t, t_cost, gd, st.prev_x, st.prev_value, st.prev_gradient,
-                                       lo, hi, gl, gmask, G);
-          } else {
-            t_new = cubic_interp_min(st.x_cost, st.g0, st.t, t_cost, gd, lo, hi);
-          }
-          if (t_new * st.dmax < 1e-9) ls_failed = true;
-        }
-        if (!ls_failed) {
-          st.prev_x = st.t;
-          st.prev_value = t_cost;
-          st.prev_gradient = gd;
-          st.flags = sample_ok ? (st.flags | kPrevOk) : (st.flags & ~kPrevOk);
-          st.t = t_new;
-          __syncwarp(gmask);
-          for (int c = gl; c < P; c += G) cand[c] = project_param(xs[c] + t_new * delta[c], c, nbd);
-          next_sample = true;  // evaluate the next line-search sample
-        } else if (st.t != 1.0) {
-          // line search failed: the un-shortened TR step is the candidate (delta unchanged)
-          st.t = 1.0;
-          __syncwarp(gmask);
-          for (int c = gl; c < P; c += G) cand[c] = project_param(xs[c] + delta[c], c, nbd);
-          st.phase = kFullStep;
-          next_sample = true;
+    // ---- phase logic: the group's first lane alone, on the group's shared-memory state -----------------------
+    if (gl == 0 && live) {
+      LmState& st = *gs;
+      const int nbd = pbs->nbd;
+      double* cur = ws + ((st.flags & kSwapped) ? L::kBuf1 : L::kBuf0);    // normal equations at x
+      double* trial = ws + ((st.flags & kSwapped) ? L::kBuf0 : L::kBuf1);  // normal equations at the trial point
+      const double t_cost = trial[0];        // cost of the differentiated evaluation (line search, next x_cost)
+      const double t_cost_plain = trial[1];  // cost of the plain evaluation (candidate cost)
+      const bool eval_ok = (fl & (kResidualBad | kJacobianBad)) == 0;
+      bool take_step = false;    // proceed to accept/reject with `cand`
+      bool finished = false;     // the solve of this problem has terminated
+      bool next_sample = false;  // another trial point has been set up in `cand`
+      const int row = st.n_eval;  // trace row of this evaluation
+      const double tr_iter = (double)st.iteration, tr_phase = (double)st.phase, tr_t = st.t;
+      double tr_aux = NAN, tr_code = 0.0;
+      ++st.n_eval;
+      if (fl & kNoHessian) ++st.n_light;
+
+      // ===== part A: classify the evaluated point (init / line-search sample / full step), accept or reject
+      if (st.phase == kInit) {
+        st.cost_initial = st.cost_final = t_cost;
+        if (!eval_ok) {
+          st.term = kFailEvaluation;
+          finished = true;
         } else {
-          take_step = true;  // t is still 1: this trial IS Plus(x, delta)
+          // x <- projected seed; cur <- trial; Jacobi scaling from the column norms (= sqrt of diag(J^T J))
+          for (int c = 0; c < P; ++c) {
+            xs[c] = cand[c];
+            scale[c] = 1.0 / (1.0 + sqrt(trial[L::h(c, c)]));
+          }
+          st.flags ^= kSwapped;
+          { double* tmp = cur; cur = trial; trial = tmp; }
+          st.x_cost = t_cost;
+          st.se_cost = t_cost;
+          st.it_cost = t_cost;
+          st.flags |= kItSuccessful;
         }
-      }
-    } else {  // kFullStep: evaluation of Plus(x, delta) after a failed line search
-      take_step = true;
-    }
-
-    if (take_step) {
-      const double cand_cost = (fl & kResidualBad) ? DBL_MAX : t_cost;
-      const bool tol_armed = (prm.ceres_compat < 210) || (st.flags & kAnySuccess);
-      double step_norm = 0.0;
-      SMPC_UNROLL for (int c = 0; c < P; ++c) {
-        const double dd = xs[c] - cand[c];
-        step_norm += dd * dd;
-      }
-      step_norm = sqrt(step_norm);
-      const double cost_change = st.x_cost - cand_cost;
-      if (tol_armed && step_norm <= prm.param_tol * (st.x_norm + prm.param_tol)) {
-        --st.iteration;
-        st.term = kConvParameter;
-        finished = true;
-      } else if (tol_armed && fabs(cost_change) <= prm.fn_tol * st.x_cost) {
-        --st.iteration;
-        st.term = kConvFunction;
-        finished = true;
-      } else {
-        const double rho = (cand_cost >= DBL_MAX) ? -DBL_MAX : cost_change / st.model_cost_change;
-        if (rho > 1e-3) {  // HandleSuccessfulStep
-          if (fl & kJacobianBad) {
-            --st.iteration;
-            st.term = kFailEvaluation;
-            finished = true;
+      } else if (st.phase == kLineSearch) {
+        // Armijo sufficient decrease at step t along delta (projected); the evaluation has already tested it
+        // (kNoHessian <=> rejected), so both sides use one and the same comparison
+        if (!(fl & kNoHessian)) {
+          take_step = true;  // success: delta <- t * delta, candidate = this trial point
+          tr_code = 1.0;
+        } else {
+          tr_aux = t_cost - (st.x_cost + 1e-4 * st.g0 * st.t);
+          double gd = 0.0;
+          for (int c = 0; c < P; ++c) gd += delta[c] * trial[L::g(c)];
+          ++st.ls_iters;
+          bool ls_failed = st.ls_iters >= 20;
+          double t_new = st.t;
+          if (!ls_failed) {
+            const double lo = 1e-3 * st.t, hi = 0.6 * st.t;
+            if (!eval_ok) {
+              t_new = fmin(fmax(st.t * 0.5, lo), hi);
+            } else if (st.flags & kPrevOk) {
+              t_new = quintic_interp_min(st.x_cost, st.g0, st.t, t_cost, gd, st.prev_x, st.prev_value, st.prev_gradient,
+                                         lo, hi, 0, 0u, 1);
+            } else {
+              t_new = cubic_interp_min(st.x_cost, st.g0, st.t, t_cost, gd, lo, hi);
+            }
+            if (t_new * st.dmax < 1e-9) ls_failed = true;
+          }
+          if (!ls_failed) {
+            st.prev_x = st.t;
+            st.prev_value = t_cost;
+            st.prev_gradient = gd;
+            st.flags = eval_ok ? (st.flags | kPrevOk) : (st.flags & ~kPrevOk);
+            st.t = t_new;
+            for (int c = 0; c < P; ++c) cand[c] = project_param(xs[c] + t_new * delta[c], c, nbd);
+            next_sample = true;  // evaluate the next line-search sample
           } else {
-            __syncwarp(gmask);
-            for (int c = gl; c < P; c += G) xs[c] = cand[c];
-            __syncwarp(gmask);
-            st.flags ^= kSwapped;
-            { double* tmp = cur; cur = trial; trial = tmp; }
-            st.x_cost = cand_cost;
-            st.flags |= kAnySuccess | kItSuccessful;
-            st.flags &= ~kReuseDiagonal;
+            // line search failed: the un-shortened TR step Plus(x, delta) is the candidate (delta unchanged). It needs
+            // a full evaluation — also when t is still 1 and this very point was just sampled without its J^T J.
+            st.t = 1.0;
+            for (int c = 0; c < P; ++c) cand[c] = project_param(xs[c] + delta[c], c, nbd);
+            st.phase = kFullStep;
+            next_sample = true;
+          }
+        }
+      } else {  // kFullStep: evaluation of Plus(x, delta) after a failed line search
+        take_step = true;
+      }
+
+      if (take_step) {
+        tr_code += 2.0;
+        const double cand_cost = (fl & kResidualBad) ? DBL_MAX : t_cost_plain;
+        const bool tol_armed = (prm.ceres_compat < 210) || (st.flags & kAnySuccess);
+        double step_norm = 0.0;
+        for (int c = 0; c < P; ++c) {
+          const double dd = xs[c] - cand[c];
+          step_norm += dd * dd;
+        }
+        step_norm = sqrt(step_norm);
+        const double cost_change = st.x_cost - cand_cost;
+        if (tol_armed && step_norm <= prm.param_tol * (st.x_norm + prm.param_tol)) {
+          --st.iteration;
+          st.term = kConvParameter;
+          finished = true;
+        } else if (tol_armed && fabs(cost_change) <= prm.fn_tol * st.x_cost) {
+          --st.iteration;
+          st.term = kConvFunction;
+          finished = true;
+        } else {
+          // TrustRegionStepEvaluator::StepQuality (monotonic steps): measured from the step evaluator's current cost
+          const double rho = (cand_cost >= DBL_MAX) ? -DBL_MAX : (st.se_cost - cand_cost) / st.model_cost_change;
+          tr_aux = rho;
+          if (rho > 1e-3) {  // HandleSuccessfulStep
+            if (fl & kJacobianBad) {
+              --st.iteration;
+              st.term = kFailEvaluation;
+              finished = true;
+            } else {
+              tr_code += 4.0;
+              for (int c = 0; c < P; ++c) xs[c] = cand[c];
+              st.flags ^= kSwapped;
+              { double* tmp = cur; cur = trial; trial = tmp; }
+              st.x_cost = t_cost;
+              st.se_cost = cand_cost;
+              st.flags |= kAnySuccess | kItSuccessful;
+              st.flags &= ~kReuseDiagonal;
+              st.it_cost = t_cost;
+              const double qq = 2.0 * rho - 1.0;
+              st.radius = fmin(1e16, st.radius / fmax(1.0 / 3.0, 1.0 - qq * qq * qq));
+              st.decrease_factor = 2.0;
+            }
+          } else {
+            st.flags &= ~kItSuccessful;
+            st.flags |= kReuseDiagonal;
             st.it_cost = cand_cost;
-            const double qq = 2.0 * rho - 1.0;
-            st.radius = fmin(1e16, st.radius / fmax(1.0 / 3.0, 1.0 - qq * qq * qq));
-            st.decrease_factor = 2.0;
+            st.radius = st.radius / st.decrease_factor;
+            st.decrease_factor *= 2.0;
           }
-        } else {
-          st.flags &= ~kItSuccessful;
-          st.flags |= kReuseDiagonal;
-          st.it_cost = cand_cost;
-          st.radius = st.radius / st.decrease_factor;
-          st.decrease_factor *= 2.0;
         }
       }
-    }
 
-    }  // ===== end of part A
-#ifdef SMPC_MID_BARRIER
-    __syncthreads();  // part B (the LM step) is another large code region: enter it together as well
-#endif
+      // ===== part B: a new outer iteration starts here (after iteration zero or after accept / reject)
+      if (!finished && !next_sample) {
+        if (st.flags & kItSuccessful) {  // x changed: refresh |x| and the projected-gradient max norm
+          double xn = 0.0, gm = 0.0;
+          for (int c = 0; c < P; ++c) {
+            const double xv = xs[c];
+            xn += xv * xv;
+            gm = fmax(gm, fabs(xv - project_param(xv - cur[L::g(c)], c, nbd)));
+          }
+          st.x_norm = sqrt(xn);
+          st.gmax = gm;
+        }
+        for (;;) {
+          // FinalizeIterationAndCheckIfMinimizerCanContinue
+          if ((st.flags & kItSuccessful) && st.x_cost < st.minimum_cost) {
+            st.minimum_cost = st.x_cost;
+            for (int c = 0; c < P; ++c) best[c] = xs[c];
+          }
+          st.cost_final = fmin(st.cost_final, st.it_cost);
+          if (prm.max_evaluations > 0 && st.n_eval >= prm.max_evaluations) { st.term = kNoConvergence; finished = true; break; }
+          if (st.iteration >= prm.max_iterations) { st.term = kNoConvergence; finished = true; break; }
+          if ((st.flags & kItSuccessful) && st.gmax <= prm.gradient_tol) { st.term = kConvGradient; finished = true; break; }
+          if (st.radius <= 1e-32) { st.term = kConvRadius; finished = true; break; }
+          ++st.iteration;
 
-    // ---- a new outer iteration starts here (after iteration zero or after accept / reject) ----
-    if (live && !finished && !next_sample) {
-      if (st.flags & kItSuccessful) {  // x changed: refresh |x| and the projected-gradient max norm
-        double xn = 0.0, gm = 0.0;
-        SMPC_UNROLL for (int c = 0; c < P; ++c) {
-          const double xv = xs[c];
-          xn += xv * xv;
-          gm = fmax(gm, fabs(xv - project_param(xv - cur[L::g(c)], c, nbd)));
-        }
-        st.x_norm = sqrt(xn);
-        st.gmax = gm;
-      }
-      for (;;) {
-        // FinalizeIterationAndCheckIfMinimizerCanContinue
-        if ((st.flags & kItSuccessful) && st.x_cost < st.minimum_cost) {
-          st.minimum_cost = st.x_cost;
-          __syncwarp(gmask);
-          for (int c = gl; c < P; c += G) best[c] = xs[c];
-          __syncwarp(gmask);
-        }
-        st.cost_final = fmin(st.cost_final, st.it_cost);
-        if (st.iteration >= prm.max_iterations) { st.term = kNoConvergence; finished = true; break; }
-        if ((st.flags & kItSuccessful) && st.gmax <= prm.gradient_tol) { st.term = kConvGradient; finished = true; break; }
-        if (st.radius <= 1e-32) { st.term = kConvRadius; finished = true; break; }
-        ++st.iteration;
-
-        // LevenbergMarquardtStrategy::ComputeStep on the column-scaled normal equations
-        __syncwarp(gmask);
-        if (!(st.flags & kReuseDiagonal)) {
-          for (int c = gl; c < P; c += G) {
-            const double scv = scale[c];
-            diag[c] = fmin(fmax(scv * scv * cur[L::h(0, 0) + c * (c + 1) / 2 + c], 1e-6), 1e32);
-          }
-        }
-        __syncwarp(gmask);
-        st.flags |= kReuseDiagonal;
-        double sc[P], Lc[L::NH], step[P];
-        const double inv_radius = 1.0 / st.radius;
-        SMPC_UNROLL for (int c = 0; c < P; ++c) sc[c] = scale[c];
-        SMPC_UNROLL for (int a = 0; a < P; ++a) {
-          SMPC_UNROLL for (int bq = 0; bq <= a; ++bq) Lc[a * (a + 1) / 2 + bq] = sc[a] * sc[bq] * cur[L::h(a, bq)];
-          Lc[a * (a + 1) / 2 + a] += diag[a] * inv_radius;  // (sqrt(diag / radius))^2 of the LM strategy
-        }
-        bool step_ok = true;
-        SMPC_UNROLL for (int jc = 0; jc < P; ++jc) {  // Cholesky, in place, lower triangle
-          double d = Lc[jc * (jc + 1) / 2 + jc];
-          SMPC_UNROLL for (int k = 0; k < jc; ++k) d -= Lc[jc * (jc + 1) / 2 + k] * Lc[jc * (jc + 1) / 2 + k];
-          if (!(d > 0.0)) step_ok = false;
-          const double inv_d = rsqrt(d);
-          Lc[jc * (jc + 1) / 2 + jc] = inv_d;  // store 1/L_jj
-          SMPC_UNROLL for (int i = jc + 1; i < P; ++i) {
-            double sacc = Lc[i * (i + 1) / 2 + jc];
-            SMPC_UNROLL for (int k = 0; k < jc; ++k) sacc -= Lc[i * (i + 1) / 2 + k] * Lc[jc * (jc + 1) / 2 + k];
-            Lc[i * (i + 1) / 2 + jc] = sacc * inv_d;
-          }
-        }
-        SMPC_UNROLL for (int i = 0; i < P; ++i) {  // forward substitution
-          double sacc = sc[i] * cur[L::g(i)];
-          SMPC_UNROLL for (int k = 0; k < i; ++k) sacc -= Lc[i * (i + 1) / 2 + k] * step[k];
-          step[i] = sacc * Lc[i * (i + 1) / 2 + i];
-        }
-        SMPC_UNROLL for (int i = P - 1; i >= 0; --i) {  // back substitution
-          double sacc = step[i];
-          SMPC_UNROLL for (int k = i + 1; k < P; ++k) sacc -= Lc[k * (k + 1) / 2 + i] * step[k];
-          step[i] = sacc * Lc[i * (i + 1) / 2 + i];
-        }
-        SMPC_UNROLL for (int c = 0; c < P; ++c) {
-          step_ok = step_ok && isfinite(step[c]);
-          step[c] = -step[c];
-        }
-        // model_cost_change = -(Js s)'(r + Js s / 2) = -s'(Js' r) - s'(Js' Js) s / 2
-        double lin = 0.0, quad = 0.0;
-        SMPC_UNROLL for (int a = 0; a < P; ++a) {
-          const double sa = sc[a] * step[a];
-          lin += sa * cur[L::g(a)];
-          double rowv = 0.0;
-          SMPC_UNROLL for (int bq = 0; bq < a; ++bq) rowv += cur[L::h(a, bq)] * (sc[bq] * step[bq]);
-          quad += sa * (2.0 * rowv + cur[L::h(a, a)] * sa);
-        }
-        st.model_cost_change = -lin - 0.5 * quad;
-        const bool valid = step_ok && (st.model_cost_change > 0.0);
-        if (valid) {
-          st.n_invalid = 0;
-          double g0 = 0.0, dmax = 0.0;
-          SMPC_UNROLL for (int c = 0; c < P; ++c) {
-            const double dl = step[c] * sc[c];
-            g0 += cur[L::g(c)] * dl;
-            dmax = fmax(dmax, fabs(dl));
-            step[c] = dl;
-          }
-          st.g0 = g0;
-          st.dmax = dmax;
-          __syncwarp(gmask);
-          if (gl == 0) {
-            SMPC_UNROLL for (int c = 0; c < P; ++c) {
-              delta[c] = step[c];
-              cand[c] = project_param(xs[c] + step[c], c, nbd);
+          // LevenbergMarquardtStrategy::ComputeStep on the column-scaled normal equations
+          if (!(st.flags & kReuseDiagonal)) {
+            for (int c = 0; c < P; ++c) {
+              const double scv = scale[c];
+              diag[c] = fmin(fmax(scv * scv * cur[L::h(c, c)], 1e-6), 1e32);
             }
           }
-          break;
+          st.flags |= kReuseDiagonal;
+          double sc[P], Lc[L::NH], step[P];
+          const double inv_radius = 1.0 / st.radius;
+          SMPC_UNROLL for (int c = 0; c < P; ++c) sc[c] = scale[c];
+          SMPC_UNROLL for (int a = 0; a < P; ++a) {
+            SMPC_UNROLL for (int bq = 0; bq <= a; ++bq) Lc[a * (a + 1) / 2 + bq] = sc[a] * sc[bq] * cur[L::h(a, bq)];
+            Lc[a * (a + 1) / 2 + a] += diag[a] * inv_radius;  // (sqrt(diag / radius))^2 of the LM strategy
+          }
+          bool step_ok = true;
+          SMPC_UNROLL for (int jc = 0; jc < P; ++jc) {  // Cholesky, in place, lower triangle
+            double d = Lc[jc * (jc + 1) / 2 + jc];
+            SMPC_UNROLL for (int k = 0; k < jc; ++k) d -= Lc[jc * (jc + 1) / 2 + k] * Lc[jc * (jc + 1) / 2 + k];
+            if (!(d > 0.0)) step_ok = false;
+            const double inv_d = rsqrt(d);
+            Lc[jc * (jc + 1) / 2 + jc] = inv_d;  // store 1/L_jj
+            SMPC_UNROLL for (int i = jc + 1; i < P; ++i) {
+              double sacc = Lc[i * (i + 1) / 2 + jc];
+              SMPC_UNROLL for (int k = 0; k < jc; ++k) sacc -= Lc[i * (i + 1) / 2 + k] * Lc[jc * (jc + 1) / 2 + k];
+              Lc[i * (i + 1) / 2 + jc] = sacc * inv_d;
+            }
+          }
+          SMPC_UNROLL for (int i = 0; i < P; ++i) {  // forward substitution
+            double sacc = sc[i] * cur[L::g(i)];
+            SMPC_UNROLL for (int k = 0; k < i; ++k) sacc -= Lc[i * (i + 1) / 2 + k] * step[k];
+            step[i] = sacc * Lc[i * (i + 1) / 2 + i];
+          }
+          SMPC_UNROLL for (int i = P - 1; i >= 0; --i) {  // back substitution
+            double sacc = step[i];
+            SMPC_UNROLL for (int k = i + 1; k < P; ++k) sacc -= Lc[k * (k + 1) / 2 + i] * step[k];
+            step[i] = sacc * Lc[i * (i + 1) / 2 + i];
+          }
+          SMPC_UNROLL for (int c = 0; c < P; ++c) {
+            step_ok = step_ok && isfinite(step[c]);
+            step[c] = -step[c];
+          }
+          // model_cost_change = -(Js s)'(r + Js s / 2) = -s'(Js' r) - s'(Js' Js) s / 2
+          double lin = 0.0, quad = 0.0;
+          SMPC_UNROLL for (int a = 0; a < P; ++a) {
+            const double sa = sc[a] * step[a];
+            lin += sa * cur[L::g(a)];
+            double rowv = 0.0;
+            SMPC_UNROLL for (int bq = 0; bq < a; ++bq) rowv += cur[L::h(a, bq)] * (sc[bq] * step[bq]);
+            quad += sa * (2.0 * rowv + cur[L::h(a, a)] * sa);
+          }
+          st.model_cost_change = -lin - 0.5 * quad;
+          const bool valid = step_ok && (st.model_cost_change > 0.0);
+          if (valid) {
+            st.n_invalid = 0;
+            double g0 = 0.0, dmax = 0.0;
+            SMPC_UNROLL for (int c = 0; c < P; ++c) {
+              const double dl = step[c] * sc[c];
+              g0 += cur[L::g(c)] * dl;
+              dmax = fmax(dmax, fabs(dl));
+              delta[c] = dl;
+              cand[c] = project_param(xs[c] + dl, c, nbd);
+            }
+            st.g0 = g0;
+            st.dmax = dmax;
+            break;
+          }
+          // HandleInvalidStep
+          if (++st.n_invalid >= 5) {
+            --st.iteration;
+            st.term = kFailInvalidSteps;
+            finished = true;
+            break;
+          }
+          st.radius /= st.decrease_factor;
+          st.decrease_factor *= 2.0;
+          st.flags &= ~kItSuccessful;
+          st.it_cost = st.x_cost;
         }
-        // HandleInvalidStep
-        if (++st.n_invalid >= 5) {
-          --st.iteration;
-          st.term = kFailInvalidSteps;
-          finished = true;
-          break;
+        if (!finished) {
+          st.phase = kLineSearch;
+          st.t = 1.0;
+          st.ls_iters = 0;
+          st.flags &= ~kPrevOk;
         }
-        st.radius /= st.decrease_factor;
-        st.decrease_factor *= 2.0;
-        st.flags &= ~kItSuccessful;
-        st.it_cost = st.x_cost;
       }
-      if (!finished) {
-        st.phase = kLineSearch;
-        st.t = 1.0;
-        st.ls_iters = 0;
-        st.flags &= ~kPrevOk;
+      if (finished) {
+        st.flags |= kFinished;
+        tr_code += 8.0 + 16.0 * (double)st.term;
       }
+      if (rs.trace != nullptr)
+        trace_row(rs, st.b, row, tr_iter, tr_phase, tr_t, t_cost, take_step ? t_cost_plain : NAN, tr_aux, tr_code, st.radius);
     }
+    __syncwarp(gmask);
 
-    if (live && finished) {
+    if (live && (gs->flags & kFinished)) {
       // results. Solution = best accepted iterate when usable (Solver::Summary::IsSolutionUsable), else the seed.
+      const LmState& st = *gs;
       const bool usable = st.term <= kNoConvergence;
       const int b = st.b;
-      __syncwarp(gmask);
+      const int Pb = 2 * pbs->nb;
       double x[P];
-      SMPC_UNROLL for (int c = 0; c < P; ++c) x[c] = usable ? best[c] : __ldg(bt.u0 + (size_t)b * P + c);
+      SMPC_UNROLL for (int c = 0; c < P; ++c)
+        x[c] = (c < Pb) ? (usable ? best[c] : ld_in<PPL>(bt.u0 + (size_t)b * P + c)) : 0.0;
       if (gl == 0) {
         if (rs.u) {
-          SMPC_UNROLL for (int c = 0; c < P; ++c) rs.u[(size_t)b * P + c] = x[c];
+          SMPC_UNROLL for (int c = 0; c < P; ++c)
+            if (c < Pb) rs.u[(size_t)b * P + c] = x[c];
         }
         if (rs.cost_initial) rs.cost_initial[b] = st.cost_initial;
         if (rs.cost_final) rs.cost_final[b] = st.cost_final;
@@ -1553,13 +1673,16 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
         if (rs.termination) rs.termination[b] = st.term;
         if (rs.usable) rs.usable[b] = usable ? 1 : 0;
         if (rs.n_evals) {
-          rs.n_evals[2 * b] = st.n_eval;
-          rs.n_evals[2 * b + 1] = 0;
+          rs.n_evals[2 * b] = st.n_eval - st.n_light;
+          rs.n_evals[2 * b + 1] = st.n_light;
         }
       }
-      if (rs.cmds || rs.path) expand_outputs<NB, G>(prm, bt, rs, *pbs, b, x, lane);
-      st.phase = kFetch;
-      st.flags &= ~kLive;
+      if (rs.cmds || rs.path) expand_outputs<NB, G>(bt, rs, *pbs, b, x, lane);
+      __syncwarp(gmask);
+      if (gl == 0) {
+        gs->phase = kFetch;
+        gs->flags &= ~(kLive | kFinished);
+      }
     }
     __syncwarp(gmask);
   }

@@ -141,6 +141,9 @@ int make_dev_params(const smpc_params& p, int S, smpc::DevParams* d) {
   d->gradient_tol = p.gradient_tol;
   d->max_iterations = p.max_iterations;
   d->ceres_compat = p.ceres_compat ? p.ceres_compat : 200;
+  d->max_evaluations = p.max_evaluations > 0 ? p.max_evaluations : 0;
+  d->control_horizon = p.control_horizon;
+  d->block_length = p.parameter_block_length;
   return SMPC_OK;
 }
 
@@ -175,6 +178,7 @@ void to_dev_batch(const smpc_batch& in, smpc::DevBatch* d) {
   d->costmaps = in.costmaps;
   d->costmap_origin = in.costmap_origin;
   d->costmap_index = in.costmap_index;
+  d->n_steps_each = in.n_steps_each;
   d->arrival = nullptr;
   d->park_state = nullptr;
   d->park_ring = nullptr;
@@ -195,6 +199,8 @@ void to_dev_result(const smpc_result& out, smpc::DevResult* d) {
   d->termination = out.termination;
   d->usable = out.usable;
   d->n_evals = out.n_evals;
+  d->trace = (out.trace_rows > 0) ? out.trace : nullptr;
+  d->trace_rows = out.trace_rows;
 }
 
 size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
@@ -346,6 +352,8 @@ void smpc_params_default(smpc_params* p) {
   p->desired_linear_vel = 0.5;
   p->fov_angle = M_PI / 4.0;
   p->ceres_compat = 200;
+  p->max_evaluations = 0;
+  p->omni_solve = 0;
 }
 
 int smpc_params_from_yaml(const char* yaml_path, const char* plugin_name, smpc_params* p) {
@@ -612,7 +620,7 @@ int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out) {
 
   // ---- device staging: every array whole, same layout as the host's, so a chunk is a pointer offset
   struct Item { const void* host; size_t per_problem; size_t shared_bytes; char* dev; };
-  enum { kPose, kU0, kPath, kGoal, kAgents, kHas, kIndex, kMaps, kOrigin, kItems };
+  enum { kPose, kU0, kPath, kGoal, kAgents, kHas, kIndex, kMaps, kOrigin, kNEach, kItems };
   Item items[kItems] = {
       {in->pose0, 3 * 8, 0, nullptr},
       {in->u0, P * 8, 0, nullptr},
@@ -623,6 +631,7 @@ int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out) {
       {host_index, 4, 0, nullptr},
       {in->costmaps, maps_per_problem ? map_cells : 0, maps_per_problem ? 0 : M * map_cells, nullptr},
       {in->costmap_origin, maps_per_problem ? 16 : 0, maps_per_problem ? 0 : M * 16, nullptr},
+      {in->n_steps_each, 4, 0, nullptr},
   };
   size_t total = 0;
   for (auto& it : items)
@@ -633,11 +642,13 @@ int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out) {
     if (it.host) it.dev = static_cast<char*>(cin.take(it.per_problem * B + it.shared_bytes));
 
   struct OItem { void* host; size_t per_problem; char* dev; };
-  enum { kOU, kOCmds, kOPath, kOCi, kOCf, kOIt, kOTerm, kOUsable, kOEvals, kOItems };
+  enum { kOU, kOCmds, kOPath, kOCi, kOCf, kOIt, kOTerm, kOUsable, kOEvals, kOTrace, kOItems };
+  const size_t trace_rows = (out->trace && out->trace_rows > 0) ? static_cast<size_t>(out->trace_rows) : 0;
   OItem oitems[kOItems] = {
       {out->u, P * 8, nullptr},        {out->cmds, S1 * 2 * 8, nullptr}, {out->path, S1 * 3 * 8, nullptr},
       {out->cost_initial, 8, nullptr}, {out->cost_final, 8, nullptr},    {out->iterations, 4, nullptr},
       {out->termination, 4, nullptr},  {out->usable, 1, nullptr},        {out->n_evals, 2 * 4, nullptr},
+      {trace_rows ? out->trace : nullptr, trace_rows * 8 * 8, nullptr},
   };
   size_t ototal = 0;
   for (auto& it : oitems)
@@ -646,6 +657,14 @@ int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out) {
   Carver cout_(h->out_buf.ptr);
   for (auto& it : oitems)
     if (it.host) it.dev = static_cast<char*>(cout_.take(it.per_problem * B));
+  // Rows a problem does not write (beyond its own horizon / blocks with n_steps_each, unused trace rows) come back as
+  // zero bytes (trace: NaN) instead of stale staging memory.
+  if (in->n_steps_each) SMPC_CUDA(cudaMemsetAsync(h->out_buf.ptr, 0, ototal, h->stream));
+  if (trace_rows) SMPC_CUDA(cudaMemsetAsync(oitems[kOTrace].dev, 0xFF, trace_rows * 64 * B, h->stream));
+  if (in->n_steps_each || trace_rows) {
+    SMPC_CUDA(cudaEventRecord(h->ev_shared, h->stream));
+    SMPC_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_shared, 0));
+  }
 
   // ---- people-free batch with one costmap per problem: the maps are 90 % of the input bytes. They stream in on the
   //      second stream WHILE the solve runs: problems are handed out in index order and a group waits until the
@@ -654,7 +673,7 @@ int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out) {
   // Large batches stream their other per-problem arrays (seed path, pose, start controls: 0.5 kB per problem) the same
   // way once those are worth more than the extra copy calls (>= 8 MB).
   bool stream_maps = false;   // streaming mode on (the name is historical: maps were the first thing streamed)
-  bool streamed[kItems] = {false, false, false, false, false, false, false, false, false};
+  bool streamed[kItems] = {false, false, false, false, false, false, false, false, false, false};
   if (h->stream_maps && n_chunks == 1 && !(A > 0 && in->has_people) && B >= 1024) {
     size_t small_bytes = 0;
     for (int k = 0; k < kItems; ++k)
@@ -717,6 +736,7 @@ int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out) {
     din.costmap_index = static_cast<const int32_t*>(at(kIndex));
     din.costmaps = static_cast<const uint8_t*>(at(kMaps));
     din.costmap_origin = static_cast<const double*>(at(kOrigin));
+    din.n_steps_each = static_cast<const int32_t*>(at(kNEach));
     if (maps_per_problem) din.n_costmaps = static_cast<int>(n);
     auto oat = [&](int k) -> void* { return oitems[k].dev ? oitems[k].dev + oitems[k].per_problem * c0 : nullptr; };
     smpc_result dout;
@@ -729,6 +749,8 @@ int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out) {
     dout.termination = static_cast<int32_t*>(oat(kOTerm));
     dout.usable = static_cast<uint8_t*>(oat(kOUsable));
     dout.n_evals = static_cast<int32_t*>(oat(kOEvals));
+    dout.trace = static_cast<double*>(oat(kOTrace));
+    dout.trace_rows = static_cast<int>(trace_rows);
     if (stream_maps) {
       // Feed the solve its streamed inputs, piece by piece, each followed by its arrival count. Everything is enqueued BEFORE
       // the kernel launch: the copies then make progress whether or not the launch call returns early (profilers,
@@ -780,7 +802,7 @@ int smpc_eval_batch_device(smpc_handle* h, const smpc_batch* in, const double* x
   if (rc != SMPC_OK) return rc;
   smpc::DevBatch bt;
   to_dev_batch(*in, &bt);
-  smpc::DevEvalOut eo{out->cost, out->grad, out->hess, out->ok};
+  smpc::DevEvalOut eo{out->cost, out->cost_plain, out->grad, out->hess, out->ok};
   SMPC_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
   rc = pack_agents(h, &bt, st);
@@ -818,6 +840,7 @@ int smpc_eval_batch(smpc_handle* h, const smpc_batch* in, const double* x, smpc_
         {in->costmaps, M * in->size_x * in->size_y, (void**)&din.costmaps},
         {in->costmap_origin, M * 2 * 8, (void**)&din.costmap_origin},
         {in->costmap_index, B * 4, (void**)&din.costmap_index},
+        {in->n_steps_each, B * 4, (void**)&din.n_steps_each},
         {x, B * P * 8, (void**)&dx},
     };
     size_t total = 0;
@@ -833,14 +856,15 @@ int smpc_eval_batch(smpc_handle* h, const smpc_batch* in, const double* x, smpc_
       SMPC_CUDA(cudaMemcpyAsync(d, it.host, it.bytes, cudaMemcpyHostToDevice, h->stream));
       *it.dev = d;
     }
-    const size_t ob[4] = {B * 8, B * P * 8, B * NH * 8, B};
-    void* hostp[4] = {out->cost, out->grad, out->hess, out->ok};
-    void** devp[4] = {(void**)&dout.cost, (void**)&dout.grad, (void**)&dout.hess, (void**)&dout.ok};
+    const size_t ob[5] = {B * 8, B * P * 8, B * NH * 8, B, B * 8};
+    void* hostp[5] = {out->cost, out->grad, out->hess, out->ok, out->cost_plain};
+    void** devp[5] = {(void**)&dout.cost, (void**)&dout.grad, (void**)&dout.hess, (void**)&dout.ok,
+                      (void**)&dout.cost_plain};
     size_t ototal = 0;
-    for (int i = 0; i < 4; ++i) ototal += hostp[i] ? align256(ob[i]) : 0;
+    for (int i = 0; i < 5; ++i) ototal += hostp[i] ? align256(ob[i]) : 0;
     SMPC_CUDA(h->out_buf.reserve(ototal));
     Carver co(h->out_buf.ptr);
-    for (int i = 0; i < 4; ++i) *devp[i] = hostp[i] ? co.take(ob[i]) : nullptr;
+    for (int i = 0; i < 5; ++i) *devp[i] = hostp[i] ? co.take(ob[i]) : nullptr;
   }
   rc = smpc_eval_batch_device(h, &din, dx, &dout, nullptr);
   if (rc != SMPC_OK) return rc;
@@ -851,6 +875,8 @@ int smpc_eval_batch(smpc_handle* h, const smpc_batch* in, const double* x, smpc_
     if (out->grad) SMPC_CUDA(cudaMemcpyAsync(out->grad, dout.grad, B * P * 8, cudaMemcpyDeviceToHost, h->stream));
     if (out->hess) SMPC_CUDA(cudaMemcpyAsync(out->hess, dout.hess, B * NH * 8, cudaMemcpyDeviceToHost, h->stream));
     if (out->ok) SMPC_CUDA(cudaMemcpyAsync(out->ok, dout.ok, B, cudaMemcpyDeviceToHost, h->stream));
+    if (out->cost_plain)
+      SMPC_CUDA(cudaMemcpyAsync(out->cost_plain, dout.cost_plain, B * 8, cudaMemcpyDeviceToHost, h->stream));
     SMPC_CUDA(cudaStreamSynchronize(h->stream));
   }
   return SMPC_OK;

@@ -316,7 +316,7 @@ int smpc_optimize(smpc_handle* h, smpc_optimize_io* io) {
   double goal_yaw = robot.back().v[2];
   uint8_t has_people = io->n_people != 0;
   double origin[2] = {io->origin_x, io->origin_y};
-  smpc_batch in;
+  smpc_batch in{};
   std::memset(&in, 0, sizeof(in));
   in.n_problems = 1;
   in.n_steps = S;
@@ -338,7 +338,7 @@ int smpc_optimize(smpc_handle* h, smpc_optimize_io* io) {
   uint8_t usable = 0;
   int32_t termination = 0, iterations = 0;
   double c0 = 0.0, c1 = 0.0;
-  smpc_result out;
+  smpc_result out{};
   std::memset(&out, 0, sizeof(out));
   out.cmds = cmds_out.data();
   out.path = path_out.data();

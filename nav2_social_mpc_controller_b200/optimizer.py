@@ -94,13 +94,16 @@ class Optimizer:
     # ---- level-1 solve, host buffers (numpy or pinned torch CPU tensors) --------------------------------
     def solve_batch(self, batch, out: dict | None = None,
                     want=("u", "cmds", "cost_initial", "cost_final", "iterations", "termination", "usable",
-                          "n_evals")) -> dict:
-        """H2D copy of the batch, one solve launch, D2H copy of the results (all inside the C call)."""
+                          "n_evals"), trace_rows: int = 0) -> dict:
+        """H2D copy of the batch, one solve launch, D2H copy of the results (all inside the C call).
+        trace_rows > 0 adds out["trace"] [B][trace_rows][8] (per-evaluation solver trace, include/smpc.h)."""
         self._need()
         nb = self.dims(batch.n_steps)[2]
         if out is None:
             shapes = abi.result_shapes(batch.n_problems, batch.n_steps, nb)
             out = {k: np.zeros(shapes[k][0], dtype=shapes[k][1]) for k in want}
+            if trace_rows > 0:
+                out["trace"] = np.full((batch.n_problems, trace_rows, 8), np.nan)
         st = batch.struct()
         rs = abi.make_result_struct(out)
         _lib.check(_lib.lib().smpc_solve_batch(self._h, C.byref(st), C.byref(rs)))
@@ -191,9 +194,9 @@ class Optimizer:
         B = batch.n_problems
         x = np.ascontiguousarray(x, dtype=np.float64).reshape(B, P)
         out = dict(cost=np.zeros(B), grad=np.zeros((B, P)), hess=np.zeros((B, P * (P + 1) // 2)),
-                   ok=np.zeros(B, dtype=np.uint8))
+                   ok=np.zeros(B, dtype=np.uint8), cost_plain=np.zeros(B))
         eo = abi.SmpcEvalOut()
-        for k in ("cost", "grad", "hess", "ok"):
+        for k in ("cost", "grad", "hess", "ok", "cost_plain"):
             setattr(eo, k, out[k].ctypes.data)
         st = batch.struct()
         _lib.check(_lib.lib().smpc_eval_batch(self._h, C.byref(st), x.ctypes.data, C.byref(eo)))

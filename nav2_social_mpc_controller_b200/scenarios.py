@@ -374,6 +374,17 @@ def crowd(B: int = 65536, A: int = 20, param_set: str = "soc_work_obst", config_
     return _finish(p, seed, S, agents, np.ones(B), cms, np.zeros((M, 2)), idx, res)
 
 
+def with_horizons(batch: Batch, n_steps_each) -> Batch:
+    """The same batch with per-problem horizons S_b <= n_steps (include/smpc.h n_steps_each): robots near their goal get
+    a shorter seed from the trajectorizer (reference src/path_trajectorizer.cpp:152) and with it fewer steps, a shorter
+    control horizon and fewer parameter blocks (src/optimizer.cpp:248-249). Arrays keep the stride of n_steps."""
+    n = np.ascontiguousarray(n_steps_each, dtype=np.int32).reshape(batch.n_problems)
+    assert n.min() >= 1 and n.max() <= batch.n_steps
+    arr = dict(batch.arrays)
+    arr["n_steps_each"] = n
+    return dataclasses.replace(batch, arrays=arr)
+
+
 def multistart(n_robots: int = 256, n_starts: int = 1024, config_id: int = 4, **overrides) -> Batch:
     """BASELINE config 4: `n_starts` perturbed initial control sequences per robot (start 0 unperturbed),
     u0 = clamp(seed u0 + N(0, diag(0.1, 0.3)^2)) per block. Problems of one robot are contiguous."""

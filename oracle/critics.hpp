@@ -22,8 +22,10 @@ namespace smpc_oracle {
 
 // One problem, viewed through the C-ABI batch layout of include/smpc.h.
 struct ProblemView {
-  int S = 0;   // optimised steps N_v (src/optimizer.cpp:237,251)
+  int S = 0;   // optimised steps N_v of THIS problem (src/optimizer.cpp:237,251)
+  int S1 = 0;  // row stride of the step-indexed arrays = (largest S of the batch) + 1 (include/smpc.h n_steps_each)
   int A = 0;   // agent columns per step
+  int ceres_compat = 200;  // < 210: std::numeric_limits<Jet> is NOT specialised (see proxemics_residual)
   int ch = 0;  // min(control_horizon, S)          src/optimizer.cpp:248
   int bl = 0;  // min(parameter_block_length, ch)  src/optimizer.cpp:249
   int nb = 0;  // ceil(ch/bl) parameter blocks     src/optimizer.cpp:254-261
@@ -42,7 +44,7 @@ struct ProblemView {
   double w_distance = 0, w_social = 0, w_velocity = 0, w_angle = 0, w_agent_angle = 0, w_prox = 0, w_vf = 0,
          w_obstacle = 0, w_goal = 0;
 
-  double agent(int step, int k, int c) const { return agents[(static_cast<size_t>(k) * 6 + c) * (S + 1) + step]; }
+  double agent(int step, int k, int c) const { return agents[(static_cast<size_t>(k) * 6 + c) * S1 + step]; }
   int block_of(int j) const { return j < ch ? j / bl : (ch - 1) / bl; }
   int blocks_seen(int i) const { return block_of(i) + 1; }  // src/optimizer.cpp:271-288
 };
@@ -161,12 +163,28 @@ inline T social_work_residual(const ProblemView& p, const T* const* u, int i) {
   return T(p.w_social) * total;
 }
 
+// std::numeric_limits<T>::max() as proxemics_cost_function.hpp:128 sees it. For T = double it is DBL_MAX. For
+// T = ceres::Jet the answer depends on the Ceres release: the std::numeric_limits<ceres::Jet<T, N>> specialisation
+// was added in Ceres 2.1.0; with Ceres 2.0.0 (Ubuntu 22.04 / ROS 2 Humble, ceres_compat < 210) the PRIMARY template
+// answers and returns a value-initialised Jet, i.e. 0 with a zero derivative.
+template <class T>
+struct IsJet {
+  static constexpr bool value = false;
+};
+template <int N>
+struct IsJet<Jet<N>> {
+  static constexpr bool value = true;
+};
+
 // ProxemicsCost, proxemics_cost_function.hpp:83-151; alpha 3, d0 0.5 (proxemics_cost_function.cpp:37-38).
+// Ceres 2.0.0 consequence of the note above: in every DIFFERENTIATED evaluation (Jacobian or gradient requested)
+// min_distance starts at Jet(0), std::min keeps it (no squared distance is < 0), and the residual is the constant
+// w * alpha * exp(-0) with a zero Jacobian row; cost-only (double) evaluations see the true minimum distance.
 template <class T>
 inline T proxemics_residual(const ProblemView& p, const T* const* u, int i) {
   T robot[6];
   robot_state(p, u, i, robot);
-  T min_d = T(std::numeric_limits<double>::max());
+  T min_d = (IsJet<T>::value && p.ceres_compat < 210) ? T(0.0) : T(std::numeric_limits<double>::max());
   for (int k = 0; k < p.A; ++k) {
     if (p.agent(i + 1, k, 3) == -1.0) continue;
     Vec2<T> diff{robot[0] - T(p.agent(i + 1, k, 0)), robot[1] - T(p.agent(i + 1, k, 1))};

@@ -31,20 +31,32 @@ bool derive_dims(const smpc_params* p, int S, int* ch, int* bl, int* nb, int* n_
   return true;
 }
 
+// Row width of u0 / u: the parameter blocks of the LONGEST horizon of the batch (a shorter problem uses the first
+// nb_b of them, the rest stay untouched).
+int batch_blocks(const smpc_params* p, const smpc_batch* in) {
+  int ch, bl, nb, nbd;
+  if (!derive_dims(p, in->n_steps, &ch, &bl, &nb, &nbd)) return 0;
+  return nb;
+}
+
 bool make_view(const smpc_params* p, const smpc_batch* in, int b, ProblemView* v) {
-  const int S = in->n_steps, A = in->n_agents;
+  const int S1 = in->n_steps + 1, A = in->n_agents;
+  const int S = in->n_steps_each ? in->n_steps_each[b] : in->n_steps;  // per-problem horizon (include/smpc.h)
+  if (S < 1 || S > in->n_steps) return false;
   v->S = S;
+  v->S1 = S1;
   v->A = A;
+  v->ceres_compat = p->ceres_compat ? p->ceres_compat : 200;
   if (!derive_dims(p, S, &v->ch, &v->bl, &v->nb, &v->n_bounded)) return false;
   v->dt = in->dt;
   v->x0 = in->pose0[3 * b + 0];
   v->y0 = in->pose0[3 * b + 1];
   v->yaw0 = in->pose0[3 * b + 2];
-  v->u0 = in->u0 + static_cast<size_t>(b) * v->nb * 2;
-  v->px = in->path_xy + static_cast<size_t>(b) * 2 * (S + 1);
-  v->py = v->px + (S + 1);
+  v->u0 = in->u0 + static_cast<size_t>(b) * batch_blocks(p, in) * 2;
+  v->px = in->path_xy + static_cast<size_t>(b) * 2 * S1;
+  v->py = v->px + S1;
   v->goal_yaw = in->goal_yaw[b];
-  v->agents = (A > 0 && in->agents) ? in->agents + static_cast<size_t>(b) * A * 6 * (S + 1) : nullptr;
+  v->agents = (A > 0 && in->agents) ? in->agents + static_cast<size_t>(b) * A * 6 * S1 : nullptr;
   v->has_people = in->has_people ? (in->has_people[b] != 0) : false;
   if (v->agents == nullptr) v->A = 0;
   const int mi = in->costmap_index ? in->costmap_index[b] : (in->n_costmaps > 0 ? b % in->n_costmaps : 0);
@@ -189,7 +201,8 @@ static void solve_one(const smpc_params* p, const smpc_batch* in, smpc_result* o
   double x[kMaxParams];
   for (int c = 0; c < P; ++c) x[c] = v.u0[c];
   SolveSummary s = solve(v, make_options(p), x);
-  if (out->u) std::memcpy(out->u + static_cast<size_t>(b) * P, x, sizeof(double) * P);
+  const size_t Pw = 2 * static_cast<size_t>(batch_blocks(p, in));  // row width of u (longest horizon of the batch)
+  if (out->u) std::memcpy(out->u + static_cast<size_t>(b) * Pw, x, sizeof(double) * P);
   if (out->cost_initial) out->cost_initial[b] = s.initial_cost;
   if (out->cost_final) out->cost_final[b] = s.final_cost;
   if (out->iterations) out->iterations[b] = s.iterations;
@@ -200,8 +213,8 @@ static void solve_one(const smpc_params* p, const smpc_batch* in, smpc_result* o
     out->n_evals[2 * b + 1] = static_cast<int32_t>(s.evals.n_cost);
   }
   if (out->cmds || out->path)
-    expand_outputs(v, x, out->cmds ? out->cmds + static_cast<size_t>(b) * (v.S + 1) * 2 : nullptr,
-                   out->path ? out->path + static_cast<size_t>(b) * (v.S + 1) * 3 : nullptr);
+    expand_outputs(v, x, out->cmds ? out->cmds + static_cast<size_t>(b) * v.S1 * 2 : nullptr,
+                   out->path ? out->path + static_cast<size_t>(b) * v.S1 * 3 : nullptr);
 }
 
 // Loop the restated Ceres solve over problems [first, first+count) with n_threads std::threads.
@@ -260,6 +273,24 @@ int smpc_oracle_solve_trace(const smpc_params* p, const smpc_batch* in, int b, d
   if (cost_initial) *cost_initial = s.initial_cost;
   if (cost_final) *cost_final = s.final_cost;
   return rows;
+}
+
+// Per-evaluation trace of one solve (tools/flip_log.py): rows of 8 doubles, see EvalRecord in solver.hpp.
+int smpc_oracle_solve_evals(const smpc_params* p, const smpc_batch* in, int b, double* rows, int max_rows) {
+  ProblemView v;
+  if (!make_view(p, in, b, &v)) return -1;
+  const int P = 2 * v.nb;
+  double x[kMaxParams];
+  for (int c = 0; c < P; ++c) x[c] = v.u0[c];
+  SolveSummary s = solve(v, make_options(p), x, true);
+  int n = 0;
+  for (const EvalRecord& e : s.eval_rows) {
+    if (n >= max_rows) break;
+    double* t = rows + 8 * n++;
+    t[0] = e.iteration; t[1] = e.phase; t[2] = e.t; t[3] = e.cost_diff;
+    t[4] = e.cost_plain; t[5] = e.aux; t[6] = e.code; t[7] = e.radius;
+  }
+  return n;
 }
 
 // polynomial.cc restatement, exposed for unit tests: samples rows of (x, value, gradient, value_ok, gradient_ok).

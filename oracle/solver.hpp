@@ -344,7 +344,17 @@ struct IterationRecord {
   bool valid, successful;
 };
 
+// One row per distinct trial point, in evaluation order (what tools/flip_log.py aligns with the GPU solver's trace):
+// phase 1 = iteration zero, 2 = line-search sample, 3 = un-shortened step after a failed line search.
+// code: bit 0 = the sample passed the Armijo test, bit 1 = the point became the candidate, bit 2 = step accepted,
+// bit 3 = the solve terminated on this row, bits 4.. = termination type (when bit 3 is set).
+// aux: rejected line-search sample -> cost - (cost(x) + 1e-4 g0 t) (> 0 = rejected); candidate -> relative decrease.
+struct EvalRecord {
+  double iteration, phase, t, cost_diff, cost_plain, aux, code, radius;
+};
+
 struct SolveSummary {
+  std::vector<EvalRecord> eval_rows;
   double initial_cost = 0, final_cost = 0;
   int termination = T_NO_CONVERGENCE;
   bool usable = false;
@@ -472,7 +482,18 @@ inline SolveSummary solve(const ProblemView& p, const SolveOptions& opt, double*
   bool any_success = false;
   IterationRecord rec{0, x_cost, 0, gmax, 0, 0, radius, 0, true, true};
 
+  // TrustRegionStepEvaluator::current_cost_ (trust_region_step_evaluator.cc): the cost the step quality is measured
+  // from. It starts as the iteration-zero cost and, after an accepted step, becomes that step's CANDIDATE cost — the
+  // cost-only (double) evaluation — not the cost of the differentiated re-evaluation x_cost. The two are the same
+  // number unless a functor evaluates differently under Jets (proxemics with Ceres 2.0.0, critics.hpp).
+  double se_cost = x_cost;
+  if (keep_trace) sum.eval_rows.push_back({0.0, 1.0, 0.0, x_cost, NAN, NAN, 0.0, opt.initial_radius});
   auto finish = [&](int term) {
+    if (keep_trace && !sum.eval_rows.empty()) {
+      EvalRecord& e = sum.eval_rows.back();
+      e.code = static_cast<double>((static_cast<int>(e.code) | 8) + 16 * term);
+      e.radius = radius;
+    }
     sum.termination = term;
     sum.usable = (term <= T_NO_CONVERGENCE);
     sum.iterations = iteration;
@@ -494,6 +515,7 @@ inline SolveSummary solve(const ProblemView& p, const SolveOptions& opt, double*
     }
     sum.final_cost = std::min(sum.final_cost, it_cost);
     rec.radius = radius;
+    if (keep_trace && !sum.eval_rows.empty()) sum.eval_rows.back().radius = radius;
     if (keep_trace) sum.trace.push_back(rec);
     if (iteration >= opt.max_iterations) return finish(T_NO_CONVERGENCE);
     if (it_successful && gmax <= opt.gradient_tol) return finish(T_CONVERGENCE_GRADIENT);
@@ -592,8 +614,13 @@ inline SolveSummary solve(const ProblemView& p, const SolveOptions& opt, double*
       bool ls_success = false;
       ls_eval(1.0, &current);
       for (;;) {
+        const double armijo_margin = current.value - (x_cost + opt.ls_sufficient_decrease * g0 * current.x);
+        if (keep_trace)
+          sum.eval_rows.push_back({static_cast<double>(iteration), 2.0, current.x, current.value_ok ? current.value : NAN, NAN,
+                               armijo_margin, 0.0, radius});
         if (current.value_ok && !(current.value > x_cost + opt.ls_sufficient_decrease * g0 * current.x)) {
           ls_success = true;
+          if (keep_trace) sum.eval_rows.back().code = 1.0;
           break;
         }
         ++ls_iters;
@@ -617,6 +644,7 @@ inline SolveSummary solve(const ProblemView& p, const SolveOptions& opt, double*
         rec.line_search_t = current.x;
       } else {
         rec.line_search_t = -1.0;
+        if (keep_trace) sum.eval_rows.push_back({static_cast<double>(iteration), 3.0, 1.0, NAN, NAN, NAN, 0.0, radius});
       }
     }
 
@@ -625,6 +653,11 @@ inline SolveSummary solve(const ProblemView& p, const SolveOptions& opt, double*
     double cand_cost;
     if (!evaluate(p, blocks, cand.data(), &cand_cost, nullptr, nullptr, nullptr, &sum.evals))
       cand_cost = std::numeric_limits<double>::max();
+    if (keep_trace) {
+      EvalRecord& e = sum.eval_rows.back();
+      e.cost_plain = cand_cost;
+      e.code = static_cast<double>(static_cast<int>(e.code) | 2);
+    }
 
     const bool tol_armed = (opt.ceres_compat < 210) || any_success;
     // ParameterToleranceReached
@@ -648,8 +681,9 @@ inline SolveSummary solve(const ProblemView& p, const SolveOptions& opt, double*
     if (cand_cost >= std::numeric_limits<double>::max())
       rho = std::numeric_limits<double>::lowest();
     else
-      rho = (x_cost - cand_cost) / model_cost_change;
+      rho = (se_cost - cand_cost) / model_cost_change;  // TrustRegionStepEvaluator::StepQuality (monotonic steps)
     rec.relative_decrease = rho;
+    if (keep_trace) sum.eval_rows.back().aux = rho;
     if (rho > opt.min_relative_decrease) {
       // HandleSuccessfulStep
       x = cand;
@@ -663,6 +697,12 @@ inline SolveSummary solve(const ProblemView& p, const SolveOptions& opt, double*
       any_success = true;
       it_successful = true;
       it_cost = x_cost;
+      se_cost = cand_cost;  // step_evaluator_->StepAccepted(candidate_cost_, model_cost_change_)
+      if (keep_trace) {
+        EvalRecord& e = sum.eval_rows.back();
+        e.cost_diff = x_cost;
+        e.code = static_cast<double>(static_cast<int>(e.code) | 4);
+      }
       radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rho - 1.0, 3));
       radius = std::min(opt.max_radius, radius);
       decrease_factor = 2.0;

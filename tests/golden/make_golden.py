@@ -23,6 +23,15 @@ CASES = {
     "corridor_x8": lambda: sc.corridor(B=8),
     "crowd_x8_A3": lambda: sc.crowd(B=8, A=3, config_id=6, n_maps=4),
     "crowd_x4_A20": lambda: sc.crowd(B=4, A=20, n_maps=2),
+    # Ceres >= 2.1 behaviour (std::numeric_limits<Jet> specialised: ProxemicsCost has its true value and gradient in
+    # differentiated evaluations; tolerance tests armed after the first successful step)
+    "single_readme_A3_ceres220": lambda: sc.single("readme", n_people=3, ceres_compat=220),
+    "crowd_x8_A3_ceres220": lambda: sc.crowd(B=8, A=3, config_id=6, n_maps=4, ceres_compat=220),
+    "crowd_x4_A20_ceres220": lambda: sc.crowd(B=4, A=20, n_maps=2, ceres_compat=220),
+    # per-problem horizons (n_steps_each): fewer steps, shorter control horizon, fewer parameter blocks per problem
+    "mixed_horizon_crowd_x8_A3": lambda: sc.with_horizons(sc.crowd(B=8, A=3, config_id=6, n_maps=4),
+                                                          [28, 20, 13, 7, 5, 18, 2, 1]),
+    "mixed_horizon_corridor_x8": lambda: sc.with_horizons(sc.corridor(B=8), [28, 27, 12, 6, 3, 19, 11, 24]),
 }
 OUT_KEYS = ("u", "cmds", "path", "cost_initial", "cost_final", "iterations", "termination", "usable")
 

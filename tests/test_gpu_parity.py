@@ -30,6 +30,10 @@ def make_opt():
 def _eval_cases():
     return [
         ("readme_A3", lambda: sc.single("readme")),
+        ("readme_A3_ceres220", lambda: sc.single("readme", ceres_compat=220)),
+        ("crowd64_A20_ceres220", lambda: sc.crowd(B=64, A=20, ceres_compat=220)),
+        ("mixed_horizons", lambda: sc.with_horizons(sc.crowd(B=32, A=3, config_id=6),
+                                                    [28, 20, 13, 7, 5, 18, 2, 1] * 4)),
         ("params_yaml_A3", lambda: sc.single("params_yaml")),
         ("soc_work_A5", lambda: sc.single("soc_work_obst", n_people=5)),
         ("soc_work_padded", lambda: sc.single("soc_work_obst", n_people=1)),
@@ -57,6 +61,8 @@ def test_eval_matches_oracle(oracle, make_opt, name, mk):
         if not e["ok"]:
             continue
         assert got["cost"][b] == pytest.approx(e["cost"], rel=1e-11)
+        plain = oracle.evaluate(batch, b, x[b], want_jac=False)  # the cost-only evaluation of the same point
+        assert got["cost_plain"][b] == pytest.approx(plain["cost"], rel=1e-11)
         g_ref = e["grad"]
         H_ref = e["jac"].T @ e["jac"]
         assert np.abs(got["grad"][b] - g_ref).max() <= 1e-9 * max(1.0, np.abs(g_ref).max())
@@ -109,13 +115,85 @@ def test_crowd_batch_matches_oracle(oracle, make_opt):
 
 
 def test_failure_when_all_agents_invalid(oracle, make_opt):
-    """people list non-empty but every projected agent invalid -> Ceres FAILURE -> not usable."""
-    batch = sc.single("soc_work_obst", n_people=0)
+    """SURVEY Q7 (Ceres >= 2.1): people list non-empty but every projected agent invalid -> the proxemics Jacobian is
+    NaN -> Ceres FAILURE -> not usable. Under Ceres 2.0.0 (ceres_compat 200) the Jet minimum distance starts at 0, the
+    differentiated evaluation is finite and the solve runs."""
+    batch = sc.single("soc_work_obst", n_people=0, ceres_compat=220)
     batch.arrays["has_people"][:] = 1
     opt = make_opt(batch.params)
     got = opt.solve_batch(batch)
     assert got["usable"][0] == 0 and got["termination"][0] == 6
     assert np.array_equal(got["u"][0], batch.arrays["u0"][0])
+    batch = sc.single("soc_work_obst", n_people=0)
+    batch.arrays["has_people"][:] = 1
+    opt = make_opt(batch.params)
+    r = _compare_solves(oracle, opt, batch)
+    assert r["got"]["usable"][0] == 1 and r["ok"].all() and r["same_term"].all() and r["same_iters"].all()
+
+
+@pytest.mark.parametrize("group", [4, 8, 16, 32])
+def test_mixed_horizons_in_one_batch(oracle, make_opt, group):
+    """include/smpc.h n_steps_each: every problem of a batch has its own S_b (and with it ch, bl, block count and
+    bounded blocks, reference src/optimizer.cpp:248-249,373). Checked against the oracle solving each problem with its
+    own sizes; rows beyond a problem's horizon / blocks are not results (the host entry returns them as zeros)."""
+    rng = np.random.default_rng(17)
+    B = 96
+    base = sc.crowd(B=B, A=3, config_id=6, n_valid=2)
+    n_each = rng.integers(1, base.n_steps + 1, size=B)
+    n_each[:4] = [base.n_steps, 1, 2, 7]
+    batch = sc.with_horizons(base, n_each)
+    opt = make_opt(batch.params)
+    opt.set_group(group)
+    try:
+        nb = batch.n_blocks
+        shapes = sc.abi.result_shapes(B, batch.n_steps, nb)
+        out = {k: np.full(shapes[k][0], -7, dtype=shapes[k][1]) for k in ("u", "cmds", "path", "cost_initial",
+                                                                          "cost_final", "iterations", "termination",
+                                                                          "usable", "n_evals")}
+        got = opt.solve_batch(batch, out=out)
+        ref = oracle.solve_batch(batch, n_threads=8)
+        ok = 0
+        for b in range(B):
+            S_b = int(n_each[b])
+            ch, bl, nb_b, _ = sc.abi.problem_dims(batch.params.control_horizon, batch.params.parameter_block_length, S_b)
+            assert np.all(got["u"][b, nb_b:] == 0) and np.all(got["cmds"][b, S_b + 1:] == 0)
+            assert np.all(got["path"][b, S_b + 1:] == 0)
+            du = np.abs(got["u"][b, :nb_b] - ref["u"][b, :nb_b]).max()
+            dc = abs(got["cost_final"][b] - ref["cost_final"][b]) / max(abs(ref["cost_final"][b]), 1e-300)
+            good = (got["usable"][b] == ref["usable"][b]) and du <= U_ATOL and dc <= COST_RTOL
+            if good:
+                assert np.abs(got["cmds"][b, :S_b + 1] - ref["cmds"][b, :S_b + 1]).max() <= U_ATOL
+                assert np.abs(got["path"][b, :S_b + 1, :2] - ref["path"][b, :S_b + 1, :2]).max() <= U_ATOL
+            ok += good
+        assert ok >= 0.97 * B, (group, ok)
+    finally:
+        opt.set_group(0)
+
+
+def test_solver_trace_matches_oracle_trace(oracle, make_opt):
+    """smpc_result.trace: one row per trial point. On a single solve the GPU's sequence of (phase, step size, decision)
+    equals the oracle's, the costs agree to round-off and the evaluation counters add up."""
+    import ctypes as C
+    batch = sc.single("soc_work_obst")
+    opt = make_opt(batch.params)
+    got = opt.solve_batch(batch, trace_rows=256)
+    n = int(got["n_evals"][0].sum())
+    tr = got["trace"][0, :n]
+    assert np.all(np.isnan(got["trace"][0, n:, 0]))
+    rows = np.zeros((256, 8))
+    st = batch.struct()
+    oracle.lib.smpc_oracle_solve_evals.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    oracle.lib.smpc_oracle_solve_evals.restype = C.c_int
+    m = oracle.lib.smpc_oracle_solve_evals(C.byref(batch.params), C.byref(st), 0, rows.ctypes.data, 256)
+    ref = rows[:m]
+    assert m == n
+    assert np.array_equal(tr[:, 1], ref[:, 1]) and np.array_equal(tr[:, 6], ref[:, 6])      # phase, decision code
+    assert np.allclose(tr[:, 2], ref[:, 2], rtol=1e-6)                                        # step sizes
+    both = ~np.isnan(ref[:, 3])
+    assert np.allclose(tr[both, 3], ref[both, 3], rtol=1e-9)                                  # differentiated costs
+    cand = ~np.isnan(ref[:, 4])
+    assert np.allclose(tr[cand, 4], ref[cand, 4], rtol=1e-9)                                  # candidate (plain) costs
+    assert int(got["n_evals"][0, 1]) == int(((tr[:, 1] == 2) & (tr[:, 6] == 0)).sum())
 
 
 def test_empty_batch_and_bad_arguments(make_opt):

@@ -49,7 +49,9 @@ def test_residual_order_per_step(oracle):
 
 @pytest.mark.parametrize("name", ["readme", "soc_work_obst", "params_yaml"])
 def test_jet_jacobian_matches_central_differences(oracle, name):
-    b = sc.single(name, seed_offset=3)
+    # Ceres >= 2.1 semantics: every functor differentiates to the Jacobian of its own value (under Ceres 2.0.0 the
+    # proxemics rows do not: test_proxemics_under_ceres_200_jets below)
+    b = sc.single(name, seed_offset=3, ceres_compat=220)
     rng = np.random.default_rng(5)
     P = 2 * b.n_blocks
     for trial in range(3):
@@ -95,11 +97,45 @@ def test_velocity_only_known_answer(oracle):
     assert out["cost_final"][0] < 1e-10
 
 
+def test_proxemics_under_ceres_200_jets(oracle):
+    """proxemics_cost_function.hpp:128 initialises min_distance with std::numeric_limits<T>::max(). Ceres 2.0.0 has no
+    numeric_limits specialisation for Jets (added in 2.1), so under T = Jet the primary template returns Jet() = 0:
+    every DIFFERENTIATED evaluation sees the constant residual w * 3 * exp(-0) with a zero Jacobian row, while the
+    cost-only evaluation sees the true minimum distance. ceres_compat = 200 (default) models exactly that split."""
+    b = sc.single("soc_work_obst", n_people=3)
+    assert b.params.ceres_compat == 200
+    x = b.arrays["u0"][0].ravel()
+    kinds, _ = oracle.layout(b)
+    prox = kinds == K_PROX
+    plain = oracle.evaluate(b, 0, x, want_jac=False)
+    diff = oracle.evaluate(b, 0, x, want_jac=True)
+    assert plain["ok"] and diff["ok"]
+    w = b.params.proxemics_w
+    assert np.all(diff["residuals"][prox] == 3.0 * w)
+    assert np.all(diff["jac"][prox] == 0.0)
+    assert np.all(plain["residuals"][prox] < 3.0 * w) and np.all(plain["residuals"][prox] >= 0.0)
+    # every other residual is the same number in both evaluations up to round-off (Jet division multiplies by the
+    # reciprocal, ceres/jet.h, where the double evaluation divides)
+    assert np.allclose(plain["residuals"][~prox], diff["residuals"][~prox], rtol=1e-13, atol=0)
+    # Ceres >= 2.1: both evaluations agree on the proxemics rows too
+    b2 = sc.single("soc_work_obst", n_people=3, ceres_compat=220)
+    p2 = oracle.evaluate(b2, 0, x, want_jac=False)
+    d2 = oracle.evaluate(b2, 0, x, want_jac=True)
+    assert np.allclose(p2["residuals"], d2["residuals"], rtol=1e-13, atol=0)
+    assert np.array_equal(p2["residuals"], plain["residuals"])
+    # no valid agent: Jet(0) stays the minimum, the evaluation is finite and the solve runs (no FAILURE as under >= 2.1)
+    b3 = sc.single("soc_work_obst", n_people=0)
+    b3.arrays["has_people"][:] = 1
+    d3 = oracle.evaluate(b3, 0, x, want_jac=True)
+    assert d3["ok"] and np.all(d3["residuals"][prox] == 3.0 * w)
+    assert oracle.solve_batch(b3)["usable"][0] == 1
+
+
 def test_proxemics_and_social_phantom_quirks(oracle):
     """with every agent column invalid the social residual is w*(1e-6 + sum_k |F(phantom_k <- robot)|^2)
-    and the proxemics VALUE is exp(-DBL_MAX/0.25) = 0 (its jet derivative is NaN, so a differentiated evaluation
-    fails, which makes Ceres terminate with FAILURE)."""
-    b = sc.single("soc_work_obst", n_people=0)
+    and the proxemics VALUE is exp(-DBL_MAX/0.25) = 0 (under Ceres >= 2.1 its jet derivative is NaN, so a
+    differentiated evaluation fails, which makes Ceres terminate with FAILURE)."""
+    b = sc.single("soc_work_obst", n_people=0, ceres_compat=220)
     b.arrays["has_people"][:] = 1
     x = b.arrays["u0"][0].ravel()
     e = oracle.evaluate(b, 0, x, want_jac=False)
