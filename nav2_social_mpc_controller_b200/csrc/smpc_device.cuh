@@ -1411,7 +1411,7 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
       bool finished = false;     // the solve of this problem has terminated
       bool next_sample = false;  // another trial point has been set up in `cand`
       const int row = st.n_eval;  // trace row of this evaluation
-      const double tr_iter = (double)st.iteration, tr_phase = (double)st.phase, tr_t = st.t;
+      const double tr_iter = (double)st.iteration, tr_phase = (double)st.phase, tr_t = (st.phase == kInit) ? 0.0 : st.t;
       double tr_aux = NAN, tr_code = 0.0;
       ++st.n_eval;
       if (fl & kNoHessian) ++st.n_light;

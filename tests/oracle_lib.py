@@ -66,8 +66,10 @@ class Oracle:
     def evaluate(self, batch, b, x, want_jac=True):
         """Returns dict(ok, cost, residuals[m], grad[P], jac[m][P])."""
         m = self.num_residuals(batch, b)
-        P = 2 * batch.n_blocks
-        x = np.ascontiguousarray(x, dtype=np.float64).reshape(P)
+        each = batch.arrays.get("n_steps_each")
+        S_b = batch.n_steps if each is None else int(each[b])  # problem b's own horizon -> its own block count
+        P = 2 * abi.problem_dims(batch.params.control_horizon, batch.params.parameter_block_length, S_b)[2]
+        x = np.ascontiguousarray(np.asarray(x, dtype=np.float64).ravel()[:P])
         cost = C.c_double(0.0)
         res = np.zeros(m)
         grad = np.zeros(P) if want_jac else None

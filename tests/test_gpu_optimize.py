@@ -109,11 +109,18 @@ def test_optimize_failure_modes(opt_for):
     # path with fewer than 2 poses -> false (reference :158-162)
     ok, *_ = opt.optimize(poses[:1], cmds[:1], people, speed, p.time_step, costmap, (0.0, 0.0), 0.05, od)
     assert not ok
-    # 100x100 obstacle grid "is NOT valid": every person is dropped -> all projected agents invalid -> Ceres
-    # FAILURE on the NaN proxemics Jacobian -> optimize returns false
+    # 100x100 obstacle grid "is NOT valid": every person is dropped -> all projected agents invalid.
+    # Ceres >= 2.1: FAILURE on the NaN proxemics Jacobian -> optimize returns false. Ceres 2.0.0
+    # (ceres_compat 200, the default): the Jet minimum distance starts at 0, the evaluation is finite, the solve runs.
     od100 = dict(od, width=100, height=100, distances=np.zeros(10000, np.float32), indexes=np.zeros(10000, np.uint32))
     ok, path, new_cmds, proj, info = opt.optimize(poses, cmds, people, speed, p.time_step, costmap, (0.0, 0.0), 0.05,
                                                   od100)
+    assert ok and info["termination"] <= 4
+    assert np.all(proj[1:, :, 3] == -1.0)
+    p220 = sc.make_params("soc_work_obst", ceres_compat=220)
+    opt220 = opt_for(p220)
+    ok, path, new_cmds, proj, info = opt220.optimize(poses, cmds, people, speed, p.time_step, costmap, (0.0, 0.0), 0.05,
+                                                     od100)
     assert not ok and info["termination"] == 6
     assert np.all(proj[1:, :, 3] == -1.0)
     # empty obstacle grid -> std::runtime_error in the reference -> call error here

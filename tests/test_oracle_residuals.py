@@ -183,3 +183,27 @@ def test_bicubic_interpolates_grid_nodes_and_clamps(oracle):
     f, dr, dc = oracle.bicubic(cm, r, c)
     assert dr == pytest.approx((oracle.bicubic(cm, r + h, c)[0] - oracle.bicubic(cm, r - h, c)[0]) / (2 * h), rel=1e-6)
     assert dc == pytest.approx((oracle.bicubic(cm, r, c + h)[0] - oracle.bicubic(cm, r, c - h)[0]) / (2 * h), rel=1e-6)
+
+
+@pytest.mark.parametrize("name,n_people", [("readme", 3), ("soc_work_obst", 2), ("obst_only", 0)])
+def test_residuals_and_jet_jacobian_against_50_digit_mpmath(oracle, name, n_people):
+    """tests/critics_mpmath.py restates every functor from the formulas of SURVEY Appendix D in 50-digit
+    arithmetic (Jacobian by central differences with a 1e-20 step). The oracle's double residuals and its Jet<4>
+    Jacobian must agree with it to double round-off — for the differentiable semantics, i.e. Ceres >= 2.1
+    (under Ceres 2.0.0 the proxemics rows of a differentiated evaluation are the constant 3 w: checked separately)."""
+    from tests import critics_mpmath as cm
+    b = sc.single(name, n_people=n_people, seed_offset=2, ceres_compat=220) if name != "obst_only" else \
+        sc.corridor(B=1, ceres_compat=220)
+    rng = np.random.default_rng(21)
+    P = 2 * b.n_blocks
+    x = b.arrays["u0"][0].ravel() + rng.normal(0, 0.04, P)
+    x[0::2] = np.clip(x[0::2], 0.05, 0.55)
+    e = oracle.evaluate(b, 0, x)
+    assert e["ok"]
+    prob = cm.problem_from_batch(b, 0)
+    r_mp = np.array([float(v) for v in cm.residuals(prob, x)])
+    assert r_mp.size == e["residuals"].size
+    assert np.allclose(e["residuals"], r_mp, rtol=1e-12, atol=1e-12 * max(1.0, np.abs(r_mp).max()))
+    J_mp = np.array([[float(v) for v in row] for row in cm.jacobian(prob, x)])
+    scale = max(1.0, np.abs(J_mp).max())
+    assert np.abs(e["jac"] - J_mp).max() <= 1e-10 * scale, np.abs(e["jac"] - J_mp).max() / scale

@@ -118,3 +118,66 @@ def test_post_solve_expansion(oracle):
         th = th + cmds[i, 1] * b.dt
         assert path[i, 0] == pytest.approx(x, abs=1e-12) and path[i, 1] == pytest.approx(y, abs=1e-12)
         assert np.cos(path[i, 2] - th) == pytest.approx(1.0, abs=1e-12)
+
+
+def _numpy_trlm_on(oracle, batch, b):
+    """Run tests/trlm_numpy.py (the second, numpy TR-LM restatement) on problem b with the oracle's functor evaluation
+    as a black box."""
+    from tests import trlm_numpy as tn
+    each = batch.arrays.get("n_steps_each")
+    S_b = batch.n_steps if each is None else int(each[b])
+    ch, bl, nb, nbd = sc.abi.problem_dims(batch.params.control_horizon, batch.params.parameter_block_length, S_b)
+    P = 2 * nb
+    lo, hi = np.full(P, -np.inf), np.full(P, np.inf)
+    lo[0:2 * nbd:2], hi[0:2 * nbd:2] = 0.0, 0.6
+    lo[1:2 * nbd:2], hi[1:2 * nbd:2] = -1.4, 1.4
+
+    def evaluate(x, differentiated):
+        e = oracle.evaluate(batch, b, x, want_jac=differentiated)
+        return e if e["ok"] else None
+
+    p = batch.params
+    opt = tn.Options(max_iterations=p.max_iterations, function_tolerance=p.fn_tol, gradient_tolerance=p.gradient_tol,
+                     parameter_tolerance=p.param_tol, ceres_compat=p.ceres_compat or 200)
+    return tn.solve(evaluate, batch.arrays["u0"][b].ravel()[:P], lo, hi, opt), P
+
+
+def _oracle_eval_rows(oracle, batch, b):
+    import ctypes as C
+    rows = np.zeros((512, 8))
+    st = batch.struct()
+    oracle.lib.smpc_oracle_solve_evals.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    oracle.lib.smpc_oracle_solve_evals.restype = C.c_int
+    n = oracle.lib.smpc_oracle_solve_evals(C.byref(batch.params), C.byref(st), b, rows.ctypes.data, 512)
+    return rows[:n]
+
+
+def test_independent_numpy_trlm_reproduces_the_oracle_trace_on_the_golden_cases(oracle):
+    """tests/trlm_numpy.py is a second TR-LM restatement with a different structure (numpy QR on
+    the augmented system instead of Cholesky on the normal equations, Vandermonde solve + numpy.roots = companion
+    eigenvalues for the line-search polynomial, one class per Ceres component). Fed with the same functor evaluations
+    it must walk the same sequence of trial points as oracle/solver.hpp — same phases, same step sizes, same costs,
+    same termination, same iteration count, same solution — on every golden problem (both Ceres versions, mixed
+    horizons included)."""
+    from tests import golden_lib
+    n_checked = 0
+    for name, (batch, gold, _) in sorted(golden_lib.load().items()):
+        for b in range(min(batch.n_problems, 4)):
+            res, P = _numpy_trlm_on(oracle, batch, b)
+            ref = _oracle_eval_rows(oracle, batch, b)
+            assert res["termination"] == gold["termination"][b], (name, b)
+            assert res["iterations"] == gold["iterations"][b], (name, b)
+            assert bool(res["usable"]) == bool(gold["usable"][b])
+            assert np.abs(res["x"] - gold["u"][b].ravel()[:P]).max() <= 1e-7, (name, b)  # QR vs Cholesky round-off
+            assert res["cost_final"] == pytest.approx(gold["cost_final"][b], rel=1e-10)
+            rows = res["rows"]
+            assert len(rows) == len(ref), (name, b, len(rows), len(ref))
+            for (it, phase, t, c_diff, c_plain), r in zip(rows, ref):
+                assert it == r[0] and phase == r[1], (name, b)
+                assert t == pytest.approx(r[2], rel=1e-5, abs=1e-12), (name, b, it)
+                if c_diff is not None and not np.isnan(r[3]):
+                    assert c_diff == pytest.approx(r[3], rel=1e-8)
+                if c_plain is not None and not np.isnan(r[4]):
+                    assert c_plain == pytest.approx(r[4], rel=1e-8)
+            n_checked += 1
+    assert n_checked >= 20
