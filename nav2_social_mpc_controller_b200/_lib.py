@@ -10,7 +10,8 @@ import os
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsmpc.so")
+# SMPC_LIB_PATH: load another build of the same library (csrc `make DEV=1` experiment builds); still no fallback
+LIB_PATH = os.environ.get("SMPC_LIB_PATH") or os.path.join(_HERE, "libsmpc.so")
 _lib = None
 
 

@@ -20,6 +20,7 @@
 
 #include <cfloat>
 #include <cmath>
+#include <type_traits>
 
 namespace smpc {
 
@@ -60,6 +61,9 @@ struct DevBatch {
   int* park_ring;      // [B] problem ids in parking order, -1 = not published yet
   int* park_counters;  // [0] = published slots reserved (tail), [1] = slots claimed by resumers (head)
   int park_quantum;
+  // 1 = the warps of a CTA meet at a CTA barrier before every evaluation (they then walk the large evaluation code
+  // together and share its instruction-cache lines); 0 = warps run free and leave on their own
+  int cta_sync;
 };
 
 struct DevResult {
@@ -276,6 +280,18 @@ __device__ __forceinline__ double agent_angle_target(const DevBatch& bt, const P
   return pb.yaw0 + (M_PI / 6.0);
 }
 #define SMPC_UNROLL _Pragma("unroll")
+// The log2(G) levels of the Kogge-Stone scans stay a loop: unrolled, the shuffle ladder of the 2 + 4 NB scans is ~16 kB of
+// SASS per evaluation, and the evaluation is instruction-fetch bound (its code does not fit the 32 kB L1.5 I-cache)
+// (measured: -16 kB; +3..5 % with people). Small groups have 2 - 3 levels and 7 chunks per evaluation: there the loop
+// overhead costs more than the code (-25 % on 65536 people-free problems at G = 4), so they keep the ladder unrolled.
+template <int G, class F>
+__device__ __forceinline__ void scan_levels(F level) {
+  if (G <= 8) {
+    SMPC_UNROLL for (int d = 1; d < G; d <<= 1) level(d);
+  } else {
+    _Pragma("unroll 1") for (int d = 1; d < G; d <<= 1) level(d);
+  }
+}
 
 // ---------------------------------------------------------------------------------------------------
 // Work mapping: a GROUP of G lanes (G = 4, 8, 16 or 32) solves one problem, so a warp holds 32/G problems.
@@ -429,14 +445,14 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
 
     // ---- positions: two scans -----------------------------------------------------------------------------
     double sx = aj, sy = bjv;
-    SMPC_UNROLL for (int d = 1; d < G; d <<= 1) {
+    scan_levels<G>([&](int d) {
       const double tx = __shfl_up_sync(kFullMask, sx, d, G);
       const double ty = __shfl_up_sync(kFullMask, sy, d, G);
       if (gl >= d) {
         sx += tx;
         sy += ty;
       }
-    }
+    });
     const double X = (first ? pb.x0 : carry[0]) + sx;
     const double Y = (first ? pb.y0 : carry[1]) + sy;
 
@@ -552,12 +568,12 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
       sd[4 * b + 2] = -bjv * tau[b];          // dX/dw_b
       sd[4 * b + 3] = aj * tau[b];            // dY/dw_b
     }
-    SMPC_UNROLL for (int d = 1; d < G; d <<= 1) {
+    scan_levels<G>([&](int d) {
       SMPC_UNROLL for (int e = 0; e < 4 * NB; ++e) {
         const double t = __shfl_up_sync(kFullMask, sd[e], d, G);
         if (gl >= d) sd[e] += t;
       }
-    }
+    });
     if (!first) {
       SMPC_UNROLL for (int e = 0; e < 4 * NB; ++e) sd[e] += carry[4 + e];
     }
@@ -645,21 +661,26 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
       }
 
       // --- cost and g = D^T q into column `lane` of the warp's scratch red[NE][33]. First chunk: plain stores (no
-      //     zero fill, no read-modify-write); later chunks accumulate. Column of v_b: (dX, dY, 0, [b == bj]);
-      //     of w_b: (dX, dY, dTheta, 0). ---------------------------------------------------------------------
+      //     zero fill, no read-modify-write); later chunks accumulate (`first` is warp-uniform, so the two store
+      //     flavours are a branch, not a select per entry). Column of v_b: (dX, dY, 0, [b == bj]); of w_b:
+      //     (dX, dY, dTheta, 0). -----------------------------------------------------------------------------
       {
         const double c_diff = cost + 0.5 * rp * rp, c_plain = cost + cprox_plain;
         double* r0 = red + lane;
-        r0[0 * kRedStride] = (first ? 0.0 : r0[0 * kRedStride]) + c_diff;
-        r0[1 * kRedStride] = (first ? 0.0 : r0[1 * kRedStride]) + c_plain;
-        SMPC_UNROLL for (int ba = 0; ba < NB; ++ba) {
-          const double la = (ba == bj) ? 1.0 : 0.0;
-          const double twa = tau[ba] + ((ba == bj) ? dt : 0.0);  // d Theta_j / d w_ba (heading after step j)
-          double* gv = r0 + L::g(2 * ba) * kRedStride;
-          double* gw = r0 + L::g(2 * ba + 1) * kRedStride;
-          *gv = (first ? 0.0 : *gv) + (qX * sd[4 * ba + 0] + qY * sd[4 * ba + 1] + qL * la);
-          *gw = (first ? 0.0 : *gw) + (qX * sd[4 * ba + 2] + qY * sd[4 * ba + 3] + qT * twa);
-        }
+        auto put_g = [&](auto is_first) {
+          constexpr bool kFirst = decltype(is_first)::value;
+          r0[0 * kRedStride] = (kFirst ? 0.0 : r0[0 * kRedStride]) + c_diff;
+          r0[1 * kRedStride] = (kFirst ? 0.0 : r0[1 * kRedStride]) + c_plain;
+          SMPC_UNROLL for (int ba = 0; ba < NB; ++ba) {
+            const double la = (ba == bj) ? 1.0 : 0.0;
+            const double twa = tau[ba] + ((ba == bj) ? dt : 0.0);  // d Theta_j / d w_ba (heading after step j)
+            double* gv = r0 + L::g(2 * ba) * kRedStride;
+            double* gw = r0 + L::g(2 * ba + 1) * kRedStride;
+            *gv = (kFirst ? 0.0 : *gv) + (qX * sd[4 * ba + 0] + qY * sd[4 * ba + 1] + qL * la);
+            *gw = (kFirst ? 0.0 : *gw) + (qX * sd[4 * ba + 2] + qY * sd[4 * ba + 3] + qT * twa);
+          }
+        };
+        if (first) put_g(std::true_type{}); else put_g(std::false_type{});
       }
     } else if (first) {  // a lane without a step in the first chunk still owns a column of the column sums
       SMPC_UNROLL for (int e = 0; e < L::NG; ++e) red[e * kRedStride + lane] = 0.0;
@@ -714,42 +735,46 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
     if (need_h) {
       if (act) {
         double* r0 = red + lane;
-        auto acc = [&](int e, double v) {
-          double* p = r0 + e * kRedStride;
-          *p = (first ? 0.0 : *p) + v;
-        };
-        SMPC_UNROLL for (int ba = 0; ba < NB; ++ba) {
-          const double la = (ba == bj) ? 1.0 : 0.0;
-          const double twa = tau[ba] + ((ba == bj) ? dt : 0.0);
-          {  // column a = 2 ba (v_ba)
-            const double xv = sd[4 * ba + 0], yv = sd[4 * ba + 1];
-            const double t0 = mXX * xv + mXY * yv + mXL * la;
-            const double t1 = mXY * xv + mYY * yv + mYL * la;
-            const double t2 = mXT * xv + mYT * yv + mTL * la;
-            const double t3 = mXL * xv + mYL * yv + mLL * la;
-            SMPC_UNROLL for (int bb = 0; bb <= ba; ++bb) {
-              const double lb = (bb == bj) ? 1.0 : 0.0;
-              acc(L::h(2 * ba, 2 * bb), sd[4 * bb + 0] * t0 + sd[4 * bb + 1] * t1 + lb * t3);
-              if (bb < ba) {
+        auto put_h = [&](auto is_first) {
+          constexpr bool kFirst = decltype(is_first)::value;
+          auto acc = [&](int e, double v) {
+            double* p = r0 + e * kRedStride;
+            *p = (kFirst ? 0.0 : *p) + v;
+          };
+          SMPC_UNROLL for (int ba = 0; ba < NB; ++ba) {
+            const double la = (ba == bj) ? 1.0 : 0.0;
+            const double twa = tau[ba] + ((ba == bj) ? dt : 0.0);
+            {  // column a = 2 ba (v_ba)
+              const double xv = sd[4 * ba + 0], yv = sd[4 * ba + 1];
+              const double t0 = mXX * xv + mXY * yv + mXL * la;
+              const double t1 = mXY * xv + mYY * yv + mYL * la;
+              const double t2 = mXT * xv + mYT * yv + mTL * la;
+              const double t3 = mXL * xv + mYL * yv + mLL * la;
+              SMPC_UNROLL for (int bb = 0; bb <= ba; ++bb) {
+                const double lb = (bb == bj) ? 1.0 : 0.0;
+                acc(L::h(2 * ba, 2 * bb), sd[4 * bb + 0] * t0 + sd[4 * bb + 1] * t1 + lb * t3);
+                if (bb < ba) {
+                  const double twb = tau[bb] + ((bb == bj) ? dt : 0.0);
+                  acc(L::h(2 * ba, 2 * bb + 1), sd[4 * bb + 2] * t0 + sd[4 * bb + 3] * t1 + twb * t2);
+                }
+              }
+            }
+            {  // column a = 2 ba + 1 (w_ba)
+              const double xw = sd[4 * ba + 2], yw = sd[4 * ba + 3];
+              const double t0 = mXX * xw + mXY * yw + mXT * twa;
+              const double t1 = mXY * xw + mYY * yw + mYT * twa;
+              const double t2 = mXT * xw + mYT * yw + mTT * twa;
+              const double t3 = mXL * xw + mYL * yw + mTL * twa;
+              SMPC_UNROLL for (int bb = 0; bb <= ba; ++bb) {
+                const double lb = (bb == bj) ? 1.0 : 0.0;
                 const double twb = tau[bb] + ((bb == bj) ? dt : 0.0);
-                acc(L::h(2 * ba, 2 * bb + 1), sd[4 * bb + 2] * t0 + sd[4 * bb + 3] * t1 + twb * t2);
+                acc(L::h(2 * ba + 1, 2 * bb), sd[4 * bb + 0] * t0 + sd[4 * bb + 1] * t1 + lb * t3);
+                acc(L::h(2 * ba + 1, 2 * bb + 1), sd[4 * bb + 2] * t0 + sd[4 * bb + 3] * t1 + twb * t2);
               }
             }
           }
-          {  // column a = 2 ba + 1 (w_ba)
-            const double xw = sd[4 * ba + 2], yw = sd[4 * ba + 3];
-            const double t0 = mXX * xw + mXY * yw + mXT * twa;
-            const double t1 = mXY * xw + mYY * yw + mYT * twa;
-            const double t2 = mXT * xw + mYT * yw + mTT * twa;
-            const double t3 = mXL * xw + mYL * yw + mTL * twa;
-            SMPC_UNROLL for (int bb = 0; bb <= ba; ++bb) {
-              const double lb = (bb == bj) ? 1.0 : 0.0;
-              const double twb = tau[bb] + ((bb == bj) ? dt : 0.0);
-              acc(L::h(2 * ba + 1, 2 * bb), sd[4 * bb + 0] * t0 + sd[4 * bb + 1] * t1 + lb * t3);
-              acc(L::h(2 * ba + 1, 2 * bb + 1), sd[4 * bb + 2] * t0 + sd[4 * bb + 3] * t1 + twb * t2);
-            }
-          }
-        }
+        };
+        if (first) put_h(std::true_type{}); else put_h(std::false_type{});
       } else if (first) {
         SMPC_UNROLL for (int e = L::NG; e < L::NE; ++e) red[e * kRedStride + lane] = 0.0;
       }
@@ -944,6 +969,8 @@ __device__ __forceinline__ int quartic_real_parts(const double (&c)[5], double x
   const double shift = 0.25 * a;
   const double margin = 0.05 * (xhi - xlo) + 1e-3 * fabs(xhi);
   const double co[4] = {a, b, cc, d};
+  // (inlined four times on purpose: the four Newton chains are independent and interleave in the leader lane; the
+  // phase logic is on the critical path of the CTA's lock-step round, so its LATENCY matters, not its instruction count)
   auto polish = [&](double xr, double xi, double& out_re) -> bool {
     const bool near = (xr >= xlo - margin) && (xr <= xhi + margin);
     double res = 0.0;
@@ -1390,8 +1417,12 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
 #ifndef SMPC_SYNC_EVERY
 #define SMPC_SYNC_EVERY 1
 #endif
-    if ((loop_count++ % SMPC_SYNC_EVERY) == 0) {
-      if (__syncthreads_and((gs->flags & kExhausted) != 0)) break;
+    if (bt.cta_sync) {
+      if ((loop_count++ % SMPC_SYNC_EVERY) == 0) {
+        if (__syncthreads_and((gs->flags & kExhausted) != 0)) break;
+      }
+    } else if (__all_sync(kFullMask, (gs->flags & kExhausted) != 0)) {
+      break;
     }
 
     const bool live = (gs->flags & kLive) != 0;
@@ -1493,10 +1524,12 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
         step_norm = sqrt(step_norm);
         const double cost_change = st.x_cost - cand_cost;
         if (tol_armed && step_norm <= prm.param_tol * (st.x_norm + prm.param_tol)) {
+          tr_aux = step_norm / (prm.param_tol * (st.x_norm + prm.param_tol)) - 1.0;
           --st.iteration;
           st.term = kConvParameter;
           finished = true;
         } else if (tol_armed && fabs(cost_change) <= prm.fn_tol * st.x_cost) {
+          tr_aux = fabs(cost_change) - prm.fn_tol * st.x_cost;
           --st.iteration;
           st.term = kConvFunction;
           finished = true;

@@ -90,6 +90,7 @@ struct smpc_handle {
   int stream_maps = 1;   // 1 = stream per-problem costmaps under the solve (pinned host buffers only); SMPC_STREAM_MAPS=0 disables
   unsigned* arrival = nullptr;       // device: {problems whose costmap has arrived, kernel gave up waiting}
   unsigned* arrival_host = nullptr;  // pinned: the values the copy stream writes to arrival[0], one per map chunk
+  int cta_sync = -1;     // CTA barrier per evaluation: -1 = default (on), SMPC_CTA_SYNC env overrides (0 / 1)
   int forced_chunks = 0; // 0 = pick the chunk count of the host-buffer pipeline from the batch; SMPC_CHUNKS env overrides (1..8)
   int forced_group = 0;  // 0 = pick lanes-per-problem from the batch size; SMPC_GROUP env / smpc_set_group override
   std::mutex mu;
@@ -184,6 +185,7 @@ void to_dev_batch(const smpc_batch& in, smpc::DevBatch* d) {
   d->park_ring = nullptr;
   d->park_counters = nullptr;
   d->park_quantum = 0;
+  d->cta_sync = 1;
 }
 
 // Build the packed agent records of a batch in the handle's scratch buffer (one small kernel per batch).
@@ -454,6 +456,7 @@ int smpc_create(const smpc_params* p, int device, smpc_handle** out) {
   if (const char* env = std::getenv("SMPC_CHUNKS")) h->forced_chunks = std::atoi(env);
   if (const char* env = std::getenv("SMPC_STREAM_MAPS")) h->stream_maps = std::atoi(env);
   if (const char* env = std::getenv("SMPC_PARK_QUANTUM")) h->park_quantum = std::max(0, std::atoi(env));
+  if (const char* env = std::getenv("SMPC_CTA_SYNC")) h->cta_sync = std::atoi(env) != 0;
   *out = h;
   return SMPC_OK;
 }
@@ -497,6 +500,7 @@ static int launch_solve_on(smpc_handle* h, const smpc_batch* in, smpc_result* ou
   smpc::DevBatch bt;
   to_dev_batch(*in, &bt);
   bt.arrival = arrival;
+  bt.cta_sync = (h->cta_sync < 0) ? 1 : h->cta_sync;
   smpc::DevResult rs;
   to_dev_result(*out, &rs);
   rc = pack_agents_at(h, &bt, total_problems, first, stream);

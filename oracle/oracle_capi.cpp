@@ -307,8 +307,8 @@ double smpc_oracle_poly_min(const double* samples, int n, double x_min, double x
 }
 
 int smpc_oracle_poly_roots(const double* coeffs, int n, double* roots) {
-  std::vector<double> r = real_parts_of_roots(std::vector<double>(coeffs, coeffs + n));
-  for (size_t i = 0; i < r.size(); ++i) roots[i] = r[i];
+  std::vector<real> r = real_parts_of_roots(std::vector<real>(coeffs, coeffs + n));
+  for (size_t i = 0; i < r.size(); ++i) roots[i] = static_cast<double>(r[i]);
   return static_cast<int>(r.size());
 }
 

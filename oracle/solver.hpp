@@ -141,20 +141,30 @@ struct Sample {
   bool value_ok = false, gradient_ok = false;
 };
 
-inline double poly_eval(const std::vector<double>& c, double x) {  // Horner, highest degree first
-  double v = 0.0;
-  for (double ck : c) v = v * x + ck;
+// Precision note. Ceres fits the interpolating polynomial by solving the Vandermonde-type system with Eigen's
+// FullPivLU in double and finds the critical points as eigenvalues of the companion matrix. With line-search samples
+// at t ~ 1e-3 .. 1 that system is badly conditioned: the minimiser Ceres returns carries rounding noise of 1e-7 .. 1e-5
+// relative that depends on Eigen's exact operation order and is not reproducible by ANY other implementation (measured:
+// tests/trlm_numpy.py — numpy.linalg.solve + numpy.roots in double — differs from a double full-pivot LU by exactly that
+// much, and the differences feed back into the iterate path). The oracle therefore computes the SAME polynomial and the
+// SAME candidate set (midpoint, end points, real parts of the derivative's roots, in-range samples) in long double, i.e.
+// the noise-free value Ceres' result scatters around; parity checks then measure the solver under test, not the noise.
+using real = long double;
+
+inline real poly_eval(const std::vector<real>& c, real x) {  // Horner, highest degree first
+  real v = 0.0L;
+  for (real ck : c) v = v * x + ck;
   return v;
 }
 
 // Full-pivot LU solve (Eigen::FullPivLU with threshold 0 in Ceres).
-inline std::vector<double> solve_full_pivot(std::vector<std::vector<double>> a, std::vector<double> b) {
+inline std::vector<real> solve_full_pivot(std::vector<std::vector<real>> a, std::vector<real> b) {
   const int n = static_cast<int>(b.size());
   std::vector<int> colperm(n);
   for (int i = 0; i < n; ++i) colperm[i] = i;
   for (int k = 0; k < n; ++k) {
     int pr = k, pc = k;
-    double best = -1.0;
+    real best = -1.0L;
     for (int i = k; i < n; ++i)
       for (int j = k; j < n; ++j)
         if (std::fabs(a[i][j]) > best) {
@@ -162,7 +172,7 @@ inline std::vector<double> solve_full_pivot(std::vector<std::vector<double>> a, 
           pr = i;
           pc = j;
         }
-    if (best == 0.0) break;
+    if (best == 0.0L) break;
     std::swap(a[k], a[pr]);
     std::swap(b[k], b[pr]);
     if (pc != k) {
@@ -170,37 +180,38 @@ inline std::vector<double> solve_full_pivot(std::vector<std::vector<double>> a, 
       std::swap(colperm[k], colperm[pc]);
     }
     for (int i = k + 1; i < n; ++i) {
-      const double f = a[i][k] / a[k][k];
-      if (f == 0.0) continue;
+      const real f = a[i][k] / a[k][k];
+      if (f == 0.0L) continue;
       for (int j = k; j < n; ++j) a[i][j] -= f * a[k][j];
       b[i] -= f * b[k];
     }
   }
-  std::vector<double> y(n, 0.0);
+  std::vector<real> y(n, 0.0L);
   for (int i = n - 1; i >= 0; --i) {
-    double s = b[i];
+    real s = b[i];
     for (int j = i + 1; j < n; ++j) s -= a[i][j] * y[j];
-    y[i] = (a[i][i] != 0.0) ? s / a[i][i] : 0.0;
+    y[i] = (a[i][i] != 0.0L) ? s / a[i][i] : 0.0L;
   }
-  std::vector<double> xsol(n, 0.0);
+  std::vector<real> xsol(n, 0.0L);
   for (int i = 0; i < n; ++i) xsol[colperm[i]] = y[i];
   return xsol;
 }
 
-inline std::vector<double> interpolating_polynomial(const std::vector<Sample>& s) {
+inline std::vector<real> interpolating_polynomial(const std::vector<Sample>& s) {
   int nc = 0;
   for (const Sample& q : s) nc += (q.value_ok ? 1 : 0) + (q.gradient_ok ? 1 : 0);
   const int degree = nc - 1;
-  std::vector<std::vector<double>> lhs(nc, std::vector<double>(nc, 0.0));
-  std::vector<double> rhs(nc, 0.0);
+  std::vector<std::vector<real>> lhs(nc, std::vector<real>(nc, 0.0L));
+  std::vector<real> rhs(nc, 0.0L);
   int row = 0;
   for (const Sample& q : s) {
+    const real x = q.x;
     if (q.value_ok) {
-      for (int j = 0; j <= degree; ++j) lhs[row][j] = std::pow(q.x, degree - j);
+      for (int j = 0; j <= degree; ++j) lhs[row][j] = std::pow(x, static_cast<real>(degree - j));
       rhs[row++] = q.value;
     }
     if (q.gradient_ok) {
-      for (int j = 0; j < degree; ++j) lhs[row][j] = (degree - j) * std::pow(q.x, degree - j - 1);
+      for (int j = 0; j < degree; ++j) lhs[row][j] = (degree - j) * std::pow(x, static_cast<real>(degree - j - 1));
       rhs[row++] = q.gradient;
     }
   }
@@ -210,38 +221,38 @@ inline std::vector<double> interpolating_polynomial(const std::vector<Sample>& s
 // Real parts of all roots. Degree <= 2 in closed form as Ceres does (FindLinear/QuadraticPolynomialRoots);
 // higher degrees: Ceres takes eigenvalues of the balanced companion matrix — here Aberth-Ehrlich in long double,
 // an independent method converging to the same roots.
-inline std::vector<double> real_parts_of_roots(std::vector<double> c) {
+inline std::vector<real> real_parts_of_roots(std::vector<real> c) {
   size_t lead = 0;
-  while (lead + 1 < c.size() && c[lead] == 0.0) ++lead;
+  while (lead + 1 < c.size() && c[lead] == 0.0L) ++lead;
   c.erase(c.begin(), c.begin() + lead);
   const int degree = static_cast<int>(c.size()) - 1;
-  std::vector<double> roots;
+  std::vector<real> roots;
   if (degree <= 0) return roots;
   if (degree == 1) {
     roots.push_back(-c[1] / c[0]);
     return roots;
   }
   if (degree == 2) {
-    const double a = c[0], b = c[1], cc = c[2];
-    const double D = b * b - 4 * a * cc;
-    const double sD = std::sqrt(std::fabs(D));
+    const real a = c[0], b = c[1], cc = c[2];
+    const real D = b * b - 4 * a * cc;
+    const real sD = std::sqrt(std::fabs(D));
     if (D >= 0) {
       if (b >= 0) {
-        roots.push_back((-b - sD) / (2.0 * a));
-        roots.push_back((2.0 * cc) / (-b - sD));
+        roots.push_back((-b - sD) / (2.0L * a));
+        roots.push_back((2.0L * cc) / (-b - sD));
       } else {
-        roots.push_back((2.0 * cc) / (-b + sD));
-        roots.push_back((-b + sD) / (2.0 * a));
+        roots.push_back((2.0L * cc) / (-b + sD));
+        roots.push_back((-b + sD) / (2.0L * a));
       }
     } else {
-      roots.push_back(-b / (2.0 * a));
-      roots.push_back(-b / (2.0 * a));
+      roots.push_back(-b / (2.0L * a));
+      roots.push_back(-b / (2.0L * a));
     }
     return roots;
   }
   using cld = std::complex<long double>;
   std::vector<long double> m(degree + 1);
-  for (int i = 0; i <= degree; ++i) m[i] = static_cast<long double>(c[i]) / static_cast<long double>(c[0]);
+  for (int i = 0; i <= degree; ++i) m[i] = c[i] / c[0];
   long double radius = 0.0L;
   for (int i = 1; i <= degree; ++i) radius = std::max(radius, std::pow(std::fabs(m[i]), 1.0L / i));
   radius = 2.0L * radius + 1e-30L;
@@ -264,33 +275,32 @@ inline std::vector<double> real_parts_of_roots(std::vector<double> c) {
       z[i] -= step;
       moved = std::max(moved, std::abs(step) / (std::abs(z[i]) + 1e-300L));
     }
-    if (moved < 1e-18L) break;
+    if (moved < 1e-19L) break;
   }
-  for (int i = 0; i < degree; ++i) roots.push_back(static_cast<double>(z[i].real()));
+  for (int i = 0; i < degree; ++i) roots.push_back(z[i].real());
   return roots;
 }
 
-inline void minimize_polynomial(const std::vector<double>& poly, double x_min, double x_max, double* opt_x,
-                                double* opt_v) {
-  *opt_x = (x_min + x_max) / 2.0;
+inline void minimize_polynomial(const std::vector<real>& poly, real x_min, real x_max, real* opt_x, real* opt_v) {
+  *opt_x = (x_min + x_max) / 2.0L;
   *opt_v = poly_eval(poly, *opt_x);
-  const double vmin = poly_eval(poly, x_min);
+  const real vmin = poly_eval(poly, x_min);
   if (vmin < *opt_v) {
     *opt_v = vmin;
     *opt_x = x_min;
   }
-  const double vmax = poly_eval(poly, x_max);
+  const real vmax = poly_eval(poly, x_max);
   if (vmax < *opt_v) {
     *opt_v = vmax;
     *opt_x = x_max;
   }
   if (poly.size() <= 2) return;
   const int degree = static_cast<int>(poly.size()) - 1;
-  std::vector<double> d(degree);
+  std::vector<real> d(degree);
   for (int j = 0; j < degree; ++j) d[j] = (degree - j) * poly[j];
-  for (double root : real_parts_of_roots(d)) {
+  for (real root : real_parts_of_roots(d)) {
     if (root < x_min || root > x_max) continue;
-    const double v = poly_eval(poly, root);
+    const real v = poly_eval(poly, root);
     if (v < *opt_v) {
       *opt_v = v;
       *opt_x = root;
@@ -299,18 +309,18 @@ inline void minimize_polynomial(const std::vector<double>& poly, double x_min, d
 }
 
 inline double minimize_interpolating_polynomial(const std::vector<Sample>& s, double x_min, double x_max) {
-  const std::vector<double> poly = interpolating_polynomial(s);
-  double ox, ov;
+  const std::vector<real> poly = interpolating_polynomial(s);
+  real ox, ov;
   minimize_polynomial(poly, x_min, x_max, &ox, &ov);
   for (const Sample& q : s) {
     if (q.x < x_min || q.x > x_max) continue;
-    const double v = poly_eval(poly, q.x);
+    const real v = poly_eval(poly, q.x);
     if (v < ov) {
       ov = v;
       ox = q.x;
     }
   }
-  return ox;
+  return static_cast<double>(ox);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -666,6 +676,7 @@ inline SolveSummary solve(const ProblemView& p, const SolveOptions& opt, double*
     step_norm = std::sqrt(step_norm);
     rec.step_norm = step_norm;
     if (tol_armed && step_norm <= opt.param_tol * (x_norm + opt.param_tol)) {
+      if (keep_trace) sum.eval_rows.back().aux = step_norm / (opt.param_tol * (x_norm + opt.param_tol)) - 1.0;
       --iteration;  // this iteration is not recorded by Ceres
       return finish(T_CONVERGENCE_PARAMETER);
     }
@@ -673,6 +684,7 @@ inline SolveSummary solve(const ProblemView& p, const SolveOptions& opt, double*
     const double cost_change = x_cost - cand_cost;
     rec.cost_change = cost_change;
     if (tol_armed && std::fabs(cost_change) <= opt.fn_tol * x_cost) {
+      if (keep_trace) sum.eval_rows.back().aux = std::fabs(cost_change) - opt.fn_tol * x_cost;
       --iteration;
       return finish(T_CONVERGENCE_FUNCTION);
     }

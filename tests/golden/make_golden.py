@@ -53,7 +53,8 @@ def main():
             blob[f"{name}/out/{k}"] = out[k]
         ev = [oracle.evaluate(b, i, b.arrays["u0"][i]) for i in range(b.n_problems)]
         blob[f"{name}/eval/cost"] = np.array([e["cost"] for e in ev])
-        blob[f"{name}/eval/grad"] = np.array([e["grad"] for e in ev])
+        P = 2 * b.n_blocks  # a problem with a shorter horizon has fewer parameters: its row is zero-padded
+        blob[f"{name}/eval/grad"] = np.array([np.pad(e["grad"], (0, P - e["grad"].size)) for e in ev])
         print(name, "iterations", out["iterations"].tolist(), "termination", out["termination"].tolist())
     path = os.path.join(ROOT, "tests", "golden", "solve_cases.npz")
     np.savez_compressed(path, **blob)

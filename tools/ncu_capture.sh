@@ -6,7 +6,7 @@
 out=$1; tag=$2; wl=$3; shift 3
 mkdir -p $out
 env "$@" ncu --set full --clock-control none --import-source on -k regex:smpc_solve_kernel --launch-skip 3 --launch-count 1 \
-  -f -o $out/prof_$tag python bench.py --workload $wl --steps 2 --warmup 3 --no-cpu-baseline --latency-calls 0 \
+  -f -o $out/prof_$tag python bench.py --workload $wl --steps 2 --warmup 3 --no-cpu-baseline --legs none \
   > $out/ncu_$tag.log 2>&1
 rc=$?
 ncu -i $out/prof_$tag.ncu-rep --page raw --csv > $out/raw_$tag.csv 2>/dev/null
