@@ -269,8 +269,58 @@ typedef struct smpc_optimize_io {
 } smpc_optimize_io;
 
 /* Returns SMPC_OK when the call itself worked (io->optimized holds the reference's return value); the
- * std::runtime_error cases of computeObstacle (src/optimizer.cpp:676-713) map to SMPC_ERR_ARGUMENT. */
+ * std::runtime_error cases of computeObstacle (src/optimizer.cpp:676-713) map to SMPC_ERR_ARGUMENT.
+ * Implemented as smpc_optimize_batch for one robot: every stage runs in the GPU kernels of the fleet tick. */
 int smpc_optimize(smpc_handle* h, smpc_optimize_io* io);
+
+/* ---- level-2 BATCH entry: bool Optimizer::optimize(...) for a fleet of robots, one call per controller tick ---------
+ * Host buffers in and out; every stage is a kernel on the handle's stream: TrajectoryMemory seeding (:174-186),
+ * people_to_status (:454-482), format_to_optimize (:484-551), project_people (:554-671 + sfm.hpp), the bounded TR-LM
+ * solve with the post-solve expansion (:241-446) and the memory update (:448-449). Robots have their OWN horizon:
+ * n_poses[b] is what the trajectorizer produced for robot b (it stops early near the goal,
+ * src/path_trajectorizer.cpp:152) and the problem is sized from it (:248-249, :492-497). The warm-start memory
+ * (previous path / cmds, one TrajectoryMemory per robot) and the costmaps / obstacle grids live on the device between
+ * calls; no device allocation happens after the first tick of a fleet shape. smpc_reset_memory forgets the memory. */
+typedef struct smpc_fleet_io {
+  int n_robots;  /* B */
+  int max_poses; /* row stride of poses / cmds / people_proj (>= every n_poses[b], e.g. trajectorizer max_steps + 1) */
+  int n_agents;  /* A people columns per robot (the reference: 3; more than A people are truncated by the caller) */
+  float time_step; /* <= 0: params.time_step */
+  /* in */
+  const int32_t* n_poses;  /* [B] seed poses per robot (cmds: n_poses - 1); < 2 -> optimized[b] = 0 (:158-162) */
+  const double* people;    /* [B][A][5] position.x/y, velocity.x/y/z */
+  const int32_t* n_people; /* [B] */
+  const double* speed;     /* [B][2] linear.x, angular.z */
+  const uint8_t* costmaps; /* [M][size_y][size_x] */
+  const double* costmap_origin; /* [M][2] */
+  const int32_t* costmap_index; /* [B] or NULL (robot b uses map b % M) */
+  int n_costmaps, size_x, size_y;
+  double resolution;
+  const uint32_t* od_indexes; /* [Mo][od_height * od_width] nearest-obstacle cell index (ObstacleDistance.indexes) */
+  const double* od_origin;    /* [Mo][2] */
+  const int32_t* od_index;    /* [B] or NULL (robot b uses grid b % Mo) */
+  int n_od_grids;
+  uint32_t od_width, od_height;
+  float od_resolution;
+  /* Costmaps and obstacle grids are re-sent to the device only when maps_version differs from the previous call's
+   * (Nav2 updates local costmaps far slower than the 20 Hz control loop); 0 = always re-send. */
+  long long maps_version;
+  /* in-out: seed -> result. A robot whose solve is not usable keeps its cmds and gets the cut + blended seed path
+   * (what format_to_optimize leaves in `path`); inactive robots are untouched. */
+  double* poses; /* [B][max_poses][3] x, y, yaw */
+  double* cmds;  /* [B][max_poses][2] linear.x, angular.z */
+  /* out */
+  int32_t* n_out;     /* [B] poses / cmds valid after the call */
+  uint8_t* optimized; /* [B] the bool Optimizer::optimize returns */
+  int32_t* termination;    /* [B] may be NULL */
+  int32_t* iterations;     /* [B] may be NULL */
+  double* cost_initial;    /* [B] may be NULL */
+  double* cost_final;      /* [B] may be NULL */
+  int32_t* project_status; /* [B] may be NULL: 1 = a person left the obstacle grid (the reference throws
+                              std::runtime_error there); such a robot is reported optimized = 0 and keeps its memory */
+  double* people_proj;     /* [B][A][6][max_poses] may be NULL (level-1 agents layout) */
+} smpc_fleet_io;
+int smpc_optimize_batch(smpc_handle* h, smpc_fleet_io* io);
 /* Forget the previous path / cmds (a fresh TrajectoryMemory). */
 int smpc_reset_memory(smpc_handle* h);
 
@@ -298,6 +348,7 @@ typedef struct smpc_project_args {
   const double* people_init;
   double* agents;
   int32_t* status; /* may be NULL */
+  const int32_t* n_steps_each; /* [B] per-problem horizon S_b <= n_steps (may be NULL); array strides stay n_steps + 1 */
 } smpc_project_args;
 int smpc_project_people_batch_device(smpc_handle* h, const smpc_project_args* a, void* stream);
 /* Host-buffer wrapper (tests): same struct with host pointers. */
@@ -328,6 +379,15 @@ typedef struct smpc_format_args {
   double* u0;
   double* path_xy;
   double* goal_yaw;
+  /* Per-robot lengths (all may be NULL / 0 = uniform): n_poses_each [B] poses kept per robot (<= n_poses = the row
+   * stride; < 2: the robot is inactive, its level-1 inputs are zeroed and has_people[b] cleared), n_prev_poses_each /
+   * n_prev_cmds_each [B] entries of the robot's memory rows (strides n_prev_poses / n_prev_cmds), cmds_stride = row
+   * stride of cmds (0: n_poses - 1), has_people [B] (may be NULL). */
+  const int32_t* n_poses_each;
+  const int32_t* n_prev_poses_each;
+  const int32_t* n_prev_cmds_each;
+  int cmds_stride;
+  uint8_t* has_people;
 } smpc_format_args;
 int smpc_format_batch_device(smpc_handle* h, const smpc_format_args* a, void* stream);
 

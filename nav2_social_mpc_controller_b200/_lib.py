@@ -62,6 +62,8 @@ def lib():
     L.smpc_measure_fp64_peak.restype = C.c_int
     L.smpc_optimize.argtypes = [C.c_void_p, P(abi.SmpcOptimizeIo)]
     L.smpc_optimize.restype = C.c_int
+    L.smpc_optimize_batch.argtypes = [C.c_void_p, P(abi.SmpcFleetIo)]
+    L.smpc_optimize_batch.restype = C.c_int
     L.smpc_reset_memory.argtypes = [C.c_void_p]
     L.smpc_reset_memory.restype = C.c_int
     L.smpc_project_people_batch.argtypes = [C.c_void_p, P(abi.SmpcProjectArgs)]
@@ -98,7 +100,7 @@ EXPORTED_SYMBOLS = (
     "smpc_create", "smpc_destroy", "smpc_solve_batch", "smpc_solve_batch_device", "smpc_eval_batch_device",
     "smpc_eval_batch", "smpc_multistart_argmin_device", "smpc_last_kernel_ms", "smpc_launch_count",
     "smpc_measure_fp64_peak", "smpc_debug_polymin", "smpc_debug_plan_chunks", "smpc_set_group",
-    "smpc_optimize", "smpc_reset_memory", "smpc_project_people_batch", "smpc_project_people_batch_device",
+    "smpc_optimize", "smpc_optimize_batch", "smpc_reset_memory", "smpc_project_people_batch", "smpc_project_people_batch_device",
     "smpc_format_batch_device", "smpc_people_to_status_device", "smpc_memory_update_device",
     "smpc_trajectorize_batch_device",
 )

@@ -240,6 +240,7 @@ class SmpcProjectArgs(C.Structure):
         ("people_init", C.c_void_p),
         ("agents", C.c_void_p),
         ("status", C.c_void_p),
+        ("n_steps_each", C.c_void_p),
     ]
 
 
@@ -264,6 +265,11 @@ class SmpcFormatArgs(C.Structure):
         ("u0", C.c_void_p),
         ("path_xy", C.c_void_p),
         ("goal_yaw", C.c_void_p),
+        ("n_poses_each", C.c_void_p),
+        ("n_prev_poses_each", C.c_void_p),
+        ("n_prev_cmds_each", C.c_void_p),
+        ("cmds_stride", C.c_int),
+        ("has_people", C.c_void_p),
     ]
 
 
@@ -284,4 +290,43 @@ class SmpcTrajectorizeArgs(C.Structure):
         ("poses", C.c_void_p),
         ("cmds", C.c_void_p),
         ("n_steps", C.c_void_p),
+    ]
+
+
+class SmpcFleetIo(C.Structure):
+    """struct smpc_fleet_io — one controller tick of a fleet (smpc_optimize_batch)."""
+    _fields_ = [
+        ("n_robots", C.c_int),
+        ("max_poses", C.c_int),
+        ("n_agents", C.c_int),
+        ("time_step", C.c_float),
+        ("n_poses", C.c_void_p),
+        ("people", C.c_void_p),
+        ("n_people", C.c_void_p),
+        ("speed", C.c_void_p),
+        ("costmaps", C.c_void_p),
+        ("costmap_origin", C.c_void_p),
+        ("costmap_index", C.c_void_p),
+        ("n_costmaps", C.c_int),
+        ("size_x", C.c_int),
+        ("size_y", C.c_int),
+        ("resolution", C.c_double),
+        ("od_indexes", C.c_void_p),
+        ("od_origin", C.c_void_p),
+        ("od_index", C.c_void_p),
+        ("n_od_grids", C.c_int),
+        ("od_width", C.c_uint32),
+        ("od_height", C.c_uint32),
+        ("od_resolution", C.c_float),
+        ("maps_version", C.c_longlong),
+        ("poses", C.c_void_p),
+        ("cmds", C.c_void_p),
+        ("n_out", C.c_void_p),
+        ("optimized", C.c_void_p),
+        ("termination", C.c_void_p),
+        ("iterations", C.c_void_p),
+        ("cost_initial", C.c_void_p),
+        ("cost_final", C.c_void_p),
+        ("project_status", C.c_void_p),
+        ("people_proj", C.c_void_p),
     ]

@@ -129,6 +129,45 @@ __device__ __forceinline__ double wrap_to_pi(double a) {
   return a;
 }
 
+// atan2(s, c) for a point (c, s) near the unit circle (the social force calls it with the cross / dot product of two
+// unit vectors, i.e. s = sin(theta), c = cos(theta) up to rounding). CUDA's general atan2 is ~135 instructions with
+// its scaling and special-case handling and was 19 % of all instructions of a 20-agent solve; this one is ~45:
+// one division (reciprocal seed + two Newton steps + residual correction) of the octant-reduced argument
+//   t = min / max                  (min <= tan(pi/8) max)        atan = P(t)
+//   t = (min - max) / (min + max)  (otherwise: |t| <= tan(pi/8)) atan = pi/4 + P(t)
+// and the odd degree-23 polynomial P(t) = t + t z Q(z), z = t^2 (Chebyshev fit on [0, tan^2(pi/8)], 2.4e-16 relative).
+// Measured against 60-digit mpmath over 2e5 angles incl. |theta| down to 1e-9: 3.3e-16 relative (1.5 ulp) — the
+// accuracy class of libm's atan2 (CUDA: 2 ulp). Inputs must be finite, not both zero and of comparable magnitude.
+__device__ __forceinline__ double atan2_unit(double s, double c) {
+  const double ax = fabs(c), ay = fabs(s);
+  const double mx = fmax(ax, ay), mn = fmin(ax, ay);
+  const bool hi = mn > 0.41421356237309503 * mx;
+  const double num = hi ? mn - mx : mn, den = hi ? mn + mx : mx;
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+  r = fma(fma(-den, r, 1.0), r, r);
+  r = fma(fma(-den, r, 1.0), r, r);
+  double t = num * r;
+  t = fma(fma(-den, t, num), r, t);
+  const double z = t * t;
+  double q = -0.01917688711906226;
+  q = fma(q, z, 0.03923165829558719);
+  q = fma(q, z, -0.0508544973794026);
+  q = fma(q, z, 0.0585814891280221);
+  q = fma(q, z, -0.06664511447381948);
+  q = fma(q, z, 0.07692183190826087);
+  q = fma(q, z, -0.09090904578123903);
+  q = fma(q, z, 0.11111111015256361);
+  q = fma(q, z, -0.14285714284666542);
+  q = fma(q, z, 0.1999999999999552);
+  q = fma(q, z, -0.3333333333333333);
+  double a = fma(t, z * q, t);
+  if (hi) a += 0.7853981633974483;
+  if (ay > ax) a = 1.5707963267948966 - a;
+  if (c < 0.0) a = 3.141592653589793 - a;
+  return copysign(a, s);
+}
+
 __device__ __forceinline__ void social_pair(double dx, double dy, double wx, double wy, PairOut& o) {
   const double kLambda = 2.0, kGamma = 0.35, kNPrime = 3.0, kN = 2.0, kFactor = 2.1;
   double d2 = dx * dx + dy * dy;
@@ -154,7 +193,7 @@ __device__ __forceinline__ void social_pair(double dx, double dy, double wx, dou
   double theta;
   o.degenerate = tiny || !(fabs(cross) > 1e-9);  // the coincident-position fix-up is not odd in d either
   if (!o.degenerate) {
-    theta = atan2(cross, dot);
+    theta = atan2_unit(cross, dot);
   } else {
     theta = wrap_to_pi(atan2(ey, ex) - atan2(iy, ix));
   }
@@ -485,7 +524,11 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
       double2 nxt_p = __ldg(rec);
       double2 nxt_v = __ldg(rec + 1);
       bool nxt_valid = __ldg(vld) != 0;
-#pragma unroll 1
+#ifndef SMPC_PAIR_UNROLL
+#define SMPC_PAIR_UNROLL 1
+#endif
+      constexpr int kPairUnroll = SMPC_PAIR_UNROLL;
+#pragma unroll kPairUnroll
       for (int k = 0; k < bt.A; ++k) {
         const double ax = nxt_p.x, ay = nxt_p.y, avx = nxt_v.x, avy = nxt_v.y;
         const bool valid = nxt_valid;

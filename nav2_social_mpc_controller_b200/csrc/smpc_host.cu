@@ -97,11 +97,16 @@ struct smpc_handle {
   // staging for the host-buffer entry points
   DeviceBuffer in_buf, out_buf;
   DeviceBuffer pack_buf;  // agent records (x, y, vx, vy) + validity bytes of the current batch
-  smpc_memory memory;  // previous path / cmds of the level-2 entry
+  smpc_memory memory;  // (unused since round 2: the level-2 memory lives on the device, smpc_fleet_state)
+  smpc_fleet_state fleet;        // fleet tick (smpc_optimize_batch)
+  smpc_fleet_state single;       // the one-robot fleet behind smpc_optimize
 };
 
 const smpc_params* smpc_handle_params(smpc_handle* h) { return &h->params; }
 smpc_memory* smpc_handle_memory(smpc_handle* h) { return &h->memory; }
+smpc_fleet_state* smpc_handle_fleet(smpc_handle* h) { return &h->fleet; }
+smpc_fleet_state* smpc_handle_single(smpc_handle* h) { return &h->single; }
+int smpc_handle_device(smpc_handle* h) { return h->device; }
 int smpc_host_fail(int code, const std::string& msg) { return fail(code, msg); }
 cudaStream_t smpc_handle_stream(smpc_handle* h) { return h->stream; }
 void smpc_handle_count_launch(smpc_handle* h) { h->launches += 1; }
@@ -479,6 +484,8 @@ void smpc_destroy(smpc_handle* h) {
   h->out_buf.release();
   h->pack_buf.release();
   h->park_buf.release();
+  h->fleet.release();
+  h->single.release();
   if (h->queue) cudaFree(h->queue);
   if (h->arrival) cudaFree(h->arrival);
   if (h->arrival_host) cudaFreeHost(h->arrival_host);

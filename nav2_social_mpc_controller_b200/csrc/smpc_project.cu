@@ -50,12 +50,14 @@ __global__ void __launch_bounds__(kWarps * 32) smpc_project_kernel(smpc_project_
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int n_warps = (gridDim.x * blockDim.x) >> 5;
-  const int S = a.n_steps, A = a.n_agents, stride = S + 1;
+  const int A = a.n_agents, stride = a.n_steps + 1;
   const double dt = (double)a.time_step;
   const double kDesired = 2.0, kObstacle = 20.0, kSigma = 0.2, kSocial = 2.1, kLambda = 2.0, kGamma = 0.35, kN = 2.0,
                kNPrime = 3.0, kRelax = 0.5;
 
   for (int b = warp; b < a.n_problems; b += n_warps) {
+    // this problem's own horizon (rows keep the stride of the batch's longest one)
+    const int S = a.n_steps_each ? min(max(a.n_steps_each[b], 1), a.n_steps) : a.n_steps;
     const double* robot = a.robot + (size_t)b * stride * 6;
     const double* init = a.people_init + (size_t)b * A * 6;
     double* out = a.agents + (size_t)b * A * 6 * stride;
@@ -270,16 +272,35 @@ __global__ void __launch_bounds__(kWarps * 32) smpc_project_kernel(smpc_project_
   }
 }
 
-// format_to_optimize (reference src/optimizer.cpp:484-551) + unpacking (:197-237), one thread per (problem, pose)
+// format_to_optimize (reference src/optimizer.cpp:484-551) + unpacking (:197-237), one thread per (problem, pose).
+// P = a.n_poses is the row stride; robot b keeps Pb = n_poses_each[b] poses (the caller has applied the max_time cut).
 __global__ void smpc_format_kernel(smpc_format_args a) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int P = a.n_poses;
   if (t >= (long long)a.n_problems * P) return;
   const int b = (int)(t / P), i = (int)(t % P);
+  const int Pb = a.n_poses_each ? a.n_poses_each[b] : P;
+  if (Pb < 2) {
+    // inactive robot ("Path has less than 2 points", :158-162): give the solve a finite one-step dummy, no people
+    if (i == 0) {
+      for (int c = 0; c < 3; ++c) a.pose0[3 * b + c] = 0.0;
+      for (int c = 0; c < 2 * a.n_blocks; ++c) a.u0[(size_t)b * a.n_blocks * 2 + c] = 0.0;
+      a.goal_yaw[b] = 0.0;
+      for (int k = 0; k < 2; ++k) {
+        a.path_xy[(size_t)b * 2 * P + k] = 0.0;
+        a.path_xy[(size_t)b * 2 * P + P + k] = 0.0;
+        for (int c = 0; c < 6; ++c) a.robot[((size_t)b * P + k) * 6 + c] = 0.0;
+      }
+      if (a.has_people) a.has_people[b] = 0;
+    }
+    return;
+  }
+  if (i >= Pb) return;
   const double* cp = a.poses + ((size_t)b * P + i) * 3;
-  const bool have_prev = a.prev_poses != nullptr && a.n_prev_poses > 0;
+  const int n_prev_poses_b = a.n_prev_poses_each ? a.n_prev_poses_each[b] : a.n_prev_poses;
+  const bool have_prev = a.prev_poses != nullptr && n_prev_poses_b > 0;
   // first tick: previous = current (TrajectoryMemory seeding, :177-181) -> blending happens against itself
-  const int n_prev_poses = have_prev ? a.n_prev_poses : P;
+  const int n_prev_poses = have_prev ? n_prev_poses_b : Pb;
   const double wp = a.current_path_w, wc = a.current_cmds_w;
   double x = cp[0], y = cp[1], yaw = cp[2];
   if (i < n_prev_poses) {
@@ -296,8 +317,10 @@ __global__ void smpc_format_kernel(smpc_format_args a) {
     lv = a.speed[2 * b];
     av = a.speed[2 * b + 1];
   } else {
-    const double* cc = a.cmds + ((size_t)b * (P - 1) + (i - 1)) * 2;
-    const bool have_pc = a.prev_cmds != nullptr && (i - 1) < a.n_prev_cmds;  // SURVEY Q11 guard
+    const int cstride = a.cmds_stride > 0 ? a.cmds_stride : P - 1;
+    const double* cc = a.cmds + ((size_t)b * cstride + (i - 1)) * 2;
+    const int n_prev_cmds_b = a.n_prev_cmds_each ? a.n_prev_cmds_each[b] : a.n_prev_cmds;
+    const bool have_pc = a.prev_cmds != nullptr && (i - 1) < n_prev_cmds_b;  // SURVEY Q11 guard
     const double* pc = have_pc ? a.prev_cmds + ((size_t)b * a.n_prev_cmds + (i - 1)) * 2 : cc;
     lv = wc * cc[0] + (1.0 - wc) * pc[0];
     av = wc * cc[1] + (1.0 - wc) * pc[1];
@@ -317,7 +340,7 @@ __global__ void smpc_format_kernel(smpc_format_args a) {
     a.pose0[3 * b + 1] = y;
     a.pose0[3 * b + 2] = atan2(2.0 * (ch * sh), ch * ch - sh * sh);  // evolving_poses[0]: setRPY (:224-226) + getYaw
   }
-  if (i == P - 1) a.goal_yaw[b] = yaw;
+  if (i == Pb - 1) a.goal_yaw[b] = yaw;
 }
 
 // PathTrajectorizer::trajectorize, reference src/path_trajectorizer.cpp:120-288; one thread per robot
@@ -429,6 +452,7 @@ int smpc_trajectorize_batch_device(smpc_handle* h, const smpc_trajectorize_args*
       !a->cmds || !a->n_steps)
     return smpc_host_fail(SMPC_ERR_ARGUMENT, "trajectorize: bad arguments");
   if (a->n_problems == 0) return SMPC_OK;
+  cudaSetDevice(smpc_handle_device(h));  // the caller may have another device current (multi-GPU processes)
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : smpc_handle_stream(h);
   smpc_trajectorize_kernel<<<(a->n_problems + 127) / 128, 128, 0, st>>>(*a);
   cudaError_t e = cudaGetLastError();
@@ -442,6 +466,7 @@ int smpc_people_to_status_device(smpc_handle* h, int n_problems, int n_agents, c
   if (!h || n_problems < 0 || n_agents < 1 || !people_raw || !n_people || !people_init)
     return smpc_host_fail(SMPC_ERR_ARGUMENT, "people_to_status: bad arguments");
   if (n_problems == 0) return SMPC_OK;
+  cudaSetDevice(smpc_handle_device(h));  // the caller may have another device current (multi-GPU processes)
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : smpc_handle_stream(h);
   const long long n = (long long)n_problems * n_agents;
   smpc_people_status_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n_problems, n_agents, people_raw, n_people, people_init,
@@ -457,6 +482,7 @@ int smpc_memory_update_device(smpc_handle* h, int n_problems, int n, const uint8
   if (!h || n_problems < 0 || n < 1 || !usable || !path || !cmds || !prev_poses || !prev_cmds)
     return smpc_host_fail(SMPC_ERR_ARGUMENT, "memory_update: bad arguments");
   if (n_problems == 0) return SMPC_OK;
+  cudaSetDevice(smpc_handle_device(h));  // the caller may have another device current (multi-GPU processes)
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : smpc_handle_stream(h);
   const long long total = (long long)n_problems * n;
   smpc_memory_update_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(n_problems, n, usable, path, cmds, prev_poses,
@@ -475,6 +501,7 @@ int smpc_format_batch_device(smpc_handle* h, const smpc_format_args* a, void* st
   if (!a->poses || !a->cmds || !a->speed || !a->robot || !a->pose0 || !a->u0 || !a->path_xy || !a->goal_yaw)
     return smpc_host_fail(SMPC_ERR_ARGUMENT, "format: missing buffer");
   if (a->n_problems == 0) return SMPC_OK;
+  cudaSetDevice(smpc_handle_device(h));  // the caller may have another device current (multi-GPU processes)
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : smpc_handle_stream(h);
   const long long n = (long long)a->n_problems * a->n_poses;
   smpc_format_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(*a);
@@ -494,6 +521,7 @@ int smpc_project_people_batch_device(smpc_handle* h, const smpc_project_args* a,
   if (a->od_width == 0 || a->od_height == 0) return smpc_host_fail(SMPC_ERR_ARGUMENT, "ObstacleDistance grid has invalid size");
   if (!(a->od_resolution > 0.0f)) return smpc_host_fail(SMPC_ERR_ARGUMENT, "ObstacleDistance grid has invalid resolution");
   if (a->n_problems == 0) return SMPC_OK;
+  cudaSetDevice(smpc_handle_device(h));  // the caller may have another device current (multi-GPU processes)
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : smpc_handle_stream(h);
   const int ctas = (a->n_problems + kWarps - 1) / kWarps;
   const int grid = ctas < 148 * 8 ? ctas : 148 * 8;
@@ -542,6 +570,324 @@ int smpc_project_people_batch(smpc_handle* h, const smpc_project_args* a) {
   }
   for (void* p : to_free) cudaFree(p);
   return rc;
+}
+
+}  // extern "C"
+
+// ===================================================================================================================
+// Level-2 BATCH entry: smpc_optimize_batch = bool Optimizer::optimize(...) (reference src/optimizer.cpp:148-452) for a
+// fleet of B robots per call, every stage a kernel on the handle's stream, per-robot horizons, per-robot warm-start
+// memory (previous path / cmds) resident on the device between ticks.
+// ===================================================================================================================
+namespace {
+
+// TrajectoryMemory seeding (:177-181): a robot without memory gets its CURRENT (uncut) seed as "previous".
+__global__ void fleet_seed_memory_kernel(int B, int stride, const int32_t* __restrict__ n_in, const double* __restrict__ poses,
+                                         const double* __restrict__ cmds, double* __restrict__ prev_poses,
+                                         double* __restrict__ prev_cmds, const int32_t* __restrict__ n_prev_poses) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)B * stride) return;
+  const int b = (int)(t / stride), i = (int)(t % stride);
+  const int n = n_in[b];
+  if (n < 2 || n_prev_poses[b] != 0) return;
+  if (i < n)
+    for (int c = 0; c < 3; ++c) prev_poses[t * 3 + c] = poses[t * 3 + c];
+  if (i < n - 1)
+    for (int c = 0; c < 2; ++c) prev_cmds[t * 2 + c] = cmds[t * 2 + c];
+}
+
+__global__ void fleet_seed_len_kernel(int B, const int32_t* __restrict__ n_in, int32_t* n_prev_poses, int32_t* n_prev_cmds) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  if (n_in[b] >= 2 && n_prev_poses[b] == 0) {
+    n_prev_poses[b] = n_in[b];
+    n_prev_cmds[b] = n_in[b] - 1;
+  }
+}
+
+// Post-solve (:384-449): where the solve is usable the optimised path / cmds replace the seed and become the robot's
+// memory; where it is not (or a person left the obstacle grid: the reference throws there) the robot keeps its cmds,
+// its path is the cut + blended seed format_to_optimize left behind, and its memory stays as it was.
+struct FleetFinish {
+  int B, stride;
+  const int32_t* n_in;
+  const int32_t* n_each;  // poses optimised per robot (after the max_time cut), 0 = inactive (fewer than 2 poses)
+  const uint8_t* usable;
+  const int32_t* status;
+  const double* robot;     // [B][stride][6] blended seed
+  const double* path;      // [B][stride][3] solve output
+  const double* cmds_new;  // [B][stride][2] solve output
+  double* poses_io;        // [B][stride][3] in: seed, out: result
+  double* cmds_io;         // [B][stride][2]
+  double* prev_poses;
+  double* prev_cmds;
+  int32_t* n_prev_poses;
+  int32_t* n_prev_cmds;
+  int32_t* n_out;
+  uint8_t* optimized;
+};
+
+__global__ void fleet_finish_kernel(FleetFinish a) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)a.B * a.stride) return;
+  const int b = (int)(t / a.stride), i = (int)(t % a.stride);
+  const int n = a.n_each[b];
+  const bool active = n >= 2;
+  const bool ok = active && a.usable[b] != 0 && a.status[b] == 0;
+  if (i == 0) {
+    a.optimized[b] = ok ? 1 : 0;
+    a.n_out[b] = active ? n : a.n_in[b];
+    if (ok) {
+      a.n_prev_poses[b] = n;
+      a.n_prev_cmds[b] = n;
+    }
+  }
+  if (!active || i >= n) return;
+  if (ok) {
+    for (int c = 0; c < 3; ++c) {
+      const double v = a.path[t * 3 + c];
+      a.poses_io[t * 3 + c] = v;
+      a.prev_poses[t * 3 + c] = v;
+    }
+    for (int c = 0; c < 2; ++c) {
+      const double v = a.cmds_new[t * 2 + c];
+      a.cmds_io[t * 2 + c] = v;
+      a.prev_cmds[t * 2 + c] = v;
+    }
+  } else {
+    for (int c = 0; c < 3; ++c) a.poses_io[t * 3 + c] = a.robot[t * 6 + c];
+  }
+}
+
+struct Carve {
+  char* base;
+  size_t off = 0;
+  explicit Carve(void* b) : base(static_cast<char*>(b)) {}
+  template <class T>
+  T* take(size_t count) {
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += (count * sizeof(T) + 255) & ~static_cast<size_t>(255);
+    return p;
+  }
+};
+
+#define FLEET_CUDA(call)                                                                                   \
+  do {                                                                                                     \
+    cudaError_t e__ = (call);                                                                              \
+    if (e__ != cudaSuccess) return smpc_host_fail(SMPC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+}  // namespace
+
+extern "C" {
+
+}  // extern "C"
+
+int smpc_optimize_batch_on(smpc_handle* h, smpc_fleet_state* fs, smpc_fleet_io* io) {
+  if (!h || !io || !fs) return smpc_host_fail(SMPC_ERR_ARGUMENT, "NULL argument");
+  const int B = io->n_robots, stride = io->max_poses, A = io->n_agents;
+  if (B < 0 || stride < 2 || A < 1 || A > kMaxAgents - 1)
+    return smpc_host_fail(SMPC_ERR_ARGUMENT, "optimize_batch: need n_robots >= 0, max_poses >= 2, 1 <= n_agents <= 63");
+  if (B == 0) return SMPC_OK;
+  if (!io->n_poses || !io->poses || !io->cmds || !io->people || !io->n_people || !io->speed || !io->costmaps ||
+      !io->costmap_origin || io->n_costmaps < 1 || io->size_x < 1 || io->size_y < 1 || !(io->resolution > 0.0))
+    return smpc_host_fail(SMPC_ERR_ARGUMENT, "optimize_batch: missing buffer");
+  if (!io->od_indexes || !io->od_origin || io->n_od_grids < 1)
+    return smpc_host_fail(SMPC_ERR_ARGUMENT, "ObstacleDistance is empty");  // reference: std::runtime_error (:676-680)
+  if (io->od_width == 0 || io->od_height == 0) return smpc_host_fail(SMPC_ERR_ARGUMENT, "ObstacleDistance grid has invalid size");
+  if (!(io->od_resolution > 0.0f)) return smpc_host_fail(SMPC_ERR_ARGUMENT, "ObstacleDistance grid has invalid resolution");
+  if (!io->n_out || !io->optimized) return smpc_host_fail(SMPC_ERR_ARGUMENT, "optimize_batch: n_out / optimized missing");
+  const smpc_params* prm = smpc_handle_params(h);
+  std::lock_guard<std::mutex> lk(fs->mu);
+  FLEET_CUDA(cudaSetDevice(smpc_handle_device(h)));
+  cudaStream_t st = smpc_handle_stream(h);
+
+  // ---- per-robot sizes on the host (O(B) integer work): the max_time cut of format_to_optimize (:492-497)
+  const float timestep = io->time_step > 0.0f ? io->time_step : prm->time_step, maxtime = prm->max_time;
+  const int maxsize = (int)std::round(maxtime / timestep);
+  std::vector<int32_t>& n_each = fs->host_n_each;
+  std::vector<int32_t>& s_each = fs->host_s_each;
+  n_each.assign(B, 0);
+  s_each.assign(B, 1);
+  int n_max = 0;
+  for (int b = 0; b < B; ++b) {
+    int n = io->n_poses[b];
+    if (n > stride) return smpc_host_fail(SMPC_ERR_ARGUMENT, "optimize_batch: n_poses[b] > max_poses");
+    if (n < 2) continue;  // "Path has less than 2 points, cannot optimize" -> false for this robot (:158-162)
+    if (n > maxsize) n = maxsize - 1;
+    if (n < 2) return smpc_host_fail(SMPC_ERR_ARGUMENT, "max_time / time_step leaves fewer than 2 poses");
+    n_each[b] = n;
+    s_each[b] = n - 1;
+    n_max = std::max(n_max, n);
+  }
+  const int S = stride - 1;  // array stride of the level-1 batch; every robot solves its own S_b = n_b - 1 <= S
+  int nb = 0;
+  int rc = smpc_problem_dims(prm, S, nullptr, nullptr, &nb, nullptr);
+  if (rc != SMPC_OK) return rc;
+
+  // ---- persistent per-robot memory (TrajectoryMemory per robot): re-created only when the fleet shape changes
+  if (fs->mem_robots != B || fs->mem_stride != stride) {
+    const size_t bytes = (size_t)B * stride * 5 * sizeof(double) + 2 * (size_t)B * sizeof(int32_t) + 1024;
+    FLEET_CUDA(fs->memory.reserve(bytes));
+    FLEET_CUDA(cudaMemsetAsync(fs->memory.ptr, 0, bytes, st));
+    fs->mem_robots = B;
+    fs->mem_stride = stride;
+  }
+  Carve cm(fs->memory.ptr);
+  double* prev_poses = cm.take<double>((size_t)B * stride * 3);
+  double* prev_cmds = cm.take<double>((size_t)B * stride * 2);
+  int32_t* n_prev_poses = cm.take<int32_t>(B);
+  int32_t* n_prev_cmds = cm.take<int32_t>(B);
+
+  // ---- costmaps and obstacle-distance grids stay on the device between ticks: re-sent only when maps_version changes
+  const size_t map_bytes = (size_t)io->n_costmaps * io->size_x * io->size_y;
+  const size_t od_cells = (size_t)io->od_width * io->od_height;
+  const size_t od_bytes = (size_t)io->n_od_grids * od_cells * sizeof(uint32_t);
+  const size_t maps_total = ((map_bytes + 255) & ~(size_t)255) + ((od_bytes + 255) & ~(size_t)255) +
+                            (((size_t)io->n_costmaps * 16 + 255) & ~(size_t)255) + (((size_t)io->n_od_grids * 16 + 255) & ~(size_t)255);
+  const bool resend = io->maps_version == 0 || io->maps_version != fs->maps_version || fs->maps_bytes != maps_total;
+  FLEET_CUDA(fs->maps.reserve(maps_total));
+  Carve cmaps(fs->maps.ptr);
+  uint8_t* d_maps = cmaps.take<uint8_t>(map_bytes);
+  uint32_t* d_od = cmaps.take<uint32_t>((size_t)io->n_od_grids * od_cells);
+  double* d_map_org = cmaps.take<double>((size_t)io->n_costmaps * 2);
+  double* d_od_org = cmaps.take<double>((size_t)io->n_od_grids * 2);
+  if (resend) {
+    FLEET_CUDA(cudaMemcpyAsync(d_maps, io->costmaps, map_bytes, cudaMemcpyHostToDevice, st));
+    FLEET_CUDA(cudaMemcpyAsync(d_od, io->od_indexes, od_bytes, cudaMemcpyHostToDevice, st));
+    FLEET_CUDA(cudaMemcpyAsync(d_map_org, io->costmap_origin, (size_t)io->n_costmaps * 16, cudaMemcpyHostToDevice, st));
+    FLEET_CUDA(cudaMemcpyAsync(d_od_org, io->od_origin, (size_t)io->n_od_grids * 16, cudaMemcpyHostToDevice, st));
+    fs->maps_version = io->maps_version;
+    fs->maps_bytes = maps_total;
+  }
+
+  // ---- per-tick scratch (one allocation that only ever grows)
+  const size_t BS = (size_t)B * stride;
+  size_t need = 0;
+  {
+    Carve probe(nullptr);
+    probe.take<double>(BS * 3); probe.take<double>(BS * 2); probe.take<double>((size_t)B * A * 5); probe.take<int32_t>(B);
+    probe.take<double>((size_t)B * 2); probe.take<int32_t>(B); probe.take<int32_t>(B); probe.take<int32_t>(B);
+    probe.take<int32_t>(B); probe.take<int32_t>(B);
+    probe.take<double>((size_t)B * A * 6); probe.take<uint8_t>(B); probe.take<double>(BS * 6); probe.take<double>((size_t)B * 3);
+    probe.take<double>((size_t)B * nb * 2); probe.take<double>(BS * 2); probe.take<double>(B);
+    probe.take<double>((size_t)B * A * 6 * stride); probe.take<int32_t>(B);
+    probe.take<double>(BS * 2); probe.take<double>(BS * 3); probe.take<uint8_t>(B); probe.take<int32_t>(B);
+    probe.take<int32_t>(B); probe.take<double>(B); probe.take<double>(B); probe.take<int32_t>(B); probe.take<uint8_t>(B);
+    need = probe.off;
+  }
+  FLEET_CUDA(fs->scratch.reserve(need));
+  Carve cs(fs->scratch.ptr);
+  double* d_poses = cs.take<double>(BS * 3);
+  double* d_cmds = cs.take<double>(BS * 2);
+  double* d_people = cs.take<double>((size_t)B * A * 5);
+  int32_t* d_n_people = cs.take<int32_t>(B);
+  double* d_speed = cs.take<double>((size_t)B * 2);
+  int32_t* d_n_in = cs.take<int32_t>(B);
+  int32_t* d_n_each = cs.take<int32_t>(B);
+  int32_t* d_s_each = cs.take<int32_t>(B);
+  int32_t* d_map_index = cs.take<int32_t>(B);
+  int32_t* d_od_index = cs.take<int32_t>(B);
+  double* d_init = cs.take<double>((size_t)B * A * 6);
+  uint8_t* d_has_people = cs.take<uint8_t>(B);
+  double* d_robot = cs.take<double>(BS * 6);
+  double* d_pose0 = cs.take<double>((size_t)B * 3);
+  double* d_u0 = cs.take<double>((size_t)B * nb * 2);
+  double* d_path_xy = cs.take<double>(BS * 2);
+  double* d_goal_yaw = cs.take<double>(B);
+  double* d_agents = cs.take<double>((size_t)B * A * 6 * stride);
+  int32_t* d_status = cs.take<int32_t>(B);
+  double* d_cmds_new = cs.take<double>(BS * 2);
+  double* d_path_new = cs.take<double>(BS * 3);
+  uint8_t* d_usable = cs.take<uint8_t>(B);
+  int32_t* d_term = cs.take<int32_t>(B);
+  int32_t* d_iters = cs.take<int32_t>(B);
+  double* d_cost0 = cs.take<double>(B);
+  double* d_cost1 = cs.take<double>(B);
+  int32_t* d_n_out = cs.take<int32_t>(B);
+  uint8_t* d_optimized = cs.take<uint8_t>(B);
+
+  // ---- inputs up
+  FLEET_CUDA(cudaMemcpyAsync(d_poses, io->poses, BS * 3 * 8, cudaMemcpyHostToDevice, st));
+  FLEET_CUDA(cudaMemcpyAsync(d_cmds, io->cmds, BS * 2 * 8, cudaMemcpyHostToDevice, st));
+  FLEET_CUDA(cudaMemcpyAsync(d_people, io->people, (size_t)B * A * 5 * 8, cudaMemcpyHostToDevice, st));
+  FLEET_CUDA(cudaMemcpyAsync(d_n_people, io->n_people, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  FLEET_CUDA(cudaMemcpyAsync(d_speed, io->speed, (size_t)B * 16, cudaMemcpyHostToDevice, st));
+  FLEET_CUDA(cudaMemcpyAsync(d_n_in, io->n_poses, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  FLEET_CUDA(cudaMemcpyAsync(d_n_each, n_each.data(), (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  FLEET_CUDA(cudaMemcpyAsync(d_s_each, s_each.data(), (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  if (io->costmap_index) FLEET_CUDA(cudaMemcpyAsync(d_map_index, io->costmap_index, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  if (io->od_index) FLEET_CUDA(cudaMemcpyAsync(d_od_index, io->od_index, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  FLEET_CUDA(cudaMemsetAsync(d_status, 0, (size_t)B * 4, st));
+
+  const unsigned g_bs = (unsigned)((BS + 255) / 256), g_b = (unsigned)((B + 255) / 256);
+  // ---- TrajectoryMemory seeding, people_to_status, format_to_optimize, project_people
+  fleet_seed_memory_kernel<<<g_bs, 256, 0, st>>>(B, stride, d_n_in, d_poses, d_cmds, prev_poses, prev_cmds, n_prev_poses);
+  fleet_seed_len_kernel<<<g_b, 256, 0, st>>>(B, d_n_in, n_prev_poses, n_prev_cmds);
+  smpc_people_status_kernel<<<(unsigned)(((size_t)B * A + 255) / 256), 256, 0, st>>>(B, A, d_people, d_n_people, d_init,
+                                                                                    d_has_people);
+  smpc_format_args fa{};
+  fa.n_problems = B; fa.n_poses = stride; fa.n_prev_poses = stride; fa.n_prev_cmds = stride; fa.n_blocks = nb;
+  fa.time_step = timestep; fa.current_path_w = prm->current_path_w; fa.current_cmds_w = prm->current_cmds_w;
+  fa.poses = d_poses; fa.cmds = d_cmds; fa.speed = d_speed; fa.prev_poses = prev_poses; fa.prev_cmds = prev_cmds;
+  fa.robot = d_robot; fa.pose0 = d_pose0; fa.u0 = d_u0; fa.path_xy = d_path_xy; fa.goal_yaw = d_goal_yaw;
+  fa.n_poses_each = d_n_each; fa.n_prev_poses_each = n_prev_poses; fa.n_prev_cmds_each = n_prev_cmds;
+  fa.cmds_stride = stride; fa.has_people = d_has_people;
+  smpc_format_kernel<<<g_bs, 256, 0, st>>>(fa);
+  smpc_project_args pa{};
+  pa.n_problems = B; pa.n_steps = S; pa.n_agents = A; pa.n_grids = io->n_od_grids;
+  pa.od_width = io->od_width; pa.od_height = io->od_height; pa.od_resolution = io->od_resolution;
+  pa.max_time = maxtime; pa.time_step = timestep;
+  pa.od_origin = d_od_org; pa.od_indexes = d_od; pa.od_index = io->od_index ? d_od_index : nullptr;
+  pa.robot = d_robot; pa.people_init = d_init; pa.agents = d_agents; pa.status = d_status; pa.n_steps_each = d_s_each;
+  {
+    const int ctas = (B + kWarps - 1) / kWarps;
+    smpc_project_kernel<<<ctas < 148 * 8 ? ctas : 148 * 8, kWarps * 32, 0, st>>>(pa);
+  }
+  FLEET_CUDA(cudaGetLastError());
+  for (int k = 0; k < 5; ++k) smpc_handle_count_launch(h);
+
+  // ---- the solve (level-1 path, per-robot horizons) with its post-solve expansion
+  smpc_batch bt{};
+  bt.n_problems = B; bt.n_steps = S; bt.n_agents = A; bt.n_costmaps = io->n_costmaps;
+  bt.size_x = io->size_x; bt.size_y = io->size_y; bt.resolution = io->resolution; bt.dt = (double)timestep;
+  bt.pose0 = d_pose0; bt.u0 = d_u0; bt.path_xy = d_path_xy; bt.goal_yaw = d_goal_yaw; bt.agents = d_agents;
+  bt.has_people = d_has_people; bt.costmaps = d_maps; bt.costmap_origin = d_map_org;
+  bt.costmap_index = io->costmap_index ? d_map_index : nullptr; bt.n_steps_each = d_s_each;
+  smpc_result rs{};
+  rs.cmds = d_cmds_new; rs.path = d_path_new; rs.usable = d_usable; rs.termination = d_term; rs.iterations = d_iters;
+  rs.cost_initial = d_cost0; rs.cost_final = d_cost1;
+  rc = smpc_solve_batch_device(h, &bt, &rs, st);
+  if (rc != SMPC_OK) return rc;
+
+  // ---- post-solve: outputs, memory update
+  FleetFinish ff{B, stride, d_n_in, d_n_each, d_usable, d_status, d_robot, d_path_new, d_cmds_new, d_poses, d_cmds,
+                 prev_poses, prev_cmds, n_prev_poses, n_prev_cmds, d_n_out, d_optimized};
+  fleet_finish_kernel<<<g_bs, 256, 0, st>>>(ff);
+  FLEET_CUDA(cudaGetLastError());
+  smpc_handle_count_launch(h);
+
+  // ---- results down
+  FLEET_CUDA(cudaMemcpyAsync(io->poses, d_poses, BS * 3 * 8, cudaMemcpyDeviceToHost, st));
+  FLEET_CUDA(cudaMemcpyAsync(io->cmds, d_cmds, BS * 2 * 8, cudaMemcpyDeviceToHost, st));
+  FLEET_CUDA(cudaMemcpyAsync(io->n_out, d_n_out, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  FLEET_CUDA(cudaMemcpyAsync(io->optimized, d_optimized, (size_t)B, cudaMemcpyDeviceToHost, st));
+  if (io->termination) FLEET_CUDA(cudaMemcpyAsync(io->termination, d_term, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  if (io->iterations) FLEET_CUDA(cudaMemcpyAsync(io->iterations, d_iters, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  if (io->cost_initial) FLEET_CUDA(cudaMemcpyAsync(io->cost_initial, d_cost0, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+  if (io->cost_final) FLEET_CUDA(cudaMemcpyAsync(io->cost_final, d_cost1, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+  if (io->project_status) FLEET_CUDA(cudaMemcpyAsync(io->project_status, d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  if (io->people_proj)
+    FLEET_CUDA(cudaMemcpyAsync(io->people_proj, d_agents, (size_t)B * A * 6 * stride * 8, cudaMemcpyDeviceToHost, st));
+  FLEET_CUDA(cudaStreamSynchronize(st));
+  return SMPC_OK;
+}
+
+extern "C" {
+
+int smpc_optimize_batch(smpc_handle* h, smpc_fleet_io* io) {
+  if (!h) return smpc_host_fail(SMPC_ERR_ARGUMENT, "handle is NULL");
+  return smpc_optimize_batch_on(h, smpc_handle_fleet(h), io);
 }
 
 }  // extern "C"

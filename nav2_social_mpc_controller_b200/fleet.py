@@ -1,7 +1,9 @@
 """Fleet tick on one GPU: the whole Optimizer::optimize pipeline (reference src/optimizer.cpp:148-452) for B robots
-per call, every stage a CUDA kernel of libsmpc.so — people_to_status, format_to_optimize (+ per-robot warm-start
-memory instead of the TrajectoryMemory singleton), project_people (SFM), the bounded TR-LM solve with its post-solve
-expansion, and the memory update. torch is used only to own the device buffers and the stream."""
+per call through ONE C-ABI call, smpc_optimize_batch — TrajectoryMemory seeding, people_to_status, format_to_optimize,
+project_people (SFM), the bounded TR-LM solve with its post-solve expansion and the memory update are kernels of
+libsmpc.so; the per-robot warm-start memory and the costmaps stay on the device between ticks. Robots may have
+different path lengths (the trajectorizer stops early near the goal). This file only marshals numpy buffers; torch is
+used by trajectorize_batch alone (device buffers for the seed-generation kernel)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -14,22 +16,30 @@ from .optimizer import Optimizer
 
 class FleetOptimizer:
     def __init__(self, params, n_robots: int, n_agents: int = 3, device: int = 0):
-        import torch
-        self.torch = torch
-        self.dev = torch.device("cuda", device)
+        self.device = device
         self.opt = Optimizer(device)
         self.opt.initialize(params)
         self.p = self.opt.params
         self.B, self.A = n_robots, n_agents
-        self.prev_poses = None  # [B][n][3] previous optimised path (device)
-        self.prev_cmds = None   # [B][n][2]
-        self.stream = torch.cuda.Stream(device=self.dev)
+        self._maps_key = None
+        self._maps_version = 0
+        self._torch = None
 
     def close(self):
         self.opt.close()
 
     def reset_memory(self):
-        self.prev_poses = self.prev_cmds = None
+        """Forget every robot's previous path / cmds (fresh TrajectoryMemory)."""
+        self.opt.reset_memory()
+
+    @property
+    def torch(self):
+        if self._torch is None:
+            import torch
+            self._torch = torch
+            self.dev = torch.device("cuda", self.device)
+            self.stream = torch.cuda.Stream(device=self.dev)
+        return self._torch
 
     def _t(self, a, dtype):
         return self.torch.as_tensor(np.ascontiguousarray(a, dtype=dtype)).to(self.dev)
@@ -57,86 +67,59 @@ class FleetOptimizer:
         return poses.cpu().numpy(), cmds.cpu().numpy(), n_steps.cpu().numpy()
 
     def optimize_batch(self, poses, cmds, people_raw, n_people, speed, costmaps, costmap_origin, costmap_resolution,
-                       od: dict, costmap_index=None, od_index=None) -> dict:
-        """poses [B][n][3], cmds [B][n-1][2] (trajectorizer seeds, same length for the fleet), people_raw [B][A][5],
-        n_people [B], speed [B][2], costmaps [M][sy][sx] u8, od = dict(width, height, resolution, origins [Mo][2],
-        indexes u32 [Mo][h*w]). Returns host numpy: optimized [B] (the reference's bool), cmds [B][n'][2],
-        path [B][n'][3], people_proj [B][A][6][n'], termination, iterations, cost_final."""
-        torch, L, h = self.torch, _lib.lib(), self.opt._h
+                       od: dict, costmap_index=None, od_index=None, n_poses=None, want_people_proj=True) -> dict:
+        """One controller tick for the fleet (smpc_optimize_batch). poses [B][n][3], cmds [B][>= n-1][2] (trajectorizer
+        seeds; n_poses [B] = valid poses per robot, default n for all), people_raw [B][A][5], n_people [B], speed [B][2],
+        costmaps [M][sy][sx] u8, od = dict(width, height, resolution, origins [Mo][2], indexes u32 [Mo][h*w]).
+        Returns host numpy: optimized [B] (the reference's bool), n_out [B], cmds [B][n][2], path [B][n][3] (rows valid
+        up to n_out[b]), people_proj [B][A][6][n], termination, iterations, cost_initial, cost_final, project_status.
+        Costmaps / obstacle grids are re-sent to the GPU only when the arrays passed here change identity."""
         p = self.p
         poses = np.ascontiguousarray(poses, dtype=np.float64)
-        cmds = np.ascontiguousarray(cmds, dtype=np.float64)
-        B, n_in, _ = poses.shape
+        B, n, _ = poses.shape
         assert B == self.B
-        maxsize = int(round(float(np.float32(p.max_time) / np.float32(p.time_step))))
-        n = n_in if n_in <= maxsize else maxsize - 1  # the cut of src/optimizer.cpp:492-497
-        poses, cmds = poses[:, :n], cmds[:, : n - 1]
-        S = n - 1
-        ch, bl, nb, _ = self.opt.dims(S)
-        st = self.stream.cuda_stream
-        f64 = torch.float64
-        with torch.cuda.stream(self.stream):
-            d_poses, d_cmds = self._t(poses, np.float64), self._t(cmds, np.float64)
-            d_speed = self._t(speed, np.float64)
-            d_raw, d_np = self._t(people_raw, np.float64), self._t(n_people, np.int32)
-            d_maps, d_morg = self._t(costmaps, np.uint8), self._t(costmap_origin, np.float64)
-            d_midx = None if costmap_index is None else self._t(costmap_index, np.int32)
-            d_oorg = self._t(np.asarray(od["origins"], dtype=np.float64).reshape(-1, 2), np.float64)
-            d_oidx = self._t(np.asarray(od["indexes"], dtype=np.uint32).reshape(d_oorg.shape[0], -1).view(np.int32),
-                             np.int32)
-            d_osel = None if od_index is None else self._t(od_index, np.int32)
-            init = torch.empty(B, self.A, 6, dtype=f64, device=self.dev)
-            has_people = torch.empty(B, dtype=torch.uint8, device=self.dev)
-            robot = torch.empty(B, n, 6, dtype=f64, device=self.dev)
-            pose0 = torch.empty(B, 3, dtype=f64, device=self.dev)
-            u0 = torch.empty(B, nb, 2, dtype=f64, device=self.dev)
-            path_xy = torch.empty(B, 2, n, dtype=f64, device=self.dev)
-            goal_yaw = torch.empty(B, dtype=f64, device=self.dev)
-            agents = torch.empty(B, self.A, 6, n, dtype=f64, device=self.dev)
-            status = torch.zeros(B, dtype=torch.int32, device=self.dev)
-            _lib.check(L.smpc_people_to_status_device(h, B, self.A, d_raw.data_ptr(), d_np.data_ptr(), init.data_ptr(),
-                                                      has_people.data_ptr(), st))
-            fa = abi.SmpcFormatArgs()
-            fa.n_problems, fa.n_poses, fa.n_blocks = B, n, nb
-            fa.n_prev_poses = 0 if self.prev_poses is None else self.prev_poses.shape[1]
-            fa.n_prev_cmds = 0 if self.prev_cmds is None else self.prev_cmds.shape[1]
-            fa.time_step, fa.current_path_w, fa.current_cmds_w = p.time_step, p.current_path_w, p.current_cmds_w
-            fa.poses, fa.cmds, fa.speed = d_poses.data_ptr(), d_cmds.data_ptr(), d_speed.data_ptr()
-            fa.prev_poses = None if self.prev_poses is None else self.prev_poses.data_ptr()
-            fa.prev_cmds = None if self.prev_cmds is None else self.prev_cmds.data_ptr()
-            fa.robot, fa.pose0, fa.u0 = robot.data_ptr(), pose0.data_ptr(), u0.data_ptr()
-            fa.path_xy, fa.goal_yaw = path_xy.data_ptr(), goal_yaw.data_ptr()
-            _lib.check(L.smpc_format_batch_device(h, C.byref(fa), st))
-            pa = abi.SmpcProjectArgs()
-            pa.n_problems, pa.n_steps, pa.n_agents, pa.n_grids = B, S, self.A, d_oorg.shape[0]
-            pa.od_width, pa.od_height, pa.od_resolution = int(od["width"]), int(od["height"]), float(od["resolution"])
-            pa.max_time, pa.time_step = p.max_time, p.time_step
-            pa.od_origin, pa.od_indexes = d_oorg.data_ptr(), d_oidx.data_ptr()
-            pa.od_index = None if d_osel is None else d_osel.data_ptr()
-            pa.robot, pa.people_init, pa.agents, pa.status = (robot.data_ptr(), init.data_ptr(), agents.data_ptr(),
-                                                              status.data_ptr())
-            _lib.check(L.smpc_project_people_batch_device(h, C.byref(pa), st))
-            arrays = dict(pose0=pose0, u0=u0, path_xy=path_xy, goal_yaw=goal_yaw, agents=agents, has_people=has_people,
-                          costmaps=d_maps, costmap_origin=d_morg, costmap_index=d_midx)
-            bs = abi.make_batch_struct(arrays, B, S, self.A, d_maps.shape[0], d_maps.shape[2], d_maps.shape[1],
-                                       float(costmap_resolution), float(np.float32(p.time_step)))
-            out = dict(cmds=torch.empty(B, n, 2, dtype=f64, device=self.dev),
-                       path=torch.empty(B, n, 3, dtype=f64, device=self.dev),
-                       usable=torch.empty(B, dtype=torch.uint8, device=self.dev),
-                       termination=torch.empty(B, dtype=torch.int32, device=self.dev),
-                       iterations=torch.empty(B, dtype=torch.int32, device=self.dev),
-                       cost_final=torch.empty(B, dtype=f64, device=self.dev))
-            self.opt.solve_batch_device(bs, out, stream=st)
-            if self.prev_poses is None or self.prev_poses.shape[1] != n:
-                # first tick: memory = current seed (src/optimizer.cpp:177-181); it is then overwritten where usable
-                self.prev_poses = d_poses.clone()
-                self.prev_cmds = torch.cat([d_cmds, d_cmds[:, -1:]], dim=1).contiguous()
-            _lib.check(L.smpc_memory_update_device(h, B, n, out["usable"].data_ptr(), out["path"].data_ptr(),
-                                                   out["cmds"].data_ptr(), self.prev_poses.data_ptr(),
-                                                   self.prev_cmds.data_ptr(), st))
-        self.stream.synchronize()
-        res = {k: v.cpu().numpy() for k, v in out.items()}
-        res["optimized"] = res.pop("usable").astype(bool)
-        res["people_proj"] = agents.cpu().numpy()
-        res["project_status"] = status.cpu().numpy()
+        cmds_in = np.ascontiguousarray(cmds, dtype=np.float64)
+        cmd_rows = np.zeros((B, n, 2))
+        k = min(n, cmds_in.shape[1])
+        cmd_rows[:, :k] = cmds_in[:, :k]
+        pose_rows = poses.copy()
+        n_poses = np.full(B, n, dtype=np.int32) if n_poses is None else np.ascontiguousarray(n_poses, dtype=np.int32)
+        people_raw = np.ascontiguousarray(people_raw, dtype=np.float64).reshape(B, self.A, 5)
+        n_people = np.ascontiguousarray(n_people, dtype=np.int32)
+        speed = np.ascontiguousarray(speed, dtype=np.float64).reshape(B, 2)
+        costmaps = np.ascontiguousarray(costmaps, dtype=np.uint8)
+        morg = np.ascontiguousarray(costmap_origin, dtype=np.float64).reshape(-1, 2)
+        oorg = np.ascontiguousarray(od["origins"], dtype=np.float64).reshape(-1, 2)
+        oidx = np.ascontiguousarray(od["indexes"], dtype=np.uint32).reshape(oorg.shape[0], -1)
+        key = (id(costmaps), costmaps.shape, id(od["indexes"]), morg.tobytes(), oorg.tobytes())
+        if key != self._maps_key:
+            self._maps_key = key
+            self._maps_version += 1
+        midx = None if costmap_index is None else np.ascontiguousarray(costmap_index, dtype=np.int32)
+        osel = None if od_index is None else np.ascontiguousarray(od_index, dtype=np.int32)
+        out = dict(n_out=np.zeros(B, np.int32), optimized=np.zeros(B, np.uint8), termination=np.zeros(B, np.int32),
+                   iterations=np.zeros(B, np.int32), cost_initial=np.zeros(B), cost_final=np.zeros(B),
+                   project_status=np.zeros(B, np.int32))
+        proj = np.zeros((B, self.A, 6, n)) if want_people_proj else None
+        io = abi.SmpcFleetIo()
+        io.n_robots, io.max_poses, io.n_agents, io.time_step = B, n, self.A, float(p.time_step)
+        io.n_poses, io.people, io.n_people, io.speed = (n_poses.ctypes.data, people_raw.ctypes.data,
+                                                          n_people.ctypes.data, speed.ctypes.data)
+        io.costmaps, io.costmap_origin = costmaps.ctypes.data, morg.ctypes.data
+        io.costmap_index = None if midx is None else midx.ctypes.data
+        io.n_costmaps, io.size_x, io.size_y = costmaps.shape[0], costmaps.shape[2], costmaps.shape[1]
+        io.resolution = float(costmap_resolution)
+        io.od_indexes, io.od_origin = oidx.ctypes.data, oorg.ctypes.data
+        io.od_index = None if osel is None else osel.ctypes.data
+        io.n_od_grids, io.od_width, io.od_height = oorg.shape[0], int(od["width"]), int(od["height"])
+        io.od_resolution = float(od["resolution"])
+        io.maps_version = self._maps_version
+        io.poses, io.cmds = pose_rows.ctypes.data, cmd_rows.ctypes.data
+        for k2, v in out.items():
+            setattr(io, k2, v.ctypes.data)
+        io.people_proj = None if proj is None else proj.ctypes.data
+        _lib.check(_lib.lib().smpc_optimize_batch(self.opt._h, C.byref(io)))
+        res = dict(out)
+        res["optimized"] = out["optimized"].astype(bool)
+        res["path"], res["cmds"], res["people_proj"] = pose_rows, cmd_rows, proj
         return res
