@@ -71,7 +71,7 @@ def test_optimize_matches_reference_pipeline(oracle, opt_for, param_set, n_peopl
                                                   od)
     robot, proj_ref, batch, out = _reference_tick(oracle, p, poses, cmds, None, people, speed, costmap, od)
     assert proj.shape == (len(robot), 3, 6)
-    assert np.allclose(proj, np.array(proj_ref), rtol=1e-12, atol=1e-12)  # SFM projection, host C++ vs numpy
+    assert np.allclose(proj, np.array(proj_ref), rtol=1e-10, atol=1e-10)  # SFM projection, GPU kernel vs numpy
     assert ok == bool(out["usable"][0])
     assert info["termination"] == out["termination"][0] and info["iterations"] == out["iterations"][0]
     assert info["cost_final"] == pytest.approx(out["cost_final"][0], rel=1e-8)
@@ -228,20 +228,113 @@ def test_fleet_tick_matches_per_robot_optimize(opt_for):
             got = fleet.optimize_batch(poses, cmds, people_raw, n_people, speed, costmap[None], np.zeros((1, 2)), 0.05,
                                        od_b)
             assert np.all(got["project_status"] == 0)
+            n_b = got["n_out"]
             for b in range(B):
                 ok, path, new_cmds, proj, info = singles[b].optimize(poses[b], cmds[b], scenes[b][3][:A], speed[b],
                                                                       p.time_step, costmap, (0.0, 0.0), 0.05, od)
                 assert bool(got["optimized"][b]) == ok
-                assert np.abs(got["people_proj"][b] - np.transpose(proj, (1, 2, 0))).max() <= 1e-9
+                n = int(n_b[b])
+                assert n == path.shape[0]
+                assert np.abs(got["people_proj"][b][:, :, :n] - np.transpose(proj, (1, 2, 0))).max() <= 1e-9
                 assert got["termination"][b] == info["termination"]
-                assert np.abs(got["cmds"][b] - new_cmds).max() <= 1e-6, (tick, b)
-                assert np.abs(got["path"][b][:, :2] - path[:, :2]).max() <= 1e-6
+                assert np.abs(got["cmds"][b][:n] - new_cmds).max() <= 1e-6, (tick, b)
+                assert np.abs(got["path"][b][:n, :2] - path[:, :2]).max() <= 1e-6
                 assert got["cost_final"][b] == pytest.approx(info["cost_final"], rel=1e-8)
     finally:
         fleet.close()
         for o in singles:
             o.close()
     assert n_in >= 2
+
+
+def test_fleet_tick_with_mixed_path_lengths_matches_reference_pipeline(oracle):
+    """smpc_optimize_batch with per-robot horizons: robots near their goal get shorter seeds from the trajectorizer
+    (reference src/path_trajectorizer.cpp:152) and with them fewer steps, a shorter control horizon and fewer parameter
+    blocks (src/optimizer.cpp:248-249). Every robot is checked against the reference pipeline run for it alone —
+    tests/presolve_ref.py (numpy people_to_status / format_to_optimize / project_people) + the CPU oracle — over two
+    ticks, so that the per-robot warm-start memory with its own length is exercised. A robot with a one-pose path is
+    reported not optimized and left untouched (:158-162)."""
+    from nav2_social_mpc_controller_b200.fleet import FleetOptimizer
+    lengths = [31, 24, 17, 12, 8, 5, 3, 2, 1, 31]
+    B, A = len(lengths), 3
+    scenes = [_scene("soc_work_obst", n_people=(b % 3) + 1, seed=40 + b) for b in range(B)]
+    p, od, costmap = scenes[0][0], scenes[0][6], scenes[0][5]
+    n_full = scenes[0][1].shape[0]
+    poses = np.stack([s[1] for s in scenes])
+    cmds = np.stack([s[2] for s in scenes])
+    n_poses = np.minimum(np.array(lengths), n_full).astype(np.int32)
+    speed = np.array([[0.3, 0.05]] * B)
+    people_raw = np.zeros((B, A, 5))
+    n_people = np.zeros(B, dtype=np.int32)
+    for b, s in enumerate(scenes):
+        k = min(A, s[3].shape[0])
+        people_raw[b, :k] = s[3][:k]
+        n_people[b] = k
+    od_b = dict(width=od["width"], height=od["height"], resolution=od["resolution"], origins=[[0.0, 0.0]],
+                indexes=od["indexes"])
+    fleet = FleetOptimizer(p, n_robots=B, n_agents=A)
+    prev = [None] * B
+    try:
+        for tick in range(2):
+            got = fleet.optimize_batch(poses, cmds, people_raw, n_people, speed, costmap[None], np.zeros((1, 2)), 0.05,
+                                       od_b, n_poses=n_poses)
+            for b in range(B):
+                nb_in = int(n_poses[b])
+                if nb_in < 2:
+                    assert not got["optimized"][b] and got["n_out"][b] == nb_in
+                    assert np.array_equal(got["path"][b], poses[b]) and np.array_equal(got["cmds"][b][:30], cmds[b][:30])
+                    continue
+                robot, proj_ref, batch, out = _reference_tick(oracle, p, poses[b][:nb_in], cmds[b][:nb_in - 1], prev[b],
+                                                              scenes[b][3][:A], speed[b], costmap, od)
+                n = len(robot)
+                assert got["n_out"][b] == n, (tick, b)
+                want_proj = np.transpose(np.array(proj_ref), (1, 2, 0))
+                assert np.abs(got["people_proj"][b][:, :, :n] - want_proj).max() <= 1e-9, (tick, b)
+                assert bool(got["optimized"][b]) == bool(out["usable"][0])
+                assert got["termination"][b] == out["termination"][0] and got["iterations"][b] == out["iterations"][0]
+                assert got["cost_final"][b] == pytest.approx(out["cost_final"][0], rel=1e-8)
+                assert np.abs(got["cmds"][b][:n] - out["cmds"][0]).max() <= 1e-6, (tick, b)
+                assert np.abs(got["path"][b][:n, :2] - out["path"][0][:, :2]).max() <= 1e-6
+                if out["usable"][0]:
+                    prev[b] = (out["path"][0].tolist(), out["cmds"][0].tolist())
+                elif prev[b] is None:
+                    prev[b] = (poses[b][:nb_in].tolist(), cmds[b][:nb_in - 1].tolist())
+    finally:
+        fleet.close()
+
+
+def test_fleet_maps_stay_resident_and_person_leaving_the_grid_is_reported():
+    """Costmaps / obstacle grids are re-sent only when they change (maps_version); a person who walks out of the obstacle
+    grid makes the reference throw — the fleet reports that robot as not optimized and keeps its memory."""
+    from nav2_social_mpc_controller_b200.fleet import FleetOptimizer
+    B, A = 4, 3
+    scenes = [_scene("soc_work_obst", n_people=1, seed=60 + b) for b in range(B)]
+    p, od, costmap = scenes[0][0], scenes[0][6], scenes[0][5]
+    poses = np.stack([s[1] for s in scenes])
+    cmds = np.stack([s[2] for s in scenes])
+    people_raw = np.zeros((B, A, 5))
+    for b, s in enumerate(scenes):
+        people_raw[b, 0] = s[3][0]
+    people_raw[2, 0] = [3.97, 2.0, 0.8, 0.0, 0.0]  # leaves the 4 m grid within the horizon
+    n_people = np.ones(B, dtype=np.int32)
+    speed = np.array([[0.3, 0.05]] * B)
+    od_b = dict(width=od["width"], height=od["height"], resolution=od["resolution"], origins=[[0.0, 0.0]],
+                indexes=od["indexes"])
+    maps = costmap[None].copy()
+    fleet = FleetOptimizer(p, n_robots=B, n_agents=A)
+    try:
+        a = fleet.optimize_batch(poses, cmds, people_raw, n_people, speed, maps, np.zeros((1, 2)), 0.05, od_b)
+        v1 = fleet._maps_version
+        fleet.reset_memory()
+        b = fleet.optimize_batch(poses, cmds, people_raw, n_people, speed, maps, np.zeros((1, 2)), 0.05, od_b)
+        assert fleet._maps_version == v1  # same arrays: the maps were not re-sent
+        for k in ("cmds", "path", "optimized", "termination", "cost_final"):
+            assert np.array_equal(a[k], b[k]), k
+        assert a["project_status"][2] == 1 and not a["optimized"][2]
+        assert np.array_equal(a["cmds"][2][:cmds.shape[1]], cmds[2])  # the seed cmds are kept, as the caller would
+        assert a["optimized"][[0, 1, 3]].all()
+    finally:
+        fleet.close()
 
 
 def test_gpu_trajectorize_matches_numpy_restatement():
