@@ -17,7 +17,8 @@ own 65536 scenarios (weak scaling, no collective on the solve path); the time is
              (rank 0, at every N)
   legs       the other BASELINE configs measured in the same run: configs[1] obst_only x4096, configs[3] multi-start
              256 x 1024 sharded by robot with the per-robot arg-min and the host gather inside the timed region,
-             configs[4] 10^6 problems x 50 agents STRONG scaling (10^6 / N per rank) with the final host gather,
+             configs[4] 10^6 problems x 50 agents STRONG scaling (10^6 / N per rank) with the final host gather, in the
+             reference's unicycle model and in the omnidirectional extension,
              configs[0] single-solve latency
 --impl reference times only the CPU restatement (the reference's own code needs Ceres + ROS and cannot build here).
 """
@@ -384,7 +385,7 @@ def measure(ctx, name, steps, warmup, sampler=None, with_cpu=False, threads=1):
 
 def roofline_block(ctx, res, k_ms):
     batch, S, A, nb = res["batch"], res["S"], res["A"], res["nb"]
-    P = 2 * nb
+    P = batch.dof * nb
     n_evals = res["dev_out"]["n_evals"].cpu().numpy().astype(np.float64)
     iters = res["dev_out"]["iterations"].cpu().numpy().astype(np.float64)
     term = res["dev_out"]["termination"].cpu().numpy()
@@ -506,7 +507,7 @@ def leg_multistart(ctx, steps, warmup, n_robots=256, n_starts=1024):
     return out
 
 
-def leg_scaling_sweep(ctx, steps, warmup, name="crowd_x1M_A50"):
+def leg_scaling_sweep(ctx, steps, warmup, name="crowd_x1M_A50", omni=False):
     """BASELINE configs[4]: 10^6 problems x 50 agents, STRONG scaling: every rank solves 10^6 / N problems (inputs
     resident in HBM: 70 GB of agent trajectories cannot come from the host every step), then the result table
     (u, cost_final, iterations, termination, usable) goes D2H and is gathered on rank 0: the north star's 'final host
@@ -515,13 +516,17 @@ def leg_scaling_sweep(ctx, steps, warmup, name="crowd_x1M_A50"):
     torch = ctx.torch
     builder, desc, _ = WORKLOADS[name]
     batch = builder()
+    if omni:  # (vx, vy, w) blocks: the extension of BASELINE configs[4]; no reference solve exists for it
+        batch = sc.omni(batch)
+        desc = desc.replace("(unicycle)", "(OMNIDIRECTIONAL blocks vx, vy, w: extension, checked against this repo's "
+                            "own oracle functors only — the reference has no omnidirectional solve)")
     total = TILED_TOTAL[name]
     B = total // ctx.world
     S, A, nb = batch.n_steps, batch.n_agents, batch.dims[2]
     opt = Optimizer(ctx.local_rank)
     opt.initialize(batch.params)
     _, dev_arrays = device_batch(ctx, batch, B, total)
-    shapes = abi.result_shapes(B, S, nb)
+    shapes = abi.result_shapes(B, S, nb, batch.dof)
     want = ("u", "cost_final", "iterations", "termination", "usable", "n_evals")
     dev_out = {k: torch.zeros(shapes[k][0], dtype=ctx.tdt[shapes[k][1]], device=ctx.dev) for k in want}
     dstruct = abi.make_batch_struct(dev_arrays, B, S, A, batch.n_costmaps, batch.size_x, batch.size_y,
@@ -553,7 +558,8 @@ def leg_scaling_sweep(ctx, steps, warmup, name="crowd_x1M_A50"):
                                             want=("u", "cost_final", "usable", "iterations", "termination"))
         mine = {k: got[k][:n] for k in ("u", "cost_final", "usable", "iterations", "termination")}
         out = {"workload": name, "description": desc, "scaling": "strong", "problems_total": total,
-               "problems_per_gpu": B, "model": "unicycle", "value": total * steps / (tot_ms * 1e-3), "unit": UNIT,
+               "problems_per_gpu": B, "model": "omnidirectional" if omni else "unicycle",
+               "value": total * steps / (tot_ms * 1e-3), "unit": UNIT,
                "ms_per_step": tot_ms / steps,
                "value_with_gather": total * steps / tot_g, "ms_per_step_with_gather": 1e3 * tot_g / steps,
                "gathered_bytes_per_step": int(sum(t.numel() * t.element_size() for t in pin.values())) * ctx.world,
@@ -597,7 +603,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default=HEADLINE, choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--legs", default="all", help="all | none | comma list of obst_only,multistart,scaling_sweep,latency")
+    ap.add_argument("--legs", default="all", help="all | none | comma list of obst_only,multistart,scaling_sweep,scaling_sweep_omni,latency")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--latency-calls", type=int, default=300)
     args = ap.parse_args()
@@ -615,7 +621,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libsmpc has no CPU path")
     ctx = Ctx(rank, local_rank, world)
-    legs = ("obst_only", "multistart", "scaling_sweep", "latency") if args.legs == "all" else \
+    legs = ("obst_only", "multistart", "scaling_sweep", "scaling_sweep_omni", "latency") if args.legs == "all" else \
         tuple(x for x in args.legs.split(",") if x and x != "none")
     if args.latency_calls <= 0:
         legs = tuple(x for x in legs if x != "latency")
@@ -664,6 +670,8 @@ def main():
         leg_out["multistart_256x1024"] = leg_multistart(ctx, min(args.steps, 3), 3)
     if "scaling_sweep" in legs:
         leg_out["crowd_x1M_A50"] = leg_scaling_sweep(ctx, min(args.steps, 2), 2)
+    if "scaling_sweep_omni" in legs:
+        leg_out["crowd_x1M_A50_omni"] = leg_scaling_sweep(ctx, min(args.steps, 2), 2, omni=True)
     if "latency" in legs and rank == 0:
         leg_out["single_solve_latency"] = leg_latency(ctx, args.latency_calls)
     if rank == 0:

@@ -392,7 +392,7 @@ typedef struct smpc_format_args {
 int smpc_format_batch_device(smpc_handle* h, const smpc_format_args* a, void* stream);
 
 /* ---- batched seed generation on the GPU: PathTrajectorizer::trajectorize (src/path_trajectorizer.cpp:120-288) ----
- * One thread per robot: pure-pursuit look-ahead on its global path, diff-drive (curvature law, rotate in place beyond
+ * One warp per robot (the 32 lanes search the global path for the look-ahead point): pure-pursuit on its global path, diff-drive (curvature law, rotate in place beyond
  * 90 deg) or omnidirectional branch (:190-194), forward-Euler simulation with the DOUBLE time_step, early
  * stop within 0.2 m of the goal. global_path [B][n_path][2] (path_index NULL) or [Mp][n_path][2] selected by
  * path_index [B]; pose [B][3]. Outputs poses [B][max_steps+1][3] (pose 0 = the robot pose, yaw round-tripped like

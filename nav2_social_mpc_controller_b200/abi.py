@@ -154,10 +154,11 @@ RESULT_FIELDS = ("u", "cmds", "path", "cost_initial", "cost_final", "iterations"
                  "n_evals")
 
 
-def result_shapes(n_problems: int, n_steps: int, n_blocks: int):
+def result_shapes(n_problems: int, n_steps: int, n_blocks: int, dof: int = 2):
+    """dof = parameters per block: 2 = (v, w), 3 = omnidirectional (vx, vy, w) (smpc_params.omni_solve)."""
     return {
-        "u": ((n_problems, n_blocks, 2), np.float64),
-        "cmds": ((n_problems, n_steps + 1, 2), np.float64),
+        "u": ((n_problems, n_blocks, dof), np.float64),
+        "cmds": ((n_problems, n_steps + 1, dof), np.float64),
         "path": ((n_problems, n_steps + 1, 3), np.float64),
         "cost_initial": ((n_problems,), np.float64),
         "cost_final": ((n_problems,), np.float64),

@@ -32,6 +32,7 @@ struct DevParams {
   double param_tol, fn_tol, gradient_tol;
   int max_iterations, ceres_compat, max_evaluations;
   int ch, bl, nb, n_bounded;  // of the batch's longest horizon (nb = template NB of the kernel)
+  int dof;  // parameters per block: 2 = (v, w) reference unicycle, 3 = (vx, vy, w) omnidirectional extension
   int control_horizon, block_length;  // yaml values: per-problem dims are derived from them (src/optimizer.cpp:248-249)
 };
 
@@ -347,9 +348,12 @@ __device__ __forceinline__ void scan_levels(F level) {
 // They differ only under ceres_compat < 210, where ProxemicsCost evaluates differently under Jets (evaluate()).
 constexpr int kRedStride = 33;  // odd stride of the per-warp reduction scratch: conflict-free rows and columns
 
-template <int NB>
+// D = parameters per block: 2 = (v, w), the reference's unicycle (update_state.hpp:46-61); 3 = (vx, vy, w), the
+// omnidirectional extension (holonomic Euler step x += (vx cos th - vy sin th) dt, consistent with the reference's
+// trajectorizer, path_trajectorizer.hpp:106-123; the reference has no omnidirectional SOLVE).
+template <int NB, int D = 2>
 struct Layout {
-  static constexpr int P = 2 * NB;
+  static constexpr int P = D * NB;
   static constexpr int NH = P * (P + 1) / 2;
   static constexpr int NG = 2 + P;       // cost_diff, cost_plain, g[P]: the part every evaluation reduces
   static constexpr int NE = NG + NH;     // ... plus J^T J
@@ -374,12 +378,12 @@ struct Layout {
 };
 
 // Layout<NB>::total(S) for a run-time NB (the host sizes the parking area of the time-sliced queue with it).
-__host__ __device__ constexpr int layout_total(int nb, int S) {
-  const int P = 2 * nb, NE = 2 + P + P * (P + 1) / 2, NC = 4 + 4 * nb;
+__host__ __device__ constexpr int layout_total(int nb, int S, int dof = 2) {
+  const int P = dof * nb, NE = 2 + P + P * (P + 1) / 2, NC = 4 + 4 * nb;
   return ((2 * NE + 6 * P + NC + 2 + 22 + 18 + S) | 1);
 }
 static_assert(layout_total(3, 28) == Layout<3>::total(28) && layout_total(5, 38) == Layout<5>::total(38) &&
-                  layout_total(18, 18) == Layout<18>::total(18),
+                  layout_total(18, 18) == Layout<18>::total(18) && layout_total(3, 28, 3) == Layout<3, 3>::total(28),
               "layout_total must mirror Layout<NB>::total");
 
 template <int G>
@@ -423,11 +427,11 @@ enum StateFlags {
 // its cost and directional derivative only (Ceres evaluates exactly cost + gradient there, line_search.cc), so its
 // J^T J is not built and kNoHessian is returned. st == nullptr: always build J^T J.
 // ---------------------------------------------------------------------------------------------------
-template <int NB, int G, bool PPL>
+template <int NB, int G, bool PPL, int D = 2>
 __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatch& bt, const Prob& pb, bool live,
                                              double* ws, double* red, const double* xs, int lane, double* out,
                                              const LmState* st) {
-  using L = Layout<NB>;
+  using L = Layout<NB, D>;
   constexpr int P = L::P;
   const int gl = lane & (G - 1);
   const unsigned gmask = Group<G>::mask(lane);
@@ -457,16 +461,18 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
     // block of step j (j / bl capped at the problem's last block) and d theta_j / d w_b = dt #{steps < j in block b}
     int bj = 0;
     SMPC_UNROLL for (int b = 1; b < NB; ++b) bj += (j >= b * bl && b <= last_b) ? 1 : 0;
-    double vj = xs[0], wj = xs[1];
+    double vj = xs[0], wj = xs[D - 1];
+    double vyj = 0.0;     // lateral velocity of the step's block (omnidirectional blocks only)
     double Th = pb.yaw0;  // heading AFTER step j = yaw0 + sum_b w_b dt #{steps <= j in block b}
     double tau[NB];       // d theta_j / d w_b (heading before step j)
     SMPC_UNROLL for (int b = 0; b < NB; ++b) {
       if (b == bj) {
-        vj = xs[2 * b];
-        wj = xs[2 * b + 1];
+        vj = xs[D * b];
+        wj = xs[D * b + D - 1];
+        if (D == 3) vyj = xs[D * b + 1];
       }
       tau[b] = dt * (double)steps_in_block_before(j, b, bl, last_b);
-      Th += xs[2 * b + 1] * tau[b];
+      Th += xs[D * b + D - 1] * tau[b];
     }
     Th += wj * dt;
     // one sincos per step: lane j evaluates the heading after its step; the heading before it is the
@@ -480,7 +486,9 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
       cs = first ? c0 : carry[3];
     }
     const double cdt = act ? cs * dt : 0.0, sdt = act ? sn * dt : 0.0;
-    const double aj = vj * cdt, bjv = vj * sdt;
+    // displacement of step j: unicycle v (cos, sin) dt; omnidirectional R(theta) (vx, vy) dt
+    const double aj = (D == 3) ? vj * cdt - vyj * sdt : vj * cdt;
+    const double bjv = (D == 3) ? vj * sdt + vyj * cdt : vj * sdt;
 
     // ---- positions: two scans -----------------------------------------------------------------------------
     double sx = aj, sy = bjv;
@@ -499,6 +507,7 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
     //      never live together. Each critic leaves its residual and its gradient wrt (X, Y, Theta, lv). ----------
     double ra = 0.0, caT = 0.0;                                // AgentAngle: residual, d/dTheta
     double rs = 0.0, sX = 0.0, sY = 0.0, sTh = 0.0, sL = 0.0;  // SocialWork
+    double sM = 0.0;                                           // ... d/d(lateral velocity), omnidirectional only
     double rp = 0.0, pX = 0.0, pY = 0.0;                       // Proxemics (differentiated evaluation)
     double cprox_plain = 0.0;                                  // 1/2 r^2 of Proxemics as a cost-only evaluation sees it
     if (PPL && act && pb.has_people) {  // PPL == false: the people critics are compiled out (people-free batch)
@@ -510,7 +519,9 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
         caT = 2.0 * prm.w_agent_angle * del;
       }
       // --- SocialWork (k=1) and Proxemics (k=2) ----------------------------------------------------
-      const double rvx = vj * cT, rvy = vj * sT;  // robot velocity uses lv = v_{b(i)} and the NEW heading
+      // robot velocity uses lv = v_{b(i)} and the NEW heading (omnidirectional: the body velocity rotated into the world)
+      const double rvx = (D == 3) ? vj * cT - vyj * sT : vj * cT;
+      const double rvy = (D == 3) ? vj * sT + vyj * cT : vj * sT;
       double Frx = 0.0, Fry = 0.0;
       double JFx[4] = {0, 0, 0, 0}, JFy[4] = {0, 0, 0, 0};
       double wp = 0.0;
@@ -581,7 +592,12 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
         sX = prm.w_social * G4[0];
         sY = prm.w_social * G4[1];
         sL = prm.w_social * (G4[2] * cT + G4[3] * sT);
-        sTh = prm.w_social * vj * (-G4[2] * sT + G4[3] * cT);
+        if (D == 3) {
+          sM = prm.w_social * (-G4[2] * sT + G4[3] * cT);
+          sTh = prm.w_social * (-G4[2] * rvy + G4[3] * rvx);
+        } else {
+          sTh = prm.w_social * vj * (-G4[2] * sT + G4[3] * cT);
+        }
       }
       // Proxemics: w * 3 * exp(-dmin / 0.25), proxemics_cost_function.hpp:128-149.
       //  * Ceres >= 2.1: std::numeric_limits<Jet>::max() is DBL_MAX. With no valid agent the value is 0 but the jet
@@ -632,9 +648,34 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
       __syncwarp(gmask);
     }
 
+    // Column pa of the lane's sensitivity matrix D (rows X, Y, Theta, L, M), as (dX, dY, third component) + its kind:
+    //   kind 0  v_b / vx_b : (sum cos dt, sum sin dt, [b == bj] on L)
+    //   kind 1  vy_b       : (-sum sin dt, sum cos dt, [b == bj] on M)          (omnidirectional blocks only)
+    //   kind 2  w_b        : (dX/dw_b, dY/dw_b, dTheta/dw_b on Theta)
+    // pa is a compile-time constant wherever this is called (unrolled loops), so the selects fold away.
+    auto column = [&](int pa, double& cx, double& cy, double& c3) -> int {
+      const int ba = pa / D, k = pa % D;
+      if (k == D - 1) {
+        cx = sd[4 * ba + 2];
+        cy = sd[4 * ba + 3];
+        c3 = tau[ba] + ((ba == bj) ? dt : 0.0);  // d Theta_j / d w_ba (heading after step j)
+        return 2;
+      }
+      c3 = (ba == bj) ? 1.0 : 0.0;
+      if (k == 0) {
+        cx = sd[4 * ba + 0];
+        cy = sd[4 * ba + 1];
+        return 0;
+      }
+      cx = -sd[4 * ba + 1];
+      cy = sd[4 * ba + 0];
+      return 1;
+    };
     // per-lane Gauss-Newton block wrt (X, Y, Theta, lv): M = sum c c^T (10 entries), q = sum c r
     double mXX = 0, mXY = 0, mXT = 0, mXL = 0, mYY = 0, mYT = 0, mYL = 0, mTT = 0, mTL = 0, mLL = 0;
     double qX = 0, qY = 0, qT = 0, qL = 0;
+    // omnidirectional blocks add the lateral velocity M as a fifth coordinate of the lane block
+    double mXM = 0, mYM = 0, mTM = 0, mLM = 0, mMM = 0, qM = 0;
     if (act) {
       double cost = 0.0;
       if (PPL) {  // fold the people critics in (all zero for a problem without people)
@@ -646,17 +687,29 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
         mYY += sY * sY; mYT += sY * sTh; mYL += sY * sL;
         mTT += sTh * sTh; mTL += sTh * sL; mLL += sL * sL;
         qX += sX * rs; qY += sY * rs; qT += sTh * rs; qL += sL * rs;
+        if (D == 3) {
+          mXM += sX * sM; mYM += sY * sM; mTM += sTh * sM; mLM += sL * sM; mMM += sM * sM;
+          qM += sM * rs;
+        }
         mXX += pX * pX; mXY += pX * pY; mYY += pY * pY;
         qX += pX * rp; qY += pY * rp;
       }
       // --- Velocity (k=3): w (0.6 - v_b)^2 for i < ch ---------------------------------------------------
       if (j < ch) {
         const double e = 0.6 - vj;
-        const double r = prm.w_velocity * e * e;
-        const double cL = -2.0 * prm.w_velocity * e;
-        cost += 0.5 * r * r;
-        mLL += cL * cL;
-        qL += cL * r;
+        if (D == 3) {  // omnidirectional extension: w ((0.6 - vx)^2 + vy^2)
+          const double r = prm.w_velocity * e * e + prm.w_velocity * vyj * vyj;
+          const double cL = -2.0 * prm.w_velocity * e, cM = 2.0 * prm.w_velocity * vyj;
+          cost += 0.5 * r * r;
+          mLL += cL * cL; mLM += cL * cM; mMM += cM * cM;
+          qL += cL * r; qM += cM * r;
+        } else {
+          const double r = prm.w_velocity * e * e;
+          const double cL = -2.0 * prm.w_velocity * e;
+          cost += 0.5 * r * r;
+          mLL += cL * cL;
+          qL += cL * r;
+        }
       }
       // --- GoalAlign (k=4): w * wrap(psi - Theta)^2 -----------------------------------------------------
       {
@@ -714,13 +767,11 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
           constexpr bool kFirst = decltype(is_first)::value;
           r0[0 * kRedStride] = (kFirst ? 0.0 : r0[0 * kRedStride]) + c_diff;
           r0[1 * kRedStride] = (kFirst ? 0.0 : r0[1 * kRedStride]) + c_plain;
-          SMPC_UNROLL for (int ba = 0; ba < NB; ++ba) {
-            const double la = (ba == bj) ? 1.0 : 0.0;
-            const double twa = tau[ba] + ((ba == bj) ? dt : 0.0);  // d Theta_j / d w_ba (heading after step j)
-            double* gv = r0 + L::g(2 * ba) * kRedStride;
-            double* gw = r0 + L::g(2 * ba + 1) * kRedStride;
-            *gv = (kFirst ? 0.0 : *gv) + (qX * sd[4 * ba + 0] + qY * sd[4 * ba + 1] + qL * la);
-            *gw = (kFirst ? 0.0 : *gw) + (qX * sd[4 * ba + 2] + qY * sd[4 * ba + 3] + qT * twa);
+          SMPC_UNROLL for (int pa = 0; pa < P; ++pa) {
+            double cx, cy, cs3;
+            const int kind = column(pa, cx, cy, cs3);
+            double* gp = r0 + L::g(pa) * kRedStride;
+            *gp = (kFirst ? 0.0 : *gp) + (qX * cx + qY * cy + ((kind == 0) ? qL : (kind == 1) ? qM : qT) * cs3);
           }
         };
         if (first) put_g(std::true_type{}); else put_g(std::false_type{});
@@ -735,15 +786,18 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
       if (gl == 0 && live) {
         SMPC_UNROLL for (int i = 1; i < NB; ++i) {
           if (i < pb.nbd) {
-            const double dv = xs[2 * i] - xs[2 * i - 2], dw = xs[2 * i + 1] - xs[2 * i - 1];
-            const double r = prm.w_vf * dv * dv + prm.w_vf * dw * dw;
-            const double jv = 2.0 * prm.w_vf * dv, jw = 2.0 * prm.w_vf * dw;
+            double dk[D], r = 0.0;
+            SMPC_UNROLL for (int k = 0; k < D; ++k) {
+              dk[k] = xs[D * i + k] - xs[D * (i - 1) + k];
+              r += prm.w_vf * dk[k] * dk[k];
+            }
             red[0 * kRedStride + lane] += 0.5 * r * r;
             red[1 * kRedStride + lane] += 0.5 * r * r;
-            red[L::g(2 * i - 2) * kRedStride + lane] -= jv * r;
-            red[L::g(2 * i - 1) * kRedStride + lane] -= jw * r;
-            red[L::g(2 * i) * kRedStride + lane] += jv * r;
-            red[L::g(2 * i + 1) * kRedStride + lane] += jw * r;
+            SMPC_UNROLL for (int k = 0; k < D; ++k) {
+              const double jk = 2.0 * prm.w_vf * dk[k];
+              red[L::g(D * (i - 1) + k) * kRedStride + lane] -= jk * r;
+              red[L::g(D * i + k) * kRedStride + lane] += jk * r;
+            }
           }
         }
       }
@@ -780,40 +834,20 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
         double* r0 = red + lane;
         auto put_h = [&](auto is_first) {
           constexpr bool kFirst = decltype(is_first)::value;
-          auto acc = [&](int e, double v) {
-            double* p = r0 + e * kRedStride;
-            *p = (kFirst ? 0.0 : *p) + v;
-          };
-          SMPC_UNROLL for (int ba = 0; ba < NB; ++ba) {
-            const double la = (ba == bj) ? 1.0 : 0.0;
-            const double twa = tau[ba] + ((ba == bj) ? dt : 0.0);
-            {  // column a = 2 ba (v_ba)
-              const double xv = sd[4 * ba + 0], yv = sd[4 * ba + 1];
-              const double t0 = mXX * xv + mXY * yv + mXL * la;
-              const double t1 = mXY * xv + mYY * yv + mYL * la;
-              const double t2 = mXT * xv + mYT * yv + mTL * la;
-              const double t3 = mXL * xv + mYL * yv + mLL * la;
-              SMPC_UNROLL for (int bb = 0; bb <= ba; ++bb) {
-                const double lb = (bb == bj) ? 1.0 : 0.0;
-                acc(L::h(2 * ba, 2 * bb), sd[4 * bb + 0] * t0 + sd[4 * bb + 1] * t1 + lb * t3);
-                if (bb < ba) {
-                  const double twb = tau[bb] + ((bb == bj) ? dt : 0.0);
-                  acc(L::h(2 * ba, 2 * bb + 1), sd[4 * bb + 2] * t0 + sd[4 * bb + 3] * t1 + twb * t2);
-                }
-              }
-            }
-            {  // column a = 2 ba + 1 (w_ba)
-              const double xw = sd[4 * ba + 2], yw = sd[4 * ba + 3];
-              const double t0 = mXX * xw + mXY * yw + mXT * twa;
-              const double t1 = mXY * xw + mYY * yw + mYT * twa;
-              const double t2 = mXT * xw + mYT * yw + mTT * twa;
-              const double t3 = mXL * xw + mYL * yw + mTL * twa;
-              SMPC_UNROLL for (int bb = 0; bb <= ba; ++bb) {
-                const double lb = (bb == bj) ? 1.0 : 0.0;
-                const double twb = tau[bb] + ((bb == bj) ? dt : 0.0);
-                acc(L::h(2 * ba + 1, 2 * bb), sd[4 * bb + 0] * t0 + sd[4 * bb + 1] * t1 + lb * t3);
-                acc(L::h(2 * ba + 1, 2 * bb + 1), sd[4 * bb + 2] * t0 + sd[4 * bb + 3] * t1 + twb * t2);
-              }
+          SMPC_UNROLL for (int pa = 0; pa < P; ++pa) {
+            double ax, ay, as3;
+            const int ka = column(pa, ax, ay, as3);
+            // T = M d_a over (X, Y, Theta, L, M); the third component of d_a sits on L (kind 0), M (1) or Theta (2)
+            const double t0 = mXX * ax + mXY * ay + ((ka == 0) ? mXL : (ka == 1) ? mXM : mXT) * as3;
+            const double t1 = mXY * ax + mYY * ay + ((ka == 0) ? mYL : (ka == 1) ? mYM : mYT) * as3;
+            const double t2 = mXT * ax + mYT * ay + ((ka == 0) ? mTL : (ka == 1) ? mTM : mTT) * as3;
+            const double t3 = mXL * ax + mYL * ay + ((ka == 0) ? mLL : (ka == 1) ? mLM : mTL) * as3;
+            const double t4 = mXM * ax + mYM * ay + ((ka == 0) ? mLM : (ka == 1) ? mMM : mTM) * as3;
+            SMPC_UNROLL for (int pb2 = 0; pb2 <= pa; ++pb2) {
+              double bx, by, bs3;
+              const int kb = column(pb2, bx, by, bs3);
+              double* p = r0 + L::h(pa, pb2) * kRedStride;
+              *p = (kFirst ? 0.0 : *p) + (bx * t0 + by * t1 + bs3 * ((kb == 0) ? t3 : (kb == 1) ? t4 : t2));
             }
           }
         };
@@ -825,23 +859,22 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
   }
 
   if (need_h) {
-    // VelocityFeasibility, J^T J part. Row: [2i-2] = -jv, [2i-1] = -jw, [2i] = jv, [2i+1] = jw
+    // VelocityFeasibility, J^T J part. Row of residual i: -j_k at block i-1, +j_k at block i, j_k = 2 w (u_i - u_{i-1})_k
     if (gl == 0 && live) {
       SMPC_UNROLL for (int i = 1; i < NB; ++i) {
         if (i < pb.nbd) {
-          const double dv = xs[2 * i] - xs[2 * i - 2], dw = xs[2 * i + 1] - xs[2 * i - 1];
-          const double jv = 2.0 * prm.w_vf * dv, jw = 2.0 * prm.w_vf * dw;
-          const int p0 = 2 * i - 2, p1 = 2 * i - 1, p2 = 2 * i, p3 = 2 * i + 1;
-          red[(L::h(p0, p0)) * kRedStride + lane] += jv * jv;
-          red[(L::h(p1, p0)) * kRedStride + lane] += jw * jv;
-          red[(L::h(p1, p1)) * kRedStride + lane] += jw * jw;
-          red[(L::h(p2, p0)) * kRedStride + lane] -= jv * jv;
-          red[(L::h(p2, p1)) * kRedStride + lane] -= jv * jw;
-          red[(L::h(p2, p2)) * kRedStride + lane] += jv * jv;
-          red[(L::h(p3, p0)) * kRedStride + lane] -= jw * jv;
-          red[(L::h(p3, p1)) * kRedStride + lane] -= jw * jw;
-          red[(L::h(p3, p2)) * kRedStride + lane] += jw * jv;
-          red[(L::h(p3, p3)) * kRedStride + lane] += jw * jw;
+          double jk[D];
+          SMPC_UNROLL for (int k = 0; k < D; ++k) jk[k] = 2.0 * prm.w_vf * (xs[D * i + k] - xs[D * (i - 1) + k]);
+          SMPC_UNROLL for (int k = 0; k < D; ++k) {
+            SMPC_UNROLL for (int l = 0; l < D; ++l) {
+              const double v = jk[k] * jk[l];
+              if (l <= k) {
+                red[(L::h(D * i + k, D * i + l)) * kRedStride + lane] += v;
+                red[(L::h(D * (i - 1) + k, D * (i - 1) + l)) * kRedStride + lane] += v;
+              }
+              red[(L::h(D * i + k, D * (i - 1) + l)) * kRedStride + lane] -= v;
+            }
+          }
         }
       }
     }
@@ -1158,10 +1191,14 @@ static __device__ __noinline__ double quintic_interp_min(double f0, double g0, d
 
 // Box projection of ParameterBlock::Plus: only the first n_bounded blocks carry bounds
 // (reference src/optimizer.cpp:373-379: v in [0, 0.6], w in [-1.4, 1.4]).
+// Omnidirectional blocks (extension): the lateral velocity is bounded by the same speed, vy in [-0.6, 0.6].
+template <int D>
 __device__ __forceinline__ double project_param(double v, int c, int n_bounded) {
-  if ((c >> 1) < n_bounded) {
-    if (c & 1) return fmin(fmax(v, -1.4), 1.4);
-    return fmin(fmax(v, 0.0), 0.6);
+  if ((c / D) < n_bounded) {
+    const int k = c % D;
+    if (k == D - 1) return fmin(fmax(v, -1.4), 1.4);
+    if (k == 0) return fmin(fmax(v, 0.0), 0.6);
+    return fmin(fmax(v, -0.6), 0.6);
   }
   return v;
 }
@@ -1228,9 +1265,9 @@ __device__ __forceinline__ void load_problem(const DevParams& prm, const DevBatc
 }
 
 // Agent-angle steering targets of every step -> group shared memory (once per problem).
-template <int NB, int G, bool PPL>
+template <int NB, int G, bool PPL, int D = 2>
 __device__ __forceinline__ void agent_angle_setup(const DevBatch& bt, const Prob& pb, int lane, double* ws) {
-  using L = Layout<NB>;
+  using L = Layout<NB, D>;
   const int gl = lane & (G - 1);
   if (gl == 0) {
     double s0, c0;
@@ -1249,9 +1286,9 @@ __device__ __forceinline__ void agent_angle_setup(const DevBatch& bt, const Prob
 
 // Post-solve expansion (reference src/optimizer.cpp:390-446): cmds[S+1] hold block min(i/bl, nb-1) for i < ch
 // and the last block afterwards; the path is the Euler rollout of those cmds from pose0 (pose0 excluded).
-template <int NB, int G>
+template <int NB, int G, int D = 2>
 __device__ __forceinline__ void expand_outputs(const DevBatch& bt, const DevResult& rs, const Prob& pb, int b,
-                                               const double (&x)[2 * NB], int lane) {
+                                               const double (&x)[D * NB], int lane) {
   const int gl = lane & (G - 1);
   const unsigned gmask = Group<G>::mask(lane);
   const int S = pb.S, S1 = bt.S + 1, last_b = pb.nb - 1;
@@ -1263,24 +1300,30 @@ __device__ __forceinline__ void expand_outputs(const DevBatch& bt, const DevResu
     const int i = base + gl;
     const bool act = i <= S;
     const int bi = (i < pb.ch) ? min(i / pb.bl, last_b) : last_b;
-    double v = x[0], w = x[1];
+    double v = x[0], w = x[D - 1], vy = 0.0;
     double th = yaw_rt, th_next = yaw_rt;
     SMPC_UNROLL for (int bb = 0; bb < NB; ++bb) {
       if (bb == bi) {
-        v = x[2 * bb];
-        w = x[2 * bb + 1];
+        v = x[D * bb];
+        w = x[D * bb + D - 1];
+        if (D == 3) vy = x[D * bb + 1];
       }
-      th += x[2 * bb + 1] * (bt.dt * (double)steps_in_block_before(i, bb, pb.bl, last_b));
-      th_next += x[2 * bb + 1] * (bt.dt * (double)steps_in_block_before(i + 1, bb, pb.bl, last_b));
+      th += x[D * bb + D - 1] * (bt.dt * (double)steps_in_block_before(i, bb, pb.bl, last_b));
+      th_next += x[D * bb + D - 1] * (bt.dt * (double)steps_in_block_before(i + 1, bb, pb.bl, last_b));
     }
-    if (act && rs.cmds) {
-      rs.cmds[((size_t)b * S1 + i) * 2] = v;
-      rs.cmds[((size_t)b * S1 + i) * 2 + 1] = w;
+    if (act && rs.cmds) {  // cmds [B][S+1][D]: (v, w) or (vx, vy, w)
+      rs.cmds[((size_t)b * S1 + i) * D] = v;
+      if (D == 3) rs.cmds[((size_t)b * S1 + i) * D + 1] = vy;
+      rs.cmds[((size_t)b * S1 + i) * D + D - 1] = w;
     }
     if (rs.path) {
       double sn, cs;
       sincos(th, &sn, &cs);
       double sx = act ? v * cs * bt.dt : 0.0, sy = act ? v * sn * bt.dt : 0.0;
+      if (D == 3 && act) {
+        sx = (v * cs - vy * sn) * bt.dt;
+        sy = (v * sn + vy * cs) * bt.dt;
+      }
       SMPC_UNROLL for (int d = 1; d < G; d <<= 1) {
         const double tx = __shfl_up_sync(gmask, sx, d, G), ty = __shfl_up_sync(gmask, sy, d, G);
         if (gl >= d) {
@@ -1340,10 +1383,10 @@ __device__ __forceinline__ void trace_row(const DevResult& rs, int b, int row, d
   o[4] = cost_plain; o[5] = aux; o[6] = code; o[7] = radius;
 }
 
-template <int NB, int G, bool PPL>
+template <int NB, int G, bool PPL, int D = 2>
 __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch& bt, const DevResult& rs, int* queue,
                                            double* ws, double* red, int lane) {
-  using L = Layout<NB>;
+  using L = Layout<NB, D>;
   constexpr int P = L::P;
   const int gl = lane & (G - 1);
   const unsigned gmask = Group<G>::mask(lane);
@@ -1422,17 +1465,17 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
           load_problem<PPL>(prm, bt, nb_, *pbs);
         }
         __syncwarp(gmask);
-        agent_angle_setup<NB, G, PPL>(bt, *pbs, lane, ws);
+        agent_angle_setup<NB, G, PPL, D>(bt, *pbs, lane, ws);
         if (gl == 0) {
           // IterationZero: project the start point onto the box. Blocks the problem does not use (shorter horizon than
           // the batch's) stay exactly zero: no residual touches them, so their rows of J^T J and J^T r are zero, the LM
           // diagonal keeps their pivot positive and their step is exactly zero.
-          const int Pb = 2 * pbs->nb, nbd = pbs->nbd;
+          const int Pb = D * pbs->nb, nbd = pbs->nbd;
           for (int c = 0; c < P; ++c) {
             const double v = (c < Pb) ? ld_in<PPL>(bt.u0 + (size_t)nb_ * P + c) : 0.0;
             xs[c] = v;
             best[c] = v;
-            cand[c] = project_param(v, c, nbd);
+            cand[c] = project_param<D>(v, c, nbd);
           }
           LmState z;
           z.x_cost = z.x_norm = z.gmax = 0.0;
@@ -1469,7 +1512,7 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
     }
 
     const bool live = (gs->flags & kLive) != 0;
-    const unsigned fl = evaluate<NB, G, PPL>(prm, bt, *pbs, live, ws, red, cand, lane,
+    const unsigned fl = evaluate<NB, G, PPL, D>(prm, bt, *pbs, live, ws, red, cand, lane,
                                              ws + ((gs->flags & kSwapped) ? L::kBuf0 : L::kBuf1), gs);
 
     // ---- phase logic: the group's first lane alone, on the group's shared-memory state -----------------------
@@ -1540,13 +1583,13 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
             st.prev_gradient = gd;
             st.flags = eval_ok ? (st.flags | kPrevOk) : (st.flags & ~kPrevOk);
             st.t = t_new;
-            for (int c = 0; c < P; ++c) cand[c] = project_param(xs[c] + t_new * delta[c], c, nbd);
+            for (int c = 0; c < P; ++c) cand[c] = project_param<D>(xs[c] + t_new * delta[c], c, nbd);
             next_sample = true;  // evaluate the next line-search sample
           } else {
             // line search failed: the un-shortened TR step Plus(x, delta) is the candidate (delta unchanged). It needs
             // a full evaluation — also when t is still 1 and this very point was just sampled without its J^T J.
             st.t = 1.0;
-            for (int c = 0; c < P; ++c) cand[c] = project_param(xs[c] + delta[c], c, nbd);
+            for (int c = 0; c < P; ++c) cand[c] = project_param<D>(xs[c] + delta[c], c, nbd);
             st.phase = kFullStep;
             next_sample = true;
           }
@@ -1616,7 +1659,7 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
           for (int c = 0; c < P; ++c) {
             const double xv = xs[c];
             xn += xv * xv;
-            gm = fmax(gm, fabs(xv - project_param(xv - cur[L::g(c)], c, nbd)));
+            gm = fmax(gm, fabs(xv - project_param<D>(xv - cur[L::g(c)], c, nbd)));
           }
           st.x_norm = sqrt(xn);
           st.gmax = gm;
@@ -1695,7 +1738,7 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
               g0 += cur[L::g(c)] * dl;
               dmax = fmax(dmax, fabs(dl));
               delta[c] = dl;
-              cand[c] = project_param(xs[c] + dl, c, nbd);
+              cand[c] = project_param<D>(xs[c] + dl, c, nbd);
             }
             st.g0 = g0;
             st.dmax = dmax;
@@ -1734,7 +1777,7 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
       const LmState& st = *gs;
       const bool usable = st.term <= kNoConvergence;
       const int b = st.b;
-      const int Pb = 2 * pbs->nb;
+      const int Pb = D * pbs->nb;
       double x[P];
       SMPC_UNROLL for (int c = 0; c < P; ++c)
         x[c] = (c < Pb) ? (usable ? best[c] : ld_in<PPL>(bt.u0 + (size_t)b * P + c)) : 0.0;
@@ -1753,7 +1796,7 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
           rs.n_evals[2 * b + 1] = st.n_light;
         }
       }
-      if (rs.cmds || rs.path) expand_outputs<NB, G>(bt, rs, *pbs, b, x, lane);
+      if (rs.cmds || rs.path) expand_outputs<NB, G, D>(bt, rs, *pbs, b, x, lane);
       __syncwarp(gmask);
       if (gl == 0) {
         gs->phase = kFetch;

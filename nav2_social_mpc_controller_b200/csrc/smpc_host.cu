@@ -148,6 +148,9 @@ int make_dev_params(const smpc_params& p, int S, smpc::DevParams* d) {
   d->max_iterations = p.max_iterations;
   d->ceres_compat = p.ceres_compat ? p.ceres_compat : 200;
   d->max_evaluations = p.max_evaluations > 0 ? p.max_evaluations : 0;
+  d->dof = p.omni_solve ? 3 : 2;
+  if (d->dof == 3 && d->nb > 6)
+    return fail(SMPC_ERR_UNSUPPORTED, "omni_solve is built for up to 6 parameter blocks (18 parameters)");
   d->control_horizon = p.control_horizon;
   d->block_length = p.parameter_block_length;
   return SMPC_OK;
@@ -519,7 +522,7 @@ static int launch_solve_on(smpc_handle* h, const smpc_batch* in, smpc_result* ou
   if (h->park_quantum > 0 && !people && total_problems == static_cast<size_t>(in->n_problems) &&
       in->n_problems <= (1 << 18)) {
     const size_t Bp = static_cast<size_t>(in->n_problems);
-    const size_t state_bytes = align256(Bp * smpc::layout_total(prm.nb, in->n_steps) * sizeof(double));
+    const size_t state_bytes = align256(Bp * smpc::layout_total(prm.nb, in->n_steps, prm.dof) * sizeof(double));
     const size_t ring_bytes = align256(Bp * sizeof(int));
     SMPC_CUDA(h->park_buf.reserve(state_bytes + ring_bytes + 256));
     char* base = static_cast<char*>(h->park_buf.ptr);
@@ -615,7 +618,8 @@ int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out) {
   if (rc != SMPC_OK) return rc;
   SMPC_CUDA(cudaSetDevice(h->device));
   const size_t B = in->n_problems, S1 = static_cast<size_t>(in->n_steps) + 1, A = in->agents ? in->n_agents : 0;
-  const size_t M = in->n_costmaps, P = 2 * static_cast<size_t>(nb);
+  const size_t dof = h->params.omni_solve ? 3 : 2;  // parameters per block: (v, w) or the omnidirectional (vx, vy, w)
+  const size_t M = in->n_costmaps, P = dof * static_cast<size_t>(nb);
   const size_t map_cells = static_cast<size_t>(in->size_x) * in->size_y;
 
   // ---- chunking. Costmaps follow their problems when map b belongs to problem b (no index, M == B); otherwise the
@@ -656,7 +660,7 @@ int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out) {
   enum { kOU, kOCmds, kOPath, kOCi, kOCf, kOIt, kOTerm, kOUsable, kOEvals, kOTrace, kOItems };
   const size_t trace_rows = (out->trace && out->trace_rows > 0) ? static_cast<size_t>(out->trace_rows) : 0;
   OItem oitems[kOItems] = {
-      {out->u, P * 8, nullptr},        {out->cmds, S1 * 2 * 8, nullptr}, {out->path, S1 * 3 * 8, nullptr},
+      {out->u, P * 8, nullptr},        {out->cmds, S1 * dof * 8, nullptr}, {out->path, S1 * 3 * 8, nullptr},
       {out->cost_initial, 8, nullptr}, {out->cost_final, 8, nullptr},    {out->iterations, 4, nullptr},
       {out->termination, 4, nullptr},  {out->usable, 1, nullptr},        {out->n_evals, 2 * 4, nullptr},
       {trace_rows ? out->trace : nullptr, trace_rows * 8 * 8, nullptr},
@@ -839,7 +843,7 @@ int smpc_eval_batch(smpc_handle* h, const smpc_batch* in, const double* x, smpc_
     std::lock_guard<std::mutex> lk(h->mu);
     SMPC_CUDA(cudaSetDevice(h->device));
     const size_t B = in->n_problems, S1 = static_cast<size_t>(in->n_steps) + 1, A = in->agents ? in->n_agents : 0;
-    const size_t M = in->n_costmaps, P = 2 * static_cast<size_t>(nb), NH = P * (P + 1) / 2;
+    const size_t M = in->n_costmaps, P = (h->params.omni_solve ? 3 : 2) * static_cast<size_t>(nb), NH = P * (P + 1) / 2;
     struct Item { const void* host; size_t bytes; void** dev; };
     std::vector<Item> items = {
         {in->pose0, B * 3 * 8, (void**)&din.pose0},
@@ -881,7 +885,7 @@ int smpc_eval_batch(smpc_handle* h, const smpc_batch* in, const double* x, smpc_
   if (rc != SMPC_OK) return rc;
   {
     std::lock_guard<std::mutex> lk(h->mu);
-    const size_t B = in->n_problems, P = 2 * static_cast<size_t>(nb), NH = P * (P + 1) / 2;
+    const size_t B = in->n_problems, P = (h->params.omni_solve ? 3 : 2) * static_cast<size_t>(nb), NH = P * (P + 1) / 2;
     if (out->cost) SMPC_CUDA(cudaMemcpyAsync(out->cost, dout.cost, B * 8, cudaMemcpyDeviceToHost, h->stream));
     if (out->grad) SMPC_CUDA(cudaMemcpyAsync(out->grad, dout.grad, B * P * 8, cudaMemcpyDeviceToHost, h->stream));
     if (out->hess) SMPC_CUDA(cudaMemcpyAsync(out->hess, dout.hess, B * NH * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -904,7 +908,8 @@ int smpc_multistart_argmin_device(smpc_handle* h, int n_robots, int n_starts, in
   std::lock_guard<std::mutex> lk(h->mu);
   SMPC_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
-  SMPC_CUDA(smpc::launch_argmin(n_robots, n_starts, n_blocks, cost_final, usable, u, best_index, best_cost, best_u, st));
+  SMPC_CUDA(smpc::launch_argmin(n_robots, n_starts, n_blocks * (h->params.omni_solve ? 3 : 2), cost_final, usable, u, best_index,
+                                best_cost, best_u, st));
   h->launches += 1;
   return SMPC_OK;
 }

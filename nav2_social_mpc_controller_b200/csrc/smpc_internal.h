@@ -13,7 +13,7 @@ cudaError_t launch_solve(const DevParams& prm, const DevBatch& bt, const DevResu
                          int forced_group, int forced_warps, cudaStream_t stream);
 cudaError_t launch_eval(const DevParams& prm, const DevBatch& bt, const double* x, const DevEvalOut& eo, int n_sm,
                         int forced_group, cudaStream_t stream);
-cudaError_t launch_argmin(int n_robots, int n_starts, int n_blocks, const double* cost_final, const uint8_t* usable,
+cudaError_t launch_argmin(int n_robots, int n_starts, int n_params, const double* cost_final, const uint8_t* usable,
                           const double* u, int32_t* best_index, double* best_cost, double* best_u, cudaStream_t stream);
 int max_supported_blocks();
 cudaError_t launch_pack_agents(long long n_rows, int S1, const double* agents, double* packed, uint8_t* valid,

@@ -57,7 +57,7 @@ __global__ void smpc_polymin_kernel(int n, const double* __restrict__ in, double
 }
 
 // One CTA per robot: arg-min of cost_final over its n_starts consecutive solves (usable ones only; ties -> lowest index).
-__global__ void smpc_argmin_kernel(int n_starts, int n_blocks, const double* __restrict__ cost_final,
+__global__ void smpc_argmin_kernel(int n_starts, int n_params, const double* __restrict__ cost_final,
                                    const uint8_t* __restrict__ usable, const double* __restrict__ u,
                                    int32_t* best_index, double* best_cost, double* best_u) {
   __shared__ double s_cost[32];
@@ -104,12 +104,9 @@ __global__ void smpc_argmin_kernel(int n_starts, int n_blocks, const double* __r
       best_index[robot] = (bi >= 0) ? (int32_t)(base + bi) : -1;
       best_cost[robot] = (bi >= 0) ? bc : INFINITY;
     }
-    if (best_u && lane < 2 * n_blocks) {
-      best_u[(size_t)robot * 2 * n_blocks + lane] = (bi >= 0) ? u[(base + bi) * 2 * n_blocks + lane] : NAN;
-    }
     if (best_u)
-      for (int c = 32 + lane; c < 2 * n_blocks; c += 32)
-        best_u[(size_t)robot * 2 * n_blocks + c] = (bi >= 0) ? u[(base + bi) * 2 * n_blocks + c] : NAN;
+      for (int c = lane; c < n_params; c += 32)
+        best_u[(size_t)robot * n_params + c] = (bi >= 0) ? u[(base + bi) * n_params + c] : NAN;
   }
 }
 
@@ -173,11 +170,11 @@ cudaError_t launch_eval(const DevParams& prm, const DevBatch& bt, const double* 
   }
 }
 
-cudaError_t launch_argmin(int n_robots, int n_starts, int n_blocks, const double* cost_final, const uint8_t* usable,
+cudaError_t launch_argmin(int n_robots, int n_starts, int n_params, const double* cost_final, const uint8_t* usable,
                           const double* u, int32_t* best_index, double* best_cost, double* best_u, cudaStream_t stream) {
   int threads = 32;
   while (threads < n_starts && threads < 256) threads <<= 1;
-  smpc_argmin_kernel<<<n_robots, threads, 0, stream>>>(n_starts, n_blocks, cost_final, usable, u, best_index, best_cost,
+  smpc_argmin_kernel<<<n_robots, threads, 0, stream>>>(n_starts, n_params, cost_final, usable, u, best_index, best_cost,
                                                        best_u);
   return cudaGetLastError();
 }

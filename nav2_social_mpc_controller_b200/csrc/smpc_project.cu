@@ -343,9 +343,16 @@ __global__ void smpc_format_kernel(smpc_format_args a) {
   if (i == Pb - 1) a.goal_yaw[b] = yaw;
 }
 
-// PathTrajectorizer::trajectorize, reference src/path_trajectorizer.cpp:120-288; one thread per robot
-__global__ void smpc_trajectorize_kernel(smpc_trajectorize_args a) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+// PathTrajectorizer::trajectorize (reference src/path_trajectorizer.cpp:120-288): pure-pursuit seed of up to max_steps
+// Euler steps. One WARP per robot: the time loop is sequential, but every step searches the whole global path for its
+// look-ahead point ("scanning from the end, the first pose within lookahead_dist, else the nearest one"), and that
+// search is done by the 32 lanes at once — the look-ahead point is the LARGEST index within reach (a ballot per 32
+// points, taken from the end), else an arg-min with the serial loop's tie rule (strict '<' while walking down: the
+// larger index wins). Every lane then advances the same robot state, so no broadcast is needed. Decisions are
+// bit-identical to the serial scan (same sqrt(dx^2 + dy^2) per point).
+__global__ void __launch_bounds__(128) smpc_trajectorize_kernel(smpc_trajectorize_args a) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (b >= a.n_problems) return;
   const int N = a.n_path;
   const double* path = a.global_path + (size_t)(a.path_index ? a.path_index[b] : b) * N * 2;
@@ -358,19 +365,42 @@ __global__ void smpc_trajectorize_kernel(smpc_trajectorize_args a) {
   }
   double* poses = a.poses + (size_t)b * (a.max_steps + 1) * 3;
   double* cmds = a.cmds + (size_t)b * a.max_steps * 3;
-  poses[0] = rx; poses[1] = ry; poses[2] = rth;
+  if (lane == 0) {
+    poses[0] = rx; poses[1] = ry; poses[2] = rth;
+  }
   const double gx = path[2 * (N - 1)], gy = path[2 * (N - 1) + 1];
   double goal_dist = 1000.0;
   int steps = 0;
   while (goal_dist > 0.2 && steps < a.max_steps) {
-    // look-ahead point: scanning from the END, the first pose within lookahead_dist, else the nearest one
-    double min_dist = 100.0;
+    // look-ahead point
     int wp = -1;
-    for (int i = N - 1; i >= 0; --i) {
-      const double dx = rx - path[2 * i], dy = ry - path[2 * i + 1];
-      const double d = sqrt(dx * dx + dy * dy);
-      if (d <= a.lookahead_dist) { wp = i; break; }
-      if (d < min_dist) { min_dist = d; wp = i; }
+    double best_d = 100.0;  // the reference's initial min_dist
+    int best_i = -1;
+    for (int top = N - 1; top >= 0 && wp < 0; top -= 32) {
+      const int i = top - lane;
+      double d = INFINITY;
+      if (i >= 0) {
+        const double dx = rx - path[2 * i], dy = ry - path[2 * i + 1];
+        d = sqrt(dx * dx + dy * dy);
+      }
+      const unsigned hit = __ballot_sync(0xffffffffu, d <= a.lookahead_dist);
+      if (hit) {
+        wp = top - (__ffs(hit) - 1);  // lowest lane = largest index of this group of 32
+      } else if (d < best_d) {        // within a lane the indices only go down: strict '<' keeps the larger one
+        best_d = d;
+        best_i = i;
+      }
+    }
+    if (wp < 0) {  // nothing within reach: nearest pose, ties to the larger index
+      for (int off = 16; off > 0; off >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, best_d, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, best_i, off);
+        if (od < best_d || (od == best_d && oi > best_i)) {
+          best_d = od;
+          best_i = oi;
+        }
+      }
+      wp = best_i;
     }
     if (wp < 0) wp = N - 1;  // every pose farther than 100 m: the reference would index -1 (UB); take the goal
     const double wpx = path[2 * wp], wpy = path[2 * wp + 1];
@@ -399,19 +429,21 @@ __global__ void smpc_trajectorize_kernel(smpc_trajectorize_args a) {
     rx = rx + (vx * ct + vy * cos(M_PI_2 + rth)) * a.time_step;
     ry = ry + (vx * st + vy * sin(M_PI_2 + rth)) * a.time_step;
     rth = rth + wz * a.time_step;
-    double sh, ch;
-    sincos(rth * 0.5, &sh, &ch);
-    poses[3 * (steps + 1)] = rx;
-    poses[3 * (steps + 1) + 1] = ry;
-    poses[3 * (steps + 1) + 2] = atan2(2.0 * (ch * sh), ch * ch - sh * sh);  // setRPY(0, 0, rtheta) as read back by getYaw
-    cmds[3 * steps] = vx;
-    cmds[3 * steps + 1] = vy;
-    cmds[3 * steps + 2] = wz;
+    if (lane == 0) {
+      double sh, ch;
+      sincos(rth * 0.5, &sh, &ch);
+      poses[3 * (steps + 1)] = rx;
+      poses[3 * (steps + 1) + 1] = ry;
+      poses[3 * (steps + 1) + 2] = atan2(2.0 * (ch * sh), ch * ch - sh * sh);  // setRPY(0, 0, rtheta) read back by getYaw
+      cmds[3 * steps] = vx;
+      cmds[3 * steps + 1] = vy;
+      cmds[3 * steps + 2] = wz;
+    }
     const double ex = rx - gx, ey = ry - gy;
     goal_dist = sqrt(ex * ex + ey * ey);
     ++steps;
   }
-  a.n_steps[b] = steps;
+  if (lane == 0) a.n_steps[b] = steps;
 }
 
 __global__ void smpc_people_status_kernel(int B, int A, const double* __restrict__ raw, const int32_t* __restrict__ n_people,
@@ -454,7 +486,7 @@ int smpc_trajectorize_batch_device(smpc_handle* h, const smpc_trajectorize_args*
   if (a->n_problems == 0) return SMPC_OK;
   cudaSetDevice(smpc_handle_device(h));  // the caller may have another device current (multi-GPU processes)
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : smpc_handle_stream(h);
-  smpc_trajectorize_kernel<<<(a->n_problems + 127) / 128, 128, 0, st>>>(*a);
+  smpc_trajectorize_kernel<<<(a->n_problems + 3) / 4, 128, 0, st>>>(*a);  // one warp per robot
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return smpc_host_fail(SMPC_ERR_CUDA, std::string("trajectorize kernel: ") + cudaGetErrorString(e));
   smpc_handle_count_launch(h);
@@ -698,6 +730,8 @@ int smpc_optimize_batch_on(smpc_handle* h, smpc_fleet_state* fs, smpc_fleet_io* 
   if (!(io->od_resolution > 0.0f)) return smpc_host_fail(SMPC_ERR_ARGUMENT, "ObstacleDistance grid has invalid resolution");
   if (!io->n_out || !io->optimized) return smpc_host_fail(SMPC_ERR_ARGUMENT, "optimize_batch: n_out / optimized missing");
   const smpc_params* prm = smpc_handle_params(h);
+  if (prm->omni_solve)  // the reference's Optimizer::optimize is unicycle-only (update_state.hpp:46-61)
+    return smpc_host_fail(SMPC_ERR_UNSUPPORTED, "the level-2 entries mirror Optimizer::optimize, which has no omnidirectional solve");
   std::lock_guard<std::mutex> lk(fs->mu);
   FLEET_CUDA(cudaSetDevice(smpc_handle_device(h)));
   cudaStream_t st = smpc_handle_stream(h);

@@ -100,7 +100,7 @@ class Optimizer:
         self._need()
         nb = self.dims(batch.n_steps)[2]
         if out is None:
-            shapes = abi.result_shapes(batch.n_problems, batch.n_steps, nb)
+            shapes = abi.result_shapes(batch.n_problems, batch.n_steps, nb, 3 if int(self.params.omni_solve) else 2)
             out = {k: np.zeros(shapes[k][0], dtype=shapes[k][1]) for k in want}
             if trace_rows > 0:
                 out["trace"] = np.full((batch.n_problems, trace_rows, 8), np.nan)
@@ -190,7 +190,7 @@ class Optimizer:
         """cost, J^T r, J^T J at block values x [B][NB][2] (host buffers)."""
         self._need()
         nb = self.dims(batch.n_steps)[2]
-        P = 2 * nb
+        P = (3 if int(self.params.omni_solve) else 2) * nb
         B = batch.n_problems
         x = np.ascontiguousarray(x, dtype=np.float64).reshape(B, P)
         out = dict(cost=np.zeros(B), grad=np.zeros((B, P)), hess=np.zeros((B, P * (P + 1) // 2)),

@@ -49,7 +49,8 @@ PARAM_SETS = {
 _COMMON = dict(linear_solver_type="DENSE_SCHUR", param_tol=1e-9, fn_tol=1e-5, gradient_tol=1e-8,
                max_iterations=40, debug=0, discretization=1, current_path_w=1.0, omnidirectional=0,
                traj_desired_linear_vel=0.6, max_angular_vel=1.4, transform_tolerance=0.5,
-               base_frame="base_link", desired_linear_vel=0.5, fov_angle=math.pi / 4, ceres_compat=200)
+               base_frame="base_link", desired_linear_vel=0.5, fov_angle=math.pi / 4, ceres_compat=200,
+               max_evaluations=0, omni_solve=0)
 
 
 def make_params(name: str, **overrides) -> abi.SmpcParams:
@@ -194,6 +195,11 @@ class Batch:
     def n_blocks(self) -> int:
         return self.dims[2]
 
+    @property
+    def dof(self) -> int:
+        """Parameters per block: 2 = (v, w); 3 = (vx, vy, w) when params.omni_solve is set (extension)."""
+        return 3 if int(self.params.omni_solve) else 2
+
     def struct(self, arrays: dict | None = None) -> abi.SmpcBatch:
         return abi.make_batch_struct(arrays if arrays is not None else self.arrays, self.n_problems, self.n_steps,
                                      self.n_agents, self.n_costmaps, self.size_x, self.size_y, self.resolution,
@@ -218,7 +224,7 @@ class Batch:
 
     def algorithmic_bytes_per_problem(self, unique_costmap: bool) -> int:
         """8*[3 + P + 2(S+1) + 1 + 6A(S+1)] + map + outputs 8*[P + 2(S+1) + 2] + 12."""
-        S, A, P = self.n_steps, self.n_agents, 2 * self.n_blocks
+        S, A, P = self.n_steps, self.n_agents, self.dof * self.n_blocks
         inp = 8 * (3 + P + 2 * (S + 1) + 1 + 6 * A * (S + 1))
         outp = 8 * (P + 2 * (S + 1) + 2) + 12
         return inp + outp + (self.size_x * self.size_y if unique_costmap else 0)
@@ -383,6 +389,24 @@ def with_horizons(batch: Batch, n_steps_each) -> Batch:
     arr = dict(batch.arrays)
     arr["n_steps_each"] = n
     return dataclasses.replace(batch, arrays=arr)
+
+
+def omni(batch: Batch, vy_sigma: float = 0.05, config_id: int = 70) -> Batch:
+    """The same scenarios for the OMNIDIRECTIONAL solve (extension, BASELINE configs[4]): blocks become (vx, vy, w); the
+    unicycle seed gives vx and w, the lateral start velocity is a small random value so that the vy coordinates are
+    exercised from the first iteration. The reference has no omnidirectional solve (only its trajectorizer has an omni
+    branch), so these batches are checked against this repo's own oracle functors only."""
+    rng = _rng(config_id)
+    p = abi.SmpcParams.from_buffer_copy(bytes(batch.params))
+    p.omni_solve = 1
+    u0 = batch.arrays["u0"]
+    B, nb, _ = u0.shape
+    u3 = np.zeros((B, nb, 3))
+    u3[:, :, 0], u3[:, :, 2] = u0[:, :, 0], u0[:, :, 1]
+    u3[:, :, 1] = rng.normal(0.0, vy_sigma, (B, nb))
+    arr = dict(batch.arrays)
+    arr["u0"] = np.ascontiguousarray(u3)
+    return dataclasses.replace(batch, params=p, arrays=arr)
 
 
 def multistart(n_robots: int = 256, n_starts: int = 1024, config_id: int = 4, **overrides) -> Batch:

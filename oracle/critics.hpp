@@ -26,6 +26,11 @@ struct ProblemView {
   int S1 = 0;  // row stride of the step-indexed arrays = (largest S of the batch) + 1 (include/smpc.h n_steps_each)
   int A = 0;   // agent columns per step
   int ceres_compat = 200;  // < 210: std::numeric_limits<Jet> is NOT specialised (see proxemics_residual)
+  // Parameters per block. 2 = (v, w): the reference (update_state.hpp:46-61). 3 = (vx, vy, w): the omnidirectional
+  // EXTENSION of BASELINE configs[4] — the reference has no such solve (only its trajectorizer has an omni branch,
+  // path_trajectorizer.hpp:106-123); the functors below are this repo's own definition of it, so for
+  // dof == 3 this file is a specification, not a restatement.
+  int dof = 2;
   int ch = 0;  // min(control_horizon, S)          src/optimizer.cpp:248
   int bl = 0;  // min(parameter_block_length, ch)  src/optimizer.cpp:249
   int nb = 0;  // ceil(ch/bl) parameter blocks     src/optimizer.cpp:254-261
@@ -57,9 +62,16 @@ inline void rollout(const ProblemView& p, const T* const* u, int i, T* x, T* y, 
   *th = T(p.yaw0);
   for (int j = 0; j <= i; ++j) {
     const T* blk = u[p.block_of(j)];
-    *x += blk[0] * cos(*th) * p.dt;
-    *y += blk[0] * sin(*th) * p.dt;
-    *th += blk[1] * p.dt;
+    if (p.dof == 3) {  // holonomic Euler step: body velocity (vx, vy) rotated into the world frame
+      const T c = cos(*th), s = sin(*th);
+      *x += (blk[0] * c - blk[1] * s) * p.dt;
+      *y += (blk[0] * s + blk[1] * c) * p.dt;
+      *th += blk[2] * p.dt;
+    } else {
+      *x += blk[0] * cos(*th) * p.dt;
+      *y += blk[0] * sin(*th) * p.dt;
+      *th += blk[1] * p.dt;
+    }
   }
 }
 
@@ -87,7 +99,7 @@ inline T wrap_to_pi(T a) {
 // One (me <- other) interaction of computeSocialForce, social_work_cost_function.hpp:165-223.
 // me/other are 6-vectors (x, y, yaw, t, lv, av); constants from social_work_cost_function.cpp:38-43.
 template <class T>
-inline Vec2<T> social_pair(const T* me, const Vec2<T>& me_vel, const T* other) {
+inline Vec2<T> social_pair(const T* me, const Vec2<T>& me_vel, const T* other, const Vec2<T>& o_vel) {
   const double lambda = 2.0, gamma = 0.35, n_prime = 3.0, n = 2.0, factor = 2.1;
   Vec2<T> diff{me[0] - other[0], me[1] - other[1]};
   if (norm2(diff) < T(1e-6)) diff = Vec2<T>{T(1e-6), T(0.0)};
@@ -100,7 +112,6 @@ inline Vec2<T> social_pair(const T* me, const Vec2<T>& me_vel, const T* other) {
       dir = Vec2<T>{diff.x / s, diff.y / s};
     }
   }
-  Vec2<T> o_vel{other[4] * cos(other[2]), other[4] * sin(other[2])};
   Vec2<T> dv{me_vel.x - o_vel.x, me_vel.y - o_vel.y};
   Vec2<T> iv{T(lambda) * dv.x + dir.x, T(lambda) * dv.y + dir.y};
   T ilen = norm2(iv);
@@ -126,7 +137,19 @@ inline void robot_state(const ProblemView& p, const T* const* u, int i, T* robot
   robot[3] = T((static_cast<double>(i) + 1.0) * p.dt);  // counter_step, src/optimizer.cpp:253,262
   const T* blk = u[p.block_of(i)];                        // social_work_cost_function.hpp:114-123
   robot[4] = blk[0];
-  robot[5] = blk[1];
+  robot[5] = blk[p.dof - 1];
+}
+
+// World-frame velocity of the robot at step i: lv (cos, sin)(yaw) in the reference (social_work_cost_function.hpp:
+// 181-183 with me = robot); the omnidirectional extension rotates the body velocity (vx, vy).
+template <class T>
+inline Vec2<T> robot_velocity(const ProblemView& p, const T* const* u, int i, const T* robot) {
+  if (p.dof == 3) {
+    const T* blk = u[p.block_of(i)];
+    const T c = cos(robot[2]), s = sin(robot[2]);
+    return Vec2<T>{blk[0] * c - blk[1] * s, blk[0] * s + blk[1] * c};
+  }
+  return Vec2<T>{robot[4] * cos(robot[2]), robot[4] * sin(robot[2])};
 }
 
 // SocialWorkCost::operator(), social_work_cost_function.hpp:102-150. Agents of step i are
@@ -135,13 +158,14 @@ template <class T>
 inline T social_work_residual(const ProblemView& p, const T* const* u, int i) {
   T robot[6];
   robot_state(p, u, i, robot);
-  Vec2<T> r_vel{robot[4] * cos(robot[2]), robot[4] * sin(robot[2])};
+  Vec2<T> r_vel = robot_velocity(p, u, i, robot);
   Vec2<T> f_robot{T(0.0), T(0.0)};
   for (int k = 0; k < p.A; ++k) {
     T ag[6];
     load_agent(p, i + 1, k, ag);
     if (ag[3] == T(-1.0)) continue;
-    Vec2<T> f = social_pair(robot, r_vel, ag);
+    Vec2<T> a_vel0{ag[4] * cos(ag[2]), ag[4] * sin(ag[2])};
+    Vec2<T> f = social_pair(robot, r_vel, ag, a_vel0);
     f_robot.x += f.x;
     f_robot.y += f.y;
   }
@@ -153,7 +177,7 @@ inline T social_work_residual(const ProblemView& p, const T* const* u, int i) {
     Vec2<T> a_vel{ag[4] * cos(ag[2]), ag[4] * sin(ag[2])};
     Vec2<T> f{T(0.0), T(0.0)};
     if (!(robot[3] == T(-1.0))) {
-      Vec2<T> g = social_pair(ag, a_vel, robot);
+      Vec2<T> g = social_pair(ag, a_vel, robot, r_vel);
       f.x += g.x;
       f.y += g.y;
     }
@@ -239,6 +263,10 @@ template <class T>
 inline T velocity_residual(const ProblemView& p, const T* const* u, int i) {
   if (i < p.ch) {
     T d = T(0.6) - u[i / p.bl][0];
+    if (p.dof == 3) {  // omnidirectional extension: track 0.6 m/s forward, no lateral velocity
+      T vy = u[i / p.bl][1];
+      return T(p.w_velocity) * d * d + T(p.w_velocity) * vy * vy;
+    }
     return T(p.w_velocity) * d * d;
   }
   return T(0.0);
@@ -320,6 +348,10 @@ template <class T>
 inline T vel_feasibility_residual(const ProblemView& p, const T* s1, const T* s2) {
   T dv = s1[0] - s2[0];
   T dw = s1[1] - s2[1];
+  if (p.dof == 3) {
+    T d2 = s1[2] - s2[2];
+    return T(p.w_vf) * dv * dv + T(p.w_vf) * dw * dw + T(p.w_vf) * d2 * d2;
+  }
   return T(p.w_vf) * dv * dv + T(p.w_vf) * dw * dw;
 }
 

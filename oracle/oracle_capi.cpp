@@ -47,12 +47,13 @@ bool make_view(const smpc_params* p, const smpc_batch* in, int b, ProblemView* v
   v->S1 = S1;
   v->A = A;
   v->ceres_compat = p->ceres_compat ? p->ceres_compat : 200;
+  v->dof = p->omni_solve ? 3 : 2;
   if (!derive_dims(p, S, &v->ch, &v->bl, &v->nb, &v->n_bounded)) return false;
   v->dt = in->dt;
   v->x0 = in->pose0[3 * b + 0];
   v->y0 = in->pose0[3 * b + 1];
   v->yaw0 = in->pose0[3 * b + 2];
-  v->u0 = in->u0 + static_cast<size_t>(b) * batch_blocks(p, in) * 2;
+  v->u0 = in->u0 + static_cast<size_t>(b) * batch_blocks(p, in) * (p->omni_solve ? 3 : 2);
   v->px = in->path_xy + static_cast<size_t>(b) * 2 * S1;
   v->py = v->px + S1;
   v->goal_yaw = in->goal_yaw[b];
@@ -97,39 +98,35 @@ double yaw_roundtrip(double yaw) {
   return std::atan2(2 * (qw * qz), sqw - sqz);
 }
 
-// src/optimizer.cpp:390-446: hold-last fill, block -> per-step expansion, Euler path rebuild.
+// src/optimizer.cpp:390-446: hold-last fill, block -> per-step expansion, Euler path rebuild. D = v.dof values per
+// step: (v, w), or (vx, vy, w) for the omnidirectional extension (same expansion rule, holonomic Euler step).
 void expand_outputs(const ProblemView& v, const double* u, double* cmds, double* path) {
-  const int S = v.S;
+  const int S = v.S, D = v.dof;
   // optim_velocities: entries [0, nb) hold the blocks; the reference then overwrites entries
   // [ch/bl, S) with block (ch-1)/bl (this also overwrites an unbounded trailing block's own slot with itself).
-  std::vector<double> ov(static_cast<size_t>(S) * 2);
+  std::vector<double> ov(static_cast<size_t>(S) * D);
   for (int i = 0; i < S; ++i) {
     const int src = (i < v.nb) ? i : 0;
-    ov[2 * i] = u[2 * src];
-    ov[2 * i + 1] = u[2 * src + 1];
+    for (int k = 0; k < D; ++k) ov[D * i + k] = u[D * src + k];
   }
   const int last = (v.ch - 1) / v.bl;
-  const double lv = ov[2 * last], lw = ov[2 * last + 1];
-  for (int i = v.ch / v.bl; i < S; ++i) {
-    ov[2 * i] = lv;
-    ov[2 * i + 1] = lw;
-  }
-  std::vector<double> sv(static_cast<size_t>(S + 1) * 2);
-  for (int i = 0; i < v.ch; ++i) {
-    sv[2 * i] = ov[2 * (i / v.bl)];
-    sv[2 * i + 1] = ov[2 * (i / v.bl) + 1];
-  }
-  for (int i = v.ch; i < S + 1; ++i) {
-    sv[2 * i] = ov[2 * (i - 1)];
-    sv[2 * i + 1] = ov[2 * (i - 1) + 1];
-  }
+  std::vector<double> lastv(u + D * last, u + D * last + D);
+  for (int k = 0; k < D; ++k) lastv[k] = ov[D * last + k];
+  for (int i = v.ch / v.bl; i < S; ++i)
+    for (int k = 0; k < D; ++k) ov[D * i + k] = lastv[k];
+  std::vector<double> sv(static_cast<size_t>(S + 1) * D);
+  for (int i = 0; i < v.ch; ++i)
+    for (int k = 0; k < D; ++k) sv[D * i + k] = ov[D * (i / v.bl) + k];
+  for (int i = v.ch; i < S + 1; ++i)
+    for (int k = 0; k < D; ++k) sv[D * i + k] = ov[D * (i - 1) + k];
   if (cmds) std::memcpy(cmds, sv.data(), sv.size() * sizeof(double));
   if (path) {
     double x = v.x0, y = v.y0, yaw = yaw_roundtrip(v.yaw0);
     for (int i = 0; i < S + 1; ++i) {
-      const double nx = x + sv[2 * i] * std::cos(yaw) * v.dt;
-      const double ny = y + sv[2 * i] * std::sin(yaw) * v.dt;
-      const double nyaw = yaw_roundtrip(yaw + sv[2 * i + 1] * v.dt);
+      const double vx = sv[D * i], vy = (D == 3) ? sv[D * i + 1] : 0.0, w = sv[D * i + D - 1];
+      const double nx = (D == 3) ? x + (vx * std::cos(yaw) - vy * std::sin(yaw)) * v.dt : x + vx * std::cos(yaw) * v.dt;
+      const double ny = (D == 3) ? y + (vx * std::sin(yaw) + vy * std::cos(yaw)) * v.dt : y + vx * std::sin(yaw) * v.dt;
+      const double nyaw = yaw_roundtrip(yaw + w * v.dt);
       x = nx;
       y = ny;
       yaw = nyaw;
@@ -170,7 +167,7 @@ long long smpc_oracle_count_jet_flops(const smpc_params* p, const smpc_batch* in
   ProblemView v;
   if (!make_view(p, in, b, &v)) return -1;
   const std::vector<ResidualBlock> blocks = assemble(v);
-  const int P = 2 * v.nb;
+  const int P = v.dof * v.nb;
   std::vector<double> res(blocks.size()), grad(P), jac(blocks.size() * static_cast<size_t>(P));
   double c = 0.0;
   smpc_oracle::g_jet_flops = 0;
@@ -197,11 +194,11 @@ int smpc_oracle_layout(const smpc_params* p, const smpc_batch* in, int b, int* k
 static void solve_one(const smpc_params* p, const smpc_batch* in, smpc_result* out, int b) {
   ProblemView v;
   make_view(p, in, b, &v);
-  const int P = 2 * v.nb;
+  const int P = v.dof * v.nb;
   double x[kMaxParams];
   for (int c = 0; c < P; ++c) x[c] = v.u0[c];
   SolveSummary s = solve(v, make_options(p), x);
-  const size_t Pw = 2 * static_cast<size_t>(batch_blocks(p, in));  // row width of u (longest horizon of the batch)
+  const size_t Pw = static_cast<size_t>(v.dof) * batch_blocks(p, in);  // row width of u (longest horizon of the batch)
   if (out->u) std::memcpy(out->u + static_cast<size_t>(b) * Pw, x, sizeof(double) * P);
   if (out->cost_initial) out->cost_initial[b] = s.initial_cost;
   if (out->cost_final) out->cost_final[b] = s.final_cost;
@@ -213,7 +210,7 @@ static void solve_one(const smpc_params* p, const smpc_batch* in, smpc_result* o
     out->n_evals[2 * b + 1] = static_cast<int32_t>(s.evals.n_cost);
   }
   if (out->cmds || out->path)
-    expand_outputs(v, x, out->cmds ? out->cmds + static_cast<size_t>(b) * v.S1 * 2 : nullptr,
+    expand_outputs(v, x, out->cmds ? out->cmds + static_cast<size_t>(b) * v.S1 * v.dof : nullptr,
                    out->path ? out->path + static_cast<size_t>(b) * v.S1 * 3 : nullptr);
 }
 
@@ -222,7 +219,7 @@ int smpc_oracle_solve_batch(const smpc_params* p, const smpc_batch* in, smpc_res
                             int n_threads) {
   ProblemView v;
   if (in->n_problems <= 0 || !make_view(p, in, 0, &v)) return -1;
-  if (2 * v.nb > kMaxParams) return -3;
+  if (v.dof * v.nb > kMaxParams) return -3;
   if (first < 0 || first + count > in->n_problems) return -1;
   if (n_threads < 1) n_threads = 1;
   std::atomic<int> next(first);
@@ -249,7 +246,7 @@ int smpc_oracle_solve_trace(const smpc_params* p, const smpc_batch* in, int b, d
                             int max_rows, int* termination, double* cost_initial, double* cost_final) {
   ProblemView v;
   if (!make_view(p, in, b, &v)) return -1;
-  const int P = 2 * v.nb;
+  const int P = v.dof * v.nb;
   double x[kMaxParams];
   for (int c = 0; c < P; ++c) x[c] = v.u0[c];
   SolveSummary s = solve(v, make_options(p), x, true);
@@ -279,7 +276,7 @@ int smpc_oracle_solve_trace(const smpc_params* p, const smpc_batch* in, int b, d
 int smpc_oracle_solve_evals(const smpc_params* p, const smpc_batch* in, int b, double* rows, int max_rows) {
   ProblemView v;
   if (!make_view(p, in, b, &v)) return -1;
-  const int P = 2 * v.nb;
+  const int P = v.dof * v.nb;
   double x[kMaxParams];
   for (int c = 0; c < P; ++c) x[c] = v.u0[c];
   SolveSummary s = solve(v, make_options(p), x, true);

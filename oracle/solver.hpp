@@ -78,7 +78,7 @@ constexpr int kMaxParams = 64;
 // Returns false when any residual / Jacobian entry is non-finite (ceres ResidualBlock::Evaluate validity check).
 inline bool evaluate(const ProblemView& p, const std::vector<ResidualBlock>& blocks, const double* x, double* cost,
                      double* residuals, double* gradient, double* jac, EvalCounters* cnt) {
-  const int P = 2 * p.nb;
+  const int D = p.dof, P = D * p.nb;
   const bool need_d = (gradient != nullptr) || (jac != nullptr);
   if (cnt) (need_d ? cnt->n_jacobian : cnt->n_cost)++;
   double total = 0.0;
@@ -88,12 +88,12 @@ inline bool evaluate(const ProblemView& p, const std::vector<ResidualBlock>& blo
   for (size_t k = 0; k < blocks.size(); ++k) {
     const ResidualBlock& rb = blocks[k];
     int gidx[kMaxParams];  // local parameter -> global column
-    const int np = 2 * rb.nblk;
+    const int np = D * rb.nblk;
     if (rb.kind == K_VEL_FEAS) {
-      gidx[0] = 2 * rb.blk[0];
-      gidx[1] = 2 * rb.blk[0] + 1;
-      gidx[2] = 2 * rb.blk[1];
-      gidx[3] = 2 * rb.blk[1] + 1;
+      for (int k = 0; k < D; ++k) {
+        gidx[k] = D * rb.blk[0] + k;
+        gidx[D + k] = D * rb.blk[1] + k;
+      }
     } else {
       for (int l = 0; l < np; ++l) gidx[l] = l;
     }
@@ -101,14 +101,14 @@ inline bool evaluate(const ProblemView& p, const std::vector<ResidualBlock>& blo
     double row[kMaxParams];
     if (!need_d) {
       const double* ptr[kMaxParams / 2];
-      for (int b = 0; b < rb.nblk; ++b) ptr[b] = x + gidx[2 * b];
+      for (int b = 0; b < rb.nblk; ++b) ptr[b] = x + gidx[D * b];
       r = eval_block<double>(p, rb, ptr);
       if (!std::isfinite(r)) return false;
     } else {
       // DynamicAutoDiffCostFunction: ceil(np/4) passes, 4 tangent directions each.
       J4 jets[kMaxParams];
       const J4* ptr[kMaxParams / 2];
-      for (int b = 0; b < rb.nblk; ++b) ptr[b] = jets + 2 * b;
+      for (int b = 0; b < rb.nblk; ++b) ptr[b] = jets + D * b;
       for (int start = 0; start < np; start += 4) {
         for (int l = 0; l < np; ++l) jets[l] = J4(x[gidx[l]], l - start);
         J4 out = eval_block<J4>(p, rb, ptr);
@@ -395,11 +395,16 @@ inline Bounds make_bounds(const ProblemView& p) {
     b.lo[c] = -std::numeric_limits<double>::infinity();
     b.hi[c] = std::numeric_limits<double>::infinity();
   }
+  const int D = p.dof;
   for (int k = 0; k < p.n_bounded; ++k) {
-    b.lo[2 * k] = 0.0;
-    b.hi[2 * k] = 0.6;
-    b.lo[2 * k + 1] = -1.4;
-    b.hi[2 * k + 1] = 1.4;
+    b.lo[D * k] = 0.0;
+    b.hi[D * k] = 0.6;
+    if (D == 3) {  // omnidirectional extension: the lateral velocity is bounded by the same speed
+      b.lo[D * k + 1] = -0.6;
+      b.hi[D * k + 1] = 0.6;
+    }
+    b.lo[D * k + D - 1] = -1.4;
+    b.hi[D * k + D - 1] = 1.4;
   }
   return b;
 }
@@ -437,7 +442,7 @@ inline bool cholesky_solve(int P, std::vector<double> A, const double* b, double
 inline SolveSummary solve(const ProblemView& p, const SolveOptions& opt, double* x_inout, bool keep_trace = false) {
   SolveSummary sum;
   const std::vector<ResidualBlock> blocks = assemble(p);
-  const int P = 2 * p.nb;
+  const int P = p.dof * p.nb;
   const int m = static_cast<int>(blocks.size());
   const Bounds bd = make_bounds(p);
 

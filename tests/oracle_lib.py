@@ -68,7 +68,8 @@ class Oracle:
         m = self.num_residuals(batch, b)
         each = batch.arrays.get("n_steps_each")
         S_b = batch.n_steps if each is None else int(each[b])  # problem b's own horizon -> its own block count
-        P = 2 * abi.problem_dims(batch.params.control_horizon, batch.params.parameter_block_length, S_b)[2]
+        dof = 3 if int(batch.params.omni_solve) else 2
+        P = dof * abi.problem_dims(batch.params.control_horizon, batch.params.parameter_block_length, S_b)[2]
         x = np.ascontiguousarray(np.asarray(x, dtype=np.float64).ravel()[:P])
         cost = C.c_double(0.0)
         res = np.zeros(m)
@@ -83,7 +84,7 @@ class Oracle:
                                                                           "cost_final", "iterations",
                                                                           "termination", "usable", "n_evals")):
         count = batch.n_problems - first if count is None else count
-        shapes = abi.result_shapes(batch.n_problems, batch.n_steps, batch.n_blocks)
+        shapes = abi.result_shapes(batch.n_problems, batch.n_steps, batch.n_blocks, 3 if int(batch.params.omni_solve) else 2)
         out = {k: np.zeros(shapes[k][0], dtype=shapes[k][1]) for k in want}
         rs = abi.make_result_struct(out)
         st = batch.struct()
@@ -94,7 +95,7 @@ class Oracle:
         return out
 
     def solve_trace(self, batch, b=0, max_rows=256):
-        P = 2 * batch.n_blocks
+        P = (3 if int(batch.params.omni_solve) else 2) * batch.n_blocks
         x = np.zeros(P)
         trace = np.zeros((max_rows, 10))
         term = C.c_int(0)
