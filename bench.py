@@ -572,6 +572,52 @@ def leg_scaling_sweep(ctx, steps, warmup, name="crowd_x1M_A50", omni=False):
     return out
 
 
+def leg_library_multi(ctx, steps, warmup, per_gpu=16384, A=20):
+    """SURVEY §8e through the LIBRARY: smpc_solve_batch_multi — one process (rank 0), one host thread + handle per GPU,
+    contiguous shards of one pinned host batch, results gathered into one pinned host table by the shards' own D2H
+    copies. The other ranks idle at a barrier while rank 0 drives all N GPUs."""
+    from nav2_social_mpc_controller_b200.optimizer import MultiGpuOptimizer
+    torch = ctx.torch
+    ctx.barrier()
+    out = None
+    if ctx.rank == 0:
+        base = sc.crowd(B=per_gpu, A=A)
+        n = per_gpu * ctx.world
+        arr = {}
+        for k, v in base.arrays.items():
+            if v is None or k in ("costmaps", "costmap_origin"):
+                arr[k] = v
+            else:
+                arr[k] = np.ascontiguousarray(np.tile(v, (ctx.world,) + (1,) * (v.ndim - 1)))
+        pinned = {k: (torch.from_numpy(v).pin_memory() if v is not None else None) for k, v in arr.items()}
+        host_np = {k: (t.numpy() if t is not None else None) for k, t in pinned.items()}
+        batch = sc.Batch(params=base.params, n_problems=n, n_steps=base.n_steps, n_agents=A, n_costmaps=base.n_costmaps,
+                         size_x=base.size_x, size_y=base.size_y, resolution=base.resolution, dt=base.dt, arrays=host_np)
+        shapes = abi.result_shapes(n, base.n_steps, base.dims[2])
+        host_out_t = {k: torch.zeros(shapes[k][0], dtype=ctx.tdt[shapes[k][1]]).pin_memory() for k in WANT}
+        host_out = {k: t.numpy() for k, t in host_out_t.items()}
+        multi = MultiGpuOptimizer(base.params, list(range(ctx.world)))
+        for _ in range(warmup):
+            multi.solve_batch(batch, out=host_out)
+        ts = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            multi.solve_batch(batch, out=host_out)
+            ts.append(time.perf_counter() - t0)
+        multi.close()
+        same = all(np.array_equal(host_out["u"][:per_gpu], host_out["u"][r * per_gpu:(r + 1) * per_gpu])
+                   for r in range(ctx.world))
+        out = {"workload": f"soc_work_obst A={A}, {per_gpu} problems per GPU, one host batch of {n}",
+               "entry": "smpc_solve_batch_multi (one process, one host thread + handle per GPU, pinned host buffers)",
+               "n_gpus": ctx.world, "value": n * steps / sum(ts), "unit": UNIT, "ms_per_step": 1e3 * sum(ts) / steps,
+               "h2d_bytes_per_step": int(sum(v.nbytes for v in host_np.values() if v is not None)),
+               "d2h_bytes_per_step": int(sum(v.nbytes for v in host_out.values())),
+               "shards_identical": bool(same), "usable_fraction": float(host_out["usable"].mean()),
+               "steps": steps, "warmup": warmup}
+    ctx.barrier()
+    return out
+
+
 def leg_latency(ctx, calls):
     """BASELINE configs[0]: p50 / p99 of ONE solve through the host-buffer C-ABI (H2D + kernel + D2H), rank 0."""
     from nav2_social_mpc_controller_b200.optimizer import Optimizer
@@ -603,7 +649,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default=HEADLINE, choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--legs", default="all", help="all | none | comma list of obst_only,multistart,scaling_sweep,scaling_sweep_omni,latency")
+    ap.add_argument("--legs", default="all", help="all | none | comma list of obst_only,multistart,scaling_sweep,scaling_sweep_omni,library_multi,latency")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--latency-calls", type=int, default=300)
     args = ap.parse_args()
@@ -621,7 +667,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libsmpc has no CPU path")
     ctx = Ctx(rank, local_rank, world)
-    legs = ("obst_only", "multistart", "scaling_sweep", "scaling_sweep_omni", "latency") if args.legs == "all" else \
+    legs = ("obst_only", "multistart", "scaling_sweep", "scaling_sweep_omni", "library_multi", "latency") \
+        if args.legs == "all" else \
         tuple(x for x in args.legs.split(",") if x and x != "none")
     if args.latency_calls <= 0:
         legs = tuple(x for x in legs if x != "latency")
@@ -672,6 +719,8 @@ def main():
         leg_out["crowd_x1M_A50"] = leg_scaling_sweep(ctx, min(args.steps, 2), 2)
     if "scaling_sweep_omni" in legs:
         leg_out["crowd_x1M_A50_omni"] = leg_scaling_sweep(ctx, min(args.steps, 2), 2, omni=True)
+    if "library_multi" in legs:
+        leg_out["library_multi_gpu"] = leg_library_multi(ctx, min(args.steps, 3), 2)
     if "latency" in legs and rank == 0:
         leg_out["single_solve_latency"] = leg_latency(ctx, args.latency_calls)
     if rank == 0:

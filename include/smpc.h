@@ -426,6 +426,41 @@ int smpc_people_to_status_device(smpc_handle* h, int n_problems, int n_agents, c
 int smpc_memory_update_device(smpc_handle* h, int n_problems, int n, const uint8_t* usable, const double* path,
                               const double* cmds, double* prev_poses, double* prev_cmds, void* stream);
 
+/* ---- in-library multi-GPU dispatch of the level-1 solve -------------------------------------------
+ * One handle + one host thread per GPU; the host batch is cut into contiguous shards whose boundaries are multiples of
+ * `granule` (multi-start: starts per robot, so a robot's arg-min never spans GPUs); every shard runs the ordinary
+ * host-buffer pipeline and its results land in the caller's arrays at the shard's offset (the final host gather). No
+ * collective, nothing on the solve path crosses GPUs. `devices` may name a GPU twice (two handles on it). */
+typedef struct smpc_multi smpc_multi;
+int smpc_multi_create(const smpc_params* p, int n_devices, const int* devices /* NULL: 0 .. n_devices-1 */, smpc_multi** out);
+void smpc_multi_destroy(smpc_multi* m);
+int smpc_multi_device_count(smpc_multi* m);
+int smpc_solve_batch_multi(smpc_multi* m, const smpc_batch* in, smpc_result* out, int granule);
+/* Diagnostics (no GPU needed): [lo, hi) of `shard` when n_problems are cut into n_shards at multiples of granule. */
+int smpc_debug_shard_bounds(int n_problems, int n_shards, int shard, int granule, int* lo, int* hi);
+
+/* ---- FOV people filter of SocialMPCController::computeVelocityCommands (src/social_mpc_controller.cpp:198-214) for a
+ * fleet: a person survives when it lies inside the robot's costmap (Costmap2D::worldToMap) and its bearing is within
+ * fov_angle of the robot's yaw (float roundings of the reference kept). Order-preserving; the first n_out_max
+ * survivors are written, n_people_out [B] counts ALL survivors (people.people.size(), which decides has_people).
+ * Device pointers. */
+typedef struct smpc_fov_args {
+  int n_robots;
+  int n_in_max;  /* row stride of people_in */
+  int n_out_max; /* row stride of people_out (3 for the reference's optimizer) */
+  int n_costmaps, size_x, size_y;
+  double resolution;
+  double fov_angle;             /* FollowPath.fov_angle, default pi/4 (src/social_mpc_controller.cpp:60) */
+  const double* people_in;      /* [B][n_in_max][5] position.x/y, velocity.x/y/z */
+  const int32_t* n_people_in;   /* [B] */
+  const double* pose;           /* [B][3] robot x, y, yaw */
+  const double* costmap_origin; /* [M][2] */
+  const int32_t* costmap_index; /* [B] or NULL (robot b uses map b % M) */
+  double* people_out;           /* [B][n_out_max][5] */
+  int32_t* n_people_out;        /* [B] */
+} smpc_fov_args;
+int smpc_fov_filter_batch_device(smpc_handle* h, const smpc_fov_args* a, void* stream);
+
 /* Multi-start selection: per robot arg-min of cost_final over `n_starts`
  * consecutive problems (device pointers). best_index [R] i32 (global problem
  * index, -1 if no usable start), best_cost [R], best_u [R][NB][2]. */

@@ -80,6 +80,18 @@ def lib():
     L.smpc_memory_update_device.restype = C.c_int
     L.smpc_trajectorize_batch_device.argtypes = [C.c_void_p, P(abi.SmpcTrajectorizeArgs), C.c_void_p]
     L.smpc_trajectorize_batch_device.restype = C.c_int
+    L.smpc_fov_filter_batch_device.argtypes = [C.c_void_p, P(abi.SmpcFovArgs), C.c_void_p]
+    L.smpc_fov_filter_batch_device.restype = C.c_int
+    L.smpc_multi_create.argtypes = [P(abi.SmpcParams), C.c_int, P(C.c_int), P(C.c_void_p)]
+    L.smpc_multi_create.restype = C.c_int
+    L.smpc_multi_destroy.argtypes = [C.c_void_p]
+    L.smpc_multi_destroy.restype = None
+    L.smpc_multi_device_count.argtypes = [C.c_void_p]
+    L.smpc_multi_device_count.restype = C.c_int
+    L.smpc_solve_batch_multi.argtypes = [C.c_void_p, P(abi.SmpcBatch), P(abi.SmpcResult), C.c_int]
+    L.smpc_solve_batch_multi.restype = C.c_int
+    L.smpc_debug_shard_bounds.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, P(C.c_int), P(C.c_int)]
+    L.smpc_debug_shard_bounds.restype = C.c_int
     L.smpc_set_group.argtypes = [C.c_void_p, C.c_int]
     L.smpc_set_group.restype = C.c_int
     L.smpc_debug_polymin.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -102,5 +114,6 @@ EXPORTED_SYMBOLS = (
     "smpc_measure_fp64_peak", "smpc_debug_polymin", "smpc_debug_plan_chunks", "smpc_set_group",
     "smpc_optimize", "smpc_optimize_batch", "smpc_reset_memory", "smpc_project_people_batch", "smpc_project_people_batch_device",
     "smpc_format_batch_device", "smpc_people_to_status_device", "smpc_memory_update_device",
-    "smpc_trajectorize_batch_device",
+    "smpc_trajectorize_batch_device", "smpc_fov_filter_batch_device", "smpc_multi_create", "smpc_multi_destroy",
+    "smpc_multi_device_count", "smpc_solve_batch_multi", "smpc_debug_shard_bounds",
 )

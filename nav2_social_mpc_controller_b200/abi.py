@@ -331,3 +331,24 @@ class SmpcFleetIo(C.Structure):
         ("project_status", C.c_void_p),
         ("people_proj", C.c_void_p),
     ]
+
+
+class SmpcFovArgs(C.Structure):
+    """struct smpc_fov_args — batched FOV people filter of SocialMPCController::computeVelocityCommands."""
+    _fields_ = [
+        ("n_robots", C.c_int),
+        ("n_in_max", C.c_int),
+        ("n_out_max", C.c_int),
+        ("n_costmaps", C.c_int),
+        ("size_x", C.c_int),
+        ("size_y", C.c_int),
+        ("resolution", C.c_double),
+        ("fov_angle", C.c_double),
+        ("people_in", C.c_void_p),
+        ("n_people_in", C.c_void_p),
+        ("pose", C.c_void_p),
+        ("costmap_origin", C.c_void_p),
+        ("costmap_index", C.c_void_p),
+        ("people_out", C.c_void_p),
+        ("n_people_out", C.c_void_p),
+    ]

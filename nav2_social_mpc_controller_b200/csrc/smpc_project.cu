@@ -607,6 +607,69 @@ int smpc_project_people_batch(smpc_handle* h, const smpc_project_args* a) {
 }  // extern "C"
 
 // ===================================================================================================================
+// FOV people filter of SocialMPCController::computeVelocityCommands (reference src/social_mpc_controller.cpp:198-214)
+// for a fleet: a person is kept when Costmap2D::worldToMap succeeds for its position and |bearing - yaw| < fov_angle,
+// with the reference's FLOAT roundings (angle_to_person, robot_yaw and relative_angle are floats there). One thread
+// per robot walks its people in order (the filter is an order-preserving compaction; only the first A_out survive,
+// people_to_status keeps three, src/optimizer.cpp:476-479).
+// ===================================================================================================================
+namespace {
+__global__ void smpc_fov_filter_kernel(smpc_fov_args a) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.n_robots) return;
+  const int mi = a.costmap_index ? a.costmap_index[b] : (b % a.n_costmaps);
+  const double ox = a.costmap_origin[2 * mi], oy = a.costmap_origin[2 * mi + 1];
+  const double px = a.pose[3 * b], py = a.pose[3 * b + 1];
+  double sh, ch;
+  sincos(a.pose[3 * b + 2] * 0.5, &sh, &ch);
+  const float robot_yaw = (float)atan2(2.0 * (ch * sh), ch * ch - sh * sh);  // tf2::getYaw of the pose quaternion
+  const double* in = a.people_in + (size_t)b * a.n_in_max * 5;
+  double* out = a.people_out + (size_t)b * a.n_out_max * 5;
+  const int n = min(a.n_people_in[b], a.n_in_max);
+  int kept = 0, total = 0;
+  for (int k = 0; k < n; ++k) {
+    const double wx = in[5 * k], wy = in[5 * k + 1];
+    // Costmap2D::worldToMap
+    if (wx < ox || wy < oy) continue;
+    const unsigned mx = (unsigned)((wx - ox) / a.resolution), my = (unsigned)((wy - oy) / a.resolution);
+    if (!(mx < (unsigned)a.size_x && my < (unsigned)a.size_y)) continue;
+    const float angle_to_person = (float)atan2(wy - py, wx - px);
+    // angles::shortest_angular_distance(from, to) = normalize_angle(to - from), evaluated in double on the float values
+    const double diff = (double)angle_to_person - (double)robot_yaw;
+    const double norm = fmod(fmod(diff + M_PI, 2.0 * M_PI) + 2.0 * M_PI, 2.0 * M_PI) - M_PI;
+    const float relative_angle = (float)norm;
+    if (fabs((double)relative_angle) < a.fov_angle) {
+      if (kept < a.n_out_max) {
+        for (int c = 0; c < 5; ++c) out[5 * kept + c] = in[5 * k + c];
+        ++kept;
+      }
+      ++total;
+    }
+  }
+  for (int k = kept; k < a.n_out_max; ++k)
+    for (int c = 0; c < 5; ++c) out[5 * k + c] = 0.0;
+  a.n_people_out[b] = total;  // people.people.size() after the filter (has_people = total != 0, :263)
+}
+}  // namespace
+
+extern "C" {
+int smpc_fov_filter_batch_device(smpc_handle* h, const smpc_fov_args* a, void* stream) {
+  if (!h || !a) return smpc_host_fail(SMPC_ERR_ARGUMENT, "NULL argument");
+  if (a->n_robots < 0 || a->n_in_max < 1 || a->n_out_max < 1 || a->n_costmaps < 1 || !a->people_in || !a->n_people_in ||
+      !a->pose || !a->costmap_origin || !a->people_out || !a->n_people_out || !(a->resolution > 0.0))
+    return smpc_host_fail(SMPC_ERR_ARGUMENT, "fov_filter: bad arguments");
+  if (a->n_robots == 0) return SMPC_OK;
+  cudaSetDevice(smpc_handle_device(h));
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : smpc_handle_stream(h);
+  smpc_fov_filter_kernel<<<(a->n_robots + 127) / 128, 128, 0, st>>>(*a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return smpc_host_fail(SMPC_ERR_CUDA, std::string("fov filter kernel: ") + cudaGetErrorString(e));
+  smpc_handle_count_launch(h);
+  return SMPC_OK;
+}
+}  // extern "C"
+
+// ===================================================================================================================
 // Level-2 BATCH entry: smpc_optimize_batch = bool Optimizer::optimize(...) (reference src/optimizer.cpp:148-452) for a
 // fleet of B robots per call, every stage a kernel on the handle's stream, per-robot horizons, per-robot warm-start
 // memory (previous path / cmds) resident on the device between ticks.

@@ -66,6 +66,33 @@ class FleetOptimizer:
         self.stream.synchronize()
         return poses.cpu().numpy(), cmds.cpu().numpy(), n_steps.cpu().numpy()
 
+    def filter_people_fov(self, people, n_people, pose, costmap_origin, size_x, size_y, resolution, fov_angle=None,
+                          costmap_index=None, n_out_max=None):
+        """FOV filter of SocialMPCController::computeVelocityCommands (reference src/social_mpc_controller.cpp:198-214)
+        for the fleet, on the GPU: people [B][K][5], n_people [B], pose [B][3] -> (people [B][n_out_max][5], n [B])."""
+        torch, L, h = self.torch, _lib.lib(), self.opt._h
+        people = np.ascontiguousarray(people, dtype=np.float64)
+        B, K, _ = people.shape
+        n_out_max = self.A if n_out_max is None else n_out_max
+        morg = np.ascontiguousarray(costmap_origin, dtype=np.float64).reshape(-1, 2)
+        with torch.cuda.stream(self.stream):
+            d_in, d_n = self._t(people, np.float64), self._t(n_people, np.int32)
+            d_pose, d_org = self._t(pose, np.float64), self._t(morg, np.float64)
+            d_idx = None if costmap_index is None else self._t(costmap_index, np.int32)
+            out = torch.zeros(B, n_out_max, 5, dtype=torch.float64, device=self.dev)
+            n_out = torch.zeros(B, dtype=torch.int32, device=self.dev)
+            a = abi.SmpcFovArgs()
+            a.n_robots, a.n_in_max, a.n_out_max, a.n_costmaps = B, K, n_out_max, morg.shape[0]
+            a.size_x, a.size_y, a.resolution = int(size_x), int(size_y), float(resolution)
+            a.fov_angle = float(self.p.fov_angle if fov_angle is None else fov_angle)
+            a.people_in, a.n_people_in, a.pose = d_in.data_ptr(), d_n.data_ptr(), d_pose.data_ptr()
+            a.costmap_origin = d_org.data_ptr()
+            a.costmap_index = None if d_idx is None else d_idx.data_ptr()
+            a.people_out, a.n_people_out = out.data_ptr(), n_out.data_ptr()
+            _lib.check(L.smpc_fov_filter_batch_device(h, C.byref(a), self.stream.cuda_stream))
+        self.stream.synchronize()
+        return out.cpu().numpy(), n_out.cpu().numpy()
+
     def optimize_batch(self, poses, cmds, people_raw, n_people, speed, costmaps, costmap_origin, costmap_resolution,
                        od: dict, costmap_index=None, od_index=None, n_poses=None, want_people_proj=True) -> dict:
         """One controller tick for the fleet (smpc_optimize_batch). poses [B][n][3], cmds [B][>= n-1][2] (trajectorizer

@@ -239,6 +239,43 @@ class Optimizer:
         return int(_lib.lib().smpc_launch_count(self._h))
 
 
+class MultiGpuOptimizer:
+    """smpc_solve_batch_multi: one host batch solved across several GPUs inside the library (one host thread + handle
+    per GPU, contiguous shards at multiples of `granule`, results land in the caller's host arrays). `devices` may name
+    a GPU more than once."""
+
+    def __init__(self, params, devices):
+        if isinstance(params, abi.SmpcParams):
+            params = OptimizerParams.from_struct(params)
+        self.params = params
+        devs = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        _lib.check(_lib.lib().smpc_multi_create(C.byref(params.c), len(devices), devs, C.byref(h)))
+        self._m = h
+
+    def close(self):
+        if self._m is not None:
+            _lib.lib().smpc_multi_destroy(self._m)
+            self._m = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def solve_batch(self, batch, out: dict | None = None, granule: int = 1,
+                    want=("u", "cmds", "cost_initial", "cost_final", "iterations", "termination", "usable", "n_evals")):
+        ch, bl, nb, nbd = abi.problem_dims(self.params.control_horizon, self.params.parameter_block_length, batch.n_steps)
+        if out is None:
+            shapes = abi.result_shapes(batch.n_problems, batch.n_steps, nb, 3 if int(self.params.omni_solve) else 2)
+            out = {k: np.zeros(shapes[k][0], dtype=shapes[k][1]) for k in want}
+        st = batch.struct()
+        rs = abi.make_result_struct(out)
+        _lib.check(_lib.lib().smpc_solve_batch_multi(self._m, C.byref(st), C.byref(rs), int(granule)))
+        return out
+
+
 def hess_to_dense(h_packed: np.ndarray, P: int) -> np.ndarray:
     """Row-major lower-triangle packing of include/smpc.h -> dense symmetric [.., P, P]."""
     out = np.zeros(h_packed.shape[:-1] + (P, P))

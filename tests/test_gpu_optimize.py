@@ -387,3 +387,40 @@ def test_gpu_trajectorize_matches_numpy_restatement():
                 assert poses[b, s + 1, 1] == pytest.approx(ry, abs=1e-12)
     finally:
         fleet.close()
+
+
+def test_fov_people_filter_matches_reference_arithmetic():
+    """Batched FOV filter vs a scalar restatement of reference src/social_mpc_controller.cpp:198-214 with its float
+    roundings (angle_to_person, robot_yaw, relative_angle are floats; fov_angle is a double)."""
+    from nav2_social_mpc_controller_b200.fleet import FleetOptimizer
+    rng = np.random.default_rng(8)
+    B, K = 64, 7
+    p = sc.make_params("soc_work_obst")
+    pose = np.stack([rng.uniform(1.0, 3.0, B), rng.uniform(1.0, 3.0, B), rng.uniform(-3.1, 3.1, B)], axis=1)
+    people = np.zeros((B, K, 5))
+    people[:, :, 0] = rng.uniform(-0.5, 4.5, (B, K))  # some outside the 4 x 4 m costmap
+    people[:, :, 1] = rng.uniform(-0.5, 4.5, (B, K))
+    people[:, :, 2:5] = rng.normal(0, 0.5, (B, K, 3))
+    n_people = rng.integers(0, K + 1, B).astype(np.int32)
+    fleet = FleetOptimizer(p, n_robots=B, n_agents=3)
+    try:
+        got, n_got = fleet.filter_people_fov(people, n_people, pose, np.zeros((1, 2)), 80, 80, 0.05)
+    finally:
+        fleet.close()
+    fov = float(p.fov_angle)
+    for b in range(B):
+        yaw = np.float32(sc.yaw_roundtrip(pose[b, 2]))
+        keep = []
+        for k in range(n_people[b]):
+            wx, wy = people[b, k, 0], people[b, k, 1]
+            if wx < 0.0 or wy < 0.0 or not (int(wx / 0.05) < 80 and int(wy / 0.05) < 80):
+                continue
+            ang = np.float32(math.atan2(wy - pose[b, 1], wx - pose[b, 0]))
+            d = float(ang) - float(yaw)
+            rel = np.float32(math.fmod(math.fmod(d + math.pi, 2 * math.pi) + 2 * math.pi, 2 * math.pi) - math.pi)
+            if abs(float(rel)) < fov:
+                keep.append(k)
+        assert n_got[b] == len(keep), b
+        for j, k in enumerate(keep[:3]):
+            assert np.array_equal(got[b, j], people[b, k])
+        assert np.all(got[b, min(len(keep), 3):] == 0.0)

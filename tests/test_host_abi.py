@@ -166,3 +166,23 @@ def test_host_pipeline_chunk_plan():
     # the SMPC_CHUNKS override ignores the size rule but still honours the modulo rule
     assert plan(1300, 1, 256, forced=3) == (3, 512)
     assert L.smpc_debug_plan_chunks(0, 10, 0, 1, 0, 0, 0, None, None) != 0
+
+
+def test_multi_gpu_shard_bounds_without_a_gpu():
+    """smpc_debug_shard_bounds: the contiguous cut smpc_solve_batch_multi uses — shards cover [0, n) without gaps, start
+    at multiples of the granule (multi-start: a robot's starts stay on one GPU), sizes differ by at most one granule."""
+    import ctypes as C
+    from nav2_social_mpc_controller_b200 import _lib
+    L = _lib.lib()
+    for n, world, g in [(4096, 8, 1), (262144, 8, 1024), (1000000, 3, 1), (100, 8, 16), (5, 8, 1), (1030, 4, 64)]:
+        lo, hi = C.c_int(), C.c_int()
+        prev, sizes = 0, []
+        for r in range(world):
+            assert L.smpc_debug_shard_bounds(n, world, r, g, C.byref(lo), C.byref(hi)) == 0
+            assert lo.value == prev and hi.value >= lo.value
+            assert lo.value % g == 0
+            sizes.append(hi.value - lo.value)
+            prev = hi.value
+        assert prev == n
+        full = [s for s in sizes[:-1]]
+        assert max(full) - min(full) <= g
