@@ -247,6 +247,14 @@ class Ctx:
         if self.world > 1:
             self.dist.barrier()
 
+    def host_barrier(self):
+        """Barrier on the gloo group: the waiting ranks sleep on the host. (An NCCL barrier keeps a spinning kernel on
+        every waiting rank's GPU, and kernels of two PROCESSES time-slice a GPU: rank 0 driving all GPUs through the
+        library would then get half of each.)"""
+        if self.world > 1:
+            self.torch.cuda.synchronize()
+            self.dist.barrier(group=self.gloo)
+
     def max_over_ranks(self, *vals):
         if self.world == 1:
             return vals
@@ -578,7 +586,7 @@ def leg_library_multi(ctx, steps, warmup, per_gpu=16384, A=20):
     copies. The other ranks idle at a barrier while rank 0 drives all N GPUs."""
     from nav2_social_mpc_controller_b200.optimizer import MultiGpuOptimizer
     torch = ctx.torch
-    ctx.barrier()
+    ctx.host_barrier()
     out = None
     if ctx.rank == 0:
         base = sc.crowd(B=per_gpu, A=A)
@@ -614,7 +622,7 @@ def leg_library_multi(ctx, steps, warmup, per_gpu=16384, A=20):
                "d2h_bytes_per_step": int(sum(v.nbytes for v in host_out.values())),
                "shards_identical": bool(same), "usable_fraction": float(host_out["usable"].mean()),
                "steps": steps, "warmup": warmup}
-    ctx.barrier()
+    ctx.host_barrier()
     return out
 
 
