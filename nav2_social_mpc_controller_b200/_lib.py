@@ -96,6 +96,8 @@ def lib():
     L.smpc_set_group.restype = C.c_int
     L.smpc_debug_polymin.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.smpc_debug_polymin.restype = C.c_int
+    L.smpc_debug_math.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.smpc_debug_math.restype = C.c_int
     if L.smpc_abi_version() != abi.SMPC_ABI_VERSION:
         raise ImportError("libsmpc.so ABI version mismatch")
     _lib = L
@@ -111,7 +113,7 @@ EXPORTED_SYMBOLS = (
     "smpc_abi_version", "smpc_last_error", "smpc_params_default", "smpc_params_from_yaml", "smpc_problem_dims",
     "smpc_create", "smpc_destroy", "smpc_solve_batch", "smpc_solve_batch_device", "smpc_eval_batch_device",
     "smpc_eval_batch", "smpc_multistart_argmin_device", "smpc_last_kernel_ms", "smpc_launch_count",
-    "smpc_measure_fp64_peak", "smpc_debug_polymin", "smpc_debug_plan_chunks", "smpc_set_group",
+    "smpc_measure_fp64_peak", "smpc_debug_polymin", "smpc_debug_math", "smpc_debug_plan_chunks", "smpc_set_group",
     "smpc_optimize", "smpc_optimize_batch", "smpc_reset_memory", "smpc_project_people_batch", "smpc_project_people_batch_device",
     "smpc_format_batch_device", "smpc_people_to_status_device", "smpc_memory_update_device",
     "smpc_trajectorize_batch_device", "smpc_fov_filter_batch_device", "smpc_multi_create", "smpc_multi_destroy",

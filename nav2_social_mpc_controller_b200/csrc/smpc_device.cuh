@@ -130,9 +130,62 @@ __device__ __forceinline__ double wrap_to_pi(double a) {
   return a;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Elementary functions of the pair loop. A 64-bit literal costs two move instructions (UMOV / IMAD.MOV.U32) every time
+// it is used — DFMA takes only 32-bit immediates — and the libm expansions carry a slow-path branch each; in the
+// 20-agent kernel those moves were 22 % of all executed instructions (profiles/r02_a20_before_consts_opmix.txt). The
+// coefficient tables below live in constant memory instead (LDCU.128: one uniform load per TWO doubles, hoistable),
+// and the three functions are branch-free for the argument range the social force can produce.
+// ---------------------------------------------------------------------------------------------------
+static __constant__ double kAtanTab[16] = {
+    0.41421356237309503,  // tan(pi/8)
+    -0.01917688711906226, 0.03923165829558719, -0.0508544973794026,  0.0585814891280221,
+    -0.06664511447381948, 0.07692183190826087, -0.09090904578123903, 0.11111111015256361,
+    -0.14285714284666542, 0.1999999999999552,  -0.3333333333333333,
+    0.7853981633974483,   1.5707963267948966,  3.141592653589793,    0.0};
+static __constant__ double kExpTab[14] = {
+    1.4426950408889634,      // log2(e)
+    -0.6931471805599453,     // -ln2 (high part)
+    -2.3190468138462996e-17, // -ln2 (low part)
+    // exp(r) = 1 + r + r^2 h(r), |r| <= ln2/2: h = degree-9 Chebyshev interpolant (tools/fit_exp.py), highest first
+    2.5100395159429243e-08, 2.7620101012098e-07,    2.7557268439678e-06,  2.4801521269532122e-05,
+    0.00019841269863066696, 0.0013888888917230724,  0.00833333333333006,  0.041666666666624094,
+    0.16666666666666669,    0.5000000000000001,     -708.0};
+static __constant__ double kPairTab[4] = {0.35, 1.0 / 0.35, 2.1, 1e-6};  // gamma, 1/gamma, force factor, tiny |d|
+
+// exp(x) for x <= 0 (the social force only calls it with -(d/B) - (n B theta)^2): Cody-Waite reduction x = n ln2 + r,
+// degree-11 polynomial, scaling by 2^n as a multiplication (NaN propagates). 0.62 ulp against 60-digit mpmath over
+// [-708, 0] (tools/fit_exp.py; CUDA's exp: 1 ulp). Results below 2^-1022 (x < -708) are returned as 0.
+__device__ __forceinline__ double exp_nonpos(double x) {
+  const bool under = x < kExpTab[13];
+  const double xc = under ? kExpTab[13] : x;
+  const double t = fma(xc, kExpTab[0], 6755399441055744.0);  // 1.5 * 2^52: the low word of t is rint(x log2 e)
+  const double nf = t - 6755399441055744.0;
+  double r = fma(nf, kExpTab[1], xc);
+  r = fma(nf, kExpTab[2], r);
+  double q = kExpTab[3];
+#pragma unroll
+  for (int c = 4; c <= 12; ++c) q = fma(q, r, kExpTab[c]);
+  q = fma(q, r, 1.0);
+  q = fma(q, r, 1.0);
+  const double scale = __hiloint2double((__double2loint(t) + 1023) << 20, 0);  // 2^n, n in [-1021, 0]: normal
+  return under ? 0.0 : q * scale;
+}
+
+// 1 / sqrt(x) for normal positive x: hardware seed (2^-22) + one third-order step y (1 + e/2 + 3 e^2 / 8),
+// e = 1 - x y^2 (< 1 ulp, the class of CUDA's rsqrt, without its exponent-range slow path). x = 0 gives NaN.
+__device__ __forceinline__ double rsqrt_pos(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double t = x * y;
+  const double e = fma(-t, y, 1.0);
+  const double p = fma(e, 0.375, 0.5);
+  return fma(y * e, p, y);
+}
+
 // atan2(s, c) for a point (c, s) near the unit circle (the social force calls it with the cross / dot product of two
 // unit vectors, i.e. s = sin(theta), c = cos(theta) up to rounding). CUDA's general atan2 is ~135 instructions with
-// its scaling and special-case handling and was 19 % of all instructions of a 20-agent solve; this one is ~45:
+// its scaling and special-case handling and was 19 % of all instructions of a 20-agent solve; this one is ~40:
 // one division (reciprocal seed + two Newton steps + residual correction) of the octant-reduced argument
 //   t = min / max                  (min <= tan(pi/8) max)        atan = P(t)
 //   t = (min - max) / (min + max)  (otherwise: |t| <= tan(pi/8)) atan = pi/4 + P(t)
@@ -141,8 +194,9 @@ __device__ __forceinline__ double wrap_to_pi(double a) {
 // accuracy class of libm's atan2 (CUDA: 2 ulp). Inputs must be finite, not both zero and of comparable magnitude.
 __device__ __forceinline__ double atan2_unit(double s, double c) {
   const double ax = fabs(c), ay = fabs(s);
-  const double mx = fmax(ax, ay), mn = fmin(ax, ay);
-  const bool hi = mn > 0.41421356237309503 * mx;
+  const bool steep = ay > ax;
+  const double mx = steep ? ay : ax, mn = steep ? ax : ay;
+  const bool hi = mn > kAtanTab[0] * mx;
   const double num = hi ? mn - mx : mn, den = hi ? mn + mx : mx;
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
@@ -151,39 +205,35 @@ __device__ __forceinline__ double atan2_unit(double s, double c) {
   double t = num * r;
   t = fma(fma(-den, t, num), r, t);
   const double z = t * t;
-  double q = -0.01917688711906226;
-  q = fma(q, z, 0.03923165829558719);
-  q = fma(q, z, -0.0508544973794026);
-  q = fma(q, z, 0.0585814891280221);
-  q = fma(q, z, -0.06664511447381948);
-  q = fma(q, z, 0.07692183190826087);
-  q = fma(q, z, -0.09090904578123903);
-  q = fma(q, z, 0.11111111015256361);
-  q = fma(q, z, -0.14285714284666542);
-  q = fma(q, z, 0.1999999999999552);
-  q = fma(q, z, -0.3333333333333333);
+  double q = kAtanTab[1];
+#pragma unroll
+  for (int k = 2; k <= 11; ++k) q = fma(q, z, kAtanTab[k]);
   double a = fma(t, z * q, t);
-  if (hi) a += 0.7853981633974483;
-  if (ay > ax) a = 1.5707963267948966 - a;
-  if (c < 0.0) a = 3.141592653589793 - a;
+  if (hi) a += kAtanTab[12];
+  if (steep) a = kAtanTab[13] - a;
+  if (c < 0.0) a = kAtanTab[14] - a;
   return copysign(a, s);
 }
 
+// kReferenceAngle = false: theta always from the one-atan2 form (the caller re-evaluates degenerate pairs through
+// social_pair_reference, an out-of-line call, so the two general atan2 expansions stay out of the hot loop body).
+template <bool kReferenceAngle>
 __device__ __forceinline__ void social_pair(double dx, double dy, double wx, double wy, PairOut& o) {
-  const double kLambda = 2.0, kGamma = 0.35, kNPrime = 3.0, kN = 2.0, kFactor = 2.1;
+  const double kLambda = 2.0, kNPrime = 3.0, kN = 2.0;
+  const double kGamma = kPairTab[0], kInvGamma = kPairTab[1], kFactor = kPairTab[2];
   double d2 = dx * dx + dy * dy;
   const bool tiny = d2 < 1e-12;  // |d| < 1e-6
   if (tiny) {  // coincident: fixed direction (1e-6, 0), a constant for the derivative
-    dx = 1e-6;
+    dx = kPairTab[3];
     dy = 0.0;
     d2 = dx * dx;
   }
-  const double inv_rho = rsqrt(d2);
+  const double inv_rho = rsqrt_pos(d2);
   const double rho = d2 * inv_rho;
   const double ex = dx * inv_rho, ey = dy * inv_rho;  // Eigen normalized() (|d|^2 > 0 always holds here)
   const double Ix = kLambda * wx + ex, Iy = kLambda * wy + ey;
   const double L2 = Ix * Ix + Iy * Iy;
-  const double inv_L = rsqrt(L2);
+  const double inv_L = rsqrt_pos(L2);
   const double L = L2 * inv_L;
   const double ix = Ix * inv_L, iy = Iy * inv_L;
   // theta = wrapToPi(atan2(e) - atan2(i)), the signed angle from i to e. Generic geometry: one atan2 of
@@ -193,17 +243,17 @@ __device__ __forceinline__ void social_pair(double dx, double dy, double wx, dou
   const double cross = ey * ix - ex * iy, dot = ex * ix + ey * iy;
   double theta;
   o.degenerate = tiny || !(fabs(cross) > 1e-9);  // the coincident-position fix-up is not odd in d either
-  if (!o.degenerate) {
+  if (!kReferenceAngle || !o.degenerate) {
     theta = atan2_unit(cross, dot);
   } else {
     theta = wrap_to_pi(atan2(ey, ex) - atan2(iy, ix));
   }
   const double Bq = kGamma * L;
-  const double inv_B = inv_L * (1.0 / kGamma);
+  const double inv_B = inv_L * kInvGamma;
   const double t1 = kNPrime * Bq * theta, t2 = kN * Bq * theta;
   const double base = -rho * inv_B;
-  const double E1 = exp(base - t1 * t1);
-  const double E2 = exp(base - t2 * t2);
+  const double E1 = exp_nonpos(base - t1 * t1);
+  const double E2 = exp_nonpos(base - t2 * t2);
   const double sgn = (theta > 0.0) ? 1.0 : -1.0;
   const double fv = -E1, fa = -sgn * E2;
   o.fx = kFactor * (fv * ix - fa * iy);
@@ -233,6 +283,21 @@ __device__ __forceinline__ void social_pair(double dx, double dy, double wx, dou
     const double gfa = -sgn * E2 * gu2;
     o.dfx[c] = kFactor * (ix * gfv - iy * gfa) - o.fy * gpi[c];
     o.dfy[c] = kFactor * (iy * gfv + ix * gfa) + o.fx * gpi[c];
+  }
+}
+
+// Near-degenerate pair (see above), evaluated with the reference's two-atan2 angle. Rare (exactly (anti)parallel
+// set-ups), so it is a real call: out = {fx, fy, dfx[4], dfy[4]} scaled by `sign` on the gradient.
+static __device__ __noinline__ void social_pair_reference(double dx, double dy, double wx, double wy, double sign,
+                                                          double* out) {
+  PairOut o;
+  social_pair<true>(dx, dy, wx, wy, o);
+  out[0] = o.fx;
+  out[1] = o.fy;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    out[2 + c] = sign * o.dfx[c];
+    out[6 + c] = sign * o.dfy[c];
   }
 }
 
@@ -550,13 +615,12 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
           nxt_valid = __ldg(vld + (size_t)(k + 1) * stride) != 0;
         }
         const double ddx = X - ax, ddy = Y - ay;
-        if (valid) {
+        {  // closest valid agent (proxemics), branch-free
           const double d2 = ddx * ddx + ddy * ddy;
-          if (d2 < dmin) {
-            dmin = d2;
-            pdx = ddx;
-            pdy = ddy;
-          }
+          const bool closer = valid && d2 < dmin;
+          dmin = closer ? d2 : dmin;
+          pdx = closer ? ddx : pdx;
+          pdy = closer ? ddy : pdy;
         }
         if (do_social) {
           // F(robot <- agent k) = pair(d, w) with d = robot - agent, w = v_robot - v_agent, and
@@ -565,20 +629,35 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
           // residual; only the near-degenerate branch (reference rounding decides theta = +-pi / 0) is evaluated
           // per role. Padded agents only have the agent <- robot term.
           PairOut po;
-          social_pair(ddx, ddy, rvx - avx, rvy - avy, po);
-          if (valid) {
-            Frx += po.fx;
-            Fry += po.fy;
+          social_pair<false>(ddx, ddy, rvx - avx, rvy - avy, po);
+          const bool degenerate = po.degenerate;
+          if (degenerate) {
+            double ref[10];
+            social_pair_reference(ddx, ddy, rvx - avx, rvy - avy, 1.0, ref);
+            po.fx = ref[0];
+            po.fy = ref[1];
             SMPC_UNROLL for (int c = 0; c < 4; ++c) {
-              JFx[c] += po.dfx[c];
-              JFy[c] += po.dfy[c];
+              po.dfx[c] = ref[2 + c];
+              po.dfy[c] = ref[6 + c];
             }
           }
-          if (po.degenerate) {
-            social_pair(-ddx, -ddy, avx - rvx, avy - rvy, po);  // d(-d)/dX = -1: the gradient changes sign
+          {  // robot <- agent term of valid agents only: fma(1, f, F) is F + f exactly, fma(0, f, F) is F
+            const double m = valid ? 1.0 : 0.0;
+            Frx = fma(m, po.fx, Frx);
+            Fry = fma(m, po.fy, Fry);
             SMPC_UNROLL for (int c = 0; c < 4; ++c) {
-              po.dfx[c] = -po.dfx[c];
-              po.dfy[c] = -po.dfy[c];
+              JFx[c] = fma(m, po.dfx[c], JFx[c]);
+              JFy[c] = fma(m, po.dfy[c], JFy[c]);
+            }
+          }
+          if (degenerate) {
+            double ref[10];
+            social_pair_reference(-ddx, -ddy, avx - rvx, avy - rvy, -1.0, ref);  // d(-d)/dX = -1: gradient sign
+            po.fx = ref[0];
+            po.fy = ref[1];
+            SMPC_UNROLL for (int c = 0; c < 4; ++c) {
+              po.dfx[c] = ref[2 + c];
+              po.dfy[c] = ref[6 + c];
             }
           }
           wp += po.fx * po.fx + po.fy * po.fy;
@@ -1499,7 +1578,9 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
     }
     // CTA barrier per evaluation: the warps of a CTA walk the large unrolled evaluation code together and share its
     // instruction-cache lines (measured +15..40 %); it also ends the loop once every group of the CTA is out of work
-    // (a barrier every 2nd / 3rd / 4th evaluation measured -8 / -17 / -20 %: SMPC_SYNC_EVERY stays 1)
+    // (a barrier every 2nd / 3rd / 4th evaluation measured -8 / -17 / -20 %: SMPC_SYNC_EVERY stays 1; two / three
+    // independent lock-step teams per CTA on named barriers, so that one team's single-lane phase logic could run under
+    // another team's FP64-bound evaluation, measured -3 / -6 % with 20 agents and -4 / -8 % without people)
 #ifndef SMPC_SYNC_EVERY
 #define SMPC_SYNC_EVERY 1
 #endif

@@ -940,6 +940,21 @@ int smpc_debug_polymin(smpc_handle* h, int n, const double* rows, double* out) {
   return SMPC_OK;
 }
 
+int smpc_debug_math(smpc_handle* h, int kind, int n, const double* rows, double* out) {
+  if (!h || !rows || !out || n < 0 || kind < 0 || kind > 2) return fail(SMPC_ERR_ARGUMENT, "bad debug_math arguments");
+  if (n == 0) return SMPC_OK;
+  std::lock_guard<std::mutex> lk(h->mu);
+  SMPC_CUDA(cudaSetDevice(h->device));
+  SMPC_CUDA(h->in_buf.reserve(sizeof(double) * 2 * n));
+  SMPC_CUDA(h->out_buf.reserve(sizeof(double) * n));
+  SMPC_CUDA(cudaMemcpyAsync(h->in_buf.ptr, rows, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, h->stream));
+  SMPC_CUDA(smpc::launch_math(kind, n, static_cast<const double*>(h->in_buf.ptr), static_cast<double*>(h->out_buf.ptr), h->stream));
+  SMPC_CUDA(cudaMemcpyAsync(out, h->out_buf.ptr, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  SMPC_CUDA(cudaStreamSynchronize(h->stream));
+  h->launches += 1;
+  return SMPC_OK;
+}
+
 int smpc_measure_fp64_peak(smpc_handle* h, double* tflops) {
   if (!h || !tflops) return fail(SMPC_ERR_ARGUMENT, "NULL argument");
   std::lock_guard<std::mutex> lk(h->mu);

@@ -19,5 +19,6 @@ int max_supported_blocks();
 cudaError_t launch_pack_agents(long long n_rows, int S1, const double* agents, double* packed, uint8_t* valid,
                                cudaStream_t stream);
 cudaError_t launch_polymin(int n, const double* in, double* out, cudaStream_t stream);
+cudaError_t launch_math(int kind, int n, const double* in, double* out, cudaStream_t stream);
 cudaError_t launch_dfma_peak(double* sink, int n_sm, int iters, cudaStream_t stream);
 }  // namespace smpc

@@ -56,6 +56,15 @@ __global__ void smpc_polymin_kernel(int n, const double* __restrict__ in, double
                         : cubic_interp_min(r[2], r[3], r[4], r[5], r[6], r[0], r[1]);
 }
 
+// The pair loop's own elementary functions exposed for unit tests: rows of (a, b); kind 0 exp_nonpos(a),
+// 1 rsqrt_pos(a), 2 atan2_unit(a, b).
+__global__ void smpc_math_kernel(int kind, int n, const double* __restrict__ in, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double a = in[2 * (size_t)i], b = in[2 * (size_t)i + 1];
+  out[i] = (kind == 0) ? exp_nonpos(a) : (kind == 1) ? rsqrt_pos(a) : atan2_unit(a, b);
+}
+
 // One CTA per robot: arg-min of cost_final over its n_starts consecutive solves (usable ones only; ties -> lowest index).
 __global__ void smpc_argmin_kernel(int n_starts, int n_params, const double* __restrict__ cost_final,
                                    const uint8_t* __restrict__ usable, const double* __restrict__ u,
@@ -180,6 +189,11 @@ cudaError_t launch_argmin(int n_robots, int n_starts, int n_params, const double
 }
 
 int max_supported_blocks() { return 18; }
+
+cudaError_t launch_math(int kind, int n, const double* in, double* out, cudaStream_t stream) {
+  smpc_math_kernel<<<(n + 127) / 128, 128, 0, stream>>>(kind, n, in, out);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_polymin(int n, const double* in, double* out, cudaStream_t stream) {
   smpc_polymin_kernel<<<(n + 127) / 128, 128, 0, stream>>>(n, in, out);

@@ -227,6 +227,16 @@ class Optimizer:
         _lib.check(_lib.lib().smpc_debug_polymin(self._h, rows.shape[0], rows.ctypes.data, out.ctypes.data))
         return out
 
+    def debug_math(self, kind: int, a: np.ndarray, b: np.ndarray | None = None) -> np.ndarray:
+        """The kernel's own exp_nonpos (kind 0) / rsqrt_pos (1) / atan2_unit(a, b) (2) on arrays (unit tests)."""
+        self._need()
+        a = np.ascontiguousarray(a, dtype=np.float64).ravel()
+        rows = np.stack([a, np.zeros_like(a) if b is None else np.ascontiguousarray(b, dtype=np.float64).ravel()], axis=1)
+        rows = np.ascontiguousarray(rows)
+        out = np.zeros(a.shape[0])
+        _lib.check(_lib.lib().smpc_debug_math(self._h, int(kind), a.shape[0], rows.ctypes.data, out.ctypes.data))
+        return out
+
     def measure_fp64_peak(self) -> float:
         """TFLOP/s of a DFMA-saturating microbenchmark on this GPU (roofline denominator)."""
         self._need()

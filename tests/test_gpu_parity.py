@@ -278,6 +278,36 @@ def test_multistart_argmin(make_opt):
     assert np.array_equal(best_u.cpu().numpy(), got["u"][want])
 
 
+def test_pair_loop_elementary_functions_are_libm_class(make_opt):
+    """exp_nonpos / rsqrt_pos / atan2_unit of the social-force loop (csrc/smpc_device.cuh) against 80-bit long-double
+    libm: <= 1 ulp (exp, rsqrt) and <= 2 ulp (atan2), i.e. the accuracy class of the CUDA / glibc functions they
+    replace; results below 2^-1022 flush to zero; NaN propagates."""
+    opt = make_opt(sc.make_params("soc_work_obst"))
+    rng = np.random.default_rng(11)
+    ld = np.longdouble
+    ulp = lambda got, want: np.abs((got.astype(ld) - want) / want) / ld(2.0 ** -52)
+    # exp on [-708, 0] (dense near 0 and across the range), exact zero beyond, NaN
+    x = np.concatenate([-rng.uniform(0, 708, 200000), -rng.uniform(0, 40, 200000), -10.0 ** rng.uniform(-300, 0, 20000),
+                        [0.0, -708.0, -1e-320]])
+    got = opt.debug_math(0, x)
+    assert ulp(got, np.exp(x.astype(ld))).max() <= 1.0
+    assert np.array_equal(opt.debug_math(0, np.array([-708.5, -745.0, -1e9, -np.inf])), np.zeros(4))
+    assert np.isnan(opt.debug_math(0, np.array([np.nan])))[0]
+    # rsqrt over the whole normal range
+    x = np.concatenate([10.0 ** rng.uniform(-300, 300, 200000), rng.uniform(0.5, 4.0, 200000), [1e-12, 1.0, 4.0]])
+    got = opt.debug_math(1, x)
+    assert ulp(got, 1 / np.sqrt(x.astype(ld))).max() <= 1.0
+    assert np.isnan(opt.debug_math(1, np.array([0.0])))[0]
+    # atan2 of points close to the unit circle, incl. tiny angles and the octant boundaries
+    th = np.concatenate([rng.uniform(-np.pi, np.pi, 300000), rng.choice([-1, 1], 50000) * 10.0 ** rng.uniform(-9, 0, 50000),
+                         np.arange(-8, 9) * (np.pi / 8) + 1e-9])
+    r = 1.0 + rng.uniform(-1e-12, 1e-12, th.shape[0])
+    s_, c_ = (r * np.sin(th)), (r * np.cos(th))
+    got = opt.debug_math(2, s_, c_)
+    want = np.arctan2(s_.astype(ld), c_.astype(ld))
+    assert ulp(got, want).max() <= 2.0
+
+
 def test_line_search_polynomial_minimiser_matches_oracle(oracle, make_opt):
     """Closed-form cubic / quintic Hermite minimiser on the GPU vs the oracle's polynomial.cc restatement
     (pivoted LU fit + root finding) on random line-search-like samples."""
