@@ -106,6 +106,17 @@ struct Prob {
 
 enum EvalFlags : unsigned { kResidualBad = 1u, kJacobianBad = 2u, kNoHessian = 4u };
 
+// std::max / std::min as Ceres and the reference use them: one compare + select, and a NaN in the FIRST argument
+// propagates (CUDA's fmax / fmin return the other operand and cost ~8 instructions each for that).
+// One Kogge-Stone step v += (lane takes part ? t : 0) as ONE DFMA with the 0 / 1 mask m: fma(t, 1, v) is v + t exactly
+// and fma(t, 0, v) is v (the compiler's form of `if (on) v += t` is DADD + two FSEL, and ptxas turns a predicated
+// add back into that; the scans are 14 x log2(G) such steps per evaluation). A non-finite t poisons the masked lanes
+// too — their own value is non-finite already (out-of-range shuffles return the lane's own value).
+__device__ __forceinline__ void add_masked(double& v, double t, double m) { v = fma(t, m, v); }
+
+__device__ __forceinline__ double std_max(double a, double b) { return (a < b) ? b : a; }
+__device__ __forceinline__ double std_min(double a, double b) { return (b < a) ? b : a; }
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFullMask, v, d);
@@ -151,25 +162,27 @@ static __constant__ double kExpTab[14] = {
     2.5100395159429243e-08, 2.7620101012098e-07,    2.7557268439678e-06,  2.4801521269532122e-05,
     0.00019841269863066696, 0.0013888888917230724,  0.00833333333333006,  0.041666666666624094,
     0.16666666666666669,    0.5000000000000001,     -708.0};
-static __constant__ double kPairTab[4] = {0.35, 1.0 / 0.35, 2.1, 1e-6};  // gamma, 1/gamma, force factor, tiny |d|
+// gamma, 1/gamma, force factor, coincident-position |d| and |d|^2, degenerate |sin theta|
+static __constant__ double kPairTab[6] = {0.35, 1.0 / 0.35, 2.1, 1e-6, 1e-12, 1e-9};
 
 // exp(x) for x <= 0 (the social force only calls it with -(d/B) - (n B theta)^2): Cody-Waite reduction x = n ln2 + r,
 // degree-11 polynomial, scaling by 2^n as a multiplication (NaN propagates). 0.62 ulp against 60-digit mpmath over
-// [-708, 0] (tools/fit_exp.py; CUDA's exp: 1 ulp). Results below 2^-1022 (x < -708) are returned as 0.
+// [-708, 0] (tools/fit_exp.py; CUDA's exp: 1 ulp). Arguments below -708 (results below 2^-1022) are clamped: the
+// function returns exp(-708) = 3.3e-308 there instead of a denormal or 0 — 1e-300 times smaller than anything the force
+// sums can resolve.
 __device__ __forceinline__ double exp_nonpos(double x) {
-  const bool under = x < kExpTab[13];
-  const double xc = under ? kExpTab[13] : x;
+  const double xc = (x < kExpTab[13]) ? kExpTab[13] : x;  // NaN stays NaN
   const double t = fma(xc, kExpTab[0], 6755399441055744.0);  // 1.5 * 2^52: the low word of t is rint(x log2 e)
   const double nf = t - 6755399441055744.0;
   double r = fma(nf, kExpTab[1], xc);
   r = fma(nf, kExpTab[2], r);
-  double q = kExpTab[3];
-#pragma unroll
+  double q = kExpTab[3];  // Horner: the two exp chains of a pair interleave with each other and with the gradient
+#pragma unroll            // terms that do not depend on them (Estrin's scheme measured 3 % slower: +3 instructions each)
   for (int c = 4; c <= 12; ++c) q = fma(q, r, kExpTab[c]);
   q = fma(q, r, 1.0);
   q = fma(q, r, 1.0);
   const double scale = __hiloint2double((__double2loint(t) + 1023) << 20, 0);  // 2^n, n in [-1021, 0]: normal
-  return under ? 0.0 : q * scale;
+  return q * scale;
 }
 
 // 1 / sqrt(x) for normal positive x: hardware seed (2^-22) + one third-order step y (1 + e/2 + 3 e^2 / 8),
@@ -200,14 +213,18 @@ __device__ __forceinline__ double atan2_unit(double s, double c) {
   const double num = hi ? mn - mx : mn, den = hi ? mn + mx : mx;
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
-  r = fma(fma(-den, r, 1.0), r, r);
-  r = fma(fma(-den, r, 1.0), r, r);
+  r = fma(fma(-den, r, 1.0), r, r);  // 2^-23 -> 2^-46; the quotient's own correction below squares that again
   double t = num * r;
   t = fma(fma(-den, t, num), r, t);
   const double z = t * t;
-  double q = kAtanTab[1];
-#pragma unroll
-  for (int k = 2; k <= 11; ++k) q = fma(q, z, kAtanTab[k]);
+  // Q(z), degree 10, by Estrin's scheme: dependent depth 5 instead of 10 (this polynomial sits on the pair's critical
+  // path: nothing downstream can start before theta is known). kAtanTab[11 - k] is the coefficient of z^k.
+  const double z2 = z * z, z4 = z2 * z2, z8 = z4 * z4;
+  const double a0 = fma(kAtanTab[10], z, kAtanTab[11]), a1 = fma(kAtanTab[8], z, kAtanTab[9]);
+  const double a2 = fma(kAtanTab[6], z, kAtanTab[7]), a3 = fma(kAtanTab[4], z, kAtanTab[5]);
+  const double a4 = fma(kAtanTab[2], z, kAtanTab[3]);
+  const double b0 = fma(a1, z2, a0), b1 = fma(a3, z2, a2), b2 = fma(kAtanTab[1], z2, a4);
+  const double q = fma(b2, z8, fma(b1, z4, b0));
   double a = fma(t, z * q, t);
   if (hi) a += kAtanTab[12];
   if (steep) a = kAtanTab[13] - a;
@@ -222,10 +239,10 @@ __device__ __forceinline__ void social_pair(double dx, double dy, double wx, dou
   const double kLambda = 2.0, kNPrime = 3.0, kN = 2.0;
   const double kGamma = kPairTab[0], kInvGamma = kPairTab[1], kFactor = kPairTab[2];
   double d2 = dx * dx + dy * dy;
-  const bool tiny = d2 < 1e-12;  // |d| < 1e-6
-  if (tiny) {  // coincident: fixed direction (1e-6, 0), a constant for the derivative
-    dx = kPairTab[3];
-    dy = 0.0;
+  const bool tiny = d2 < kPairTab[4];  // |d| < 1e-6
+  if (kReferenceAngle && tiny) {  // coincident: fixed direction (1e-6, 0), a constant for the derivative
+    dx = kPairTab[3];           // (the hot instantiation only FLAGS such a pair as degenerate: its caller re-evaluates
+    dy = 0.0;                   //  it through social_pair_reference)
     d2 = dx * dx;
   }
   const double inv_rho = rsqrt_pos(d2);
@@ -242,7 +259,7 @@ __device__ __forceinline__ void social_pair(double dx, double dy, double wx, dou
   // at theta = 0 and +-pi and the reference's own rounding decides the branch, so its formulation is used verbatim.
   const double cross = ey * ix - ex * iy, dot = ex * ix + ey * iy;
   double theta;
-  o.degenerate = tiny || !(fabs(cross) > 1e-9);  // the coincident-position fix-up is not odd in d either
+  o.degenerate = tiny || !(fabs(cross) > kPairTab[5]);  // the coincident-position fix-up is not odd in d either
   if (!kReferenceAngle || !o.degenerate) {
     theta = atan2_unit(cross, dot);
   } else {
@@ -260,7 +277,7 @@ __device__ __forceinline__ void social_pair(double dx, double dy, double wx, dou
   o.fy = kFactor * (fv * iy + fa * ix);
 
   // gradients wrt (dx, dy, wx, wy)
-  const double zd = tiny ? 0.0 : 1.0;
+  const double zd = (kReferenceAngle && tiny) ? 0.0 : 1.0;
   const double g_rho[2] = {zd * ex, zd * ey};                       // d rho (w part is 0)
   const double g_pe[2] = {-zd * ey * inv_rho, zd * ex * inv_rho};   // d phi_e (w part is 0)
   const double s_ie = -ix * ey + iy * ex;                           // i . e_perp
@@ -325,8 +342,8 @@ template <bool NC>
 __device__ __forceinline__ void bicubic(const uint8_t* map, int size_x, int size_y, double r, double c, double& f,
                                         double& dfdr, double& dfdc) {
   // clamp the cell index so that a non-finite / huge coordinate cannot overflow the int conversion
-  const double rf = floor(fmin(fmax(r, -4.0), (double)size_y + 4.0));
-  const double cf = floor(fmin(fmax(c, -4.0), (double)size_x + 4.0));
+  const double rf = floor(std_min(std_max(r, -4.0), (double)size_y + 4.0));
+  const double cf = floor(std_min(std_max(c, -4.0), (double)size_x + 4.0));
   const int row = (int)rf, col = (int)cf;
   const double xr = r - (double)row, xc = c - (double)col;
   int cc[4];
@@ -560,10 +577,9 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
     scan_levels<G>([&](int d) {
       const double tx = __shfl_up_sync(kFullMask, sx, d, G);
       const double ty = __shfl_up_sync(kFullMask, sy, d, G);
-      if (gl >= d) {
-        sx += tx;
-        sy += ty;
-      }
+      const double m = (gl >= d) ? 1.0 : 0.0;
+      add_masked(sx, tx, m);
+      add_masked(sy, ty, m);
     });
     const double X = (first ? pb.x0 : carry[0]) + sx;
     const double Y = (first ? pb.y0 : carry[1]) + sy;
@@ -599,7 +615,7 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
       const uint8_t* vld = pb.valid + (j + 1);
       double2 nxt_p = __ldg(rec);
       double2 nxt_v = __ldg(rec + 1);
-      bool nxt_valid = __ldg(vld) != 0;
+      unsigned char nxt_valid = __ldg(vld);  // tested only in the NEXT iteration: no wait on the load here
 #ifndef SMPC_PAIR_UNROLL
 #define SMPC_PAIR_UNROLL 1
 #endif
@@ -607,12 +623,12 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
 #pragma unroll kPairUnroll
       for (int k = 0; k < bt.A; ++k) {
         const double ax = nxt_p.x, ay = nxt_p.y, avx = nxt_v.x, avy = nxt_v.y;
-        const bool valid = nxt_valid;
+        const bool valid = nxt_valid != 0;
         if (k + 1 < bt.A) {
           const double2* r2 = rec + (size_t)(k + 1) * stride * 2;
           nxt_p = __ldg(r2);
           nxt_v = __ldg(r2 + 1);
-          nxt_valid = __ldg(vld + (size_t)(k + 1) * stride) != 0;
+          nxt_valid = __ldg(vld + (size_t)(k + 1) * stride);
         }
         const double ddx = X - ax, ddy = Y - ay;
         {  // closest valid agent (proxemics), branch-free
@@ -707,10 +723,8 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
       sd[4 * b + 3] = aj * tau[b];            // dY/dw_b
     }
     scan_levels<G>([&](int d) {
-      SMPC_UNROLL for (int e = 0; e < 4 * NB; ++e) {
-        const double t = __shfl_up_sync(kFullMask, sd[e], d, G);
-        if (gl >= d) sd[e] += t;
-      }
+      const double m = (gl >= d) ? 1.0 : 0.0;
+      SMPC_UNROLL for (int e = 0; e < 4 * NB; ++e) add_masked(sd[e], __shfl_up_sync(kFullMask, sd[e], d, G), m);
     });
     if (!first) {
       SMPC_UNROLL for (int e = 0; e < 4 * NB; ++e) sd[e] += carry[4 + e];
@@ -1275,9 +1289,9 @@ template <int D>
 __device__ __forceinline__ double project_param(double v, int c, int n_bounded) {
   if ((c / D) < n_bounded) {
     const int k = c % D;
-    if (k == D - 1) return fmin(fmax(v, -1.4), 1.4);
-    if (k == 0) return fmin(fmax(v, 0.0), 0.6);
-    return fmin(fmax(v, -0.6), 0.6);
+    const double hi = (k == D - 1) ? 1.4 : 0.6;
+    const double lo = (k == D - 1) ? -1.4 : ((k == 0) ? 0.0 : -0.6);
+    return std_min(std_max(v, lo), hi);  // SetParameterLowerBound / UpperBound projection of Ceres' Plus
   }
   return v;
 }
@@ -1649,7 +1663,7 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
           if (!ls_failed) {
             const double lo = 1e-3 * st.t, hi = 0.6 * st.t;
             if (!eval_ok) {
-              t_new = fmin(fmax(st.t * 0.5, lo), hi);
+              t_new = std_min(std_max(st.t * 0.5, lo), hi);
             } else if (st.flags & kPrevOk) {
               t_new = quintic_interp_min(st.x_cost, st.g0, st.t, t_cost, gd, st.prev_x, st.prev_value, st.prev_gradient,
                                          lo, hi, 0, 0u, 1);
@@ -1720,7 +1734,7 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
               st.flags &= ~kReuseDiagonal;
               st.it_cost = t_cost;
               const double qq = 2.0 * rho - 1.0;
-              st.radius = fmin(1e16, st.radius / fmax(1.0 / 3.0, 1.0 - qq * qq * qq));
+              st.radius = std_min(1e16, st.radius / std_max(1.0 / 3.0, 1.0 - qq * qq * qq));
               st.decrease_factor = 2.0;
             }
           } else {
@@ -1740,7 +1754,7 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
           for (int c = 0; c < P; ++c) {
             const double xv = xs[c];
             xn += xv * xv;
-            gm = fmax(gm, fabs(xv - project_param<D>(xv - cur[L::g(c)], c, nbd)));
+            gm = std_max(gm, fabs(xv - project_param<D>(xv - cur[L::g(c)], c, nbd)));
           }
           st.x_norm = sqrt(xn);
           st.gmax = gm;
@@ -1751,7 +1765,7 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
             st.minimum_cost = st.x_cost;
             for (int c = 0; c < P; ++c) best[c] = xs[c];
           }
-          st.cost_final = fmin(st.cost_final, st.it_cost);
+          st.cost_final = std_min(st.cost_final, st.it_cost);
           if (prm.max_evaluations > 0 && st.n_eval >= prm.max_evaluations) { st.term = kNoConvergence; finished = true; break; }
           if (st.iteration >= prm.max_iterations) { st.term = kNoConvergence; finished = true; break; }
           if ((st.flags & kItSuccessful) && st.gmax <= prm.gradient_tol) { st.term = kConvGradient; finished = true; break; }
@@ -1762,7 +1776,7 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
           if (!(st.flags & kReuseDiagonal)) {
             for (int c = 0; c < P; ++c) {
               const double scv = scale[c];
-              diag[c] = fmin(fmax(scv * scv * cur[L::h(c, c)], 1e-6), 1e32);
+              diag[c] = std_min(std_max(scv * scv * cur[L::h(c, c)], 1e-6), 1e32);
             }
           }
           st.flags |= kReuseDiagonal;
@@ -1817,7 +1831,7 @@ __device__ __forceinline__ void solve_loop(const DevParams& prm, const DevBatch&
             SMPC_UNROLL for (int c = 0; c < P; ++c) {
               const double dl = step[c] * sc[c];
               g0 += cur[L::g(c)] * dl;
-              dmax = fmax(dmax, fabs(dl));
+              dmax = std_max(dmax, fabs(dl));
               delta[c] = dl;
               cand[c] = project_param<D>(xs[c] + dl, c, nbd);
             }

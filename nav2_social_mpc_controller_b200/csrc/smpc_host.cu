@@ -714,6 +714,18 @@ int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out) {
 
   // ---- shared arrays first (stream 1), the second stream waits for them
   cudaStream_t lanes[2] = {h->stream, h->stream2};
+  // an error return below must not leave copies or kernels of this call in flight on either stream (the caller may
+  // free or reuse its host arrays as soon as the call returns)
+  struct Quiesce {
+    cudaStream_t a, b;
+    bool armed;
+    ~Quiesce() {
+      if (!armed) return;
+      (void)cudaStreamSynchronize(a);
+      (void)cudaStreamSynchronize(b);
+      (void)cudaGetLastError();
+    }
+  } quiesce{lanes[0], lanes[1], true};
   bool any_shared = false;
   for (auto& it : items)
     if (it.host && it.shared_bytes) {
@@ -800,6 +812,7 @@ int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out) {
                               lanes[0]));
   SMPC_CUDA(cudaStreamSynchronize(lanes[0]));
   if (n_chunks > 1 || stream_maps) SMPC_CUDA(cudaStreamSynchronize(lanes[1]));
+  quiesce.armed = false;  // both streams are idle
   if (stream_maps && h->arrival_host[kMapChunks + 1] != 0)
     return fail(SMPC_ERR_CUDA, "costmap stream stalled: the solve kernel waited 2 s for host-to-device copies");
   return SMPC_OK;

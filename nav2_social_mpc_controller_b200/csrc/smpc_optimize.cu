@@ -4,6 +4,8 @@
 // TrajectoryMemory seeding, people_to_status, format_to_optimize, project_people (SFM), the bounded TR-LM solve, the
 // post-solve expansion, the memory update — runs in the same GPU kernels a fleet uses. This file only converts the
 // reference-shaped argument block (step-major people_proj, capacity-sized arrays) and keeps its error behaviour.
+#include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -35,6 +37,15 @@ int smpc_optimize(smpc_handle* h, smpc_optimize_io* io) {
   if (!io->od.indexes || !io->od.distances) return smpc_host_fail(SMPC_ERR_ARGUMENT, "ObstacleDistance is empty");
 
   const int cap = io->capacity, A = 3;  // the reference keeps exactly three people columns (:468-479)
+  // Array stride of the one-robot fleet: constant from tick to tick (the trajectorizer never emits more than
+  // max_time / time_step + 1 poses), so that the warm-start memory survives a change of the path length or of the
+  // caller's buffer capacity — the reference's TrajectoryMemory does (ADVICE).
+  const smpc_params* prm = smpc_handle_params(h);
+  const float ts = io->time_step > 0.0f ? io->time_step : static_cast<float>(prm->time_step);
+  const int stride = std::max(cap, static_cast<int>(std::round(static_cast<float>(prm->max_time) / ts)) + 1);
+  std::vector<double> pose_rows((size_t)stride * 3, 0.0), cmd_rows((size_t)stride * 2, 0.0);
+  std::memcpy(pose_rows.data(), io->poses, sizeof(double) * 3 * io->n_poses);
+  std::memcpy(cmd_rows.data(), io->cmds, sizeof(double) * 2 * std::min(io->n_cmds, cap));
   std::vector<double> people((size_t)A * 5, 0.0);
   const int32_t n_people = io->n_people < A ? io->n_people : A;
   if (n_people > 0) std::memcpy(people.data(), io->people, sizeof(double) * 5 * n_people);
@@ -45,12 +56,12 @@ int smpc_optimize(smpc_handle* h, smpc_optimize_io* io) {
   int32_t n_out = 0, termination = 0, iterations = 0, status = 0;
   uint8_t optimized = 0;
   double c0 = 0.0, c1 = 0.0;
-  std::vector<double> proj(io->people_proj ? (size_t)A * 6 * cap : 0);
+  std::vector<double> proj(io->people_proj ? (size_t)A * 6 * stride : 0);
 
   smpc_fleet_io f;
   std::memset(&f, 0, sizeof(f));
   f.n_robots = 1;
-  f.max_poses = cap;
+  f.max_poses = stride;
   f.n_agents = A;
   f.time_step = io->time_step;
   f.n_poses = &n_poses;
@@ -70,8 +81,8 @@ int smpc_optimize(smpc_handle* h, smpc_optimize_io* io) {
   f.od_height = io->od.height;
   f.od_resolution = io->od.resolution;
   f.maps_version = 0;  // one robot: the maps travel with every call, as in the reference
-  f.poses = io->poses;
-  f.cmds = io->cmds;
+  f.poses = pose_rows.data();
+  f.cmds = cmd_rows.data();
   f.n_out = &n_out;
   f.optimized = &optimized;
   f.termination = &termination;
@@ -88,12 +99,15 @@ int smpc_optimize(smpc_handle* h, smpc_optimize_io* io) {
   io->iterations = iterations;
   io->cost_initial = c0;
   io->cost_final = c1;
+  if (n_out > cap) return smpc_host_fail(SMPC_ERR_ARGUMENT, "capacity smaller than the optimised path");
+  std::memcpy(io->poses, pose_rows.data(), sizeof(double) * 3 * n_out);
+  std::memcpy(io->cmds, cmd_rows.data(), sizeof(double) * 2 * n_out);
   io->n_poses = n_out;
   io->n_proj_steps = n_out;
   if (io->people_proj)  // [A][6][cap] -> the reference's AgentsTrajectories[step][agent][6]
     for (int i = 0; i < n_out; ++i)
       for (int k = 0; k < A; ++k)
-        for (int c = 0; c < 6; ++c) io->people_proj[((size_t)i * A + k) * 6 + c] = proj[((size_t)k * 6 + c) * cap + i];
+        for (int c = 0; c < 6; ++c) io->people_proj[((size_t)i * A + k) * 6 + c] = proj[((size_t)k * 6 + c) * stride + i];
   if (optimized) {
     io->n_cmds = n_out;
     io->optimized = 1;

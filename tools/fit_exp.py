@@ -42,7 +42,7 @@ def exp_nonpos(x, c):
     n = int(nf)
     r = fma(nf, -LN2_HI, x)
     r = fma(nf, -LN2_LO, r)
-    q = c[-1]
+    q = c[-1]  # Horner, the device function's exact operation order
     for k in reversed(c[:-1]):
         q = fma(q, r, k)
     q = fma(q, r, 1.0)  # c1

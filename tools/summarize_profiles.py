@@ -1,8 +1,10 @@
 #!/usr/bin/env python
 """Turn `ncu --set full` captures into the committed evidence under profiles/: key metrics + top stalls
-(r01_ncu_summaries.json), DRAM traffic per launch (r01_traffic.json) and source-level hot spots (text).
-Usage: tools/summarize_profiles.py DIR   (DIR holds raw_<workload>.csv raw pages exported on the GPU box by
-tools/ncu_capture.sh and, for the workloads whose report travelled back, prof_<workload>.ncu-rep)"""
+(<round>_ncu_summaries.json), DRAM traffic per launch (<round>_traffic.json) and, per report that travelled back, the
+executed-instruction mix by opcode and by source line (text).
+Usage: tools/summarize_profiles.py DIR [ROUND=r02]   (DIR holds raw_<workload>.csv raw pages exported on the GPU box
+by tools/ncu_capture.sh and, for the workloads whose report travelled back, prof_<workload>.ncu-rep; the library in
+the tree must be the build the captures were taken from)"""
 import csv
 import glob
 import io
@@ -13,6 +15,7 @@ import sys
 
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 src = sys.argv[1]
+rnd = sys.argv[2] if len(sys.argv) > 2 else 'r02'
 keys = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
@@ -22,7 +25,7 @@ keys = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'la
         'l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
         'launch__shared_mem_per_block_dynamic']
 mult = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
-spath = os.path.join(root, 'profiles', 'r01_ncu_summaries.json')
+spath = os.path.join(root, 'profiles', f'{rnd}_ncu_summaries.json')
 summ = json.load(open(spath)) if os.path.exists(spath) else {}
 summ = {k: v for k, v in summ.items() if not k.startswith('final')}
 traffic = {}
@@ -33,7 +36,7 @@ for rawf in sorted(glob.glob(os.path.join(src, 'raw_*.csv'))):
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, vals = rows[0], rows[1], rows[2]
     kname = vals[hdr.index('Kernel Name')]
-    d = {'what': f'final round-1 build, bench.py --workload {w}', 'kernel': kname}
+    d = {'what': f'final {rnd} build, bench.py --workload {w}', 'kernel': kname}
     for h, u, v in zip(hdr, units, vals):
         if h in keys:
             d[h] = f'{v} {u}'.strip()
@@ -64,16 +67,22 @@ for rawf in sorted(glob.glob(os.path.join(src, 'raw_*.csv'))):
     traffic[w] = {'bytes': g('dram__bytes_read.sum') + g('dram__bytes_write.sum'),
                   'read_bytes': g('dram__bytes_read.sum'), 'write_bytes': g('dram__bytes_write.sum'),
                   'unit': 'bytes per launch',
-                  'source': f'ncu --set full capture of `bench.py --workload {w}` (final_{w} in r01_ncu_summaries.json)'}
+                  'source': f'ncu --set full capture of `bench.py --workload {w}` (final_{w} in {rnd}_ncu_summaries.json)'}
     import re
-    m = re.search(r'smpc_solve_kernel<(\d+), (\d+), (\d+)', kname)
-    mangled = f'smpc_solve_kernelILi{m.group(1)}ELi{m.group(2)}ELi{m.group(3)}E'
+    m = re.search(r'smpc_solve_kernel<(\d+), (\d+), (\d+), (\d+), (\d+), (\d+)>', kname)
+    a = m.groups()
+    mangled = f'smpc_solve_kernelILi{a[0]}ELi{a[1]}ELi{a[2]}ELb{a[3]}ELi{a[4]}ELi{a[5]}E'  # EXACT: no other variant matches
     if os.path.exists(rep):
-        out = subprocess.run(['python', os.path.join(root, 'tools', 'ncu_hotspots.py'), rep, mangled, '25'],
-                             capture_output=True, text=True).stdout
-        open(os.path.join(root, 'profiles', f'r01_final_{w}_hotspots.txt'), 'w').write(out)
+        lib = os.path.join(root, 'nav2_social_mpc_controller_b200', 'libsmpc.so')
+        mix = subprocess.run(['python', os.path.join(root, 'tools', 'ncu_opmix.py'), rep], capture_output=True, text=True).stdout
+        lines = subprocess.run(['python', os.path.join(root, 'tools', 'ncu_opmix_lines.py'), rep, mangled, lib, '45'],
+                               capture_output=True, text=True).stdout
+        head = (f'# {kname}\n# bench.py --workload {w}, ncu --set full --clock-control none (one launch)\n'
+                f'# executed warp instructions by opcode, then by source line of csrc/smpc_device.cuh (share of all, opcode mix)\n')
+        open(os.path.join(root, 'profiles', f'{rnd}_final_{w}_hotspots.txt'), 'w').write(
+            head + '\n'.join(mix.splitlines()[:26]) + '\n\n' + lines)
     print(w, d['gpu__time_duration.sum'], 'issue', d['smsp__issue_active.avg.pct_of_peak_sustained_active'], 'fp64',
           d['sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active'], d['top_stalls_per_issue'],
           'dram MB r/w', traffic[w]['read_bytes'] / 1e6, traffic[w]['write_bytes'] / 1e6)
 json.dump(summ, open(spath, 'w'), indent=1)
-json.dump(traffic, open(os.path.join(root, 'profiles', 'r01_traffic.json'), 'w'), indent=1)
+json.dump(traffic, open(os.path.join(root, 'profiles', f'{rnd}_traffic.json'), 'w'), indent=1)
