@@ -267,40 +267,49 @@ __device__ __forceinline__ void social_pair(double dx, double dy, double wx, dou
   }
   const double Bq = kGamma * L;
   const double inv_B = inv_L * kInvGamma;
-  const double t1 = kNPrime * Bq * theta, t2 = kN * Bq * theta;
+  const double Bth = Bq * theta;
+  const double t1 = kNPrime * Bth, t2 = kN * Bth;
   const double base = -rho * inv_B;
   const double E1 = exp_nonpos(base - t1 * t1);
   const double E2 = exp_nonpos(base - t2 * t2);
-  const double sgn = (theta > 0.0) ? 1.0 : -1.0;
-  const double fv = -E1, fa = -sgn * E2;
-  o.fx = kFactor * (fv * ix - fa * iy);
-  o.fy = kFactor * (fv * iy + fa * ix);
+  // fa = -sgn(theta) exp(.), sgn(0) = -1 as in the reference; the hot instantiation never sees theta == 0 (that is
+  // cross == 0: degenerate), so the sign is a bit operation there
+  const double fv = -E1, fa = kReferenceAngle ? ((theta > 0.0) ? -E2 : E2) : copysign(E2, -theta);
+  const double Fix = kFactor * ix, Fiy = kFactor * iy;
+  const double a = Fix * fv, b = Fiy * fa, c = Fiy * fv, d = Fix * fa;
+  o.fx = a - b;
+  o.fy = c + d;
 
-  // gradients wrt (dx, dy, wx, wy)
-  const double zd = (kReferenceAngle && tiny) ? 0.0 : 1.0;
-  const double g_rho[2] = {zd * ex, zd * ey};                       // d rho (w part is 0)
-  const double g_pe[2] = {-zd * ey * inv_rho, zd * ex * inv_rho};   // d phi_e (w part is 0)
-  const double s_ie = -ix * ey + iy * ex;                           // i . e_perp
-  const double c_ie = ix * ex + iy * ey;                            // i_perp . e_perp
-  double gL[4] = {s_ie * g_pe[0], s_ie * g_pe[1], kLambda * ix, kLambda * iy};
-  double gpi[4] = {c_ie * inv_L * g_pe[0], c_ie * inv_L * g_pe[1], -kLambda * iy * inv_L, kLambda * ix * inv_L};
-  const double rho_B2 = rho * inv_B * inv_B * kGamma;  // d(-rho/B)/dL
+  // Gradients wrt (dx, dy, wx, wy) by the chain rule through the four scalars the force depends on: rho = |d|, phi_e
+  // (direction of d), L = |I|, phi_i (direction of I), with theta = phi_e - phi_i, B = gamma L and
+  //   u_n = -rho / B - (n B theta)^2,   fv = -exp(u_3),  fa = -sgn(theta) exp(u_2),   f = F Rot(phi_i) (fv, fa):
+  //   d u_n = -d rho / B + (rho / (B L)) dL + k_n (gamma theta dL + B (d phi_e - d phi_i)),   k_n = -2 n^2 B theta.
+  // First the partials of (fx, fy) wrt (rho, L, phi_e, phi_i) — X*, Y* below — then the 2x4 Jacobian from
+  //   d rho = e,  d phi_e = e_perp / rho,  dL = (i . e_perp) d phi_e + lambda i dw,
+  //   d phi_i = ((i . e) / L) d phi_e + (lambda / L) i_perp dw.
+  const double zd = (kReferenceAngle && tiny) ? 0.0 : 1.0;  // coincident fix-up: d is a constant
+  const double gr0 = zd * ex, gr1 = zd * ey;
+  const double ge0 = -zd * ey * inv_rho, ge1 = zd * ex * inv_rho;
   const double k1 = -2.0 * t1 * kNPrime, k2 = -2.0 * t2 * kN;
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const double grho = (c < 2) ? g_rho[c] : 0.0;
-    const double gpe = (c < 2) ? g_pe[c] : 0.0;
-    const double gB = kGamma * gL[c];
-    const double gth = gpe - gpi[c];
-    const double common = -grho * inv_B + rho_B2 * gL[c];
-    const double inner = theta * gB + Bq * gth;
-    const double gu1 = common + k1 * inner;
-    const double gu2 = common + k2 * inner;
-    const double gfv = -E1 * gu1;
-    const double gfa = -sgn * E2 * gu2;
-    o.dfx[c] = kFactor * (ix * gfv - iy * gfa) - o.fy * gpi[c];
-    o.dfy[c] = kFactor * (iy * gfv + ix * gfa) + o.fx * gpi[c];
-  }
+  const double m1 = fma(a, k1, -(b * k2)), m2 = fma(c, k1, d * k2);
+  const double thg = theta * kGamma;
+  const double rho_BL = -base * inv_L;  // d(-rho / B) / dL
+  const double Xr = -inv_B * o.fx, Yr = -inv_B * o.fy;
+  const double XL = fma(thg, m1, rho_BL * o.fx), YL = fma(thg, m2, rho_BL * o.fy);
+  const double Xe = Bq * m1, Ye = Bq * m2;
+  const double Xi = -Xe - o.fy, Yi = o.fx - Ye;  // through theta, and through the rotation of f itself
+  const double cil = dot * inv_L;                // (i . e) / L;  i . e_perp = -cross
+  const double Xd = fma(Xi, cil, fma(XL, -cross, Xe)), Yd = fma(Yi, cil, fma(YL, -cross, Ye));  // total d / d phi_e
+  o.dfx[0] = fma(Xd, ge0, Xr * gr0);
+  o.dfx[1] = fma(Xd, ge1, Xr * gr1);
+  o.dfy[0] = fma(Yd, ge0, Yr * gr0);
+  o.dfy[1] = fma(Yd, ge1, Yr * gr1);
+  const double lil = kLambda * inv_L;
+  const double XLl = kLambda * XL, Xil = lil * Xi, YLl = kLambda * YL, Yil = lil * Yi;
+  o.dfx[2] = fma(XLl, ix, -(Xil * iy));
+  o.dfx[3] = fma(XLl, iy, Xil * ix);
+  o.dfy[2] = fma(YLl, ix, -(Yil * iy));
+  o.dfy[3] = fma(YLl, iy, Yil * ix);
 }
 
 // Near-degenerate pair (see above), evaluated with the reference's two-atan2 angle. Rare (exactly (anti)parallel
@@ -625,10 +634,11 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
         const double ax = nxt_p.x, ay = nxt_p.y, avx = nxt_v.x, avy = nxt_v.y;
         const bool valid = nxt_valid != 0;
         if (k + 1 < bt.A) {
-          const double2* r2 = rec + (size_t)(k + 1) * stride * 2;
-          nxt_p = __ldg(r2);
-          nxt_v = __ldg(r2 + 1);
-          nxt_valid = __ldg(vld + (size_t)(k + 1) * stride);
+          rec += (size_t)stride * 2;
+          vld += stride;
+          nxt_p = __ldg(rec);
+          nxt_v = __ldg(rec + 1);
+          nxt_valid = __ldg(vld);
         }
         const double ddx = X - ax, ddy = Y - ay;
         {  // closest valid agent (proxemics), branch-free
@@ -676,13 +686,13 @@ __device__ __forceinline__ unsigned evaluate(const DevParams& prm, const DevBatc
               po.dfy[c] = ref[6 + c];
             }
           }
-          wp += po.fx * po.fx + po.fy * po.fy;
-          SMPC_UNROLL for (int c = 0; c < 4; ++c) G4[c] += 2.0 * (po.fx * po.dfx[c] + po.fy * po.dfy[c]);
+          wp = fma(po.fy, po.fy, fma(po.fx, po.fx, wp));
+          SMPC_UNROLL for (int c = 0; c < 4; ++c) G4[c] = fma(po.fy, po.dfy[c], fma(po.fx, po.dfx[c], G4[c]));  // (x 2 below)
         }
       }
       if (do_social) {
         const double wr = Frx * Frx + Fry * Fry;
-        SMPC_UNROLL for (int c = 0; c < 4; ++c) G4[c] += 2.0 * (Frx * JFx[c] + Fry * JFy[c]);
+        SMPC_UNROLL for (int c = 0; c < 4; ++c) G4[c] = 2.0 * fma(Fry, JFy[c], fma(Frx, JFx[c], G4[c]));
         rs = prm.w_social * (wr + wp + 1e-6);
         sX = prm.w_social * G4[0];
         sY = prm.w_social * G4[1];

@@ -16,8 +16,8 @@ for f in glob.glob(os.path.join(src, "bench_*.json")):
         continue
     rows[d["config"]["workload"]] = d
 print("| workload (`bench.py --workload`) | GPU solves/s (resident) | ms / batch | e2e solves/s | CPU restatement solves/s "
-      "(threads) | e2e ÷ CPU | FP64 frac | mean evals / iters | parity (prefix) | p50 single solve |")
-print("|---|---|---|---|---|---|---|---|---|---|")
+      "(threads) | e2e ÷ CPU | FP64 frac | evaluations (with JᵀJ + gradient-only) / iterations | parity (prefix) |")
+print("|---|---|---|---|---|---|---|---|---|")
 for w in order:
     if w not in rows:
         continue
@@ -25,8 +25,8 @@ for w in order:
     cb, pv = d.get("cpu_baseline", {}), d.get("parity_vs_oracle", {})
     n = pv.get("problems", 0)
     ok = round(pv.get("within_1e-6_u_and_1e-8_cost", 0) * n)
-    lat = d.get("latency_ms", {})
+    sv = d["solver"]
     print(f"| `{w}` | {d['value'] / 1e6:.3f} M | {d['ms_per_step']:.2f} | {d['e2e']['value'] / 1e6:.3f} M | "
           f"{cb.get('value', 0) / 1e3:.2f} k ({cb.get('cores')}) | {d['e2e']['value'] / max(cb.get('value', 1), 1):.0f}× | "
-          f"{d['roofline']['frac']:.3f} | {d['solver']['mean_evaluations']:.1f} / {d['solver']['mean_iterations']:.1f} | "
-          f"{ok}/{n} | {lat.get('p50', float('nan')):.2f} ms |")
+          f"{d['roofline']['frac']:.3f} | {sv['mean_evaluations_with_JtJ']:.1f} + {sv['mean_evaluations_gradient_only']:.1f} / "
+          f"{sv['mean_iterations']:.1f} | {ok}/{n} |")
