@@ -626,6 +626,63 @@ def leg_library_multi(ctx, steps, warmup, per_gpu=16384, A=20):
     return out
 
 
+def leg_fleet_tick(ctx, steps, warmup, robots=16384, A=20):
+    """SURVEY §8f / VERDICT item 5-6: the whole Optimizer::optimize tick for a fleet through ONE C call
+    (smpc_optimize_batch): host buffers hold what the controller has — seed path and cmds, RAW people (x, y, vx, vy,
+    vz), speed — and the SFM crowd projection, the solve with per-robot horizons, the post-solve expansion and the
+    warm-start memory update run on the device; costmaps and obstacle grids stay resident. Compared with the level-1
+    e2e arm (which ships the PROJECTED agent trajectories, 6 x (S+1) doubles per agent) the tick moves ~14x fewer
+    bytes per robot. Every rank runs its own fleet (weak scaling); wall clock per tick, max over ranks."""
+    from nav2_social_mpc_controller_b200.fleet import FleetOptimizer
+    rng = np.random.default_rng(20261018 + 77 + ctx.rank)
+    p = sc.make_params("soc_work_obst")
+    B = robots
+    pose = np.stack([rng.uniform(0.5, 1.0, B), 2.0 + rng.uniform(-0.3, 0.3, B), rng.uniform(-0.3, 0.3, B)], axis=1)
+    gp = sc._straight_path(B, np.full(B, 0.6), np.full(B, 2.0))
+    poses_h, cmds_h = sc.pure_pursuit_seed(gp, pose, p)
+    people = np.zeros((B, A, 5))
+    people[:, :, 0] = rng.uniform(1.0, 3.0, (B, A))  # nobody leaves the 4 m obstacle grid within the horizon
+    people[:, :, 1] = rng.uniform(1.0, 3.0, (B, A))
+    people[:, :, 2:4] = rng.uniform(-0.5, 0.5, (B, A, 2))
+    n_people = np.full(B, A, dtype=np.int32)
+    speed = np.tile([0.3, 0.0], (B, 1))
+    costmap = sc.wall_costmap(80, 80, 0.05, walls_y=(0.6, 3.4))[None]
+    rows = np.arange(80)[:, None] * np.ones((1, 80), dtype=int)
+    cols = np.ones((80, 1), dtype=int) * np.arange(80)[None, :]
+    near = np.where(np.abs(rows - 12) <= np.abs(rows - 68), 12, 68)
+    od = dict(width=80, height=80, resolution=0.05, origins=[[0.0, 0.0]], indexes=(near * 80 + cols).astype(np.uint32).ravel())
+    fl = FleetOptimizer(p, n_robots=B, n_agents=A, device=ctx.local_rank)
+    cmds2 = np.ascontiguousarray(cmds_h[:, :, :2])
+
+    def tick():
+        return fl.optimize_batch(poses_h, cmds2, people, n_people, speed, costmap, np.zeros((1, 2)), 0.05, od,
+                                 want_people_proj=False)
+    for _ in range(warmup):
+        r = tick()
+    ctx.barrier()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        r = tick()
+        ts.append(time.perf_counter() - t0)
+    fl.close()
+    (tot,) = ctx.max_over_ranks(float(sum(ts)))
+    n = poses_h.shape[1]
+    h2d = B * (n * 3 * 8 + n * 2 * 8 + A * 5 * 8 + 4 + 2 * 8 + 4)
+    d2h = B * (n * 3 * 8 + n * 2 * 8 + 4 + 1 + 4 + 4 + 8 + 8 + 4)
+    level1 = B * 8 * (3 + 6 + 2 * n + 1 + 6 * A * n)
+    if ctx.rank != 0:
+        return None
+    return {"workload": f"fleet tick: {B} robots per GPU x {A} people, soc_work_obst params, seed paths of {n} poses",
+            "entry": "smpc_optimize_batch (host buffers in / out; people projection, solve, post-solve and warm-start "
+                     "memory on the device; maps resident)",
+            "scaling": "weak", "value": ctx.world * B * steps / tot, "unit": "robot ticks/s",
+            "ms_per_step": 1e3 * tot / steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "level1_e2e_h2d_bytes_for_the_same_fleet": int(level1), "h2d_reduction": round(level1 / h2d, 1),
+            "optimized_fraction": float(r["optimized"].mean()), "mean_iterations": float(r["iterations"].mean()),
+            "steps": steps, "warmup": warmup}
+
+
 def leg_latency(ctx, calls):
     """BASELINE configs[0]: p50 / p99 of ONE solve through the host-buffer C-ABI (H2D + kernel + D2H), rank 0."""
     from nav2_social_mpc_controller_b200.optimizer import Optimizer
@@ -657,7 +714,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default=HEADLINE, choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--legs", default="all", help="all | none | comma list of obst_only,multistart,scaling_sweep,scaling_sweep_omni,library_multi,latency")
+    ap.add_argument("--legs", default="all", help="all | none | comma list of obst_only,multistart,scaling_sweep,scaling_sweep_omni,library_multi,fleet_tick,latency")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--latency-calls", type=int, default=300)
     args = ap.parse_args()
@@ -675,7 +732,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libsmpc has no CPU path")
     ctx = Ctx(rank, local_rank, world)
-    legs = ("obst_only", "multistart", "scaling_sweep", "scaling_sweep_omni", "library_multi", "latency") \
+    legs = ("obst_only", "multistart", "scaling_sweep", "scaling_sweep_omni", "library_multi", "fleet_tick", "latency") \
         if args.legs == "all" else \
         tuple(x for x in args.legs.split(",") if x and x != "none")
     if args.latency_calls <= 0:
@@ -729,6 +786,8 @@ def main():
         leg_out["crowd_x1M_A50_omni"] = leg_scaling_sweep(ctx, min(args.steps, 2), 2, omni=True)
     if "library_multi" in legs:
         leg_out["library_multi_gpu"] = leg_library_multi(ctx, min(args.steps, 3), 2)
+    if "fleet_tick" in legs:
+        leg_out["fleet_tick_A20"] = leg_fleet_tick(ctx, min(args.steps, 5), 2)
     if "latency" in legs and rank == 0:
         leg_out["single_solve_latency"] = leg_latency(ctx, args.latency_calls)
     if rank == 0:
