@@ -85,7 +85,12 @@ inline bool evaluate(const ProblemView& p, const std::vector<ResidualBlock>& blo
   if (gradient)
     for (int c = 0; c < P; ++c) gradient[c] = 0.0;
   using J4 = Jet<4>;
-  for (size_t k = 0; k < blocks.size(); ++k) {
+  for (size_t kk = 0; kk < blocks.size(); ++kk) {
+#ifdef SMPC_ORACLE_REVERSE_SUM  // tools/oracle_sensitivity.py: cost and gradient summed over the residual blocks in the
+    const size_t k = blocks.size() - 1 - kk;  // opposite order — an equally valid rounding of the same sums (Ceres' own
+#else                                         // order depends on its thread count)
+    const size_t k = kk;
+#endif
     const ResidualBlock& rb = blocks[k];
     int gidx[kMaxParams];  // local parameter -> global column
     const int np = D * rb.nblk;
@@ -149,7 +154,11 @@ struct Sample {
 // much, and the differences feed back into the iterate path). The oracle therefore computes the SAME polynomial and the
 // SAME candidate set (midpoint, end points, real parts of the derivative's roots, in-range samples) in long double, i.e.
 // the noise-free value Ceres' result scatters around; parity checks then measure the solver under test, not the noise.
+#ifdef SMPC_ORACLE_POLY_DOUBLE  // tools/oracle_sensitivity.py: the same polynomial code in double, as Ceres computes it
+using real = double;
+#else
 using real = long double;
+#endif
 
 inline real poly_eval(const std::vector<real>& c, real x) {  // Horner, highest degree first
   real v = 0.0L;
