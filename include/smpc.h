@@ -223,10 +223,11 @@ int smpc_eval_batch_device(smpc_handle* h, const smpc_batch* in, const double* x
 int smpc_eval_batch(smpc_handle* h, const smpc_batch* in, const double* x, smpc_eval_out* out);
 
 /* ---- level-2 entry: mirrors bool Optimizer::optimize(...) (optimizer.hpp:167-170) for ONE robot ------------------
- * Pre-solve stages run on the host exactly as in the reference (people_to_status src/optimizer.cpp:454-482,
- * format_to_optimize :484-551 with the handle's previous path / cmds standing in for the TrajectoryMemory singleton
- * (trajectory_memory.hpp), project_people :554-671 + sfm.hpp, computeObstacle :673-728); the solve and the
- * post-solve expansion run on the GPU (level-1 path); the handle's memory is updated like :448-449. */
+ * One-robot fleet tick (smpc_optimize_batch with B = 1, 3 people columns): every stage runs on the GPU in the
+ * reference's arithmetic order — people_to_status src/optimizer.cpp:454-482, format_to_optimize :484-551 with the
+ * handle's device-resident previous path / cmds standing in for the TrajectoryMemory singleton
+ * (trajectory_memory.hpp), project_people :554-671 + sfm.hpp, computeObstacle :673-728, the solve and the post-solve
+ * expansion (level-1 kernel), the memory update :448-449. */
 typedef struct smpc_obstacle_distance { /* obstacle_distance_msgs::msg::ObstacleDistance */
   uint32_t width;
   uint32_t height;

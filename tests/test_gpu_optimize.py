@@ -337,6 +337,51 @@ def test_fleet_maps_stay_resident_and_person_leaving_the_grid_is_reported():
         fleet.close()
 
 
+def test_fleet_edge_cases_short_paths_and_changing_lengths_keep_the_memory():
+    """Robots whose seed path has fewer than 2 poses return optimized = False (src/optimizer.cpp:158-162) without
+    disturbing their neighbours; a robot whose path gets shorter from one tick to the next (approaching the goal) keeps
+    its warm-start memory — the second tick of the fleet equals the second tick of a one-robot optimizer fed the same
+    two paths (the reference's TrajectoryMemory survives a change of the path length)."""
+    from nav2_social_mpc_controller_b200.fleet import FleetOptimizer
+    from nav2_social_mpc_controller_b200.optimizer import Optimizer
+    B, A = 3, 3
+    scenes = [_scene("soc_work_obst", n_people=1, seed=80 + b) for b in range(B)]
+    p, od, costmap = scenes[0][0], scenes[0][6], scenes[0][5]
+    poses = np.stack([s[1] for s in scenes])
+    cmds = np.stack([s[2] for s in scenes])
+    n = poses.shape[1]
+    people_raw = np.zeros((B, A, 5))
+    for b, s in enumerate(scenes):
+        people_raw[b, 0] = s[3][0]
+    n_people = np.ones(B, dtype=np.int32)
+    speed = np.array([[0.3, 0.05]] * B)
+    od_b = dict(width=od["width"], height=od["height"], resolution=od["resolution"], origins=[[0.0, 0.0]],
+                indexes=od["indexes"])
+    maps = costmap[None].copy()
+    fleet = FleetOptimizer(p, n_robots=B, n_agents=A)
+    single = Optimizer(0)
+    single.initialize(p)
+    try:
+        n1 = np.array([n, 1, n], dtype=np.int32)  # robot 1 has no path to optimise
+        t1 = fleet.optimize_batch(poses, cmds, people_raw, n_people, speed, maps, np.zeros((1, 2)), 0.05, od_b, n_poses=n1)
+        assert t1["optimized"].tolist() == [True, False, True]
+        n2 = np.array([n, 1, n - 6], dtype=np.int32)  # robot 2's path got shorter
+        t2 = fleet.optimize_batch(poses, cmds, people_raw, n_people, speed, maps, np.zeros((1, 2)), 0.05, od_b, n_poses=n2)
+        assert t2["optimized"].tolist() == [True, False, True] and t2["n_out"][2] <= n - 6
+        # the same two ticks for robot 2 alone through the one-robot entry
+        s = scenes[2]
+        ok1, *_ = single.optimize(s[1], s[2], s[3][:1], speed[2], p.time_step, costmap, (0.0, 0.0), 0.05, od)
+        ok2, path2, cmds2, _, _ = single.optimize(s[1][:n - 6], s[2][:n - 6], s[3][:1], speed[2], p.time_step, costmap,
+                                                  (0.0, 0.0), 0.05, od)
+        assert ok1 and ok2
+        k = int(t2["n_out"][2])
+        assert k == path2.shape[0]
+        assert np.array_equal(t2["cmds"][2][:k], cmds2[:k]) and np.array_equal(t2["path"][2][:k], path2[:k])
+    finally:
+        fleet.close()
+        single.close()
+
+
 def test_gpu_trajectorize_matches_numpy_restatement():
     """Seed generation kernel vs scenarios.pure_pursuit_seed (numpy restatement of reference
     src/path_trajectorizer.cpp:120-288), diff-drive branch, goals beyond the horizon; plus the early stop near the
