@@ -42,10 +42,10 @@ int smpc_optimize(smpc_handle* h, smpc_optimize_io* io) {
   // caller's buffer capacity — the reference's TrajectoryMemory does (ADVICE).
   const smpc_params* prm = smpc_handle_params(h);
   const float ts = io->time_step > 0.0f ? io->time_step : static_cast<float>(prm->time_step);
-  const int stride = std::max(cap, static_cast<int>(std::round(static_cast<float>(prm->max_time) / ts)) + 1);
+  const int stride = std::max(io->n_poses, static_cast<int>(std::round(static_cast<float>(prm->max_time) / ts)) + 1);
   std::vector<double> pose_rows((size_t)stride * 3, 0.0), cmd_rows((size_t)stride * 2, 0.0);
   std::memcpy(pose_rows.data(), io->poses, sizeof(double) * 3 * io->n_poses);
-  std::memcpy(cmd_rows.data(), io->cmds, sizeof(double) * 2 * std::min(io->n_cmds, cap));
+  std::memcpy(cmd_rows.data(), io->cmds, sizeof(double) * 2 * std::min(io->n_cmds, stride));
   std::vector<double> people((size_t)A * 5, 0.0);
   const int32_t n_people = io->n_people < A ? io->n_people : A;
   if (n_people > 0) std::memcpy(people.data(), io->people, sizeof(double) * 5 * n_people);
