@@ -447,7 +447,9 @@ def leg_multistart(ctx, steps, warmup, n_robots=256, n_starts=1024):
     from nav2_social_mpc_controller_b200.optimizer import Optimizer
     from nav2_social_mpc_controller_b200.sharding import shard_bounds
     torch = ctx.torch
-    full = sc.multistart(n_robots, n_starts)
+    # scenario sharing (smpc_batch.scenario_index): the scene of a robot is ONE row of the input arrays, read by its
+    # 1024 starts; only the start controls u0 and the row index are per problem
+    full = sc.multistart(n_robots, n_starts, shared=True)
     lo, hi = shard_bounds(full.n_problems, ctx.world, ctx.rank, granule=n_starts)
     batch = full.slice(lo, hi)
     R = (hi - lo) // n_starts
@@ -501,6 +503,7 @@ def leg_multistart(ctx, steps, warmup, n_robots=256, n_starts=1024):
         ok = bool(np.array_equal(gathered["index"][:R], want_idx)) and gathered["index"].shape[0] == n_robots
         out = {"workload": "multistart_256x1024", "description": WORKLOADS["multistart_256x1024"][1],
                "scaling": "strong", "sharding": f"by robot: {R} robots x {n_starts} starts per rank",
+               "inputs": "scenario sharing: one scene row per robot + per-start u0 (smpc_batch.scenario_index)",
                "value": full.n_problems * steps / (tot_ms * 1e-3), "unit": UNIT, "ms_per_step": tot_ms / steps,
                "robots_per_sec": n_robots * steps / (tot_ms * 1e-3),
                "timed_region": "solve kernel + per-robot arg-min kernel (CUDA events, max over ranks)",

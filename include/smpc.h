@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define SMPC_ABI_VERSION 2
+#define SMPC_ABI_VERSION 3
 #define SMPC_MAX_BLOCKS 18 /* control_horizon 18 with parameter_block_length 1: the "36x36 class" */
 
 /* Return codes of every entry point. Per-problem solver outcomes are NOT call
@@ -141,6 +141,12 @@ typedef struct smpc_batch {
    * u0 / u rows and does not write the rest of its output rows (smpc_solve_batch returns them zero-filled,
    * smpc_solve_batch_device leaves the caller's memory untouched). */
   const int32_t* n_steps_each;
+  /* Scenario sharing (multi-start: many start points u0 of ONE scene). When scenario_index != NULL the arrays pose0,
+   * path_xy, goal_yaw, agents, has_people, n_steps_each and costmap_index have n_scenarios rows instead of n_problems
+   * and problem b reads row scenario_index[b] (costmap of row r without an index: r % M); u0 and every output stay per
+   * problem. The scene of 1024 starts then crosses the bus once and stays in L2 instead of 1024 times. */
+  const int32_t* scenario_index; /* [B] in [0, n_scenarios), or NULL */
+  int n_scenarios;
 } smpc_batch;
 
 /* Per-problem outputs. Any pointer may be NULL (that output is skipped).

@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import numpy as np
 
-SMPC_ABI_VERSION = 2
+SMPC_ABI_VERSION = 3
 SMPC_MAX_BLOCKS = 18
 
 # enum smpc_termination
@@ -86,6 +86,8 @@ class SmpcBatch(C.Structure):
         ("costmap_origin", C.c_void_p),
         ("costmap_index", C.c_void_p),
         ("n_steps_each", C.c_void_p),
+        ("scenario_index", C.c_void_p),
+        ("n_scenarios", C.c_int),
     ]
 
 
@@ -133,10 +135,13 @@ def _ptr(a):
 
 
 BATCH_FIELDS = ("pose0", "u0", "path_xy", "goal_yaw", "agents", "has_people", "costmaps",
-                "costmap_origin", "costmap_index", "n_steps_each")
+                "costmap_origin", "costmap_index", "n_steps_each", "scenario_index")
+# with scenario_index these have one row per SCENE (n_scenarios), not per problem (include/smpc.h)
+SCENE_FIELDS = ("pose0", "path_xy", "goal_yaw", "agents", "has_people", "costmap_index", "n_steps_each")
 BATCH_DTYPES = {"pose0": np.float64, "u0": np.float64, "path_xy": np.float64, "goal_yaw": np.float64,
                 "agents": np.float64, "has_people": np.uint8, "costmaps": np.uint8,
-                "costmap_origin": np.float64, "costmap_index": np.int32, "n_steps_each": np.int32}
+                "costmap_origin": np.float64, "costmap_index": np.int32, "n_steps_each": np.int32,
+                "scenario_index": np.int32}
 
 
 def make_batch_struct(arrays: dict, n_problems: int, n_steps: int, n_agents: int, n_costmaps: int,
@@ -147,6 +152,7 @@ def make_batch_struct(arrays: dict, n_problems: int, n_steps: int, n_agents: int
     b.size_x, b.size_y, b.resolution, b.dt = size_x, size_y, float(resolution), float(dt)
     for f in BATCH_FIELDS:
         setattr(b, f, _ptr(arrays.get(f)))
+    b.n_scenarios = int(arrays["pose0"].shape[0]) if arrays.get("scenario_index") is not None else 0
     return b
 
 

@@ -65,6 +65,9 @@ struct DevBatch {
   // 1 = the warps of a CTA meet at a CTA barrier before every evaluation (they then walk the large evaluation code
   // together and share its instruction-cache lines); 0 = warps run free and leave on their own
   int cta_sync;
+  // scenario sharing: problem b reads row scenario[b] of the per-scene arrays (NULL: row b); n_rows = rows of those arrays
+  const int32_t* scenario;
+  int n_rows;
 };
 
 struct DevResult {
@@ -1343,6 +1346,7 @@ __device__ __forceinline__ void wait_for_costmap(unsigned* arrival, int b) {
 template <bool NC>
 __device__ __forceinline__ void load_problem(const DevParams& prm, const DevBatch& bt, int b, Prob& pb) {
   const int S1 = bt.S + 1;
+  if (bt.scenario) b = ld_in<NC>(bt.scenario + b);  // row of the per-scene arrays; u0 and the outputs stay per problem
   const int Sb = bt.n_steps_each ? min(max(__ldg(bt.n_steps_each + b), 1), bt.S) : bt.S;
   pb.S = Sb;
   pb.ch = min(prm.control_horizon, Sb);   // src/optimizer.cpp:248

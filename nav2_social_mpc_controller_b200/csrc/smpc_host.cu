@@ -166,6 +166,7 @@ int check_batch(const smpc_batch* in) {
     return fail(SMPC_ERR_ARGUMENT, "costmap missing (the reference always dereferences costmap->getCharMap())");
   if (!(in->resolution > 0.0)) return fail(SMPC_ERR_ARGUMENT, "costmap resolution must be > 0");
   if (!(in->dt > 0.0)) return fail(SMPC_ERR_ARGUMENT, "dt must be > 0");
+  if (in->scenario_index && in->n_scenarios < 1) return fail(SMPC_ERR_ARGUMENT, "scenario_index given but n_scenarios < 1");
   return SMPC_OK;
 }
 
@@ -194,6 +195,8 @@ void to_dev_batch(const smpc_batch& in, smpc::DevBatch* d) {
   d->park_counters = nullptr;
   d->park_quantum = 0;
   d->cta_sync = 1;
+  d->scenario = in.scenario_index;
+  d->n_rows = in.scenario_index ? in.n_scenarios : in.n_problems;
 }
 
 // Build the packed agent records of a batch in the handle's scratch buffer (one small kernel per batch).
@@ -222,7 +225,12 @@ int pack_agents_at(smpc_handle* h, smpc::DevBatch* bt, size_t total_problems, si
   bt->agents_valid = nullptr;
   if (bt->A <= 0 || bt->agents == nullptr) return SMPC_OK;
   const size_t S1 = static_cast<size_t>(bt->S) + 1;
-  const size_t all_rows = total_problems * bt->A, rows = static_cast<size_t>(bt->B) * bt->A;
+  if (bt->scenario) {  // per-scene arrays: all n_rows scenes are packed once (scenario batches are never chunked)
+    total_problems = static_cast<size_t>(bt->n_rows);
+    first = 0;
+  }
+  const size_t all_rows = total_problems * bt->A;
+  const size_t rows = (bt->scenario ? static_cast<size_t>(bt->n_rows) : static_cast<size_t>(bt->B)) * bt->A;
   const size_t rec_bytes = align256(all_rows * S1 * 4 * sizeof(double));
   SMPC_CUDA(h->pack_buf.reserve(rec_bytes + all_rows * S1));
   double* packed = static_cast<double*>(h->pack_buf.ptr) + first * bt->A * S1 * 4;
@@ -625,28 +633,38 @@ int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out) {
   // ---- chunking. Costmaps follow their problems when map b belongs to problem b (no index, M == B); otherwise the
   //      M maps are shared: they go up once, ahead of the first chunk, and every chunk start must keep b % M intact.
   // an explicit identity index (map b for problem b) is the same thing as no index with M == B
-  bool identity_index = (in->costmap_index != nullptr) && (M == B);
+  bool identity_index = (in->costmap_index != nullptr) && (M == B) && (in->scenario_index == nullptr);
   for (size_t b = 0; identity_index && b < B; ++b) identity_index = in->costmap_index[b] == static_cast<int32_t>(b);
   const int32_t* host_index = identity_index ? nullptr : in->costmap_index;
-  const bool maps_per_problem = (host_index == nullptr) && (M == B);
+  // scenario sharing: the per-scene arrays (R rows) go up once like shared costmaps and the batch is one launch — only
+  // u0 and the scenario index are per problem, so there is nothing worth chunking or streaming
+  const bool scenes = in->scenario_index != nullptr;
+  const size_t R = scenes ? static_cast<size_t>(in->n_scenarios) : B;
+  const bool maps_per_problem = !scenes && (host_index == nullptr) && (M == B);
   size_t n_chunks = 1, chunk = B;
-  plan_chunks(h->n_sm, B, A > 0 && in->has_people, M, maps_per_problem, host_index != nullptr, h->forced_chunks, &n_chunks,
-              &chunk);
+  if (!scenes)
+    plan_chunks(h->n_sm, B, A > 0 && in->has_people, M, maps_per_problem, host_index != nullptr, h->forced_chunks,
+                &n_chunks, &chunk);
 
   // ---- device staging: every array whole, same layout as the host's, so a chunk is a pointer offset
   struct Item { const void* host; size_t per_problem; size_t shared_bytes; char* dev; };
-  enum { kPose, kU0, kPath, kGoal, kAgents, kHas, kIndex, kMaps, kOrigin, kNEach, kItems };
+  enum { kPose, kU0, kPath, kGoal, kAgents, kHas, kIndex, kMaps, kOrigin, kNEach, kScene, kItems };
+  // per-scene arrays: per problem normally, ONE shared block of R rows with scenario sharing
+  auto scene_item = [&](const void* host, size_t row_bytes) {
+    return scenes ? Item{host, 0, row_bytes * R, nullptr} : Item{host, row_bytes, 0, nullptr};
+  };
   Item items[kItems] = {
-      {in->pose0, 3 * 8, 0, nullptr},
+      scene_item(in->pose0, 3 * 8),
       {in->u0, P * 8, 0, nullptr},
-      {in->path_xy, 2 * S1 * 8, 0, nullptr},
-      {in->goal_yaw, 8, 0, nullptr},
-      {A ? in->agents : nullptr, A * 6 * S1 * 8, 0, nullptr},
-      {in->has_people, 1, 0, nullptr},
-      {host_index, 4, 0, nullptr},
+      scene_item(in->path_xy, 2 * S1 * 8),
+      scene_item(in->goal_yaw, 8),
+      scene_item(A ? in->agents : nullptr, A * 6 * S1 * 8),
+      scene_item(in->has_people, 1),
+      scene_item(host_index, 4),
       {in->costmaps, maps_per_problem ? map_cells : 0, maps_per_problem ? 0 : M * map_cells, nullptr},
       {in->costmap_origin, maps_per_problem ? 16 : 0, maps_per_problem ? 0 : M * 16, nullptr},
-      {in->n_steps_each, 4, 0, nullptr},
+      scene_item(in->n_steps_each, 4),
+      {in->scenario_index, 4, 0, nullptr},
   };
   size_t total = 0;
   for (auto& it : items)
@@ -688,8 +706,8 @@ int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out) {
   // Large batches stream their other per-problem arrays (seed path, pose, start controls: 0.5 kB per problem) the same
   // way once those are worth more than the extra copy calls (>= 8 MB).
   bool stream_maps = false;   // streaming mode on (the name is historical: maps were the first thing streamed)
-  bool streamed[kItems] = {false, false, false, false, false, false, false, false, false, false};
-  if (h->stream_maps && n_chunks == 1 && !(A > 0 && in->has_people) && B >= 1024) {
+  bool streamed[kItems] = {false, false, false, false, false, false, false, false, false, false, false};
+  if (h->stream_maps && n_chunks == 1 && !scenes && !(A > 0 && in->has_people) && B >= 1024) {
     size_t small_bytes = 0;
     for (int k = 0; k < kItems; ++k)
       if (k != kMaps && items[k].host && items[k].per_problem) small_bytes += items[k].per_problem * B;
@@ -764,6 +782,7 @@ int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out) {
     din.costmaps = static_cast<const uint8_t*>(at(kMaps));
     din.costmap_origin = static_cast<const double*>(at(kOrigin));
     din.n_steps_each = static_cast<const int32_t*>(at(kNEach));
+    din.scenario_index = static_cast<const int32_t*>(at(kScene));
     if (maps_per_problem) din.n_costmaps = static_cast<int>(n);
     auto oat = [&](int k) -> void* { return oitems[k].dev ? oitems[k].dev + oitems[k].per_problem * c0 : nullptr; };
     smpc_result dout;
@@ -857,18 +876,20 @@ int smpc_eval_batch(smpc_handle* h, const smpc_batch* in, const double* x, smpc_
     SMPC_CUDA(cudaSetDevice(h->device));
     const size_t B = in->n_problems, S1 = static_cast<size_t>(in->n_steps) + 1, A = in->agents ? in->n_agents : 0;
     const size_t M = in->n_costmaps, P = (h->params.omni_solve ? 3 : 2) * static_cast<size_t>(nb), NH = P * (P + 1) / 2;
+    const size_t R = in->scenario_index ? static_cast<size_t>(in->n_scenarios) : B;  // rows of the per-scene arrays
     struct Item { const void* host; size_t bytes; void** dev; };
     std::vector<Item> items = {
-        {in->pose0, B * 3 * 8, (void**)&din.pose0},
+        {in->pose0, R * 3 * 8, (void**)&din.pose0},
         {in->u0, B * P * 8, (void**)&din.u0},
-        {in->path_xy, B * 2 * S1 * 8, (void**)&din.path_xy},
-        {in->goal_yaw, B * 8, (void**)&din.goal_yaw},
-        {A ? in->agents : nullptr, B * A * 6 * S1 * 8, (void**)&din.agents},
-        {in->has_people, B, (void**)&din.has_people},
+        {in->path_xy, R * 2 * S1 * 8, (void**)&din.path_xy},
+        {in->goal_yaw, R * 8, (void**)&din.goal_yaw},
+        {A ? in->agents : nullptr, R * A * 6 * S1 * 8, (void**)&din.agents},
+        {in->has_people, R, (void**)&din.has_people},
         {in->costmaps, M * in->size_x * in->size_y, (void**)&din.costmaps},
         {in->costmap_origin, M * 2 * 8, (void**)&din.costmap_origin},
-        {in->costmap_index, B * 4, (void**)&din.costmap_index},
-        {in->n_steps_each, B * 4, (void**)&din.n_steps_each},
+        {in->costmap_index, R * 4, (void**)&din.costmap_index},
+        {in->n_steps_each, R * 4, (void**)&din.n_steps_each},
+        {in->scenario_index, B * 4, (void**)&din.scenario_index},
         {x, B * P * 8, (void**)&dx},
     };
     size_t total = 0;

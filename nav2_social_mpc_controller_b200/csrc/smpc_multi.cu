@@ -91,11 +91,12 @@ int smpc_solve_batch_multi(smpc_multi* m, const smpc_batch* in, smpc_result* out
   const size_t dof = m->params.omni_solve ? 3 : 2;
   const size_t S1 = static_cast<size_t>(in->n_steps) + 1, A = in->agents ? in->n_agents : 0, P = dof * nb;
   const size_t cells = static_cast<size_t>(in->size_x) * in->size_y;
-  const bool maps_per_problem = in->costmap_index == nullptr && in->n_costmaps == B;
+  const bool scenes = in->scenario_index != nullptr;  // per-scene arrays are shared by all shards, whole
+  const bool maps_per_problem = !scenes && in->costmap_index == nullptr && in->n_costmaps == B;
   // shared maps addressed by b % M: a shard starting at `lo` would see map (b - lo) % M, so give every problem its
   // explicit index (cheap: 4 bytes per problem)
   const int32_t* index = in->costmap_index;
-  if (!maps_per_problem && index == nullptr) {
+  if (!scenes && !maps_per_problem && index == nullptr) {
     m->index_scratch.resize(B);
     for (long long b = 0; b < B; ++b) m->index_scratch[b] = static_cast<int32_t>(b % in->n_costmaps);
     index = m->index_scratch.data();
@@ -110,14 +111,20 @@ int smpc_solve_batch_multi(smpc_multi* m, const smpc_batch* in, smpc_result* out
     pool.emplace_back([&, r, lo, hi]() {
       smpc_batch s = *in;
       s.n_problems = static_cast<int>(hi - lo);
-      s.pose0 = in->pose0 + 3 * lo;
       s.u0 = in->u0 + P * lo;
-      s.path_xy = in->path_xy + 2 * S1 * lo;
-      s.goal_yaw = in->goal_yaw + lo;
-      s.agents = A ? in->agents + A * 6 * S1 * lo : nullptr;
-      s.has_people = in->has_people ? in->has_people + lo : nullptr;
-      s.n_steps_each = in->n_steps_each ? in->n_steps_each + lo : nullptr;
-      if (maps_per_problem) {
+      if (scenes) {
+        s.scenario_index = in->scenario_index + lo;
+      } else {
+        s.pose0 = in->pose0 + 3 * lo;
+        s.path_xy = in->path_xy + 2 * S1 * lo;
+        s.goal_yaw = in->goal_yaw + lo;
+        s.agents = A ? in->agents + A * 6 * S1 * lo : nullptr;
+        s.has_people = in->has_people ? in->has_people + lo : nullptr;
+        s.n_steps_each = in->n_steps_each ? in->n_steps_each + lo : nullptr;
+      }
+      if (scenes) {
+        // costmap_index (if any) is per scene row: unchanged
+      } else if (maps_per_problem) {
         s.costmaps = in->costmaps + cells * lo;
         s.costmap_origin = in->costmap_origin + 2 * lo;
         s.n_costmaps = s.n_problems;

@@ -208,16 +208,31 @@ class Batch:
     def slice(self, lo: int, hi: int) -> "Batch":
         """Problems [lo, hi) as a new batch (costmaps are shared, indices kept)."""
         arr = {}
+        shared = self.arrays.get("scenario_index") is not None  # per-scene arrays stay whole
         for k, v in self.arrays.items():
             if v is None:
                 arr[k] = None
-            elif k in ("costmaps", "costmap_origin"):
+            elif k in ("costmaps", "costmap_origin") or (shared and k in abi.SCENE_FIELDS):
                 arr[k] = v
             else:
                 arr[k] = np.ascontiguousarray(v[lo:hi])
-        if arr.get("costmap_index") is None:
+        if arr.get("costmap_index") is None and not shared:
             arr["costmap_index"] = (np.arange(lo, hi) % self.n_costmaps).astype(np.int32)
         return dataclasses.replace(self, n_problems=hi - lo, arrays=arr)
+
+    def expanded(self) -> "Batch":
+        """A scenario-sharing batch written out with one row per problem (what the oracle and older callers read)."""
+        idx = self.arrays.get("scenario_index")
+        if idx is None:
+            return self
+        arr = {}
+        for k, v in self.arrays.items():
+            if k == "scenario_index":
+                continue
+            arr[k] = np.ascontiguousarray(v[idx]) if (v is not None and k in abi.SCENE_FIELDS) else v
+        if arr.get("costmap_index") is None:
+            arr["costmap_index"] = (idx % self.n_costmaps).astype(np.int32)
+        return dataclasses.replace(self, arrays=arr)
 
     def input_bytes(self) -> int:
         return int(sum(v.nbytes for v in self.arrays.values() if v is not None))
@@ -409,18 +424,25 @@ def omni(batch: Batch, vy_sigma: float = 0.05, config_id: int = 70) -> Batch:
     return dataclasses.replace(batch, params=p, arrays=arr)
 
 
-def multistart(n_robots: int = 256, n_starts: int = 1024, config_id: int = 4, **overrides) -> Batch:
+def multistart(n_robots: int = 256, n_starts: int = 1024, config_id: int = 4, shared: bool = False, **overrides) -> Batch:
     """BASELINE config 4: `n_starts` perturbed initial control sequences per robot (start 0 unperturbed),
-    u0 = clamp(seed u0 + N(0, diag(0.1, 0.3)^2)) per block. Problems of one robot are contiguous."""
+    u0 = clamp(seed u0 + N(0, diag(0.1, 0.3)^2)) per block. Problems of one robot are contiguous.
+    shared = True: the scene arrays keep ONE row per robot and `scenario_index` maps the starts onto them
+    (smpc_batch.scenario_index); Batch.expanded() gives the same problems written out per start."""
     base = crowd(B=n_robots, A=3, config_id=config_id, n_maps=min(256, n_robots), **overrides)
     rng = _rng(config_id + 100)
     B = n_robots * n_starts
     arr = {}
     for k, v in base.arrays.items():
-        if v is None or k in ("costmaps", "costmap_origin"):
+        if v is None or k in ("costmaps", "costmap_origin") or (shared and k in abi.SCENE_FIELDS):
             arr[k] = v
         else:
             arr[k] = np.ascontiguousarray(np.repeat(v, n_starts, axis=0))
+    if shared:
+        arr["u0"] = np.ascontiguousarray(np.repeat(base.arrays["u0"], n_starts, axis=0))
+        arr["scenario_index"] = np.repeat(np.arange(n_robots, dtype=np.int32), n_starts)
+        if arr.get("costmap_index") is None:
+            arr["costmap_index"] = (np.arange(n_robots) % base.n_costmaps).astype(np.int32)
     nb = base.n_blocks
     noise = rng.normal(0.0, 1.0, (n_robots, n_starts, nb, 2)) * np.array([0.1, 0.3])
     noise[:, 0] = 0.0

@@ -675,6 +675,46 @@ def test_omnidirectional_solve_matches_oracle(oracle, make_opt, kind, floor):
     assert np.all(np.abs(got["u"][:, :nbd, 1]) <= 0.6 + 1e-15) and np.all(got["u"][:, :nbd, 0] >= 0.0)
 
 
+def test_scenario_sharing_is_bit_identical_to_the_expanded_batch(make_opt):
+    """smpc_batch.scenario_index: the starts of a multi-start batch read ONE row of the scene arrays per robot. Same
+    problems, same kernel, same bits as the batch written out per start — through the host-buffer entry, the device
+    entry, the evaluation entry and the multi-GPU dispatcher (granule = starts per robot)."""
+    import torch
+    from nav2_social_mpc_controller_b200.optimizer import MultiGpuOptimizer
+    shared = sc.multistart(n_robots=6, n_starts=40, shared=True)
+    full = shared.expanded()
+    assert shared.arrays["pose0"].shape[0] == 6 and full.arrays["pose0"].shape[0] == 240
+    assert shared.input_bytes() < full.input_bytes() // 10
+    opt = make_opt(shared.params)
+    want = ("u", "cmds", "path", "cost_final", "iterations", "termination", "usable", "n_evals")
+    a = opt.solve_batch(full, want=want)
+    b = opt.solve_batch(shared, want=want)
+    for k in want:
+        assert np.array_equal(a[k], b[k]), k
+    assert len(np.unique(a["cost_final"])) > 6  # the starts really differ
+    # evaluation entry
+    ea, eb = opt.eval_batch(full, full.arrays["u0"]), opt.eval_batch(shared, shared.arrays["u0"])
+    for k in ("cost", "grad", "hess"):
+        assert np.array_equal(ea[k], eb[k]), k
+    # device entry
+    dev = torch.device("cuda", 0)
+    d_arr = {k: (torch.from_numpy(v).to(dev) if v is not None else None) for k, v in shared.arrays.items()}
+    shapes = sc.abi.result_shapes(shared.n_problems, shared.n_steps, shared.n_blocks)
+    d_out = {k: torch.zeros(shapes[k][0], dtype=getattr(torch, np.dtype(shapes[k][1]).name), device=dev)
+             for k in ("u", "cost_final", "usable")}
+    opt.solve_batch_device(shared.struct(d_arr), d_out)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out["u"].cpu().numpy(), a["u"]) and np.array_equal(d_out["cost_final"].cpu().numpy(), a["cost_final"])
+    # multi-GPU dispatcher: shards of whole robots, the scene arrays go to every shard
+    multi = MultiGpuOptimizer(shared.params, [0, 0, 0] if torch.cuda.device_count() < 2 else [0, 1, 0])
+    try:
+        m = multi.solve_batch(shared, granule=40)
+    finally:
+        multi.close()
+    for k in ("u", "cost_final", "iterations", "usable"):
+        assert np.array_equal(m[k], a[k]), k
+
+
 @pytest.mark.parametrize("kind", ["crowd", "corridor_maps_per_problem", "shared_maps_modulo", "multistart"])
 def test_in_library_multi_gpu_dispatch_is_bit_identical(kind):
     """smpc_solve_batch_multi: contiguous shards, one host thread + handle per GPU, results written into the caller's
