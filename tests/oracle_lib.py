@@ -50,6 +50,7 @@ class Oracle:
         return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
 
     def num_residuals(self, batch, b=0):
+        batch = batch.expanded()  # scenario-sharing batches: the oracle reads one row per problem
         st = batch.struct()
         return self.lib.smpc_oracle_num_residuals(C.byref(batch.params), C.byref(st), b)
 
@@ -57,6 +58,7 @@ class Oracle:
         m = self.num_residuals(batch, b)
         kinds = np.zeros(m, dtype=np.int32)
         steps = np.zeros(m, dtype=np.int32)
+        batch = batch.expanded()  # scenario-sharing batches: the oracle reads one row per problem
         st = batch.struct()
         ip = C.POINTER(C.c_int)
         self.lib.smpc_oracle_layout(C.byref(batch.params), C.byref(st), b, kinds.ctypes.data_as(ip),
@@ -75,6 +77,7 @@ class Oracle:
         res = np.zeros(m)
         grad = np.zeros(P) if want_jac else None
         jac = np.zeros((m, P)) if want_jac else None
+        batch = batch.expanded()  # scenario-sharing batches: the oracle reads one row per problem
         st = batch.struct()
         ok = self.lib.smpc_oracle_evaluate(C.byref(batch.params), C.byref(st), b, self._dp(x), C.byref(cost),
                                            self._dp(res), self._dp(grad), self._dp(jac))
@@ -87,6 +90,7 @@ class Oracle:
         shapes = abi.result_shapes(batch.n_problems, batch.n_steps, batch.n_blocks, 3 if int(batch.params.omni_solve) else 2)
         out = {k: np.zeros(shapes[k][0], dtype=shapes[k][1]) for k in want}
         rs = abi.make_result_struct(out)
+        batch = batch.expanded()  # scenario-sharing batches: the oracle reads one row per problem
         st = batch.struct()
         rc = self.lib.smpc_oracle_solve_batch(C.byref(batch.params), C.byref(st), C.byref(rs), first, count,
                                               n_threads)
@@ -100,6 +104,7 @@ class Oracle:
         trace = np.zeros((max_rows, 10))
         term = C.c_int(0)
         ci, cf = C.c_double(0), C.c_double(0)
+        batch = batch.expanded()  # scenario-sharing batches: the oracle reads one row per problem
         st = batch.struct()
         rows = self.lib.smpc_oracle_solve_trace(C.byref(batch.params), C.byref(st), b, self._dp(x), self._dp(trace),
                                                 max_rows, C.byref(term), C.byref(ci), C.byref(cf))
