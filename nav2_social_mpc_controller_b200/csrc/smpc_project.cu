@@ -11,6 +11,7 @@
 
 #include "../../include/smpc.h"
 #include "smpc_host_state.h"
+#include "smpc_math.cuh"
 
 namespace {
 
@@ -26,6 +27,34 @@ __device__ __forceinline__ double wrap_pi(double a) {
   while (a <= -M_PI) a += 2 * M_PI;
   while (a > M_PI) a -= 2 * M_PI;
   return a;
+}
+
+// lightsfm social force of one agent pair exactly as the reference writes it (sfm.hpp:239-281): d = other - me,
+// w = my velocity - other's. Out of line: the projection kernel only comes here for degenerate geometry (coincident
+// agents, zero interaction vector, |sin theta| < 1e-9 — e.g. two people standing still, where theta == 0 switches the
+// lateral term off), where the two-atan2 form and its exact-zero tests decide the result.
+__device__ __noinline__ void sfm_pair_reference(double dx, double dy, double wx, double wy, double* fx, double* fy) {
+  const double kSocial = 2.1, kLambda = 2.0, kGamma = 0.35, kN = 2.0, kNPrime = 3.0;
+  const double z = dx * dx + dy * dy;
+  const double dn = sqrt(z);
+  double ex = dx, ey = dy;
+  if (z > 0.0) {
+    ex = dx / dn;
+    ey = dy / dn;
+  }
+  const double Ix = kLambda * wx + ex, Iy = kLambda * wy + ey;
+  const double il = sqrt(Ix * Ix + Iy * Iy);
+  const double ix = Ix / il, iy = Iy / il;
+  const double a1 = wrap_pi(atan2(iy, ix));
+  const double a2 = wrap_pi(atan2(ey, ex));
+  const double th = wrap_pi(a2 - a1);
+  const double B = kGamma * il;
+  const double fv = -exp(-dn / B - (kNPrime * B * th) * (kNPrime * B * th));
+  double sgn = -1.0;
+  if (th == 0) sgn = 0; else if (th > 0) sgn = 1;
+  const double fa = -sgn * exp(-dn / B - (kN * B * th) * (kN * B * th));
+  *fx = kSocial * (fv * ix + fa * (-iy));
+  *fy = kSocial * (fv * iy + fa * ix);
 }
 
 // computeObstacle: the vector the reference stores in obstacles1 (agent - nearest obstacle cell)
@@ -192,27 +221,31 @@ __global__ void __launch_bounds__(kWarps * 32) smpc_project_kernel(smpc_project_
         for (int k = 0; k <= n; ++k) {
           if (k == slot) continue;
           const double dx = s.px[k] - px, dy = s.py[k] - py;
-          const double z = dx * dx + dy * dy;
-          const double dn = sqrt(z);
-          double ex = dx, ey = dy;
-          if (z > 0.0) {
-            ex = dx / dn;
-            ey = dy / dn;
-          }
           const double wx = vx - s.vx[k], wy = vy - s.vy[k];
+          // Generic geometry: unit vectors by reciprocal square roots, ONE atan2 of (cross, dot) for the angle from the
+          // interaction direction i to e, the kernel's own exp (smpc_math.cuh; each within ~1 ulp of the libm call it
+          // replaces — the projected trajectories move by ~1e-15). Degenerate geometry: the reference's formulation.
+          const double z = dx * dx + dy * dy;
+          const double inv_dn = smpc::rsqrt_pos(z);  // NaN for z == 0: caught by the test on `cross` below
+          const double dn = z * inv_dn, ex = dx * inv_dn, ey = dy * inv_dn;
           const double Ix = kLambda * wx + ex, Iy = kLambda * wy + ey;
-          const double il = sqrt(Ix * Ix + Iy * Iy);
-          const double ix = Ix / il, iy = Iy / il;
-          const double a1 = wrap_pi(atan2(iy, ix));
-          const double a2 = wrap_pi(atan2(ey, ex));
-          const double th = wrap_pi(a2 - a1);
-          const double B = kGamma * il;
-          const double fv = -exp(-dn / B - (kNPrime * B * th) * (kNPrime * B * th));
-          double sgn = -1.0;
-          if (th == 0) sgn = 0; else if (th > 0) sgn = 1;
-          const double fa = -sgn * exp(-dn / B - (kN * B * th) * (kN * B * th));
-          sfx += kSocial * (fv * ix + fa * (-iy));
-          sfy += kSocial * (fv * iy + fa * ix);
+          const double L2 = Ix * Ix + Iy * Iy;
+          const double inv_il = smpc::rsqrt_pos(L2);
+          const double il = L2 * inv_il, ix = Ix * inv_il, iy = Iy * inv_il;
+          const double cross = ey * ix - ex * iy, dot = ex * ix + ey * iy;
+          if (fabs(cross) > 1e-9) {  // false for NaN
+            const double th = smpc::atan2_unit(cross, dot);
+            const double Bth = kGamma * il * th, base = -dn * inv_il * (1.0 / kGamma);
+            const double fv = -smpc::exp_nonpos(base - (kNPrime * Bth) * (kNPrime * Bth));
+            const double fa = -copysign(smpc::exp_nonpos(base - (kN * Bth) * (kN * Bth)), th);
+            sfx += kSocial * (fv * ix - fa * iy);
+            sfy += kSocial * (fv * iy + fa * ix);
+          } else {
+            double rx, ry;
+            sfm_pair_reference(dx, dy, wx, wy, &rx, &ry);
+            sfx += rx;
+            sfy += ry;
+          }
         }
         fx += sfx;
         fy += sfy;
