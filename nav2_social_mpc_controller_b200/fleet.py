@@ -94,22 +94,31 @@ class FleetOptimizer:
         return out.cpu().numpy(), n_out.cpu().numpy()
 
     def optimize_batch(self, poses, cmds, people_raw, n_people, speed, costmaps, costmap_origin, costmap_resolution,
-                       od: dict, costmap_index=None, od_index=None, n_poses=None, want_people_proj=True) -> dict:
+                       od: dict, costmap_index=None, od_index=None, n_poses=None, want_people_proj=True,
+                       inplace=False) -> dict:
         """One controller tick for the fleet (smpc_optimize_batch). poses [B][n][3], cmds [B][>= n-1][2] (trajectorizer
         seeds; n_poses [B] = valid poses per robot, default n for all), people_raw [B][A][5], n_people [B], speed [B][2],
         costmaps [M][sy][sx] u8, od = dict(width, height, resolution, origins [Mo][2], indexes u32 [Mo][h*w]).
         Returns host numpy: optimized [B] (the reference's bool), n_out [B], cmds [B][n][2], path [B][n][3] (rows valid
         up to n_out[b]), people_proj [B][A][6][n], termination, iterations, cost_initial, cost_final, project_status.
-        Costmaps / obstacle grids are re-sent to the GPU only when the arrays passed here change identity."""
+        Costmaps / obstacle grids are re-sent to the GPU only when the arrays passed here change identity.
+        inplace = True: poses [B][n][3] and cmds [B][n][2] (C-contiguous float64) are the in/out buffers of the C call
+        themselves, like the reference's in-out path / cmds arguments — no copies on the Python side."""
         p = self.p
         poses = np.ascontiguousarray(poses, dtype=np.float64)
         B, n, _ = poses.shape
         assert B == self.B
-        cmds_in = np.ascontiguousarray(cmds, dtype=np.float64)
-        cmd_rows = np.zeros((B, n, 2))
-        k = min(n, cmds_in.shape[1])
-        cmd_rows[:, :k] = cmds_in[:, :k]
-        pose_rows = poses.copy()
+        if inplace:
+            if not (isinstance(cmds, np.ndarray) and cmds.dtype == np.float64 and cmds.flags.c_contiguous
+                    and cmds.shape == (B, n, 2)):
+                raise ValueError("inplace needs cmds as a C-contiguous float64 array of shape [B][n][2]")
+            cmd_rows, pose_rows = cmds, poses
+        else:
+            cmds_in = np.ascontiguousarray(cmds, dtype=np.float64)
+            cmd_rows = np.zeros((B, n, 2))
+            k = min(n, cmds_in.shape[1])
+            cmd_rows[:, :k] = cmds_in[:, :k]
+            pose_rows = poses.copy()
         n_poses = np.full(B, n, dtype=np.int32) if n_poses is None else np.ascontiguousarray(n_poses, dtype=np.int32)
         people_raw = np.ascontiguousarray(people_raw, dtype=np.float64).reshape(B, self.A, 5)
         n_people = np.ascontiguousarray(n_people, dtype=np.int32)
