@@ -63,6 +63,31 @@ struct DeviceBuffer {
   }
 };
 
+struct PinnedBuffer {  // page-locked host staging owned by a handle
+  void* ptr = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (ptr) cudaFreeHost(ptr);
+    ptr = nullptr;
+    cap = 0;
+    const size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaHostAlloc(&ptr, want, cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (ptr) cudaFreeHost(ptr);
+    ptr = nullptr;
+    cap = 0;
+  }
+};
+
+// Small host batches (single solves, a robot's few problems): every input array is first gathered into ONE page-locked
+// staging block laid out like the device staging, so the call makes one host-to-device and one device-to-host copy
+// instead of ~10 + ~9 small ones (each a driver round trip of several microseconds from pageable memory).
+constexpr size_t kPackedBytes = 256u << 10;
+
 const char* const kSolverTypes[] = {"DENSE_SCHUR", "SPARSE_SCHUR", "DENSE_NORMAL_CHOLESKY", "DENSE_QR",
                                     "SPARSE_NORMAL_CHOLESKY"};  // reference optimizer.hpp:71-77
 
@@ -87,6 +112,7 @@ struct smpc_handle {
   int forced_warps = 0;  // 0 = pick warps-per-CTA from the batch size; SMPC_WARPS env overrides (4 / 16 with people, 4 / 12 without)
   int park_quantum = 32; // evaluations per time slice of the solve queue (0 = off); SMPC_PARK_QUANTUM env overrides
   DeviceBuffer park_buf; // parked group states + ring + counters of the time-sliced queue
+  PinnedBuffer pin_in, pin_out;  // staging of the packed small-batch path (kPackedBytes)
   int stream_maps = 1;   // 1 = stream per-problem costmaps under the solve (pinned host buffers only); SMPC_STREAM_MAPS=0 disables
   unsigned* arrival = nullptr;       // device: {problems whose costmap has arrived, kernel gave up waiting}
   unsigned* arrival_host = nullptr;  // pinned: the values the copy stream writes to arrival[0], one per map chunk
@@ -495,6 +521,8 @@ void smpc_destroy(smpc_handle* h) {
   h->out_buf.release();
   h->pack_buf.release();
   h->park_buf.release();
+  h->pin_in.release();
+  h->pin_out.release();
   h->fleet.release();
   h->single.release();
   if (h->queue) cudaFree(h->queue);
@@ -744,9 +772,20 @@ int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out) {
       (void)cudaGetLastError();
     }
   } quiesce{lanes[0], lanes[1], true};
+  // small batch: one staged block in, one staged block out (kPackedBytes)
+  const bool packed = n_chunks == 1 && !stream_maps && total <= kPackedBytes && ototal <= kPackedBytes;
+  if (packed) {
+    SMPC_CUDA(h->pin_in.reserve(total));
+    SMPC_CUDA(h->pin_out.reserve(ototal));
+    char* stage = static_cast<char*>(h->pin_in.ptr);
+    const char* dev0 = static_cast<const char*>(h->in_buf.ptr);
+    for (auto& it : items)
+      if (it.host) std::memcpy(stage + (it.dev - dev0), it.host, it.per_problem * B + it.shared_bytes);
+    SMPC_CUDA(cudaMemcpyAsync(h->in_buf.ptr, stage, total, cudaMemcpyHostToDevice, lanes[0]));
+  }
   bool any_shared = false;
   for (auto& it : items)
-    if (it.host && it.shared_bytes) {
+    if (!packed && it.host && it.shared_bytes) {
       SMPC_CUDA(cudaMemcpyAsync(it.dev, it.host, it.shared_bytes, cudaMemcpyHostToDevice, lanes[0]));
       any_shared = true;
     }
@@ -760,7 +799,7 @@ int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out) {
     cudaStream_t st = lanes[c & 1];
     for (int k = 0; k < kItems; ++k) {
       const Item& it = items[k];
-      if (it.host && it.per_problem && !streamed[k])
+      if (!packed && it.host && it.per_problem && !streamed[k])
         SMPC_CUDA(cudaMemcpyAsync(it.dev + it.per_problem * c0, static_cast<const char*>(it.host) + it.per_problem * c0,
                                   it.per_problem * n, cudaMemcpyHostToDevice, st));
     }
@@ -821,6 +860,10 @@ int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out) {
     rc = launch_solve_on(h, &din, &dout, h->queue + c, B, c0, /*timed=*/n_chunks == 1, st,
                          stream_maps ? h->arrival : nullptr);
     if (rc != SMPC_OK) return rc;
+    if (packed) {
+      SMPC_CUDA(cudaMemcpyAsync(h->pin_out.ptr, h->out_buf.ptr, ototal, cudaMemcpyDeviceToHost, st));
+      continue;
+    }
     for (auto& it : oitems)
       if (it.host)
         SMPC_CUDA(cudaMemcpyAsync(static_cast<char*>(it.host) + it.per_problem * c0, it.dev + it.per_problem * c0,
@@ -832,6 +875,12 @@ int smpc_solve_batch(smpc_handle* h, const smpc_batch* in, smpc_result* out) {
   SMPC_CUDA(cudaStreamSynchronize(lanes[0]));
   if (n_chunks > 1 || stream_maps) SMPC_CUDA(cudaStreamSynchronize(lanes[1]));
   quiesce.armed = false;  // both streams are idle
+  if (packed) {
+    const char* stage = static_cast<const char*>(h->pin_out.ptr);
+    const char* dev0 = static_cast<const char*>(h->out_buf.ptr);
+    for (auto& it : oitems)
+      if (it.host) std::memcpy(it.host, stage + (it.dev - dev0), it.per_problem * B);
+  }
   if (stream_maps && h->arrival_host[kMapChunks + 1] != 0)
     return fail(SMPC_ERR_CUDA, "costmap stream stalled: the solve kernel waited 2 s for host-to-device copies");
   return SMPC_OK;
