@@ -36,10 +36,32 @@ struct smpc_devbuf {
   }
 };
 
+// growing page-locked host allocation
+struct smpc_pinbuf {
+  void* ptr = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (ptr) cudaFreeHost(ptr);
+    ptr = nullptr;
+    cap = 0;
+    const size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaHostAlloc(&ptr, want, cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (ptr) cudaFreeHost(ptr);
+    ptr = nullptr;
+    cap = 0;
+  }
+};
+
 // device-resident state of the fleet tick (smpc_optimize_batch): per-robot TrajectoryMemory, cached maps, scratch
 struct smpc_fleet_state {
   std::mutex mu;
   smpc_devbuf scratch, maps, memory;
+  smpc_pinbuf pin_in, pin_out, pin_maps;  // staging of small ticks: one copy per direction (see smpc_optimize_batch_on)
   int mem_robots = 0, mem_stride = 0;
   long long maps_version = -1;
   size_t maps_bytes = 0;
@@ -49,6 +71,9 @@ struct smpc_fleet_state {
     scratch.release();
     maps.release();
     memory.release();
+    pin_in.release();
+    pin_out.release();
+    pin_maps.release();
     forget();
     maps_version = -1;
   }

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstring>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -882,7 +883,21 @@ int smpc_optimize_batch_on(smpc_handle* h, smpc_fleet_state* fs, smpc_fleet_io* 
   uint32_t* d_od = cmaps.take<uint32_t>((size_t)io->n_od_grids * od_cells);
   double* d_map_org = cmaps.take<double>((size_t)io->n_costmaps * 2);
   double* d_od_org = cmaps.take<double>((size_t)io->n_od_grids * 2);
-  if (resend) {
+  // Small ticks (one robot: Optimizer::optimize itself) are dominated by per-copy driver overhead, not bytes: their
+  // inputs, maps and results travel as ONE staged page-locked block each instead of ~14 + 4 + 10 separate copies.
+  constexpr size_t kPackedTick = 256u << 10;
+  if (resend && maps_total <= kPackedTick) {
+    FLEET_CUDA(fs->pin_maps.reserve(maps_total));
+    char* stage = static_cast<char*>(fs->pin_maps.ptr);
+    const char* dev0 = static_cast<const char*>(fs->maps.ptr);
+    std::memcpy(stage + (reinterpret_cast<const char*>(d_maps) - dev0), io->costmaps, map_bytes);
+    std::memcpy(stage + (reinterpret_cast<const char*>(d_od) - dev0), io->od_indexes, od_bytes);
+    std::memcpy(stage + (reinterpret_cast<const char*>(d_map_org) - dev0), io->costmap_origin, (size_t)io->n_costmaps * 16);
+    std::memcpy(stage + (reinterpret_cast<const char*>(d_od_org) - dev0), io->od_origin, (size_t)io->n_od_grids * 16);
+    FLEET_CUDA(cudaMemcpyAsync(fs->maps.ptr, stage, maps_total, cudaMemcpyHostToDevice, st));
+    fs->maps_version = io->maps_version;
+    fs->maps_bytes = maps_total;
+  } else if (resend) {
     FLEET_CUDA(cudaMemcpyAsync(d_maps, io->costmaps, map_bytes, cudaMemcpyHostToDevice, st));
     FLEET_CUDA(cudaMemcpyAsync(d_od, io->od_indexes, od_bytes, cudaMemcpyHostToDevice, st));
     FLEET_CUDA(cudaMemcpyAsync(d_map_org, io->costmap_origin, (size_t)io->n_costmaps * 16, cudaMemcpyHostToDevice, st));
@@ -901,9 +916,10 @@ int smpc_optimize_batch_on(smpc_handle* h, smpc_fleet_state* fs, smpc_fleet_io* 
     probe.take<int32_t>(B); probe.take<int32_t>(B);
     probe.take<double>((size_t)B * A * 6); probe.take<uint8_t>(B); probe.take<double>(BS * 6); probe.take<double>((size_t)B * 3);
     probe.take<double>((size_t)B * nb * 2); probe.take<double>(BS * 2); probe.take<double>(B);
-    probe.take<double>((size_t)B * A * 6 * stride); probe.take<int32_t>(B);
+    probe.take<double>((size_t)B * A * 6 * stride);
     probe.take<double>(BS * 2); probe.take<double>(BS * 3); probe.take<uint8_t>(B); probe.take<int32_t>(B);
     probe.take<int32_t>(B); probe.take<double>(B); probe.take<double>(B); probe.take<int32_t>(B); probe.take<uint8_t>(B);
+    probe.take<int32_t>(B);
     need = probe.off;
   }
   FLEET_CUDA(fs->scratch.reserve(need));
@@ -926,7 +942,6 @@ int smpc_optimize_batch_on(smpc_handle* h, smpc_fleet_state* fs, smpc_fleet_io* 
   double* d_path_xy = cs.take<double>(BS * 2);
   double* d_goal_yaw = cs.take<double>(B);
   double* d_agents = cs.take<double>((size_t)B * A * 6 * stride);
-  int32_t* d_status = cs.take<int32_t>(B);
   double* d_cmds_new = cs.take<double>(BS * 2);
   double* d_path_new = cs.take<double>(BS * 3);
   uint8_t* d_usable = cs.take<uint8_t>(B);
@@ -936,18 +951,34 @@ int smpc_optimize_batch_on(smpc_handle* h, smpc_fleet_state* fs, smpc_fleet_io* 
   double* d_cost1 = cs.take<double>(B);
   int32_t* d_n_out = cs.take<int32_t>(B);
   uint8_t* d_optimized = cs.take<uint8_t>(B);
+  int32_t* d_status = cs.take<int32_t>(B);
+  // the scratch starts with the ten input arrays (d_poses .. d_od_index) and ends with the result scalars
+  // (d_usable .. d_status): each group is one contiguous span
+  const char* scratch0 = static_cast<const char*>(fs->scratch.ptr);
+  const size_t in_span = reinterpret_cast<const char*>(d_init) - scratch0;
+  const size_t tail_off = reinterpret_cast<const char*>(d_usable) - scratch0, tail_span = need - tail_off;
+  const size_t io_span = reinterpret_cast<const char*>(d_people) - scratch0;  // d_poses + d_cmds: in/out
+  const bool packed = in_span <= kPackedTick && tail_span + io_span <= kPackedTick;
 
   // ---- inputs up
-  FLEET_CUDA(cudaMemcpyAsync(d_poses, io->poses, BS * 3 * 8, cudaMemcpyHostToDevice, st));
-  FLEET_CUDA(cudaMemcpyAsync(d_cmds, io->cmds, BS * 2 * 8, cudaMemcpyHostToDevice, st));
-  FLEET_CUDA(cudaMemcpyAsync(d_people, io->people, (size_t)B * A * 5 * 8, cudaMemcpyHostToDevice, st));
-  FLEET_CUDA(cudaMemcpyAsync(d_n_people, io->n_people, (size_t)B * 4, cudaMemcpyHostToDevice, st));
-  FLEET_CUDA(cudaMemcpyAsync(d_speed, io->speed, (size_t)B * 16, cudaMemcpyHostToDevice, st));
-  FLEET_CUDA(cudaMemcpyAsync(d_n_in, io->n_poses, (size_t)B * 4, cudaMemcpyHostToDevice, st));
-  FLEET_CUDA(cudaMemcpyAsync(d_n_each, n_each.data(), (size_t)B * 4, cudaMemcpyHostToDevice, st));
-  FLEET_CUDA(cudaMemcpyAsync(d_s_each, s_each.data(), (size_t)B * 4, cudaMemcpyHostToDevice, st));
-  if (io->costmap_index) FLEET_CUDA(cudaMemcpyAsync(d_map_index, io->costmap_index, (size_t)B * 4, cudaMemcpyHostToDevice, st));
-  if (io->od_index) FLEET_CUDA(cudaMemcpyAsync(d_od_index, io->od_index, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  struct Src { void* dev; const void* host; size_t bytes; };
+  const Src srcs[] = {
+      {d_poses, io->poses, BS * 3 * 8},          {d_cmds, io->cmds, BS * 2 * 8},
+      {d_people, io->people, (size_t)B * A * 5 * 8}, {d_n_people, io->n_people, (size_t)B * 4},
+      {d_speed, io->speed, (size_t)B * 16},      {d_n_in, io->n_poses, (size_t)B * 4},
+      {d_n_each, n_each.data(), (size_t)B * 4},  {d_s_each, s_each.data(), (size_t)B * 4},
+      {d_map_index, io->costmap_index, (size_t)B * 4}, {d_od_index, io->od_index, (size_t)B * 4},
+  };
+  if (packed) {
+    FLEET_CUDA(fs->pin_in.reserve(in_span));
+    char* stage = static_cast<char*>(fs->pin_in.ptr);
+    for (const Src& c : srcs)
+      if (c.host) std::memcpy(stage + (static_cast<const char*>(c.dev) - scratch0), c.host, c.bytes);
+    FLEET_CUDA(cudaMemcpyAsync(fs->scratch.ptr, stage, in_span, cudaMemcpyHostToDevice, st));
+  } else {
+    for (const Src& c : srcs)
+      if (c.host) FLEET_CUDA(cudaMemcpyAsync(c.dev, c.host, c.bytes, cudaMemcpyHostToDevice, st));
+  }
   FLEET_CUDA(cudaMemsetAsync(d_status, 0, (size_t)B * 4, st));
 
   const unsigned g_bs = (unsigned)((BS + 255) / 256), g_b = (unsigned)((B + 255) / 256);
@@ -998,17 +1029,31 @@ int smpc_optimize_batch_on(smpc_handle* h, smpc_fleet_state* fs, smpc_fleet_io* 
   smpc_handle_count_launch(h);
 
   // ---- results down
-  FLEET_CUDA(cudaMemcpyAsync(io->poses, d_poses, BS * 3 * 8, cudaMemcpyDeviceToHost, st));
-  FLEET_CUDA(cudaMemcpyAsync(io->cmds, d_cmds, BS * 2 * 8, cudaMemcpyDeviceToHost, st));
-  FLEET_CUDA(cudaMemcpyAsync(io->n_out, d_n_out, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
-  FLEET_CUDA(cudaMemcpyAsync(io->optimized, d_optimized, (size_t)B, cudaMemcpyDeviceToHost, st));
-  if (io->termination) FLEET_CUDA(cudaMemcpyAsync(io->termination, d_term, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
-  if (io->iterations) FLEET_CUDA(cudaMemcpyAsync(io->iterations, d_iters, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
-  if (io->cost_initial) FLEET_CUDA(cudaMemcpyAsync(io->cost_initial, d_cost0, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
-  if (io->cost_final) FLEET_CUDA(cudaMemcpyAsync(io->cost_final, d_cost1, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
-  if (io->project_status) FLEET_CUDA(cudaMemcpyAsync(io->project_status, d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  struct Dst { void* host; const void* dev; size_t bytes; };
+  const Dst dsts[] = {
+      {io->poses, d_poses, BS * 3 * 8},           {io->cmds, d_cmds, BS * 2 * 8},
+      {io->n_out, d_n_out, (size_t)B * 4},        {io->optimized, d_optimized, (size_t)B},
+      {io->termination, d_term, (size_t)B * 4},   {io->iterations, d_iters, (size_t)B * 4},
+      {io->cost_initial, d_cost0, (size_t)B * 8}, {io->cost_final, d_cost1, (size_t)B * 8},
+      {io->project_status, d_status, (size_t)B * 4},
+  };
   if (io->people_proj)
     FLEET_CUDA(cudaMemcpyAsync(io->people_proj, d_agents, (size_t)B * A * 6 * stride * 8, cudaMemcpyDeviceToHost, st));
+  if (packed) {  // [d_poses, d_cmds] and [d_usable .. d_status] into one staging block, then scattered on the host
+    FLEET_CUDA(fs->pin_out.reserve(io_span + tail_span));
+    char* stage = static_cast<char*>(fs->pin_out.ptr);
+    FLEET_CUDA(cudaMemcpyAsync(stage, fs->scratch.ptr, io_span, cudaMemcpyDeviceToHost, st));
+    FLEET_CUDA(cudaMemcpyAsync(stage + io_span, scratch0 + tail_off, tail_span, cudaMemcpyDeviceToHost, st));
+    FLEET_CUDA(cudaStreamSynchronize(st));
+    for (const Dst& c : dsts) {
+      if (!c.host) continue;
+      const size_t off = static_cast<const char*>(c.dev) - scratch0;
+      std::memcpy(c.host, stage + (off < io_span ? off : io_span + (off - tail_off)), c.bytes);
+    }
+    return SMPC_OK;
+  }
+  for (const Dst& c : dsts)
+    if (c.host) FLEET_CUDA(cudaMemcpyAsync(c.host, c.dev, c.bytes, cudaMemcpyDeviceToHost, st));
   FLEET_CUDA(cudaStreamSynchronize(st));
   return SMPC_OK;
 }
