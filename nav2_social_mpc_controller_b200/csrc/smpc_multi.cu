@@ -123,7 +123,7 @@ int smpc_solve_batch_multi(smpc_multi* m, const smpc_batch* in, smpc_result* out
         s.n_steps_each = in->n_steps_each ? in->n_steps_each + lo : nullptr;
       }
       if (scenes) {
-        // costmap_index (if any) is per scene row: unchanged
+        s.costmap_index = in->costmap_index;  // per scene row, like every other per-scene array: unchanged
       } else if (maps_per_problem) {
         s.costmaps = in->costmaps + cells * lo;
         s.costmap_origin = in->costmap_origin + 2 * lo;

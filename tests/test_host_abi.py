@@ -168,6 +168,23 @@ def test_host_pipeline_chunk_plan():
     assert L.smpc_debug_plan_chunks(0, 10, 0, 1, 0, 0, 0, None, None) != 0
 
 
+def test_scenario_sharing_batches_expand_to_the_per_problem_layout():
+    """smpc_batch.scenario_index (multi-start): the shared-scene form of a batch and its per-problem form describe the
+    same problems; slices keep the scene arrays whole and cut only u0 / scenario_index."""
+    plain = sc.multistart(n_robots=5, n_starts=7)
+    shared = sc.multistart(n_robots=5, n_starts=7, shared=True)
+    full = shared.expanded()
+    assert shared.arrays["pose0"].shape[0] == 5 and shared.arrays["u0"].shape[0] == 35
+    assert shared.struct().n_scenarios == 5 and plain.struct().n_scenarios == 0 and full.struct().n_scenarios == 0
+    for k, v in plain.arrays.items():
+        if v is not None:
+            assert np.array_equal(v, full.arrays[k]), k
+    part = shared.slice(7, 21)
+    assert part.n_problems == 14 and part.arrays["pose0"].shape[0] == 5
+    assert part.arrays["scenario_index"].tolist() == [1] * 7 + [2] * 7
+    assert np.array_equal(part.expanded().arrays["agents"], plain.slice(7, 21).arrays["agents"])
+
+
 def test_multi_gpu_shard_bounds_without_a_gpu():
     """smpc_debug_shard_bounds: the contiguous cut smpc_solve_batch_multi uses — shards cover [0, n) without gaps, start
     at multiples of the granule (multi-start: a robot's starts stay on one GPU), sizes differ by at most one granule."""
