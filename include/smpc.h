@@ -499,7 +499,7 @@ int smpc_debug_plan_chunks(int n_sm, int n_problems, int has_people, int n_costm
 /* Diagnostics for unit tests: run the line-search interpolating-polynomial minimiser (Ceres polynomial.cc
  * restatement) on n host rows of (lo, hi, f0, g0, t1, f1, g1, t2, f2, g2); t2 <= 0 selects the 2-sample case. */
 int smpc_debug_polymin(smpc_handle* h, int n, const double* rows, double* out);
-/* Diagnostics for unit tests: the pair loop's own elementary functions (csrc/smpc_device.cuh) on n host rows of
+/* Diagnostics for unit tests: the social-force loops' own elementary functions (csrc/smpc_math.cuh) on n host rows of
  * (a, b): kind 0 = exp_nonpos(a) (a <= 0), 1 = rsqrt_pos(a) (a > 0, normal), 2 = atan2_unit(a, b) (|(b, a)| ~ 1). */
 int smpc_debug_math(smpc_handle* h, int kind, int n, const double* rows, double* out);
 

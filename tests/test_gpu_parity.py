@@ -279,7 +279,7 @@ def test_multistart_argmin(make_opt):
 
 
 def test_pair_loop_elementary_functions_are_libm_class(make_opt):
-    """exp_nonpos / rsqrt_pos / atan2_unit of the social-force loop (csrc/smpc_device.cuh) against 80-bit long-double
+    """exp_nonpos / rsqrt_pos / atan2_unit of the social-force loops (csrc/smpc_math.cuh) against 80-bit long-double
     libm: <= 1 ulp (exp, rsqrt) and <= 2 ulp (atan2), i.e. the accuracy class of the CUDA / glibc functions they
     replace; arguments whose result would be below 2^-1022 are clamped (never garbage); NaN propagates."""
     opt = make_opt(sc.make_params("soc_work_obst"))

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Coefficients of the device exp_nonpos() polynomial (csrc/smpc_device.cuh): exp(r) = 1 + r + r^2 h(r) on the reduced
+"""Coefficients of the device exp_nonpos() polynomial (csrc/smpc_math.cuh): exp(r) = 1 + r + r^2 h(r) on the reduced
 range |r| <= ln2/2, h = degree-9 Chebyshev interpolant (60-digit mpmath), and the error of the whole double-precision
 evaluation (fma emulated exactly) against mpmath over x in [-708, 0]. Run: python tools/fit_exp.py"""
 import random
