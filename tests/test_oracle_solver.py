@@ -181,3 +181,24 @@ def test_independent_numpy_trlm_reproduces_the_oracle_trace_on_the_golden_cases(
                     assert c_plain == pytest.approx(r[4], rel=1e-8)
             n_checked += 1
     assert n_checked >= 20
+
+
+def test_perturbed_oracle_variants_build_and_agree_on_well_conditioned_problems(oracle):
+    """tools/oracle_sensitivity.py measures the noise floor of the restated algorithm with three variants of the SAME
+    oracle source (FMA contraction, double instead of long-double line-search polynomial, reverse summation order). They
+    must build, and on well-conditioned people-free problems they must land on the oracle's own result."""
+    import ctypes as C
+    import os
+    import subprocess
+    from tests import oracle_lib
+    here = os.path.dirname(os.path.abspath(__file__))
+    odir = os.path.join(os.path.dirname(here), "oracle")
+    names = ["liboracle_fma.so", "liboracle_polydouble.so", "liboracle_revsum.so"]
+    subprocess.run(["make", "-C", odir, "-s"] + names, check=True)
+    batch = sc.corridor(B=24)
+    base = oracle.solve_batch(batch, n_threads=4)
+    for name in names:
+        other = oracle_lib.Oracle(C.CDLL(os.path.join(odir, name))).solve_batch(batch, n_threads=4)
+        assert np.array_equal(other["termination"], base["termination"]), name
+        assert np.array_equal(other["iterations"], base["iterations"]), name
+        assert np.abs(other["u"] - base["u"]).max() <= 1e-6, name
