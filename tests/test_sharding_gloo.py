@@ -26,7 +26,7 @@ def test_shard_bounds_cover_and_align():
         shard_bounds(10, 2, 0, 4)
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, shared=False):
     import torch.distributed as dist
     from nav2_social_mpc_controller_b200.sharding import solve_sharded
     from tests import oracle_lib
@@ -34,7 +34,7 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     o = oracle_lib.load()
-    batch = sc.multistart(n_robots=6, n_starts=4)
+    batch = sc.multistart(n_robots=6, n_starts=4, shared=shared)  # shared: one scene row per robot (scenario_index)
 
     def solve(sub):
         r = o.solve_batch(sub, want=("u", "cost_final", "usable", "termination"))
@@ -46,14 +46,15 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_two_rank_sharded_solve_matches_single_process(oracle):
+@pytest.mark.parametrize("shared", [False, True])
+def test_two_rank_sharded_solve_matches_single_process(oracle, shared):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, shared)) for r in range(2)]
     for p in procs:
         p.start()
     got = q.get(timeout=240)
